@@ -1,0 +1,186 @@
+/*
+ * monortm_b200.h -- C ABI of libmonortm_b200.so, the B200 (sm_100a) replacement
+ * for monoRTM's monochromatic optical-depth + radiance hot path.
+ *
+ * Drop-in boundary (all citations relative to /root/reference):
+ *   mrtm_stage_lines  <- the module data GET_LNFL fills (src/lnfl_mod.f90:9-18, 22-133)
+ *   mrtm_modm         <- SUBROUTINE MODM    (src/modm.f90:21-25, call src/monortm.f90:557-561)
+ *   mrtm_calctmr      <- SUBROUTINE CALCTMR (src/RTMmono.f90:239,  call src/monortm.f90:567)
+ *   mrtm_rtm          <- SUBROUTINE RTM     (src/RTMmono.f90:13-14, call src/monortm.f90:573-574)
+ *   mrtm_profile(s)   <- the three calls fused, optical depths kept in HBM
+ *
+ * Conventions: every array is Fortran column-major (first index fastest),
+ * REAL == double, INTEGER == int64_t (the parity build linuxGNUdbl uses
+ * -fdefault-real-8 -fdefault-integer-8, build/makefile.common:195-198), except
+ * brd_mol_flg which the reference itself declares integer*4.  Pointers are
+ * caller-owned host memory unless the name ends in _dev; the library never
+ * frees or retains them after the call returns.  Every function returns 0 on
+ * success or an MRTM_E* code (the reference STOPs; the Fortran shim turns a
+ * non-zero code into STOP, monortm_b200/shim/monortm_gpu_shim.f90).  One ctx
+ * per process/GPU; calls on a ctx are not re-entrant.  There is no CPU
+ * fallback: without a usable sm_100 device mrtm_init fails with MRTM_ENODEV.
+ */
+#ifndef MONORTM_B200_H
+#define MONORTM_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MRTM_MXMOL 39     /* src/lblparams.f90:28 */
+#define MRTM_MXBRDMOL 7   /* src/struct_types.f90:25 */
+#define MRTM_NSCOR1 42    /* scor(42,9), src/modm.f90:142 */
+#define MRTM_NSCOR2 9
+
+enum {
+    MRTM_OK = 0,
+    MRTM_ENODEV = 1,       /* no CUDA device / not sm_100 */
+    MRTM_ECUDA = 2,        /* CUDA runtime error (see mrtm_last_error) */
+    MRTM_EARG = 3,         /* bad argument / dimension */
+    MRTM_ENOLINES = 4,     /* mrtm_stage_lines has not been called */
+    MRTM_ELINEFILE = 5,    /* malformed line store (LC flag not 1/3/5: lnfl_mod.f90:61-63; bad isotope) */
+    MRTM_ERANGE = 6,       /* spectral range needs continuum branches not built (V2 >= 820 cm-1) */
+    MRTM_ESDVOIGT = 7,     /* REAL(v) < 0 in SDVOIGT: modm.f90:1062 STOP */
+    MRTM_EIDU = 8,         /* IDU != 1: RTMmono.f90:173 STOP */
+    MRTM_ENOMEM = 9,
+    MRTM_EIO = 10,         /* host helpers: file missing / malformed */
+    MRTM_ETIPS = 11        /* partition sum <= 0 or T outside 70..3000 K: tips_2003.f90:271-277 */
+};
+
+typedef struct mrtm_ctx mrtm_ctx;
+
+/* Per-call options that have no counterpart in the reference's argument lists.
+ * Zero-initialise for reference behaviour. */
+typedef struct mrtm_opts {
+    /* Frequency sharding: the reference derives the line-load range,
+     * the continuum grid and the gridded-interpolation origin from wn(1), wn(nwn)
+     * (modm.f90:180-185, 218-219).  A rank that holds only wn(iw0+1 : iw0+nwn) of a
+     * global grid passes the global v1, v2 and its 0-based offset iw0 here.
+     * use_global_range == 0 -> v1 = wn[0], v2 = wn[nwn-1], iw0 = 0. */
+    int32_t use_global_range;
+    int32_t reserved0;
+    double v1_global, v2_global;
+    int64_t iw0;
+    /* Verification: when non-NULL (host, (nwn,nlay)) the line kernel also returns, per
+     * (frequency, layer), the number of (molecule,record) pairs that pass the cutoff
+     * test modm.f90:384 and an order-independent 64-bit hash of them. */
+    int64_t *sel_count;
+    uint64_t *sel_hash;
+    /* Asynchronous device-resident mode: CUDA stream (cudaStream_t) to run on; NULL =
+     * the context's own stream. */
+    void *stream;
+} mrtm_opts;
+
+/* ---- context ------------------------------------------------------------------------- */
+int mrtm_init(int device, mrtm_ctx **ctx);
+int mrtm_free(mrtm_ctx *ctx);
+const char *mrtm_strerror(int code);
+const char *mrtm_last_error(mrtm_ctx *ctx);   /* detail of the last failure on ctx (may be NULL ctx) */
+const char *mrtm_version(void);
+
+/* ---- line store ---------------------------------------------------------------------- */
+/* Stage the line list once as a structure-of-arrays in HBM.  Arguments are the module
+ * arrays of src/lnfl_mod.f90:9-13 exactly as GET_LNFL leaves them: nblm(39); iso and the
+ * REAL arrays dimensioned (39, iim) [element (mo,ii) at (mo-1)+(ii-1)*39]; brd_mol_*
+ * dimensioned (7,7,iim).  The H2O self-width fix-up of modm.f90:841 is applied to the
+ * staged copy (the caller's alps is not modified). */
+int mrtm_stage_lines(mrtm_ctx *ctx, const int64_t nblm[MRTM_MXMOL], int64_t iim,
+                     const int64_t *iso, const double *xnu0, const double *deltnu,
+                     const double *e, const double *alps, const double *alpf,
+                     const double *x, const double *xg, const double *s0,
+                     const double *rmol, const double *sdep,
+                     const int32_t *brd_mol_flg, const double *brd_mol_tmp,
+                     const double *brd_mol_hw, const double *brd_mol_shft);
+/* number of logical lines staged (coupling-coefficient records are not lines) */
+int64_t mrtm_num_lines(mrtm_ctx *ctx);
+
+/* ---- MODM ---------------------------------------------------------------------------- */
+/* Replaces CALL MODM(IPR,ICP,NWN,WN,dvset,NLAY,P,T,CLW,O,O_BY_MOL,OC,O_CLW,ODXSEC,NMOL,
+ * WKL,WBRODL,SCLCPL,SCLHW,Y0RES,HFILE,cntnmScaleFac,ixsect,IBRD)  (src/modm.f90:21-25).
+ * Differences: IPR/ICP/HFILE are dropped (ICP is never consulted; the line
+ * file is staged by mrtm_stage_lines); tips_2003 (modm.f90:250) stays on the Fortran side
+ * and its result crosses as scor(42,9,nlay); odxsec is IN/OUT: with ixsect==1 the caller
+ * passes monortm_xsec_sub's result in it (modm.f90:197-198), otherwise it is zeroed.
+ *   wn(nwn) ascending; p,t,clw,wbrodl(nlay); wkl(39,nlay) molec/cm2;
+ *   o,o_clw,odxsec (nwn,nlay); o_by_mol,oc (nwn,39,nlay).  Any output may be NULL.
+ *   cntnm[7] = xself,xfrgn,xco2c,xo3cn,xo2cn,xn2cn,xrayl (src/CntnmFactors.f90:17-19). */
+int mrtm_modm(mrtm_ctx *ctx, int64_t nwn, const double *wn, double dvset, int64_t nlay,
+              const double *p, const double *t, const double *clw,
+              double *o, double *o_by_mol, double *oc, double *o_clw, double *odxsec,
+              int64_t nmol, const double *wkl, const double *wbrodl,
+              double sclcpl, double sclhw, double y0res, const double cntnm[7],
+              int64_t ixsect, int64_t ibrd, const double *scor, const mrtm_opts *opts);
+
+/* ---- CALCTMR / RTM --------------------------------------------------------------------- */
+/* CALL CALCTMR(NLAYRS,NWN,WN,T,TZ,O,TMR)  (src/RTMmono.f90:239).  tz is (0:nlayrs). */
+int mrtm_calctmr(mrtm_ctx *ctx, int64_t nlayrs, int64_t nwn, const double *wn,
+                 const double *t, const double *tz, const double *o, double *tmr);
+
+/* CALL RTM(IOUT,IRT,NWN,WN,NLAY,T,TZ,O,TMPSFC,RUP,TRTOT,RDN,REFLC,EMISS,RAD,TB,IDU)
+ * (src/RTMmono.f90:13-14).  tmpsfc is in/out: set to 2.75 for irt 2,3 (RTMmono.f90:122). */
+int mrtm_rtm(mrtm_ctx *ctx, int64_t iout, int64_t irt, int64_t nwn, const double *wn,
+             int64_t nlay, const double *t, const double *tz, const double *o,
+             double *tmpsfc, double *rup, double *trtot, double *rdn,
+             const double *reflc, const double *emiss, double *rad, double *tb, int64_t idu);
+
+/* ---- fused path ------------------------------------------------------------------------ */
+/* MODM + CALCTMR + RTM for nprof profiles in one call; optical depths stay in HBM.
+ * Profile arrays carry a trailing profile dimension: p,t,clw,wbrodl (nlay,nprof);
+ * tz (0:nlay, nprof) i.e. (nlay+1,nprof); wkl (39,nlay,nprof); scor (42,9,nlay,nprof);
+ * tmpsfc (nprof) in/out; emiss,reflc (nwn) shared by all profiles.
+ * Outputs (nwn,nprof): rad,tb,tmr,trtot,rup,rdn.  Optional (may be NULL):
+ * o (nwn,nlay,nprof) layer optical depths; otot_by_mol (39,nwn,nprof) = layer sums of
+ * o_by_mol+oc per molecule (what STOREOUT prints, src/monortm_sub.F90:649-656). */
+int mrtm_profiles(mrtm_ctx *ctx, int64_t nprof, int64_t nwn, const double *wn, double dvset,
+                  int64_t nlay, const double *p, const double *t, const double *tz,
+                  const double *clw, int64_t nmol, const double *wkl, const double *wbrodl,
+                  const double *scor, double sclcpl, double sclhw, double y0res,
+                  const double cntnm[7], int64_t ibrd, int64_t irt, int64_t iout, int64_t idu,
+                  double *tmpsfc, const double *emiss, const double *reflc,
+                  double *rad, double *tb, double *tmr, double *trtot, double *rup, double *rdn,
+                  double *o, double *otot_by_mol, const mrtm_opts *opts);
+
+/* Same computation with every array already resident in device memory (layouts as above),
+ * asynchronous on opts->stream; nothing is copied to the host.  Used when the caller keeps
+ * inputs/outputs in HBM (ensembles, multi-GPU shards gathered with NCCL). */
+int mrtm_profiles_dev(mrtm_ctx *ctx, int64_t nprof, int64_t nwn, const double *wn_dev, double dvset,
+                      int64_t nlay, const double *p, const double *t, const double *tz,
+                      const double *clw, int64_t nmol, const double *wkl, const double *wbrodl,
+                      const double *scor, double sclcpl, double sclhw, double y0res,
+                      const double cntnm[7], int64_t ibrd, int64_t irt, int64_t iout, int64_t idu,
+                      double *tmpsfc, const double *emiss_dev, const double *reflc_dev,
+                      double *rad_dev, double *tb_dev, double *tmr_dev, double *trtot_dev,
+                      double *rup_dev, double *rdn_dev, double *o_dev, const mrtm_opts *opts);
+
+/* ---- instrumentation ------------------------------------------------------------------- */
+typedef struct mrtm_stats {
+    int64_t kernel_launches;     /* kernels launched by this ctx since the last reset */
+    int64_t lines_staged;
+    double last_lines_kernel_ms; /* CUDA-event time of the last line-shape kernel launch(es) of a call */
+    double last_rt_kernel_ms;
+    double last_derive_kernel_ms;
+    double nominal_evals;        /* (logical line, layer, frequency) triples of the last call */
+    double inwindow_evals;       /* triples that pass modm.f90:384 (needs opts->sel_count) else -1 */
+} mrtm_stats;
+int mrtm_get_stats(mrtm_ctx *ctx, mrtm_stats *st);
+int mrtm_reset_stats(mrtm_ctx *ctx);
+/* FP64 FMA micro-benchmark on the ctx device: returns achieved TFLOP/s (2 flop per DFMA). */
+int mrtm_fp64_peak(mrtm_ctx *ctx, double *tflops);
+
+/* ---- host helpers (the harness side of SURVEY 8f-1; no GPU needed) ---------------------- */
+/* GET_LNFL (src/lnfl_mod.f90:22-133): read a TAPE3 into caller-allocated lnfl_mod-layout
+ * arrays of second dimension iim. */
+int mrtm_host_get_lnfl(const char *hfile, double v1, double v2, int64_t iim, int64_t nblm[MRTM_MXMOL],
+                       int64_t *iso, double *xnu0, double *deltnu, double *e, double *alps,
+                       double *alpf, double *x, double *xg, double *s0, double *rmol, double *sdep,
+                       int32_t *brd_mol_flg, double *brd_mol_tmp, double *brd_mol_hw,
+                       double *brd_mol_shft);
+/* TIPS_2003 (src/tips_2003.f90:2-298): scor(42,9) = Q(296)/Q(T) for molecules 1..mol_max. */
+int mrtm_host_tips_2003(int64_t mol_max, double temp, double *scor);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,816 @@
+// mrtm_api.cu -- context, staging upload, orchestration and the extern "C" entry points of
+// libmonortm_b200.so (include/monortm_b200.h).  No CPU fallback exists: every compute entry
+// point needs a live sm_100 device.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "mrtm_kernels.cuh"
+#include "mrtm_stage.h"
+#include "tables/mtckd_tables.inc"
+
+namespace mrtm {
+const double* tips_qoft();
+const double* tips_tdat();
+int tips_rows();
+int tips_row(int mol, int iso);
+}  // namespace mrtm
+
+using namespace mrtm;
+
+// ---------------------------------------------------------------------------------------------
+struct DevBuf {   // grow-only device scratch
+    void* p = nullptr;
+    size_t cap = 0;
+};
+
+struct mrtm_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[8];
+    std::string err;
+    bool have_lines = false;
+    HostLines hl;
+    LinesDev ld;
+    std::vector<void*> line_allocs;
+    Segment* seg_dev = nullptr;
+    ContTablesDev tb;
+    TipsDev tips;
+    std::vector<void*> table_allocs;
+    int32_t* tips_row_dev = nullptr;
+    int* errflag_dev = nullptr;
+    DevBuf b_layer, b_scorc, b_absrb, b_planes, b_o, b_obm, b_oc, b_in[16], b_out[16], b_sel[2], b_tmps;
+    mrtm_stats st;
+    size_t planes_budget = (size_t)8 << 30;
+};
+
+static thread_local std::string g_err_noctx;
+
+static int set_err(mrtm_ctx* c, int code, const std::string& msg)
+{
+    if (c) c->err = msg; else g_err_noctx = msg;
+    return code;
+}
+
+#define CU(call)                                                                                  \
+    do {                                                                                          \
+        cudaError_t e_ = (call);                                                                  \
+        if (e_ != cudaSuccess)                                                                    \
+            return set_err(ctx, MRTM_ECUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); \
+    } while (0)
+
+static int ensure(mrtm_ctx* ctx, DevBuf& b, size_t bytes)
+{
+    if (bytes <= b.cap) return MRTM_OK;
+    if (b.p) CU(cudaFree(b.p));
+    b.p = nullptr;
+    b.cap = 0;
+    size_t want = bytes + bytes / 8 + 256;
+    cudaError_t e = cudaMalloc(&b.p, want);
+    if (e != cudaSuccess) return set_err(ctx, MRTM_ENOMEM, std::string("cudaMalloc: ") + cudaGetErrorString(e));
+    b.cap = want;
+    return MRTM_OK;
+}
+
+template <class T>
+static int upload(mrtm_ctx* ctx, const std::vector<T>& v, std::vector<void*>& owner, const T** out)
+{
+    void* d = nullptr;
+    size_t bytes = std::max<size_t>(v.size(), 1) * sizeof(T);
+    CU(cudaMalloc(&d, bytes));
+    owner.push_back(d);
+    if (!v.empty()) CU(cudaMemcpy(d, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+    *out = (const T*)d;
+    return MRTM_OK;
+}
+
+static int upload_arr(mrtm_ctx* ctx, const double* src, size_t n, std::vector<void*>& owner, const double** out)
+{
+    std::vector<double> v(src, src + n);
+    return upload(ctx, v, owner, out);
+}
+
+// ---------------------------------------------------------------------------------------------
+extern "C" const char* mrtm_version(void) { return "monortm_b200 0.1 (hot path of MonoRTM v5.6, MT_CKD_3.5)"; }
+
+extern "C" const char* mrtm_strerror(int code)
+{
+    switch (code) {
+    case MRTM_OK: return "ok";
+    case MRTM_ENODEV: return "no usable CUDA device (sm_100 required; there is no CPU fallback)";
+    case MRTM_ECUDA: return "CUDA runtime error";
+    case MRTM_EARG: return "bad argument";
+    case MRTM_ENOLINES: return "line list not staged (call mrtm_stage_lines first)";
+    case MRTM_ELINEFILE: return "malformed line store";
+    case MRTM_ERANGE: return "spectral range needs continuum branches that are not built (V2 >= 820 cm-1)";
+    case MRTM_ESDVOIGT: return "SDVOIGT: REAL(v) < 0 (reference STOPs, modm.f90:1062)";
+    case MRTM_EIDU: return "ERROR IN IDU. OPTION NOT SUPPORTED YET";
+    case MRTM_ENOMEM: return "out of (device) memory";
+    case MRTM_EIO: return "file missing or malformed";
+    case MRTM_ETIPS: return "TIPS: temperature outside 70-3000 K or partition sum <= 0";
+    default: return "unknown error";
+    }
+}
+
+extern "C" const char* mrtm_last_error(mrtm_ctx* ctx) { return ctx ? ctx->err.c_str() : g_err_noctx.c_str(); }
+
+extern "C" int mrtm_init(int device, mrtm_ctx** out)
+{
+    mrtm_ctx* ctx = nullptr;
+    if (!out) return MRTM_EARG;
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev <= 0)
+        return set_err(nullptr, MRTM_ENODEV, std::string("cudaGetDeviceCount: ") + cudaGetErrorString(e));
+    if (device < 0 || device >= ndev) return set_err(nullptr, MRTM_EARG, "device index out of range");
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return set_err(nullptr, MRTM_ENODEV, "cudaGetDeviceProperties failed");
+    if (prop.major != 10) return set_err(nullptr, MRTM_ENODEV, "device is not sm_100 (this library ships sm_100a code only)");
+    ctx = new mrtm_ctx();
+    ctx->device = device;
+    std::memset(&ctx->st, 0, sizeof ctx->st);
+    std::memset(&ctx->ld, 0, sizeof ctx->ld);
+    if (cudaSetDevice(device) != cudaSuccess) { delete ctx; return set_err(nullptr, MRTM_ECUDA, "cudaSetDevice failed"); }
+    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return set_err(nullptr, MRTM_ECUDA, "cudaStreamCreate failed"); }
+    for (auto& ev : ctx->ev) cudaEventCreate(&ev);
+    if (const char* s = std::getenv("MRTM_PLANES_GB")) ctx->planes_budget = (size_t)(std::atof(s) * (double)(1ull << 30));
+    // continuum + TIPS tables -> HBM (about 190 KB)
+    int rc;
+#define UP(NAME, FIELD) if ((rc = upload_arr(ctx, NAME, sizeof(NAME) / sizeof(double), ctx->table_allocs, &ctx->tb.FIELD))) { *out = ctx; return rc; }
+    UP(MTCKD_SH2O_296, sh2o_296) UP(MTCKD_SH2O_260, sh2o_260) UP(MTCKD_FH2O, fh2o) UP(MTCKD_FCO2, fco2)
+    UP(MTCKD_N2RT_296, n2_296) UP(MTCKD_N2RT_296_SF, n2_296_sf) UP(MTCKD_N2RT_220, n2_220) UP(MTCKD_N2RT_220_SF, n2_220_sf)
+    UP(MTCKD_XFAC_RHU, xfac_rhu) UP(MTCKD_CO2_TDEP_BANDHEAD, co2_tdep)
+#undef UP
+    if ((rc = upload_arr(ctx, tips_qoft(), (size_t)tips_rows() * 119, ctx->table_allocs, &ctx->tips.qoft))) { *out = ctx; return rc; }
+    if ((rc = upload_arr(ctx, tips_tdat(), 119, ctx->table_allocs, &ctx->tips.tdat))) { *out = ctx; return rc; }
+    ctx->tips.row = nullptr;
+    if (cudaMalloc(&ctx->errflag_dev, sizeof(int)) != cudaSuccess) { *out = ctx; return set_err(ctx, MRTM_ENOMEM, "cudaMalloc errflag"); }
+    cudaMemset(ctx->errflag_dev, 0, sizeof(int));
+    *out = ctx;
+    return MRTM_OK;
+}
+
+static void free_lines(mrtm_ctx* ctx)
+{
+    for (void* p : ctx->line_allocs) cudaFree(p);
+    ctx->line_allocs.clear();
+    ctx->have_lines = false;
+}
+
+extern "C" int mrtm_free(mrtm_ctx* ctx)
+{
+    if (!ctx) return MRTM_OK;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    free_lines(ctx);
+    for (void* p : ctx->table_allocs) cudaFree(p);
+    DevBuf* bufs[] = {&ctx->b_layer, &ctx->b_scorc, &ctx->b_absrb, &ctx->b_planes, &ctx->b_o, &ctx->b_obm, &ctx->b_oc, &ctx->b_sel[0], &ctx->b_sel[1], &ctx->b_tmps};
+    for (DevBuf* b : bufs) if (b->p) cudaFree(b->p);
+    for (auto& b : ctx->b_in) if (b.p) cudaFree(b.p);
+    for (auto& b : ctx->b_out) if (b.p) cudaFree(b.p);
+    if (ctx->errflag_dev) cudaFree(ctx->errflag_dev);
+    for (auto& ev : ctx->ev) cudaEventDestroy(ev);
+    cudaStreamDestroy(ctx->stream);
+    delete ctx;
+    return MRTM_OK;
+}
+
+extern "C" int64_t mrtm_num_lines(mrtm_ctx* ctx) { return (ctx && ctx->have_lines) ? ctx->hl.n : 0; }
+
+extern "C" int mrtm_stage_lines(mrtm_ctx* ctx, const int64_t nblm[MRTM_MXMOL], int64_t iim,
+                                const int64_t* iso, const double* xnu0, const double* deltnu,
+                                const double* e, const double* alps, const double* alpf,
+                                const double* x, const double* xg, const double* s0,
+                                const double* rmol, const double* sdep,
+                                const int32_t* brd_mol_flg, const double* brd_mol_tmp,
+                                const double* brd_mol_hw, const double* brd_mol_shft)
+{
+    if (!ctx) return MRTM_EARG;
+    if (!nblm || !iso || !xnu0 || !deltnu || !e || !alps || !alpf || !x || !xg || !s0 || !rmol || !sdep)
+        return set_err(ctx, MRTM_EARG, "null line array");
+    CU(cudaSetDevice(ctx->device));
+    free_lines(ctx);
+    int rc = stage_lines_host(nblm, iim, iso, xnu0, deltnu, e, alps, alpf, x, xg, s0, rmol, sdep,
+                              brd_mol_flg, brd_mol_tmp, brd_mol_hw, brd_mol_shft, ctx->hl);
+    if (rc) return set_err(ctx, rc, ctx->hl.error);
+    HostLines& h = ctx->hl;
+    LinesDev& d = ctx->ld;
+    std::memset(&d, 0, sizeof d);
+    d.n = (int32_t)h.n;
+    d.n_pad = (int32_t)h.n_pad;
+    auto& own = ctx->line_allocs;
+#define UPV(F) if ((rc = upload(ctx, h.F, own, &d.F))) return rc;
+    UPV(mol) UPV(iso) UPV(xf) UPV(cls) UPV(sidx) UPV(lcidx) UPV(brdidx)
+    UPV(xnu0) UPV(s0adj) UPV(e) UPV(alpf) UPV(alps) UPV(x) UPV(deltnu) UPV(sdep) UPV(mass)
+    UPV(lc) UPV(lc_self) UPV(brd) UPV(scor_index)
+#undef UPV
+    {
+        std::vector<unsigned long long> k(h.key.begin(), h.key.end());
+        if ((rc = upload(ctx, k, own, &d.key))) return rc;
+    }
+    d.nsi = (int32_t)h.scor_index.size();
+    {
+        const Segment* sd = nullptr;
+        if ((rc = upload(ctx, h.segments, own, &sd))) return rc;
+        ctx->seg_dev = const_cast<Segment*>(sd);
+        std::vector<int32_t> rows(h.scor_index.size());
+        for (size_t s = 0; s < rows.size(); s++) {
+            int mol = h.scor_index[s] % MRTM_NSCOR1 + 1, iso_ = h.scor_index[s] / MRTM_NSCOR1 + 1;
+            rows[s] = tips_row(mol, iso_);
+        }
+        const int32_t* rd = nullptr;
+        if ((rc = upload(ctx, rows, own, &rd))) return rc;
+        ctx->tips.row = rd;
+    }
+    ctx->have_lines = true;
+    ctx->st.lines_staged = h.n;
+    return MRTM_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// continuum index set-up (layer independent): table accessors (contnm.f90:1441-1456 and twins),
+// pre_xint (:1146-1164) and the XINT loop bounds (lblrtm_sub.f90:13-17), evaluated on the host.
+// ---------------------------------------------------------------------------------------------
+static ContGrid make_grid(double v1abs, double v2abs, int nptabs, double v1s, double v2s, double dvs, int npts, bool active)
+{
+    ContGrid g;
+    std::memset(&g, 0, sizeof g);
+    const double dvabs = 1.0, onemi = 0.999;
+    double dvc = dvs;
+    double v1c = v1abs - dvc, v2c = v2abs + dvc;
+    long long i1;
+    if (v1c < v1s) i1 = -1;
+    else i1 = (long long)((v1c - v1s) / dvs + 0.01);
+    v1c = v1s + dvs * (double)(i1 - 1);
+    long long i2 = (long long)((v2c - v1s) / dvs + 0.01);
+    long long nptc = i2 - i1 + 3;
+    if (nptc > npts) nptc = npts + 4;
+    v2c = v1c + dvs * (double)(nptc - 1);
+    long long nb1 = (long long)(2 + (v1s - v1abs) / dvabs + 1.e-5);
+    long long ist = std::max<long long>(1, nb1);
+    long long nb2 = (long long)(1 + (v2s - v1abs) / dvabs + 1.e-5);
+    long long last = std::min<long long>(nptabs, nb2);
+    long long ilo = (long long)((v1c + dvc - v1abs) / dvabs + 1. + onemi);
+    ilo = std::max(ilo, ist);
+    long long ihi = (long long)((v2c - dvc - v1abs) / dvabs + onemi);
+    ihi = std::min(ihi, last);
+    g.v1c = v1c;
+    g.dvc = dvc;
+    g.nptc = (int32_t)nptc;
+    g.i1 = (int32_t)i1;
+    g.ilo = (int32_t)ilo;
+    g.ihi = (int32_t)ihi;
+    g.active = active ? 1 : 0;
+    return g;
+}
+
+// everything below works on device pointers
+struct RunDesc {
+    int64_t nprof, nwn, nlay, nmol;
+    const double* wn;
+    double dvset;
+    const double *p, *t, *tz, *clw, *wkl, *wbrodl, *scor;
+    double sclcpl, sclhw, y0res, cntnm[7];
+    int64_t ibrd, irt, iout, idu;
+    double* tmpsfc;                 // device (nprof)
+    const double *emiss, *reflc;
+    double *rad, *tb, *tmr, *trtot, *rup, *rdn;
+    double* o;                      // (nwn,nlay,nprof) or null
+    double *o_by_mol, *oc, *o_clw;  // modm-style outputs, nprof==1 only
+    const double* odxsec;
+    long long* sel_count;
+    unsigned long long* sel_hash;
+    bool do_lines, do_tmr, do_rtm;
+    double v1, v2;
+    int64_t iw0;
+};
+
+template <int F>
+static void launch_lines(const LinesArgs& la, dim3 grid, bool sel, cudaStream_t s)
+{
+    if (sel) lines_kernel<F, true><<<grid, 128, 0, s>>>(la);
+    else lines_kernel<F, false><<<grid, 128, 0, s>>>(la);
+}
+
+static int run_device(mrtm_ctx* ctx, const RunDesc& r, cudaStream_t s)
+{
+    if (r.nprof < 1 || r.nwn < 1 || r.nlay < 1) return set_err(ctx, MRTM_EARG, "nprof, nwn, nlay must be >= 1");
+    if (r.nwn > 0x7fffffff / 64 || r.nlay > 65535) return set_err(ctx, MRTM_EARG, "nwn/nlay too large for one call");
+    mrtm_stats& st = ctx->st;
+    st.last_lines_kernel_ms = st.last_rt_kernel_ms = st.last_derive_kernel_ms = 0.;
+    const int64_t nwn = r.nwn, nlay = r.nlay;
+    DevBuf& bo = ctx->b_o;
+
+    if (r.do_lines) {
+        if (!ctx->have_lines) return set_err(ctx, MRTM_ENOLINES, mrtm_strerror(MRTM_ENOLINES));
+        if (r.nmol < 1 || r.nmol > MRTM_MXMOL) return set_err(ctx, MRTM_EARG, "nmol out of 1..39");
+        if (!(r.v2 < 820.0)) return set_err(ctx, MRTM_ERANGE, mrtm_strerror(MRTM_ERANGE));
+        if ((r.o_by_mol || r.oc || r.o_clw) && r.nprof != 1) return set_err(ctx, MRTM_EARG, "per-molecule outputs need nprof == 1");
+    }
+    if ((r.do_rtm || r.do_tmr) && r.do_rtm && r.idu != 1) return set_err(ctx, MRTM_EIDU, mrtm_strerror(MRTM_EIDU));
+
+    // spectral set-up (modm.f90:180-185)
+    const double v1 = r.v1, v2 = r.v2, dvabs = 1.0;
+    const double v1abs = (double)((long long)v1) - 3. * dvabs;
+    const double v2abs = (double)((long long)(v2 + 3. * dvabs + 0.5));
+    const int nptabs = (int)((v2abs - v1abs) / dvabs + 1.5);
+    const int nptabs_pad = ((nptabs + 4 + 3) / 4) * 4;
+
+    const HostLines& h = ctx->hl;
+    const int n_pad = r.do_lines ? (int)h.n_pad : 0;
+    // profiles per batch
+    int64_t B = r.nprof;
+    if (r.do_lines) {
+        size_t per_prof = (size_t)nlay * D_NPLANES * (size_t)n_pad * 8;
+        int64_t bmem = (int64_t)std::max<size_t>(1, ctx->planes_budget / std::max<size_t>(per_prof, 1));
+        B = std::min<int64_t>(B, bmem);
+        B = std::min<int64_t>(B, std::max<int64_t>(1, 65535 / nlay));
+    }
+    B = std::min<int64_t>(B, 65535);
+    const bool own_o = (r.o == nullptr);
+    int rc;
+    if (own_o && (rc = ensure(ctx, bo, (size_t)nwn * nlay * B * 8))) return rc;
+
+    ContArgs ca;
+    if (r.do_lines) {
+        std::memset(&ca, 0, sizeof ca);
+        const bool gate_h2o = (v2 > -20.0) && (v1 < 20000.);
+        ca.g[0] = make_grid(v1abs, v2abs, nptabs, -20.0, 20000.0, 10.0, 2003, gate_h2o && r.cntnm[0] > 0.);
+        ca.g[1] = make_grid(v1abs, v2abs, nptabs, -20.0, 20000.0, 10.0, 2003, gate_h2o && r.cntnm[1] > 0.);
+        ca.g[2] = make_grid(v1abs, v2abs, nptabs, -4.0, 10000.0, 2.0, 5003, (v2 > -20.0) && (v1 < 10000.) && r.cntnm[2] > 0);
+        ca.g[3] = make_grid(v1abs, v2abs, nptabs, -10., 350., 5.0, 73, (v2 > -10.0) && (v1 < 350.) && r.cntnm[5] > 0.);
+        ca.v1abs = v1abs;
+        ca.nptabs = nptabs;
+        ca.nptabs_pad = nptabs_pad;
+        ca.tb = ctx->tb;
+        if ((rc = ensure(ctx, ctx->b_layer, (size_t)B * nlay * sizeof(LayerDev)))) return rc;
+        if ((rc = ensure(ctx, ctx->b_scorc, (size_t)B * nlay * std::max(1, (int)ctx->ld.nsi) * 8))) return rc;
+        if ((rc = ensure(ctx, ctx->b_absrb, (size_t)B * nlay * 3 * nptabs_pad * 8))) return rc;
+        if ((rc = ensure(ctx, ctx->b_planes, (size_t)B * nlay * D_NPLANES * (size_t)n_pad * 8))) return rc;
+        CU(cudaMemsetAsync(ctx->errflag_dev, 0, sizeof(int), s));
+        st.nominal_evals = (double)h.n * (double)nlay * (double)nwn * (double)r.nprof;
+        st.inwindow_evals = -1.;
+    }
+
+    for (int64_t b0 = 0; b0 < r.nprof; b0 += B) {
+        const int64_t nb = std::min<int64_t>(B, r.nprof - b0);
+        const int64_t Lb = nb * nlay;
+        double* o_batch = own_o ? (double*)bo.p : r.o + (size_t)b0 * nwn * nlay;
+        if (r.do_lines) {
+            LayerPrepArgs pa;
+            std::memset(&pa, 0, sizeof pa);
+            pa.nlayers = Lb;
+            pa.nlay = nlay;
+            pa.nmol = (int32_t)r.nmol;
+            pa.ibrd = (int32_t)r.ibrd;
+            pa.p = r.p + (size_t)b0 * nlay;
+            pa.t = r.t + (size_t)b0 * nlay;
+            pa.clw = r.clw + (size_t)b0 * nlay;
+            pa.wkl = r.wkl + (size_t)b0 * nlay * MRTM_MXMOL;
+            pa.wbrodl = r.wbrodl + (size_t)b0 * nlay;
+            for (int i = 0; i < 7; i++) pa.cntnm[i] = r.cntnm[i];
+            pa.max_abs_deltnu = h.max_abs_deltnu;
+            pa.max_abs_brd_dshift = h.max_abs_brd_dshift;
+            pa.out = (LayerDev*)ctx->b_layer.p;
+            pa.scor_full = r.scor ? r.scor + (size_t)b0 * nlay * MRTM_NSCOR1 * MRTM_NSCOR2 : nullptr;
+            pa.tips = ctx->tips;
+            pa.nsi = ctx->ld.nsi;
+            pa.scor_index = ctx->ld.scor_index;
+            pa.scorc = (double*)ctx->b_scorc.p;
+            pa.errflag = ctx->errflag_dev;
+            layer_prep_kernel<<<(unsigned)((Lb + 127) / 128), 128, 0, s>>>(pa);
+            st.kernel_launches++;
+
+            ca.nlayers = Lb;
+            ca.lay = (const LayerDev*)ctx->b_layer.p;
+            ca.absrb = (double*)ctx->b_absrb.p;
+            size_t smem = (size_t)(ca.g[0].nptc + ca.g[1].nptc + ca.g[2].nptc + ca.g[3].nptc + 8) * 8;
+            continuum_kernel<<<(unsigned)Lb, 128, smem, s>>>(ca);
+            st.kernel_launches++;
+
+            DeriveArgs da;
+            std::memset(&da, 0, sizeof da);
+            da.nlayers = Lb;
+            da.ln = ctx->ld;
+            da.lay = (const LayerDev*)ctx->b_layer.p;
+            da.scorc = (const double*)ctx->b_scorc.p;
+            da.sclcpl = r.sclcpl;
+            da.sclhw = r.sclhw;
+            da.y0res = r.y0res;
+            da.ibrd = (int32_t)r.ibrd;
+            da.planes = (double*)ctx->b_planes.p;
+            CU(cudaEventRecord(ctx->ev[0], s));
+            derive_kernel<<<dim3((unsigned)((n_pad + 255) / 256), (unsigned)Lb), 256, 0, s>>>(da);
+            CU(cudaEventRecord(ctx->ev[1], s));
+            st.kernel_launches++;
+
+            LinesArgs la;
+            std::memset(&la, 0, sizeof la);
+            la.nwn = (int32_t)nwn;
+            la.nlay = (int32_t)nlay;
+            la.nseg = (int32_t)h.segments.size();
+            la.n_pad = n_pad;
+            la.iw0 = r.iw0;
+            la.wn = r.wn;
+            la.seg = ctx->seg_dev;
+            la.xnu0 = ctx->ld.xnu0;
+            la.mol_s = ctx->ld.mol;
+            la.xf_s = ctx->ld.xf;
+            la.sdep_s = ctx->ld.sdep;
+            la.key = ctx->ld.key;
+            la.planes = (const double*)ctx->b_planes.p;
+            la.lay = (const LayerDev*)ctx->b_layer.p;
+            la.absrb = (const double*)ctx->b_absrb.p;
+            la.nptabs = nptabs;
+            la.nptabs_pad = nptabs_pad;
+            la.v1abs = v1abs;
+            la.v2abs = v2abs;
+            la.v1 = v1;
+            la.dvset = r.dvset;
+            la.o = o_batch;
+            la.o_lds = nwn;
+            la.o_prof = nwn * nlay;
+            la.o_by_mol = r.o_by_mol;
+            la.oc = r.oc;
+            la.obm_ldm = nwn;
+            la.obm_ldk = nwn * MRTM_MXMOL;
+            la.o_clw = r.o_clw;
+            la.odxsec = r.odxsec;
+            la.sel_count = r.sel_count ? r.sel_count + (size_t)b0 * nwn * nlay : nullptr;
+            la.sel_hash = r.sel_hash ? r.sel_hash + (size_t)b0 * nwn * nlay : nullptr;
+            la.errflag = ctx->errflag_dev;
+            const bool sel = (r.sel_count != nullptr) || (r.sel_hash != nullptr);
+            const int F = (nwn >= 2048) ? 4 : ((nwn >= 512) ? 2 : 1);
+            dim3 grid((unsigned)((nwn + 128 * F - 1) / (128 * F)), (unsigned)nlay, (unsigned)nb);
+            CU(cudaEventRecord(ctx->ev[2], s));
+            if (F == 4) launch_lines<4>(la, grid, sel, s);
+            else if (F == 2) launch_lines<2>(la, grid, sel, s);
+            else launch_lines<1>(la, grid, sel, s);
+            CU(cudaEventRecord(ctx->ev[3], s));
+            st.kernel_launches++;
+            CU(cudaGetLastError());
+        }
+        if (r.do_tmr || r.do_rtm) {
+            RtArgs ra;
+            std::memset(&ra, 0, sizeof ra);
+            ra.nwn = (int32_t)nwn;
+            ra.nlay = (int32_t)nlay;
+            ra.nprof = (int32_t)nb;
+            ra.irt = (int32_t)r.irt;
+            ra.iout = (int32_t)r.iout;
+            ra.do_tmr = r.do_tmr;
+            ra.do_rtm = r.do_rtm;
+            ra.wn = r.wn;
+            ra.o = o_batch;
+            ra.o_lds = nwn;
+            ra.o_prof = nwn * nlay;
+            ra.t = r.t + (size_t)b0 * nlay;
+            ra.tz = r.tz + (size_t)b0 * (nlay + 1);
+            ra.tmpsfc = r.tmpsfc ? r.tmpsfc + b0 : nullptr;
+            ra.emiss = r.emiss;
+            ra.reflc = r.reflc;
+            auto off = [&](double* q) { return q ? q + (size_t)b0 * nwn : nullptr; };
+            ra.rad = off(r.rad); ra.tb = off(r.tb); ra.tmr = off(r.tmr);
+            ra.trtot = off(r.trtot); ra.rup = off(r.rup); ra.rdn = off(r.rdn);
+            CU(cudaEventRecord(ctx->ev[4], s));
+            rt_kernel<<<dim3((unsigned)((nwn + 127) / 128), (unsigned)nb), 128, 0, s>>>(ra);
+            CU(cudaEventRecord(ctx->ev[5], s));
+            st.kernel_launches++;
+            CU(cudaGetLastError());
+        }
+        // per-batch kernel times (needs the batch to finish; cheap next to the kernels themselves)
+        if (r.nprof > B || true) {
+            CU(cudaEventSynchronize(r.do_tmr || r.do_rtm ? ctx->ev[5] : ctx->ev[3]));
+            float ms = 0.f;
+            if (r.do_lines) {
+                cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]); st.last_derive_kernel_ms += ms;
+                cudaEventElapsedTime(&ms, ctx->ev[2], ctx->ev[3]); st.last_lines_kernel_ms += ms;
+            }
+            if (r.do_tmr || r.do_rtm) { cudaEventElapsedTime(&ms, ctx->ev[4], ctx->ev[5]); st.last_rt_kernel_ms += ms; }
+        }
+    }
+    if (r.do_lines) {
+        int flag = 0;
+        CU(cudaMemcpyAsync(&flag, ctx->errflag_dev, sizeof(int), cudaMemcpyDeviceToHost, s));
+        CU(cudaStreamSynchronize(s));
+        if (flag & 1) return set_err(ctx, MRTM_ETIPS, mrtm_strerror(MRTM_ETIPS));
+        if (flag & 2) return set_err(ctx, MRTM_ESDVOIGT, mrtm_strerror(MRTM_ESDVOIGT));
+    }
+    return MRTM_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// host-buffer wrappers
+// ---------------------------------------------------------------------------------------------
+static int h2d(mrtm_ctx* ctx, DevBuf& b, const void* src, size_t bytes, cudaStream_t s, const double** out)
+{
+    int rc = ensure(ctx, b, std::max<size_t>(bytes, 8));
+    if (rc) return rc;
+    if (src && bytes) CU(cudaMemcpyAsync(b.p, src, bytes, cudaMemcpyHostToDevice, s));
+    *out = (const double*)b.p;
+    return MRTM_OK;
+}
+
+static void fill_range(RunDesc& r, const double* wn_host, const mrtm_opts* opts)
+{
+    r.v1 = wn_host[0];
+    r.v2 = wn_host[r.nwn - 1];
+    r.iw0 = 0;
+    if (opts && opts->use_global_range) {
+        r.v1 = opts->v1_global;
+        r.v2 = opts->v2_global;
+        r.iw0 = opts->iw0;
+    }
+}
+
+extern "C" int mrtm_modm(mrtm_ctx* ctx, int64_t nwn, const double* wn, double dvset, int64_t nlay,
+                         const double* p, const double* t, const double* clw,
+                         double* o, double* o_by_mol, double* oc, double* o_clw, double* odxsec,
+                         int64_t nmol, const double* wkl, const double* wbrodl,
+                         double sclcpl, double sclhw, double y0res, const double cntnm[7],
+                         int64_t ixsect, int64_t ibrd, const double* scor, const mrtm_opts* opts)
+{
+    if (!ctx) return MRTM_EARG;
+    if (!wn || !p || !t || !clw || !wkl || !wbrodl || !cntnm || nwn < 1 || nlay < 1)
+        return set_err(ctx, MRTM_EARG, "mrtm_modm: null input or bad dimension");
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->stream;
+    RunDesc r;
+    std::memset(&r, 0, sizeof r);
+    r.nprof = 1; r.nwn = nwn; r.nlay = nlay; r.nmol = nmol; r.dvset = dvset;
+    r.sclcpl = sclcpl; r.sclhw = sclhw; r.y0res = y0res; r.ibrd = ibrd;
+    for (int i = 0; i < 7; i++) r.cntnm[i] = cntnm[i];
+    r.do_lines = true;
+    fill_range(r, wn, opts);
+    int rc;
+    const size_t fl = (size_t)nwn * nlay * 8, fml = (size_t)nwn * MRTM_MXMOL * nlay * 8;
+    if ((rc = h2d(ctx, ctx->b_in[0], wn, nwn * 8, s, &r.wn))) return rc;
+    if ((rc = h2d(ctx, ctx->b_in[1], p, nlay * 8, s, &r.p))) return rc;
+    if ((rc = h2d(ctx, ctx->b_in[2], t, nlay * 8, s, &r.t))) return rc;
+    if ((rc = h2d(ctx, ctx->b_in[3], clw, nlay * 8, s, &r.clw))) return rc;
+    if ((rc = h2d(ctx, ctx->b_in[4], wkl, nlay * MRTM_MXMOL * 8, s, &r.wkl))) return rc;
+    if ((rc = h2d(ctx, ctx->b_in[5], wbrodl, nlay * 8, s, &r.wbrodl))) return rc;
+    if (scor) { if ((rc = h2d(ctx, ctx->b_in[6], scor, (size_t)nlay * MRTM_NSCOR1 * MRTM_NSCOR2 * 8, s, &r.scor))) return rc; }
+    if (ixsect == 1 && odxsec) { if ((rc = h2d(ctx, ctx->b_in[7], odxsec, fl, s, &r.odxsec))) return rc; }
+    if ((rc = ensure(ctx, ctx->b_out[0], fl))) return rc;
+    r.o = (double*)ctx->b_out[0].p;
+    if (o_by_mol) { if ((rc = ensure(ctx, ctx->b_obm, fml))) return rc; r.o_by_mol = (double*)ctx->b_obm.p; CU(cudaMemsetAsync(r.o_by_mol, 0, fml, s)); }
+    if (oc) { if ((rc = ensure(ctx, ctx->b_oc, fml))) return rc; r.oc = (double*)ctx->b_oc.p; CU(cudaMemsetAsync(r.oc, 0, fml, s)); }
+    if (o_clw) { if ((rc = ensure(ctx, ctx->b_out[1], fl))) return rc; r.o_clw = (double*)ctx->b_out[1].p; }
+    if (opts && opts->sel_count) { if ((rc = ensure(ctx, ctx->b_sel[0], fl))) return rc; r.sel_count = (long long*)ctx->b_sel[0].p; }
+    if (opts && opts->sel_hash) { if ((rc = ensure(ctx, ctx->b_sel[1], fl))) return rc; r.sel_hash = (unsigned long long*)ctx->b_sel[1].p; }
+    if ((rc = run_device(ctx, r, s))) return rc;
+    if (o) CU(cudaMemcpyAsync(o, r.o, fl, cudaMemcpyDeviceToHost, s));
+    if (o_by_mol) CU(cudaMemcpyAsync(o_by_mol, r.o_by_mol, fml, cudaMemcpyDeviceToHost, s));
+    if (oc) CU(cudaMemcpyAsync(oc, r.oc, fml, cudaMemcpyDeviceToHost, s));
+    if (o_clw) CU(cudaMemcpyAsync(o_clw, r.o_clw, fl, cudaMemcpyDeviceToHost, s));
+    if (r.sel_count) CU(cudaMemcpyAsync(opts->sel_count, r.sel_count, fl, cudaMemcpyDeviceToHost, s));
+    if (r.sel_hash) CU(cudaMemcpyAsync(opts->sel_hash, r.sel_hash, fl, cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    if (odxsec && ixsect != 1) std::memset(odxsec, 0, fl);    // modm.f90:193
+    if (r.sel_count) {
+        double tot = 0.;
+        for (size_t i = 0; i < (size_t)nwn * nlay; i++) tot += (double)opts->sel_count[i];
+        ctx->st.inwindow_evals = tot;
+    }
+    return MRTM_OK;
+}
+
+static int run_rt_host(mrtm_ctx* ctx, bool do_tmr, bool do_rtm, int64_t iout, int64_t irt, int64_t nwn,
+                       const double* wn, int64_t nlay, const double* t, const double* tz, const double* o,
+                       double* tmpsfc, double* rup, double* trtot, double* rdn, const double* reflc,
+                       const double* emiss, double* rad, double* tb, double* tmr, int64_t idu)
+{
+    if (!ctx) return MRTM_EARG;
+    if (!wn || !t || !tz || !o || nwn < 1 || nlay < 1) return set_err(ctx, MRTM_EARG, "rt: null input or bad dimension");
+    if (do_rtm && idu != 1) return set_err(ctx, MRTM_EIDU, mrtm_strerror(MRTM_EIDU));
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->stream;
+    RunDesc r;
+    std::memset(&r, 0, sizeof r);
+    r.nprof = 1; r.nwn = nwn; r.nlay = nlay; r.irt = irt; r.iout = iout; r.idu = idu;
+    r.do_tmr = do_tmr; r.do_rtm = do_rtm;
+    int rc;
+    const double* od = nullptr;
+    if ((rc = h2d(ctx, ctx->b_in[0], wn, nwn * 8, s, &r.wn))) return rc;
+    if ((rc = h2d(ctx, ctx->b_in[2], t, nlay * 8, s, &r.t))) return rc;
+    if ((rc = h2d(ctx, ctx->b_in[8], tz, (nlay + 1) * 8, s, &r.tz))) return rc;
+    if ((rc = h2d(ctx, ctx->b_out[0], o, (size_t)nwn * nlay * 8, s, &od))) return rc;
+    r.o = (double*)od;
+    double tsfc = 0.;
+    if (do_rtm) {
+        if (!tmpsfc || !reflc || !emiss) return set_err(ctx, MRTM_EARG, "rtm: null tmpsfc/reflc/emiss");
+        if (irt == 3 || irt == 2) *tmpsfc = 2.75;             // RTMmono.f90:113-123
+        tsfc = *tmpsfc;
+        const double* q;
+        if ((rc = h2d(ctx, ctx->b_tmps, &tsfc, 8, s, &q))) return rc;
+        r.tmpsfc = (double*)q;
+        if ((rc = h2d(ctx, ctx->b_in[9], emiss, nwn * 8, s, &r.emiss))) return rc;
+        if ((rc = h2d(ctx, ctx->b_in[10], reflc, nwn * 8, s, &r.reflc))) return rc;
+    }
+    double** outs[6] = {&r.rad, &r.tb, &r.tmr, &r.trtot, &r.rup, &r.rdn};
+    double* hosts[6] = {rad, tb, tmr, trtot, rup, rdn};
+    for (int i = 0; i < 6; i++) {
+        if ((rc = ensure(ctx, ctx->b_out[2 + i], nwn * 8))) return rc;
+        *outs[i] = (double*)ctx->b_out[2 + i].p;
+    }
+    if ((rc = run_device(ctx, r, s))) return rc;
+    for (int i = 0; i < 6; i++)
+        if (hosts[i]) CU(cudaMemcpyAsync(hosts[i], *outs[i], nwn * 8, cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    return MRTM_OK;
+}
+
+extern "C" int mrtm_calctmr(mrtm_ctx* ctx, int64_t nlayrs, int64_t nwn, const double* wn,
+                            const double* t, const double* tz, const double* o, double* tmr)
+{
+    return run_rt_host(ctx, true, false, 0, 3, nwn, wn, nlayrs, t, tz, o, nullptr, nullptr, nullptr, nullptr,
+                       nullptr, nullptr, nullptr, nullptr, tmr, 1);
+}
+
+extern "C" int mrtm_rtm(mrtm_ctx* ctx, int64_t iout, int64_t irt, int64_t nwn, const double* wn,
+                        int64_t nlay, const double* t, const double* tz, const double* o,
+                        double* tmpsfc, double* rup, double* trtot, double* rdn,
+                        const double* reflc, const double* emiss, double* rad, double* tb, int64_t idu)
+{
+    return run_rt_host(ctx, false, true, iout, irt, nwn, wn, nlay, t, tz, o, tmpsfc, rup, trtot, rdn, reflc,
+                       emiss, rad, tb, nullptr, idu);
+}
+
+extern "C" int mrtm_profiles_dev(mrtm_ctx* ctx, int64_t nprof, int64_t nwn, const double* wn_dev, double dvset,
+                                 int64_t nlay, const double* p, const double* t, const double* tz,
+                                 const double* clw, int64_t nmol, const double* wkl, const double* wbrodl,
+                                 const double* scor, double sclcpl, double sclhw, double y0res,
+                                 const double cntnm[7], int64_t ibrd, int64_t irt, int64_t iout, int64_t idu,
+                                 double* tmpsfc, const double* emiss_dev, const double* reflc_dev,
+                                 double* rad_dev, double* tb_dev, double* tmr_dev, double* trtot_dev,
+                                 double* rup_dev, double* rdn_dev, double* o_dev, const mrtm_opts* opts)
+{
+    if (!ctx) return MRTM_EARG;
+    if (!wn_dev || !p || !t || !tz || !clw || !wkl || !wbrodl || !cntnm || !tmpsfc || !emiss_dev || !reflc_dev)
+        return set_err(ctx, MRTM_EARG, "mrtm_profiles_dev: null input");
+    if (!opts || !opts->use_global_range)
+        return set_err(ctx, MRTM_EARG, "mrtm_profiles_dev: opts->use_global_range with v1_global/v2_global is required (wn lives on the device)");
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t s = opts->stream ? (cudaStream_t)opts->stream : ctx->stream;
+    RunDesc r;
+    std::memset(&r, 0, sizeof r);
+    r.nprof = nprof; r.nwn = nwn; r.nlay = nlay; r.nmol = nmol; r.dvset = dvset; r.wn = wn_dev;
+    r.p = p; r.t = t; r.tz = tz; r.clw = clw; r.wkl = wkl; r.wbrodl = wbrodl; r.scor = scor;
+    r.sclcpl = sclcpl; r.sclhw = sclhw; r.y0res = y0res; r.ibrd = ibrd; r.irt = irt; r.iout = iout; r.idu = idu;
+    for (int i = 0; i < 7; i++) r.cntnm[i] = cntnm[i];
+    r.tmpsfc = tmpsfc; r.emiss = emiss_dev; r.reflc = reflc_dev;
+    r.rad = rad_dev; r.tb = tb_dev; r.tmr = tmr_dev; r.trtot = trtot_dev; r.rup = rup_dev; r.rdn = rdn_dev;
+    r.o = o_dev;
+    r.do_lines = true; r.do_tmr = true; r.do_rtm = true;
+    r.v1 = opts->v1_global; r.v2 = opts->v2_global; r.iw0 = opts->iw0;
+    return run_device(ctx, r, s);
+}
+
+extern "C" int mrtm_profiles(mrtm_ctx* ctx, int64_t nprof, int64_t nwn, const double* wn, double dvset,
+                             int64_t nlay, const double* p, const double* t, const double* tz,
+                             const double* clw, int64_t nmol, const double* wkl, const double* wbrodl,
+                             const double* scor, double sclcpl, double sclhw, double y0res,
+                             const double cntnm[7], int64_t ibrd, int64_t irt, int64_t iout, int64_t idu,
+                             double* tmpsfc, const double* emiss, const double* reflc,
+                             double* rad, double* tb, double* tmr, double* trtot, double* rup, double* rdn,
+                             double* o, double* otot_by_mol, const mrtm_opts* opts)
+{
+    if (!ctx) return MRTM_EARG;
+    if (!wn || !p || !t || !tz || !clw || !wkl || !wbrodl || !cntnm || !tmpsfc || !emiss || !reflc || nprof < 1 || nwn < 1 || nlay < 1)
+        return set_err(ctx, MRTM_EARG, "mrtm_profiles: null input or bad dimension");
+    if (idu != 1) return set_err(ctx, MRTM_EIDU, mrtm_strerror(MRTM_EIDU));
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->stream;
+    RunDesc r;
+    std::memset(&r, 0, sizeof r);
+    r.nprof = nprof; r.nwn = nwn; r.nlay = nlay; r.nmol = nmol; r.dvset = dvset;
+    r.sclcpl = sclcpl; r.sclhw = sclhw; r.y0res = y0res; r.ibrd = ibrd; r.irt = irt; r.iout = iout; r.idu = idu;
+    for (int i = 0; i < 7; i++) r.cntnm[i] = cntnm[i];
+    r.do_lines = true; r.do_tmr = true; r.do_rtm = true;
+    fill_range(r, wn, opts);
+    int rc;
+    const size_t L = (size_t)nprof * nlay;
+    if ((rc = h2d(ctx, ctx->b_in[0], wn, nwn * 8, s, &r.wn))) return rc;
+    if ((rc = h2d(ctx, ctx->b_in[1], p, L * 8, s, &r.p))) return rc;
+    if ((rc = h2d(ctx, ctx->b_in[2], t, L * 8, s, &r.t))) return rc;
+    if ((rc = h2d(ctx, ctx->b_in[3], clw, L * 8, s, &r.clw))) return rc;
+    if ((rc = h2d(ctx, ctx->b_in[4], wkl, L * MRTM_MXMOL * 8, s, &r.wkl))) return rc;
+    if ((rc = h2d(ctx, ctx->b_in[5], wbrodl, L * 8, s, &r.wbrodl))) return rc;
+    if (scor) { if ((rc = h2d(ctx, ctx->b_in[6], scor, L * MRTM_NSCOR1 * MRTM_NSCOR2 * 8, s, &r.scor))) return rc; }
+    if ((rc = h2d(ctx, ctx->b_in[8], tz, (size_t)nprof * (nlay + 1) * 8, s, &r.tz))) return rc;
+    if ((rc = h2d(ctx, ctx->b_in[9], emiss, nwn * 8, s, &r.emiss))) return rc;
+    if ((rc = h2d(ctx, ctx->b_in[10], reflc, nwn * 8, s, &r.reflc))) return rc;
+    if (irt == 3 || irt == 2) for (int64_t i = 0; i < nprof; i++) tmpsfc[i] = 2.75;   // RTMmono.f90:113-123
+    { const double* q; if ((rc = h2d(ctx, ctx->b_tmps, tmpsfc, nprof * 8, s, &q))) return rc; r.tmpsfc = (double*)q; }
+    double** outs[6] = {&r.rad, &r.tb, &r.tmr, &r.trtot, &r.rup, &r.rdn};
+    double* hosts[6] = {rad, tb, tmr, trtot, rup, rdn};
+    const size_t fo = (size_t)nwn * nprof * 8;
+    for (int i = 0; i < 6; i++) {
+        if ((rc = ensure(ctx, ctx->b_out[2 + i], fo))) return rc;
+        *outs[i] = (double*)ctx->b_out[2 + i].p;
+    }
+    const size_t fl = (size_t)nwn * nlay * nprof * 8;
+    if (o) { if ((rc = ensure(ctx, ctx->b_out[0], fl))) return rc; r.o = (double*)ctx->b_out[0].p; }
+    if (opts && opts->sel_count) { if ((rc = ensure(ctx, ctx->b_sel[0], fl))) return rc; r.sel_count = (long long*)ctx->b_sel[0].p; }
+    if (opts && opts->sel_hash) { if ((rc = ensure(ctx, ctx->b_sel[1], fl))) return rc; r.sel_hash = (unsigned long long*)ctx->b_sel[1].p; }
+
+    if (!otot_by_mol) {
+        if ((rc = run_device(ctx, r, s))) return rc;
+    } else {
+        // per-molecule column sums need the (nwn,39,nlay) planes: one profile at a time
+        const size_t fml = (size_t)nwn * MRTM_MXMOL * nlay * 8;
+        if ((rc = ensure(ctx, ctx->b_obm, fml))) return rc;
+        if ((rc = ensure(ctx, ctx->b_oc, fml))) return rc;
+        if ((rc = ensure(ctx, ctx->b_out[1], (size_t)MRTM_MXMOL * nwn * nprof * 8))) return rc;
+        double lines_ms = 0., rt_ms = 0., der_ms = 0.;
+        for (int64_t ip = 0; ip < nprof; ip++) {
+            RunDesc q = r;
+            q.nprof = 1;
+            q.p += ip * nlay; q.t += ip * nlay; q.clw += ip * nlay; q.wbrodl += ip * nlay;
+            q.wkl += ip * nlay * MRTM_MXMOL; q.tz += ip * (nlay + 1);
+            if (q.scor) q.scor += (size_t)ip * nlay * MRTM_NSCOR1 * MRTM_NSCOR2;
+            q.tmpsfc += ip;
+            q.rad += ip * nwn; q.tb += ip * nwn; q.tmr += ip * nwn; q.trtot += ip * nwn; q.rup += ip * nwn; q.rdn += ip * nwn;
+            if (q.o) q.o += (size_t)ip * nwn * nlay;
+            if (q.sel_count) q.sel_count += (size_t)ip * nwn * nlay;
+            if (q.sel_hash) q.sel_hash += (size_t)ip * nwn * nlay;
+            q.o_by_mol = (double*)ctx->b_obm.p;
+            q.oc = (double*)ctx->b_oc.p;
+            CU(cudaMemsetAsync(q.o_by_mol, 0, fml, s));
+            CU(cudaMemsetAsync(q.oc, 0, fml, s));
+            if ((rc = run_device(ctx, q, s))) return rc;
+            lines_ms += ctx->st.last_lines_kernel_ms; rt_ms += ctx->st.last_rt_kernel_ms; der_ms += ctx->st.last_derive_kernel_ms;
+            colsum_kernel<<<dim3((unsigned)((nwn + 127) / 128), MRTM_MXMOL), 128, 0, s>>>(
+                (int)nwn, (int)nlay, q.o_by_mol, q.oc, nwn, nwn * MRTM_MXMOL,
+                (double*)ctx->b_out[1].p + (size_t)ip * MRTM_MXMOL * nwn);
+            ctx->st.kernel_launches++;
+        }
+        ctx->st.last_lines_kernel_ms = lines_ms; ctx->st.last_rt_kernel_ms = rt_ms; ctx->st.last_derive_kernel_ms = der_ms;
+        ctx->st.nominal_evals = (double)ctx->hl.n * (double)nlay * (double)nwn * (double)nprof;
+        CU(cudaMemcpyAsync(otot_by_mol, ctx->b_out[1].p, (size_t)MRTM_MXMOL * nwn * nprof * 8, cudaMemcpyDeviceToHost, s));
+    }
+    for (int i = 0; i < 6; i++)
+        if (hosts[i]) CU(cudaMemcpyAsync(hosts[i], *outs[i], fo, cudaMemcpyDeviceToHost, s));
+    if (o) CU(cudaMemcpyAsync(o, r.o, fl, cudaMemcpyDeviceToHost, s));
+    if (r.sel_count) CU(cudaMemcpyAsync(opts->sel_count, r.sel_count, fl, cudaMemcpyDeviceToHost, s));
+    if (r.sel_hash) CU(cudaMemcpyAsync(opts->sel_hash, r.sel_hash, fl, cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    if (r.sel_count) {
+        double tot = 0.;
+        for (size_t i = 0; i < (size_t)nwn * nlay * nprof; i++) tot += (double)opts->sel_count[i];
+        ctx->st.inwindow_evals = tot;
+    }
+    return MRTM_OK;
+}
+
+extern "C" int mrtm_get_stats(mrtm_ctx* ctx, mrtm_stats* st)
+{
+    if (!ctx || !st) return MRTM_EARG;
+    *st = ctx->st;
+    return MRTM_OK;
+}
+
+extern "C" int mrtm_reset_stats(mrtm_ctx* ctx)
+{
+    if (!ctx) return MRTM_EARG;
+    int64_t keep = ctx->st.lines_staged;
+    std::memset(&ctx->st, 0, sizeof ctx->st);
+    ctx->st.lines_staged = keep;
+    return MRTM_OK;
+}
+
+extern "C" int mrtm_fp64_peak(mrtm_ctx* ctx, double* tflops)
+{
+    if (!ctx || !tflops) return MRTM_EARG;
+    CU(cudaSetDevice(ctx->device));
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, ctx->device));
+    const int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 20000;
+    DevBuf& b = ctx->b_out[15];
+    int rc = ensure(ctx, b, (size_t)blocks * threads * 8);
+    if (rc) return rc;
+    cudaStream_t s = ctx->stream;
+    fp64_peak_kernel<<<blocks, threads, 0, s>>>((double*)b.p, 1000);   // warm-up
+    double best = 0.;
+    for (int rep = 0; rep < 5; rep++) {
+        CU(cudaEventRecord(ctx->ev[6], s));
+        fp64_peak_kernel<<<blocks, threads, 0, s>>>((double*)b.p, iters);
+        CU(cudaEventRecord(ctx->ev[7], s));
+        CU(cudaEventSynchronize(ctx->ev[7]));
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, ctx->ev[6], ctx->ev[7]);
+        double fl = 2.0 * 8.0 * (double)iters * (double)blocks * (double)threads;
+        best = std::max(best, fl / (ms * 1e-3) / 1e12);
+        ctx->st.kernel_launches++;
+    }
+    *tflops = best;
+    return MRTM_OK;
+}

@@ -1,0 +1,95 @@
+/*
+ * monortm_oracle.h -- TEST INFRASTRUCTURE ONLY.
+ *
+ * CPU restatement (plain C, built -O0 -ffp-contract=off -fcx-fortran-rules to
+ * mirror the reference's linuxGNUdbl build, build/makefile.common:195-198) of
+ * the monoRTM optical-depth + radiance hot path.  Only tests/,
+ * __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs
+ * may load this library; the product (monortm_b200/) never does.
+ *
+ * PARITY UNPINNED: the reference ships no golden outputs, no TAPE3 line file
+ * and cannot be compiled here (no Fortran compiler).
+ * The restatement is pinned only by (i) analytic identities, (ii) an
+ * independent scipy.special.wofz check of the Humlicek routine and (iii) the
+ * reference's own input fixtures (run/in), see tests/test_oracle_*.py.
+ *
+ * All arrays are Fortran column-major, exactly as the reference holds them.
+ */
+#ifndef MONORTM_ORACLE_H
+#define MONORTM_ORACLE_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ORC_MXMOL 39      /* lblparams.f90:28 */
+#define ORC_MXBRDMOL 7    /* struct_types.f90:25 */
+
+/* Line store as lnfl_mod holds it (src/lnfl_mod.f90:5-13): element (mo,ii) of a
+ * (39,IIM) array is at [(mo-1) + (ii-1)*39]; brd arrays (7,7,IIM) at
+ * [(mo-1) + (k-1)*7 + (ii-1)*49].  iim is the allocated second dimension. */
+typedef struct {
+    int64_t iim;
+    int64_t nblm[ORC_MXMOL];
+    int64_t *iso;
+    double *xnu0, *deltnu, *e, *alps, *alpf, *x, *xg, *s0, *rmol, *sdep;
+    int32_t *brd_mol_flg;
+    double *brd_mol_tmp, *brd_mol_hw, *brd_mol_shft;
+} orc_lines;
+
+/* allocate / free a zero-initialised line store */
+orc_lines *orc_lines_alloc(int64_t iim);
+void orc_lines_free(orc_lines *ln);
+
+/* GET_LNFL (src/lnfl_mod.f90:22-133): read TAPE3 for [v1-25, v2+25], block
+ * granular.  Returns 0, or >0 on error (message in orc_last_error()). */
+int orc_get_lnfl(const char *hfile, double v1, double v2, orc_lines *ln);
+
+/* MODM (src/modm.f90:21-274) with tips_2003 hoisted to the caller:
+ * scor is (42,9,nlay).  o,o_clw,odxsec are (nwn,nlay); o_by_mol,oc are
+ * (nwn,39,nlay).  odxsec_in may be NULL (ixsect=0) else (nwn,nlay) added as the
+ * reference adds monortm_xsec_sub's result.  sel_count/sel_hash (nwn,nlay) may
+ * be NULL: number and order-independent hash of the (molecule,record) pairs
+ * passing the cutoff test modm.f90:384.  n_voigt (may be NULL) returns the
+ * number of shape evaluations that took the Voigt branch (modm.f90:430). */
+int orc_modm(int64_t nwn, const double *wn, double dvset, int64_t nlay,
+             const double *p, const double *t, const double *clw,
+             double *o, double *o_by_mol, double *oc, double *o_clw, double *odxsec,
+             int64_t nmol, const double *wkl, const double *wbrodl,
+             double sclcpl, double sclhw, double y0res,
+             const double cntnm[7], int64_t ixsect, const double *odxsec_in,
+             int64_t ibrd, const double *scor, orc_lines *ln,
+             int64_t *sel_count, uint64_t *sel_hash, int64_t *n_voigt);
+
+/* CALCTMR (src/RTMmono.f90:239-325). tz is (0:nlay). */
+int orc_calctmr(int64_t nlayrs, int64_t nwn, const double *wn, const double *t,
+                const double *tz, const double *o, double *tmr);
+
+/* RTM (src/RTMmono.f90:13-155) incl. RAD_UP_DN (157-221).  tmpsfc is in/out
+ * (set to 2.75 for irt 2,3: RTMmono.f90:122). */
+int orc_rtm(int64_t iout, int64_t irt, int64_t nwn, const double *wn, int64_t nlay,
+            const double *t, const double *tz, const double *o, double *tmpsfc,
+            double *rup, double *trtot, double *rdn, const double *reflc,
+            const double *emiss, double *rad, double *tb, int64_t idu);
+
+/* building blocks exposed for unit tests */
+void orc_w4(double x, double y, double *re, double *im);                 /* modm.f90:1100-1130 */
+void orc_sd_humlicek(double x1, double y1, double x2, double y2, double *re, double *im); /* :1150-1251 */
+double orc_sdvoigt(double deltnu, double alphal, double alphad, double sdep, int *err);   /* :965-1087 */
+double orc_radfn(double vi, double xkt);                                 /* lblrtm_sub.f90:36-97 */
+double orc_odclw(double wn, double temp, double clw);                    /* CloudOptProp.f90:29-53 */
+double orc_bb_fn(double v, double fbeta);                                /* RTMmono.f90:223-237 */
+/* CONTNM(JRAD=0) for one species selector im in {1,2,3,7,22,99} (modm.f90:207-215):
+ * fills absrb[0..nptabs-1] on the 1 cm-1 grid; wk is the 60-element /FILHDR/ WK. */
+int orc_contnm_one(int64_t im, const double cntnm[7], double pave, double tave,
+                   const double *wk, double wbroad, int64_t nmol, double v1, double v2,
+                   double v1abs, double v2abs, int64_t nptabs, double *absrb);
+uint64_t orc_line_key(int64_t mol, int64_t rec);  /* splitmix64 of (mol<<32 | rec), 1-based */
+const char *orc_last_error(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

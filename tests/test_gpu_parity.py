@@ -1,0 +1,92 @@
+"""GPU parity: the CUDA path (through the C ABI) against the CPU oracle on the same seeded inputs.
+
+Bars (BASELINE.json north_star): selected-line set per (frequency, layer) bit-exact; layer optical
+depths within 1e-9 relative; brightness temperatures within 1e-5 K.
+"""
+import numpy as np
+import pytest
+
+import harness
+from monortm_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+OD_RTOL = 1e-9      # north_star: layer optical depths within 1e-9 relative
+TB_ATOL = 1e-5      # north_star: brightness temperatures within 1e-5 K
+
+
+def check_case(case, od_rtol=OD_RTOL):
+    ref = harness.run_oracle(case)
+    gpu = harness.run_gpu(case)
+    # selected line set: bit exact (count and order-independent hash of (molecule, record) pairs)
+    assert np.array_equal(gpu["sel_count"], ref["sel_count"])
+    assert np.array_equal(gpu["sel_hash"], ref["sel_hash"])
+    assert harness.rel_diff(gpu["o"], ref["o"]) < od_rtol
+    # per-molecule line and continuum optical depths: relative to the layer total where tiny
+    scale = np.abs(ref["o"])[:, None, :]
+    assert np.max(np.abs(gpu["o_by_mol"] - ref["o_by_mol"]) / scale) < od_rtol
+    assert np.max(np.abs(gpu["oc"] - ref["oc"]) / scale) < od_rtol
+    assert np.max(np.abs(gpu["o_clw"] - ref["o_clw"]) / np.abs(ref["o"])) < od_rtol
+    assert np.max(np.abs(gpu["tb"] - ref["tb"])) < TB_ATOL
+    assert np.max(np.abs(gpu["tmr"] - ref["tmr"])) < TB_ATOL
+    for k in ("rad", "rup", "rdn", "trtot"):
+        assert harness.rel_diff(gpu[k], ref[k], floor=1e-300) < 1e-8, k
+    assert gpu["tmpsfc"] == ref["tmpsfc"]
+    assert gpu["stats"]["kernel_launches"] >= 4
+    return ref, gpu
+
+
+def test_c1_channels_downwelling():
+    case = harness.make_case(n_filler=512, nlay=19, wn=synth.freq_c1_channels(), irt=3)
+    ref, gpu = check_case(case)
+    assert gpu["tmpsfc"] == 2.75      # RTMmono.f90:122
+
+
+def test_c1_sweep_gridded_upwelling():
+    wn, dv = synth.freq_c1_sweep()
+    case = harness.make_case(n_filler=512, nlay=25, wn=wn, dvset=dv, irt=1, tmpsfc=290.0, emis=0.6)
+    check_case(case)
+
+
+def test_c2_sounder_channels_up():
+    case = harness.make_case(n_filler=1024, nlay=40, wn=synth.freq_c2_sounder(), irt=1, tmpsfc=285.0, emis=0.9)
+    check_case(case)
+
+
+def test_cloudy_up_and_down():
+    wn = np.linspace(0.0055, 55.0, 160)
+    for irt in (1, 3):
+        case = harness.make_case(n_filler=768, nlay=30, wn=wn, irt=irt, clw=True)
+        ref, gpu = check_case(case)
+        assert np.any(ref["o_clw"] > 0)
+
+
+def test_voigt_and_dense_grid():
+    # a dense grid around the 22 GHz H2O line and the O2 band, upper layers take the Voigt branch
+    wn = np.concatenate([0.741691 + np.linspace(-2e-4, 2e-4, 97), 2.0 + np.linspace(-0.05, 0.05, 160)])
+    wn.sort()
+    case = harness.make_case(n_filler=256, nlay=60, wn=wn, irt=3)
+    ref, gpu = check_case(case)
+    assert ref["n_voigt"] > 0
+
+
+def test_coverage_lines_co2_lc_sdep_ibrd():
+    wn = np.linspace(0.5, 50.0, 200)
+    kw = dict(n_co2=12, n_sdep=8, n_generic_lc=8, brd_fraction=0.2)
+    for ibrd in (0, 1):
+        case = harness.make_case(n_filler=384, nlay=24, wn=wn, irt=1, ibrd=ibrd, line_kw=kw)
+        check_case(case)
+
+
+def test_continuum_factors_and_scalings():
+    wn = np.linspace(0.2, 30.0, 64)
+    case = harness.make_case(n_filler=256, nlay=16, wn=wn, irt=3, cntnm=(0.7, 1.2, 1.0, 1.0, 1.0, 0.0, 1.0),
+                             sclcpl=0.87, sclhw=1.1, y0res=0.01)
+    check_case(case)
+
+
+def test_large_frequency_tiles():
+    # exercises the F=4 kernel variant and tile edges (nwn not a multiple of the tile)
+    wn = 5.5e-5 * np.arange(1, 2600 + 1) * 300.0
+    case = harness.make_case(n_filler=192, nlay=6, wn=wn, irt=1)
+    check_case(case)
