@@ -1,0 +1,353 @@
+#!/usr/bin/env python3
+"""bench.py -- headline benchmark of the monoRTM hot path on B200 (contract: see DESIGN.md section 6).
+
+Workload (config.workload): the per-GPU shard of BASELINE config 3, the dense monochromatic sweep
+0-55 cm-1 (wn_i = 5.5e-5*i) x 100 layers, sharded by frequency.  Each GPU takes a contiguous block of
+`--nwn-per-gpu` frequencies of the global grid (weak scaling: N GPUs cover N blocks; 8 x 125000 is the
+full 1e6-point config), runs MODM + CALCTMR + RTM for it and the ranks all-gather the six spectra
+with NCCL.  Line list: TAPE3-synth "fast-like" (4096 filler + physical seed lines).
+
+metric  : line x layer x frequency evaluations per second (nominal triples)
+value   : device-resident (inputs in HBM), CUDA-event timed, max over ranks
+e2e     : the same through the public host-buffer C ABI call (mrtm_profiles), H2D + D2H inside
+--impl reference : the CPU oracle (the C restatement of the reference; the Fortran reference cannot
+          be compiled in this image) farmed over all host cores on a bounded sample of the workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+NLAY = 100
+N_FILLER = 4096
+DV = 5.5e-5
+NWN_GLOBAL_FULL = 1000000
+FLOP_PER_INWINDOW_EVAL = 12.0     # Lorentz, no coupling, hoisted per-(line,layer) terms
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--nwn-per-gpu", type=int, default=int(os.environ.get("MRTM_BENCH_NWN", 16384)))
+    ap.add_argument("--cpu-sample-nwn", type=int, default=24)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def build_inputs(nwn, rank, world):
+    """Synthetic C3 shard: a contiguous block of `nwn` frequencies of the GLOBAL 1e6-point grid, centred
+    in this rank's 1/world-th of the grid; one 100-layer profile.  v1, v2 are the global range."""
+    import harness
+    from monortm_b200 import api, synth
+    v1, v2 = DV * 1, DV * NWN_GLOBAL_FULL
+    part = NWN_GLOBAL_FULL // world
+    iw0 = rank * part + max(0, (part - nwn) // 2)
+    wn = DV * np.arange(iw0 + 1, iw0 + nwn + 1, dtype=np.float64)
+    ls = harness.synthetic_store(N_FILLER, v1=v1, v2=v2)
+    prof = synth.synthetic_profiles(1, NLAY, seed0=1000, clw_layers=False, nmol=22)
+    scor = api.scor_for_layers(22, prof["t"])
+    return dict(wn=wn, ls=ls, prof=prof, scor=scor, v1=v1, v2=v2, iw0=iw0,
+                emiss=np.full(nwn, 0.9), reflc=np.full(nwn, 0.1), tmpsfc=288.2, irt=1)
+
+
+class ClockSampler(threading.Thread):
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu):
+        super().__init__(daemon=True)
+        self.gpu, self.rows, self.stop_flag = gpu, [], False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                for ln in out.strip().split("\n"):
+                    f = [x.strip() for x in ln.split(",")]
+                    if len(f) >= 9:
+                        self.rows.append(f)
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unsampled"]}
+        sm = sorted(float(r[1]) for r in self.rows)
+        reasons = set()
+        for r in self.rows:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.rows[0][2]), "reasons": sorted(reasons),
+                "samples": len(self.rows), "power_w_max": max(float(r[3]) for r in self.rows)}
+
+
+def cpu_sample(inp, nwn_sample, opt="O0"):
+    """Time the CPU oracle on `nwn_sample` evenly spaced frequencies of this shard (all layers, all lines)."""
+    import harness
+    idx = np.linspace(0, len(inp["wn"]) - 1, nwn_sample).astype(int)
+    wn = inp["wn"][idx]
+    pr = inp["prof"]
+    t0 = time.time()
+    m = harness.oracle_modm(inp["ls"], wn, 0.0, pr["p"][:, 0], pr["t"][:, 0], pr["clw"][:, 0], 22, pr["wkl"][:, :, 0],
+                            pr["wbrodl"][:, 0], inp["scor"][:, :, :, 0], opt=opt)
+    harness.oracle_calctmr(wn, pr["t"][:, 0], pr["tz"][:, 0], m["o"])
+    harness.oracle_rtm(1, inp["irt"], wn, pr["t"][:, 0], pr["tz"][:, 0], m["o"], inp["tmpsfc"], inp["reflc"][idx], inp["emiss"][idx])
+    dt = time.time() - t0
+    nlines = logical_lines(inp["ls"])
+    return dt, float(nlines) * NLAY * nwn_sample, float(m["sel_count"].sum())
+
+
+def logical_lines(ls):
+    """Logical lines = records that are not coupling-coefficient records (SURVEY 8d unit of work)."""
+    n = 0
+    for i in range(39):
+        k = int(ls.nblm[i])
+        xg = ls.xg[i, :k]
+        j = 0
+        while j < k:
+            n += 1
+            j += 2 if xg[j] in (-1.0, -3.0, -5.0) else 1
+    return n
+
+
+def _farm_worker(args):
+    nwn, rank, world, lo, hi = args
+    inp = build_inputs(nwn, rank, world)
+    sub = dict(inp)
+    sub["wn"] = inp["wn"][lo:hi]
+    sub["emiss"], sub["reflc"] = inp["emiss"][lo:hi], inp["reflc"][lo:hi]
+    dt, nominal, inwin = cpu_sample(sub, hi - lo)
+    return dt, nominal, inwin
+
+
+def run_reference(args):
+    """Reference arm: the oracle (C port of the reference, -O0 like linuxGNUdbl) farmed over all host cores.
+    Each step = `cores` disjoint chunks of cpu-sample-nwn frequencies of the rank-0 shard."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import multiprocessing as mp
+    cores = os.cpu_count() or 1
+    nwn = args.nwn_per_gpu
+    per = max(2, args.cpu_sample_nwn // 4)
+    stride = max(per, (nwn - per) // max(cores, 1))
+    chunks = [(nwn, 0, args.gpus, (c * stride) % (nwn - per), (c * stride) % (nwn - per) + per) for c in range(cores)]
+    build_inputs(nwn, 0, args.gpus)          # build/cached once before forking
+    times = []
+    nominal = 0.0
+    with mp.get_context("fork").Pool(cores) as pool:
+        for it in range(args.warmup + args.steps):
+            t0 = time.time()
+            res = pool.map(_farm_worker, chunks)
+            dt = time.time() - t0
+            if it >= args.warmup:
+                times.append(dt)
+                nominal = sum(r[1] for r in res)
+    ms = 1e3 * float(np.mean(times))
+    val = nominal / (ms * 1e-3)
+    sample = "%d processes x %d frequencies x %d layers x all lines per step (oracle -O0, process farm)" % (cores, per, NLAY)
+    line = {"metric": "line x layer x frequency evaluations/s", "value": val, "unit": "evals/s", "impl": "reference",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(args),
+            "cpu_baseline": {"value": val, "unit": "evals/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": val, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def workload_config(args):
+    return {"workload": "C3 dense monochromatic sweep 0-55 cm-1 (wn_i=5.5e-5*i), frequency-sharded: %d frequencies/GPU "
+                        "(a contiguous block centred in each rank's 1/N of the global 1e6-point grid) x %d layers x TAPE3-synth "
+                        "fast-like line list (%d filler + physical seed lines), IRT=1, MODM+CALCTMR+RTM per step"
+                        % (args.nwn_per_gpu, NLAY, N_FILLER),
+            "nwn_per_gpu": args.nwn_per_gpu, "nlay": NLAY, "sharding": "frequency", "parallelism": "freq-shard x%d" % args.gpus,
+            "l2": "L2 flushed (256 MiB write) between timed steps"}
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    from monortm_b200 import api
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product has no CPU path")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+
+    nwn = args.nwn_per_gpu
+    inp = build_inputs(nwn, rank, world)
+    sess = api.Session(local)
+    nlines = sess.stage_lines(inp["ls"])
+    pr = inp["prof"]
+
+    # ---- device-resident buffers (torch is only the allocator / stream / NCCL plumbing)
+    def dv(a):
+        return torch.from_numpy(np.ascontiguousarray(np.asarray(a).reshape(-1, order="F"))).to(dev)
+    d = {k: dv(pr[k]) for k in ("p", "t", "tz", "clw", "wkl", "wbrodl")}
+    d["wn"], d["scor"] = dv(inp["wn"]), dv(inp["scor"])
+    d["emiss"], d["reflc"] = dv(inp["emiss"]), dv(inp["reflc"])
+    d["tmpsfc"] = torch.tensor([inp["tmpsfc"]], dtype=torch.float64, device=dev)
+    outs = torch.zeros(6, nwn, dtype=torch.float64, device=dev)            # rad,tb,tmr,trtot,rup,rdn
+    gathered = torch.zeros(world, 6, nwn, dtype=torch.float64, device=dev) if world > 1 else None
+    ptrs = {k: v.data_ptr() for k, v in d.items()}
+    for i, k in enumerate(("rad", "tb", "tmr", "trtot", "rup", "rdn")):
+        ptrs[k] = outs[i].data_ptr()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    stream = torch.cuda.current_stream()
+
+    def step_dev():
+        sess.profiles_dev(1, nwn, NLAY, 22, 0.0, ptrs, inp["v1"], inp["v2"], inp["iw0"], inp["irt"], stream=stream.cuda_stream)
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, outs)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- warm-up, then K timed steps (per-step CUDA events, L2 flushed between steps)
+    for _ in range(max(args.warmup, 3)):
+        step_dev()
+    barrier()
+    sess.reset_stats()
+    sampler = ClockSampler(local)
+    sampler.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    lines_ms, rt_ms, derive_ms = [], [], []
+    barrier()
+    t_wall0 = time.time()
+    for i in range(args.steps):
+        flush.zero_()
+        ev[i][0].record(stream)
+        step_dev()
+        ev[i][1].record(stream)
+        st = sess.stats()
+        lines_ms.append(st["last_lines_kernel_ms"]); rt_ms.append(st["last_rt_kernel_ms"]); derive_ms.append(st["last_derive_kernel_ms"])
+    barrier()
+    t_wall = time.time() - t_wall0
+    dev_ms = sum(a.elapsed_time(b) for a, b in ev)
+    launches = sess.stats()["kernel_launches"]
+    tmax = torch.tensor([dev_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    ms_per_step = float(tmax.item()) / args.steps
+    nominal_per_step = float(nlines) * NLAY * nwn * world
+    value = nominal_per_step / (ms_per_step * 1e-3)
+
+    # ---- e2e: host buffers through mrtm_profiles (pinned inputs, H2D + D2H inside the timed region)
+    def pin(a):
+        t = torch.from_numpy(np.ascontiguousarray(np.asarray(a).reshape(-1, order="F"))).pin_memory()
+        return t
+    hp = {k: pin(pr[k]) for k in ("p", "t", "tz", "clw", "wkl", "wbrodl")}
+    hp["wn"], hp["scor"], hp["emiss"], hp["reflc"] = pin(inp["wn"]), pin(inp["scor"]), pin(inp["emiss"]), pin(inp["reflc"])
+    hprof = dict(nlay=NLAY, nprof=1, nmol=22,
+                 p=hp["p"].numpy().reshape(NLAY, 1, order="F"), t=hp["t"].numpy().reshape(NLAY, 1, order="F"),
+                 tz=hp["tz"].numpy().reshape(NLAY + 1, 1, order="F"), clw=hp["clw"].numpy().reshape(NLAY, 1, order="F"),
+                 wbrodl=hp["wbrodl"].numpy().reshape(NLAY, 1, order="F"), wkl=hp["wkl"].numpy().reshape(39, NLAY, 1, order="F"))
+    hscor = hp["scor"].numpy().reshape(42, 9, NLAY, 1, order="F")
+    h2d_bytes = sum(hp[k].numel() * 8 for k in hp)
+    d2h_bytes = 6 * nwn * 8
+
+    def step_e2e():
+        return sess.profiles(hp["wn"].numpy(), 0.0, hprof, hscor, inp["irt"], inp["tmpsfc"], hp["emiss"].numpy(),
+                             hp["reflc"].numpy(), global_range=(inp["v1"], inp["v2"], inp["iw0"]))
+    for _ in range(2):
+        step_e2e()
+    barrier()
+    e2e_steps = max(2, min(args.steps, 5))
+    t0 = time.time()
+    for _ in range(e2e_steps):
+        r = step_e2e()
+        if world > 1:
+            outs.copy_(torch.from_numpy(np.stack([r[k][:, 0] for k in ("rad", "tb", "tmr", "trtot", "rup", "rdn")])))
+            dist.all_gather_into_tensor(gathered, outs)
+    barrier()
+    e2e_ms = 1e3 * (time.time() - t0) / e2e_steps
+    te = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = nominal_per_step / (float(te.item()) * 1e-3)
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+
+    if rank == 0:
+        # in-window fraction: exact counts (selection-instrumented kernel) on a 1/64 frequency subsample
+        sub = np.arange(0, nwn, 64)
+        rsel = sess.modm(inp["wn"][sub], 0.0, pr["p"][:, 0], pr["t"][:, 0], pr["clw"][:, 0], 22, pr["wkl"][:, :, 0],
+                         pr["wbrodl"][:, 0], inp["scor"][:, :, :, 0], want_by_mol=False, selection=True,
+                         global_range=(inp["v1"], inp["v2"], 0))
+        inwin_frac = float(rsel["sel_count"].sum()) / (float(nlines) * NLAY * len(sub))
+        fp64_peak = sess.fp64_peak_tflops()
+        lk_ms = float(np.mean(lines_ms))
+        inwin_per_launch = inwin_frac * float(nlines) * NLAY * nwn
+        achieved = inwin_per_launch * FLOP_PER_INWINDOW_EVAL / (lk_ms * 1e-3) / 1e12
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+        rt_bytes = (8.0 * NLAY + 48.0 + 8.0) * nwn
+        rt_k_ms = float(np.mean(rt_ms))
+        line = {
+            "metric": "line x layer x frequency evaluations/s", "value": value, "unit": "evals/s",
+            "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(args),
+            "spectra_per_s": world / (ms_per_step * 1e-3),
+            "inwindow_evals_per_s": value * inwin_frac, "inwindow_fraction": inwin_frac, "logical_lines": nlines,
+            "e2e": {"value": e2e_value, "unit": "evals/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
+                    "ms_per_step": float(te.item())},
+            "gpu_launches": int(launches),
+            "wall_ms_per_step_incl_flush": 1e3 * t_wall / args.steps,
+            "clocks": sampler.summary(),
+            "roofline": {"bound": "fp64", "kernel": "lines_kernel", "achieved": achieved, "peak": fp64_peak,
+                         "unit": "TFLOP/s", "frac": achieved / fp64_peak if fp64_peak else None, "traffic": None,
+                         "peak_source": "measured live: mrtm_fp64_peak DFMA probe (MEASURED_PEAKS.json has no FP64 figure)",
+                         "flop_per_inwindow_eval": FLOP_PER_INWINDOW_EVAL, "kernel_ms": lk_ms,
+                         "share_of_step": lk_ms / ms_per_step},
+            "roofline_rt": {"bound": "hbm", "kernel": "rt_kernel", "achieved": rt_bytes / (rt_k_ms * 1e-3) / 1e9 if rt_k_ms else None,
+                            "peak": hbm_peak, "unit": "GB/s", "frac": (rt_bytes / (rt_k_ms * 1e-3) / 1e9) / hbm_peak if rt_k_ms else None,
+                            "kernel_ms": rt_k_ms, "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s"},
+            "derive_kernel_ms": float(np.mean(derive_ms)),
+        }
+        if not args.no_cpu_baseline:
+            dt, nominal, inwin = cpu_sample(inp, args.cpu_sample_nwn)
+            line["cpu_baseline"] = {"value": nominal / dt, "unit": "evals/s", "cores": 1, "kind": "port",
+                                    "sample": "%d evenly spaced frequencies of the shard x %d layers x all %d lines, oracle -O0 "
+                                              "(C restatement; the Fortran reference cannot be compiled here), %.1f s" %
+                                              (args.cpu_sample_nwn, NLAY, nlines, dt)}
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

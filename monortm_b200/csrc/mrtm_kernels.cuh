@@ -540,6 +540,54 @@ __device__ __noinline__ double odclw_tkc(double wn, double temp, double clw)
     return alpha * clw;
 }
 
+// ---- TMA (bulk async copy) + mbarrier primitives used to stream line-parameter tiles ---------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
+{
+    uint32_t done;
+    const uint32_t addr = smem_u32(bar);
+    do {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n" : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+// reciprocal of a strictly positive normal double: MUFU seed (rel. err <= 2^-20) and one
+// third-order step r0*(1+e+e^2), e = 1-x*r0: error e^3 <= 2^-60, i.e. ~1 ulp after rounding.
+__device__ __forceinline__ double rcp3(double x)
+{
+    double r0;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r0) : "d"(x));
+    double e = fma(-x, r0, 1.0);
+    double t = fma(e, e, e);
+    return fma(r0, t, r0);
+}
+
+constexpr int kTile = 256;      // lines per smem tile
+constexpr int kStages = 2;
+
+// lines_kernel, version 2: line-parameter tiles (XNU, H2, CN, P3 planes) are streamed into shared
+// memory with TMA bulk copies, double buffered on mbarriers; per segment the sorted static centres
+// are binary-searched for the window and for the three narrow bands in which per-thread tests are
+// needed (window edges, the WN+Xnu<=25 boundary, the Voigt zone); everything between the bands runs
+// in branch-free interior loops (one or two Lorentzians per line, pedestal summed separately).
 template <int F, bool SEL>
 __global__ void __launch_bounds__(128) lines_kernel(LinesArgs a)
 {
@@ -557,6 +605,10 @@ __global__ void __launch_bounds__(128) lines_kernel(LinesArgs a)
     const double* __restrict__ pP4 = pl + (size_t)D_P4 * a.n_pad;
     const double* __restrict__ pVT = pl + (size_t)D_VT * a.n_pad;
 
+    __shared__ __align__(128) double s_tile[kStages][4][kTile];
+    __shared__ __align__(8) uint64_t s_bar[kStages];
+    __shared__ double s_lo[NT / 32], s_hi[NT / 32];
+
     // this thread's frequencies (strided so global accesses coalesce)
     const int base = blockIdx.x * (NT * F);
     double wn[F];
@@ -570,19 +622,23 @@ __global__ void __launch_bounds__(128) lines_kernel(LinesArgs a)
         wlo = fmin(wlo, wn[f]);
         whi = fmax(whi, wn[f]);
     }
-    // CTA-wide frequency extent
-    __shared__ double s_lo[NT / 32], s_hi[NT / 32];
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) {
         wlo = fmin(wlo, __shfl_xor_sync(0xffffffffu, wlo, off));
         whi = fmax(whi, __shfl_xor_sync(0xffffffffu, whi, off));
     }
     if ((tid & 31) == 0) { s_lo[tid >> 5] = wlo; s_hi[tid >> 5] = whi; }
+    if (tid == 0) {
+        for (int i = 0; i < kStages; i++) mbar_init(&s_bar[i], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
     __syncthreads();
     wlo = fmin(fmin(s_lo[0], s_lo[1]), fmin(s_lo[2], s_lo[3]));
     whi = fmax(fmax(s_hi[0], s_hi[1]), fmax(s_hi[2], s_hi[3]));
     const double sm = ly.shift_margin;
     const double winL = wlo - kDELTNUC - sm, winR = whi + kDELTNUC + sm;
+    const double rp = ly.rp, rp2 = ly.rp2;
+    uint32_t phase_bits = 0;    // per-stage mbarrier phase parity (bit i = stage i)
 
     double osum[F], sf[F];
     long long cnt[F];
@@ -610,6 +666,13 @@ __global__ void __launch_bounds__(128) lines_kernel(LinesArgs a)
         }
     };
 
+    // slow path shared by the predicated loops: the Voigt branch of modm.f90:427-431
+    auto voigt_term = [&](int mol, int q, double w, double xnu) -> double {
+        double sls = lsf_general(mol, a.xf_s[q], rp, rp2, pl[(size_t)D_AIP * a.n_pad + q], pl[(size_t)D_BIP * a.n_pad + q],
+                                 pl[(size_t)D_H * a.n_pad + q], w, xnu, pl[(size_t)D_AD * a.n_pad + q], a.sdep_s[q], true, &err);
+        return pl[(size_t)D_STILD * a.n_pad + q] * sls;
+    };
+
     for (int s = 0; s < a.nseg; s++) {
         const Segment sg = a.seg[s];
         if (sg.mol != cur_mol) {
@@ -618,12 +681,6 @@ __global__ void __launch_bounds__(128) lines_kernel(LinesArgs a)
         }
         if (ly.wk[sg.mol - 1] == 0.) continue;            // W_SPECIES == 0: molecule skipped (:318-321)
         const int cls = sg.cls;
-        int q0 = sg.begin, q1 = sg.end;
-        const bool windowed = (cls == CLS_PED) || (cls == CLS_O2) || (cls == CLS_GENERAL && sg.mol != 7);
-        if (windowed) {
-            q0 = lower_bound_d(a.xnu0, sg.begin, sg.end, winL);
-            q1 = upper_bound_d(a.xnu0, sg.begin, sg.end, winR);
-        }
         if (SEL && sg.mol == 7) {                          // every O2 line passes modm.f90:384
 #pragma unroll
             for (int f = 0; f < F; f++) { cnt[f] += sg.count_all; hsh[f] += sg.hash_all; }
@@ -632,47 +689,162 @@ __global__ void __launch_bounds__(128) lines_kernel(LinesArgs a)
             const bool has_win = (cls != CLS_O2_LC35);
             const bool force_both = (cls == CLS_O2_LC35);
             const bool count_sel = SEL && (cls == CLS_PED);
-            for (int q = q0; q < q1; q++) {
-                const double xnu = pXNU[q], h2 = pH2[q], cn = pCN[q], ped = pP3[q], vt = pVT[q];
+            // ---- sub-ranges (warp-uniform): bp[] ascending, mode per sub-range
+            int q0 = sg.begin, q1 = sg.end;
+            int eb = sg.begin, ec = sg.end;              // [q0,eb) and [ec,q1): window-edge bands
+            int n0 = sg.end, n1 = sg.end;                // [n0,n1): WN+Xnu<=25 boundary band; < n0: both resonances
+            if (has_win) {
+                q0 = lower_bound_d(a.xnu0, sg.begin, sg.end, winL);
+                q1 = upper_bound_d(a.xnu0, sg.begin, sg.end, winR);
+                eb = upper_bound_d(a.xnu0, q0, q1, whi - kDELTNUC + sm);
+                ec = lower_bound_d(a.xnu0, q0, q1, wlo + kDELTNUC - sm);
+                n0 = lower_bound_d(a.xnu0, q0, q1, kDELTNUC - whi - sm);
+                n1 = upper_bound_d(a.xnu0, q0, q1, kDELTNUC - wlo + sm + 1e-9);
+            }
+            const double vb = sg.vfac * ly.sqrt_t + sm + 1e-9;
+            const int v0 = lower_bound_d(a.xnu0, q0, q1, wlo - vb);
+            const int v1 = upper_bound_d(a.xnu0, q0, q1, whi + vb);
+            int bp[10];
+            int nbp = 0;
+            bp[nbp++] = q0;
+            {
+                int c[6] = {eb, ec, n0, n1, v0, v1};
+                // insertion sort of the 6 candidates, clipped to [q0,q1]
+                for (int i = 0; i < 6; i++) { c[i] = c[i] < q0 ? q0 : (c[i] > q1 ? q1 : c[i]); }
+                for (int i = 1; i < 6; i++) { int v = c[i], j = i - 1; while (j >= 0 && c[j] > v) { c[j + 1] = c[j]; j--; } c[j + 1] = v; }
+                for (int i = 0; i < 6; i++) if (c[i] > bp[nbp - 1]) bp[nbp++] = c[i];
+            }
+            if (q1 > bp[nbp - 1]) bp[nbp++] = q1;
+            const int nsub = nbp - 1;
+
+            // ---- stream [q0,q1) through the double-buffered tile pipeline
+            const int t0 = q0 & ~3;                       // 32-byte aligned tile origin
+            const int ntile = (q1 > t0) ? (q1 - t0 + kTile - 1) / kTile : 0;
+            auto issue = [&](int t) {
+                const int st = t % kStages;
+                const int qs = t0 + t * kTile;
+                int n = a.n_pad - qs;
+                n = n > kTile ? kTile : n;
+                const uint32_t bytes = (uint32_t)n * 8u;
+                mbar_expect_tx(&s_bar[st], 4u * bytes);
+                tma_load_1d(&s_tile[st][0][0], pXNU + qs, bytes, &s_bar[st]);
+                tma_load_1d(&s_tile[st][1][0], pH2 + qs, bytes, &s_bar[st]);
+                tma_load_1d(&s_tile[st][2][0], pCN + qs, bytes, &s_bar[st]);
+                tma_load_1d(&s_tile[st][3][0], pP3 + qs, bytes, &s_bar[st]);
+            };
+            if (ntile > 0 && tid == 0) issue(0);
+            double psum[F];
 #pragma unroll
-                for (int f = 0; f < F; f++) {
-                    const double dm = wn[f] - xnu;                      // WN-Xnu
-                    const double sp = wn[f] + xnu;                      // WN+Xnu
-                    const bool inwin = !has_win || !(fabs(dm) > kDELTNUC);
-                    if (count_sel && inwin) { cnt[f]++; hsh[f] += a.key[q]; }
-                    if (inwin && fabs(dm) <= vt) {                      // Voigt branch (:427), rare
-                        double sls = lsf_general(sg.mol, a.xf_s[q], ly.rp, ly.rp2, pl[(size_t)D_AIP * a.n_pad + q],
-                                                 pl[(size_t)D_BIP * a.n_pad + q], pl[(size_t)D_H * a.n_pad + q],
-                                                 wn[f], xnu, pl[(size_t)D_AD * a.n_pad + q], a.sdep_s[q], true, &err);
-                        sf[f] += pl[(size_t)D_STILD * a.n_pad + q] * sls;
+            for (int f = 0; f < F; f++) psum[f] = 0.;
+            double pacc = 0.;                              // pedestal total of the interior ranges (uniform)
+            for (int t = 0; t < ntile; t++) {
+                const int st = t % kStages;
+                if (t + 1 < ntile && tid == 0) issue(t + 1);
+                mbar_wait(&s_bar[st], (phase_bits >> st) & 1u);
+                phase_bits ^= (1u << st);
+                const double* __restrict__ tX = s_tile[st][0];
+                const double* __restrict__ tH = s_tile[st][1];
+                const double* __restrict__ tC = s_tile[st][2];
+                const double* __restrict__ tP = s_tile[st][3];
+                const int tb = t0 + t * kTile, te = tb + kTile;
+                for (int u = 0; u < nsub; u++) {
+                    int lo = bp[u] > tb ? bp[u] : tb;
+                    int hi = bp[u + 1] < te ? bp[u + 1] : te;
+                    if (lo >= hi) continue;
+                    const int x = bp[u];
+                    const bool edge = has_win && ((x < eb) || (x >= ec));
+                    const bool mixedneg = has_win && (x >= n0) && (x < n1);
+                    const bool vz = (x >= v0) && (x < v1);
+                    if (edge || mixedneg || vz) {
+                        // ---- predicated loop: exact per-thread window / resonance / Voigt tests
+                        for (int q = lo; q < hi; q++) {
+                            const int j = q - tb;
+                            const double xnu = tX[j], h2 = tH[j], cn = tC[j], ped = tP[j];
+                            const double vt = pVT[q];
+#pragma unroll
+                            for (int f = 0; f < F; f++) {
+                                const double dm = wn[f] - xnu;                      // WN-Xnu
+                                const double sp = wn[f] + xnu;                      // WN+Xnu
+                                const bool inwin = !has_win || !(fabs(dm) > kDELTNUC);
+                                if (count_sel && inwin) { cnt[f]++; hsh[f] += a.key[q]; }
+                                if (inwin && fabs(dm) <= vt) {                      // Voigt branch (:427), rare
+                                    sf[f] += voigt_term(sg.mol, q, wn[f], xnu);
+                                } else {
+                                    const bool neg = force_both || (sp <= kDELTNUC);     // DIFF <= 0
+                                    const double r1 = rcp3(fma(dm, dm, h2));
+                                    const double r2 = rcp3(fma(sp, sp, h2));
+                                    double val = cn * (r1 + (neg ? r2 : 0.)) - (neg ? 2. * ped : ped);
+                                    sf[f] += inwin ? val : 0.;
+                                }
+                            }
+                        }
+                    } else if (force_both || x < n0) {
+                        // ---- interior, both resonances: cn*(1/a+1/b) = cn*(a+b)/(a*b), one reciprocal
+                        if (count_sel) {
+                            unsigned long long hs = 0ull;
+                            for (int q = lo; q < hi; q++) hs += a.key[q];
+#pragma unroll
+                            for (int f = 0; f < F; f++) { cnt[f] += hi - lo; hsh[f] += hs; }
+                        }
+#pragma unroll 2
+                        for (int q = lo; q < hi; q++) {
+                            const int j = q - tb;
+                            const double xnu = tX[j], h2 = tH[j], cn = tC[j];
+                            pacc += 2. * tP[j];                     // pedestal counted for both (modm.f90:749)
+#pragma unroll
+                            for (int f = 0; f < F; f++) {
+                                const double dm = wn[f] - xnu, sp = wn[f] + xnu;
+                                const double aa = fma(dm, dm, h2), bb = fma(sp, sp, h2);
+                                const double r = rcp3(aa * bb);
+                                psum[f] = fma(cn * (aa + bb), r, psum[f]);
+                            }
+                        }
                     } else {
-                        const bool neg = force_both || (sp <= kDELTNUC);     // DIFF <= 0
-                        const double r1 = fast_rcp(fma(dm, dm, h2));
-                        const double r2 = fast_rcp(fma(sp, sp, h2));
-                        double val = cn * (r1 + (neg ? r2 : 0.)) - (neg ? 2. * ped : ped);
-                        sf[f] += inwin ? val : 0.;
+                        // ---- interior, single resonance (modm.f90:751)
+                        if (count_sel) {
+                            unsigned long long hs = 0ull;
+                            for (int q = lo; q < hi; q++) hs += a.key[q];
+#pragma unroll
+                            for (int f = 0; f < F; f++) { cnt[f] += hi - lo; hsh[f] += hs; }
+                        }
+#pragma unroll 4
+                        for (int q = lo; q < hi; q++) {
+                            const int j = q - tb;
+                            const double xnu = tX[j], h2 = tH[j], cn = tC[j];
+                            pacc += tP[j];
+#pragma unroll
+                            for (int f = 0; f < F; f++) {
+                                const double dm = wn[f] - xnu;
+                                psum[f] = fma(cn, rcp3(fma(dm, dm, h2)), psum[f]);
+                            }
+                        }
                     }
                 }
+                __syncthreads();       // all reads of this stage done before it is refilled
             }
+#pragma unroll
+            for (int f = 0; f < F; f++) sf[f] += psum[f] - pacc;
         } else if (cls == CLS_O2_LC1) {
-            for (int q = q0; q < q1; q++) {
+            for (int q = sg.begin; q < sg.end; q++) {
                 const double xnu = pXNU[q], h2 = pH2[q], cg = pP3[q], cq = pP4[q], vt = pVT[q];
 #pragma unroll
                 for (int f = 0; f < F; f++) {
                     const double dm = wn[f] - xnu, sp = wn[f] + xnu;
                     if (fabs(dm) <= vt) {
-                        double sls = lsf_general(sg.mol, a.xf_s[q], ly.rp, ly.rp2, pl[(size_t)D_AIP * a.n_pad + q],
-                                                 pl[(size_t)D_BIP * a.n_pad + q], pl[(size_t)D_H * a.n_pad + q],
-                                                 wn[f], xnu, pl[(size_t)D_AD * a.n_pad + q], a.sdep_s[q], true, &err);
-                        sf[f] += pl[(size_t)D_STILD * a.n_pad + q] * sls;
+                        sf[f] += voigt_term(sg.mol, q, wn[f], xnu);
                     } else {
-                        const double r1 = fast_rcp(fma(dm, dm, h2));
-                        const double r2 = fast_rcp(fma(sp, sp, h2));
+                        const double r1 = rcp3(fma(dm, dm, h2));
+                        const double r2 = rcp3(fma(sp, sp, h2));
                         sf[f] += fma(cq, dm, cg) * r1 + fma(-cq, sp, cg) * r2;
                     }
                 }
             }
         } else {   // CLS_GENERAL: faithful case tree per (line, frequency)
+            int q0 = sg.begin, q1 = sg.end;
+            if (sg.mol != 7) {
+                q0 = lower_bound_d(a.xnu0, sg.begin, sg.end, winL);
+                q1 = upper_bound_d(a.xnu0, sg.begin, sg.end, winR);
+            }
             for (int q = q0; q < q1; q++) {
                 const double xnu = pXNU[q], vt = pVT[q];
                 const double hw = pl[(size_t)D_H * a.n_pad + q], ad = pl[(size_t)D_AD * a.n_pad + q];
@@ -685,7 +857,7 @@ __global__ void __launch_bounds__(128) lines_kernel(LinesArgs a)
                     if ((fabs(dm) > kDELTNUC) && (sg.mol != 7)) continue;          // modm.f90:384
                     if (SEL && sg.mol != 7) { cnt[f]++; hsh[f] += a.key[q]; }
                     const bool voigt = fabs(dm) <= vt;
-                    sf[f] += st * lsf_general(sg.mol, xf, ly.rp, ly.rp2, aip, bip, hw, wn[f], xnu, ad, a.sdep_s[q], voigt, &err);
+                    sf[f] += st * lsf_general(sg.mol, xf, rp, rp2, aip, bip, hw, wn[f], xnu, ad, a.sdep_s[q], voigt, &err);
                 }
             }
         }
