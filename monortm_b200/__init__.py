@@ -5,7 +5,7 @@ this package is the thin host side: ctypes bindings, a mirror of the reference's
 RTM operator interface, the TAPE3 / MONORTM_PROF.IN harness readers and the synthetic inputs.
 There is no CPU fallback: importing works anywhere, computing needs the built library and a B200.
 """
-from . import _capi, linefile, synth, profio  # noqa: F401
+from . import _capi, linefile, synth, profio, sharding  # noqa: F401
 from .api import MonortmError, Session, scor_for_layers, tips_2003  # noqa: F401
 
 __version__ = "0.1.0"

@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libmonortm_b200.so")
+LIB_PATH = os.environ.get("MRTM_LIB", os.path.join(_HERE, "lib", "libmonortm_b200.so"))
 
 MXMOL = 39
 NSCOR = 42 * 9

@@ -580,6 +580,17 @@ __device__ __forceinline__ double rcp3(double x)
     return fma(r0, t, r0);
 }
 
+#ifndef MRTM_LINES_MINB
+#define MRTM_LINES_MINB 4
+#endif
+#ifndef MRTM_UNROLL_SINGLE
+#define MRTM_UNROLL_SINGLE 4
+#endif
+#ifndef MRTM_UNROLL_BOTH
+#define MRTM_UNROLL_BOTH 2
+#endif
+#define MRTM_PRAGMA(x) _Pragma(#x)
+#define MRTM_UNROLL(n) MRTM_PRAGMA(unroll n)
 constexpr int kTile = 256;      // lines per smem tile
 constexpr int kStages = 2;
 
@@ -589,7 +600,7 @@ constexpr int kStages = 2;
 // needed (window edges, the WN+Xnu<=25 boundary, the Voigt zone); everything between the bands runs
 // in branch-free interior loops (one or two Lorentzians per line, pedestal summed separately).
 template <int F, bool SEL>
-__global__ void __launch_bounds__(128) lines_kernel(LinesArgs a)
+__global__ void __launch_bounds__(128, MRTM_LINES_MINB) lines_kernel(LinesArgs a)
 {
     constexpr int NT = 128;
     const int tid = threadIdx.x;
@@ -786,7 +797,7 @@ __global__ void __launch_bounds__(128) lines_kernel(LinesArgs a)
 #pragma unroll
                             for (int f = 0; f < F; f++) { cnt[f] += hi - lo; hsh[f] += hs; }
                         }
-#pragma unroll 2
+MRTM_UNROLL(MRTM_UNROLL_BOTH)
                         for (int q = lo; q < hi; q++) {
                             const int j = q - tb;
                             const double xnu = tX[j], h2 = tH[j], cn = tC[j];
@@ -807,7 +818,7 @@ __global__ void __launch_bounds__(128) lines_kernel(LinesArgs a)
 #pragma unroll
                             for (int f = 0; f < F; f++) { cnt[f] += hi - lo; hsh[f] += hs; }
                         }
-#pragma unroll 4
+MRTM_UNROLL(MRTM_UNROLL_SINGLE)
                         for (int q = lo; q < hi; q++) {
                             const int j = q - tb;
                             const double xnu = tX[j], h2 = tH[j], cn = tC[j];

@@ -1,0 +1,143 @@
+"""The C-ABI library loads without a GPU, exports every symbol include/monortm_b200.h declares, fails
+loudly when no device exists, and its host helpers (TIPS, PROF reader, tables) behave."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+import harness
+from monortm_b200 import _capi, api, profio
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    src = open(os.path.join(ROOT, "include", "monortm_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(mrtm_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = _capi.load_library()
+    names = _declared_symbols()
+    assert len(names) >= 17
+    for n in names:
+        assert hasattr(lib, n), n
+        assert n in _capi.SIGNATURES, "ctypes signature missing for " + n
+    assert b"monortm_b200" in lib.mrtm_version()
+    assert b"no CPU fallback" in lib.mrtm_strerror(1)
+
+
+def test_no_gpu_means_loud_failure():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(api.MonortmError) as e:
+        api.Session(0)
+    assert e.value.code == 1      # MRTM_ENODEV
+
+
+def test_tips_scor():
+    s296 = api.tips_2003(22, 296.0)
+    for mol, niso in ((1, 6), (2, 9), (3, 9), (7, 3), (22, 1)):
+        assert np.allclose(s296[mol - 1, :niso], 1.0, rtol=1e-14)
+    # independent Lagrange evaluation on the committed table for H2O 161 at 250 K
+    txt = open(os.path.join(ROOT, "monortm_b200", "csrc", "tables", "tips_tables.inc")).read()
+    q = np.array([float(x) for x in re.search(r"TIPS_QOFT\[\d+\] = \{(.*?)\};", txt, re.S).group(1).split(",") if x.strip()])
+    tdat = np.array([float(x) for x in re.search(r"TIPS_TDAT\[\d+\] = \{(.*?)\};", txt, re.S).group(1).split(",") if x.strip()])
+    q161 = q[:119]
+
+    def lag4(t):
+        i = int(np.searchsorted(tdat, t))       # first tdat >= t  (0-based) -> Fortran I = i+1
+        idx = [i - 2, i - 1, i, i + 1]
+        out = 0.0
+        for a in idx:
+            w = 1.0
+            for b in idx:
+                if a != b:
+                    w *= (t - tdat[b]) / (tdat[a] - tdat[b])
+            out += w * q161[a]
+        return out
+    s = api.tips_2003(22, 250.0)
+    assert abs(s[0, 0] - lag4(296.0) / lag4(250.0)) < 1e-13
+    assert s[0, 0] > 1.0 and api.tips_2003(22, 320.0)[0, 0] < 1.0      # Q grows with T
+    with pytest.raises(api.MonortmError):
+        api.tips_2003(22, 60.0)                                          # outside 70-3000 K -> STOP
+    with pytest.raises(api.MonortmError):
+        api.tips_2003(34, 250.0)                                         # molecule 34 (O): Q=0 -> STOP
+
+
+def test_tables_spot_values():
+    # literal values typed from the reference DATA statements
+    inc = open(os.path.join(ROOT, "monortm_b200", "csrc", "tables", "mtckd_tables.inc")).read()
+
+    def arr(name):
+        m = re.search(name + r"\[(\d+)\] = \{(.*?)\};", inc, re.S)
+        v = np.array([float(x) for x in m.group(2).split(",") if x.strip()])
+        assert len(v) == int(m.group(1))
+        return v
+    s296 = arr("MTCKD_SH2O_296")
+    assert len(s296) == 2003 and s296[0] == 2.731e-01 and s296[2] == 2.877E-01 and s296[-1] == 9.558e-12  # contnm.f90:1493-1497,1934
+    s260 = arr("MTCKD_SH2O_260")
+    assert s260[0] == 5.998e-01 and s260[1] == 6.382e-01                                                 # contnm.f90:2000
+    fh = arr("MTCKD_FH2O")
+    assert fh[0] == 1.205e-02 and fh[1] == 1.126e-02                                                     # contnm.f90:2509
+    co2 = arr("MTCKD_FCO2")
+    assert len(co2) == 5003 and co2[0] == 8.391e-13 and co2[2] == 8.345e-13                              # contnm.f90:3050-3052
+    n2 = arr("MTCKD_N2RT_296")
+    assert len(n2) == 73 and n2[0] == 0.4303E-06 and n2[-1] == 0.2428E-09                                # contnm.f90:4246,4260
+    assert arr("MTCKD_N2RT_296_SF")[0] == 1.3534
+    x = arr("MTCKD_XFAC_RHU")
+    assert len(x) == 63 and x[0] == 0.7620 and x[-1] == 1.0450                                           # contnm.f90:186-202
+    sm = open(os.path.join(ROOT, "monortm_b200", "csrc", "tables", "smass_table.inc")).read()
+    v = [float(t) for t in re.search(r"\{(.*?)\};", sm, re.S).group(1).split(",") if t.strip()]
+    assert v[0] == 18.01 and v[9 * 6] == 31.99 and v[9 * 21] == 28.01                                    # isotope.incl
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/src"), reason="reference tree not present")
+def test_tables_regenerate_identically(tmp_path):
+    import subprocess
+    import sys
+    import shutil
+    tabs = os.path.join(ROOT, "monortm_b200", "csrc", "tables")
+    keep = str(tmp_path / "keep")
+    shutil.copytree(tabs, keep)
+    subprocess.check_call([sys.executable, os.path.join(ROOT, "tools", "gen_tables.py")], stdout=subprocess.DEVNULL)
+    for f in os.listdir(keep):
+        assert open(os.path.join(keep, f)).read() == open(os.path.join(tabs, f)).read(), f
+
+
+def test_prof_reader_on_reference_fixtures():
+    g = os.path.join(ROOT, "tests", "golden")
+    a = profio.read_prof_in(os.path.join(g, "MONORTM_PROF.IN_sav"))[0]
+    b = profio.read_prof_in(os.path.join(g, "MONORTM_PROF.IN_liquid_cloud"))[0]
+    assert a["nlay"] == 19 and a["nmol"] == 22 and a["irt"] == 3          # ANGLE=0 < 90 -> downwelling
+    assert a["p"][0, 0] == 972.2109 and a["t"][0, 0] == 285.94 and a["tz"][0, 0] == 288.20 and a["tz"][1, 0] == 283.65
+    assert a["wkl"][0, 0, 0] == 1.2207059E+22 and a["wbrodl"][0, 0] == 1.5169132E+22
+    assert a["wkl"][21, 0, 0] == 1.3375841E+24
+    assert np.all(a["clw"] == 0)
+    assert list(b["clw"][2:5, 0]) == [0.03, 0.04, 0.03] and b["clw"].sum() == pytest.approx(0.10)
+    for k in ("p", "t", "tz", "wkl", "wbrodl"):
+        assert np.array_equal(a[k], b[k])
+    assert np.all(np.diff(a["p"][:, 0]) < 0)                               # surface-most layer first (IDU=1)
+
+
+def test_oracle_on_reference_profile_fixture():
+    """C1: the shipped IATM=0 profile x the 4 MWR channels through the oracle, cloudy vs clear."""
+    from monortm_b200 import synth
+    g = os.path.join(ROOT, "tests", "golden")
+    wn = synth.freq_c1_channels()
+    ls = harness.synthetic_store(512, v1=float(wn[0]), v2=float(wn[-1]))
+    out = {}
+    for name in ("MONORTM_PROF.IN_sav", "MONORTM_PROF.IN_liquid_cloud"):
+        pr = profio.read_prof_in(os.path.join(g, name))[0]
+        scor = api.scor_for_layers(22, pr["t"])
+        case = dict(ls=ls, wn=wn, dvset=0.0, prof=pr, scor=scor, irt=pr["irt"], cntnm=(1.,) * 7, ibrd=0, nmol=22,
+                    tmpsfc=2.75, emiss=np.ones(4), reflc=np.zeros(4))
+        out[name] = harness.run_oracle(case)
+    clear, cloudy = out["MONORTM_PROF.IN_sav"], out["MONORTM_PROF.IN_liquid_cloud"]
+    assert np.all(clear["tb"] > 5) and np.all(clear["tb"] < 150)           # downwelling TBs (synthetic filler lines add to the real ones)
+    assert np.all(cloudy["tb"] > clear["tb"] + 1.0)                        # 0.1 mm of liquid adds several K
+    assert np.all(cloudy["o_clw"][:, 2:5] > 0) and np.all(cloudy["o_clw"][:, :2] == 0)

@@ -1,0 +1,228 @@
+"""CPU tests that pin the oracle (oracle/monortm_oracle.c) with analytic identities and independent
+implementations.  The reference ships no golden outputs, so these identities --
+plus the committed self-generated regression vectors in tests/golden -- are what anchors it."""
+import ctypes as C
+
+import numpy as np
+import pytest
+from scipy.special import wofz
+
+import harness
+
+RADCN1 = 1.191042722E-12
+RADCN2 = 1.4387752
+
+
+def _w4(x, y):
+    lib = harness.oracle_lib()
+    re, im = C.c_double(), C.c_double()
+    lib.orc_w4(x, y, C.byref(re), C.byref(im))
+    return complex(re.value, im.value)
+
+
+def test_w4_matches_faddeeva_within_stated_accuracy():
+    # "MAXIMUM RELATIVE ERROR OF BOTH REAL AND IMAGINARY PARTS IS <1*10**(-4)", modm.f90:1094
+    rng = np.random.default_rng(1)
+    pts = [(0.0, 1e-3), (0.3, 0.05), (1.0, 0.1), (3.0, 0.5), (5.4, 0.2), (6.0, 0.01), (10.0, 4.0), (20.0, 0.5),
+           (0.5, 20.0), (2.0, 0.15), (4.0, 0.6)]
+    pts += [(float(x), float(y)) for x, y in zip(rng.uniform(0, 25, 200), 10 ** rng.uniform(-3, 1.3, 200))]
+    for x, y in pts:
+        w = _w4(x, y)
+        ref = wofz(complex(x, y))
+        assert abs(w.real - ref.real) <= 1.2e-4 * abs(ref.real) + 1e-12, (x, y, w, ref)
+
+
+def test_w4_region_boundaries_follow_reference():
+    # regions switch at |x|+y = 15 and 5.5 and at y = 0.195|x|-0.176 (modm.f90:1105,1109,1114)
+    for x, y in ((14.9999, 0.0001), (15.0, 0.0), (5.4999, 0.0001), (5.5, 0.0), (3.0, 0.195 * 3 - 0.176 - 1e-9)):
+        w = _w4(x, y)
+        assert np.isfinite(w.real) and np.isfinite(w.imag)
+    # region I formula: t*.5641896/(.5+t*t) with t = y - ix
+    x, y = 20.0, 1.0
+    t = complex(y, -x)
+    assert abs(_w4(x, y) - t * .5641896 / (.5 + t * t)) < 1e-15
+
+
+def test_sd_humlicek_reduces_to_w4_difference():
+    lib = harness.oracle_lib()
+    re, im = C.c_double(), C.c_double()
+    for (x1, y1, x2, y2) in ((0.2, 3.0, 0.2, 9.0), (1.0, 0.8, 1.0, 2.0), (7.0, 9.0, 7.0, 12.0)):
+        lib.orc_sd_humlicek(x1, y1, x2, y2, C.byref(re), C.byref(im))
+        d = wofz(complex(x1, y1)) - wofz(complex(x2, y2))
+        assert abs(re.value - d.real) < 3e-4 * max(abs(d.real), 1e-3)
+
+
+def test_sdvoigt_limits():
+    lib = harness.oracle_lib()
+    err = C.c_int(0)
+    # alphad = 0 -> zeta == 1 -> pure Lorentz shortcut (modm.f90:1017)
+    v = lib.orc_sdvoigt(0.03, 0.05, 0.0, 0.0, C.byref(err))
+    assert abs(v - 0.05 / (3.1415926535898 * (0.05 ** 2 + 0.03 ** 2))) < 1e-15
+    # Voigt ~ Gaussian core when alphal << alphad: peak = sqrt(ln2/pi)/alphad * Re w(i y)
+    ad, al = 1e-3, 1e-6
+    v = lib.orc_sdvoigt(0.0, al, ad, 0.0, C.byref(err))
+    y = np.sqrt(np.log(2.0)) * al / ad
+    assert abs(v - np.sqrt(np.log(2) / 3.1415926535898) / ad * wofz(1j * y).real) < 2e-4 * v
+    # area of the Voigt profile ~ 1
+    d = np.linspace(-0.05, 0.05, 20001)
+    prof = np.array([lib.orc_sdvoigt(float(x), 2e-4, 1e-3, 0.0, C.byref(err)) for x in d])
+    assert abs(np.trapezoid(prof, d) - 1.0) < 5e-3
+    # speed-dependent branch stays positive and close to the plain Voigt for small SDEP effects
+    vs = lib.orc_sdvoigt(2e-4, 2e-4, 1e-3, 0.08, C.byref(err))
+    v0 = lib.orc_sdvoigt(2e-4, 2e-4, 1e-3, 0.0, C.byref(err))
+    assert err.value == 0 and vs > 0 and abs(vs - v0) < 0.2 * v0
+
+
+def test_radfn_three_regimes():
+    lib = harness.oracle_lib()
+    xkt = 250.0 / RADCN2
+    assert lib.orc_radfn(1.0, xkt) == 0.5 * (1.0 / xkt) * 1.0                  # x <= 0.01
+    v = 50.0
+    x = v / xkt
+    assert abs(lib.orc_radfn(v, xkt) - v * np.tanh(x / 2)) < 1e-13 * v          # (1-e)/(1+e) == tanh(x/2)
+    assert lib.orc_radfn(5000.0, xkt) == 5000.0                                 # x > 10
+    assert lib.orc_radfn(3.0, 0.0) == 3.0                                       # XKT <= 0
+
+
+def test_planck_roundtrip_and_isothermal_layer_identity():
+    # one isothermal layer, levels at the layer temperature: bb == bba so the Pade term collapses and
+    # RDN = B(T)(1-exp(-tau)) (RTMmono.f90:215-216); TB inverts Planck (:150-151)
+    lib = harness.oracle_lib()
+    wn = np.array([0.7, 2.0, 6.1, 30.0])
+    T = 271.3
+    tau = np.array([1e-3, 0.4, 2.5, 30.0])
+    o = np.asfortranarray(tau.reshape(4, 1))
+    r = harness.oracle_rtm(1, 3, wn, [T], [T, T], o, 300.0, np.zeros(4), np.ones(4))
+    B = np.array([lib.orc_bb_fn(float(v), RADCN2 / T) for v in wn])
+    assert np.allclose(r["rdn"], B * (1 - np.exp(-tau)), rtol=1e-14)
+    assert np.allclose(r["trtot"], np.exp(-tau), rtol=1e-15)
+    assert r["tmpsfc"] == 2.75                                                 # RTMmono.f90:122
+    cosmic = np.array([lib.orc_bb_fn(float(v), RADCN2 / 2.75) for v in wn])
+    assert np.allclose(r["rad"], r["rdn"] + np.exp(-tau) * cosmic, rtol=1e-14)
+    # opaque layer: TB -> T
+    assert abs(r["tb"][3] - T) < 1e-9
+    # mean radiating temperature of an isothermal atmosphere is T
+    tmr = harness.oracle_calctmr(wn, [T], [T, T], o)
+    assert np.allclose(tmr, T, atol=1e-9)
+
+
+def test_rtm_upwelling_limits():
+    wn = np.array([1.0, 5.0])
+    o = np.asfortranarray(np.full((2, 3), 1e-12))
+    t, tz = [250., 240., 230.], [255., 245., 235., 225.]
+    r = harness.oracle_rtm(1, 1, wn, t, tz, o, 290.0, np.zeros(2), np.ones(2))
+    # transparent atmosphere, emissivity 1: TB = surface temperature
+    assert np.allclose(r["tb"], 290.0, atol=1e-6)
+    assert r["tmpsfc"] == 290.0
+    with pytest.raises(RuntimeError):
+        harness.oracle_rtm(1, 1, wn, t, tz, o, 290.0, np.zeros(2), np.ones(2), idu=0)   # RTMmono.f90:173 STOP
+
+
+def test_cloud_liquid_od():
+    lib = harness.oracle_lib()
+    assert lib.orc_odclw(1.0, 280.0, 0.0) == 0.0
+    a1 = lib.orc_odclw(1.0, 280.0, 0.1)
+    assert a1 > 0 and abs(lib.orc_odclw(1.0, 280.0, 0.2) - 2 * a1) < 1e-15
+    # mass absorption coefficient at 31.4 GHz, 0 C is roughly 0.1 m2/kg per (kg/m2)  (Turner et al.)
+    a = lib.orc_odclw(31.4 / 29.9792458, 273.15, 1.0)
+    assert 0.05 < a < 0.3
+    # absorption grows with frequency in the microwave and with supercooling at 31 GHz
+    assert lib.orc_odclw(3.0, 280.0, 1.0) > lib.orc_odclw(1.0, 280.0, 1.0)
+    assert lib.orc_odclw(1.0, 253.15, 1.0) > lib.orc_odclw(1.0, 293.15, 1.0)
+
+
+def _contnm(im, factors, pave=800., tave=270., v1=0.2, v2=30.):
+    lib = harness.oracle_lib()
+    wk = np.zeros(60)
+    wk[0], wk[1], wk[6], wk[21] = 3e22, 6e20, 3.5e23, 1.3e24
+    v1abs = float(int(v1)) - 3.
+    v2abs = float(int(v2 + 3.5))
+    npt = int((v2abs - v1abs) + 1.5)
+    ab = np.zeros(npt + 2)
+    f = np.array(factors, dtype=np.float64)
+    rc = lib.orc_contnm_one(im, f.ctypes.data_as(C.c_void_p), pave, tave, wk.ctypes.data_as(C.c_void_p), 1.3e24, 22,
+                            v1, v2, v1abs, v2abs, npt, ab.ctypes.data_as(C.c_void_p))
+    assert rc == 0, lib.orc_last_error()
+    return ab[:npt]
+
+
+def test_continuum_scaling_and_selectors():
+    one = (1.,) * 7
+    h = _contnm(1, one)
+    assert np.all(h[3:-3] > 0)
+    # self + foreign add (modm.f90:213 selects both for H2O); each scales linearly with its factor
+    hs = _contnm(1, (1., 0., 1., 1., 1., 1., 1.))
+    hf = _contnm(1, (0., 1., 1., 1., 1., 1., 1.))
+    assert np.allclose(hs + hf, h, rtol=1e-13)
+    assert np.allclose(_contnm(1, (2., 0., 1., 1., 1., 1., 1.)), 2 * hs, rtol=1e-13)
+    # species without a microwave continuum give zero (gates contnm.f90:536,657)
+    assert np.all(_contnm(3, one) == 0) and np.all(_contnm(7, one) == 0) and np.all(_contnm(99, one) == 0)
+    n2 = _contnm(22, one)
+    co2 = _contnm(2, one)
+    assert np.all(n2[3:-3] > 0) and np.all(co2[3:-3] > 0)
+    # N2 CIA scales with density squared: doubling pressure quadruples amagat*rho... tau_fac ~ amagat
+    assert np.allclose(_contnm(22, one, pave=400.) * 2, n2, rtol=1e-12)
+    # out-of-range request is refused rather than silently wrong
+    lib = harness.oracle_lib()
+    wk = np.zeros(60)
+    ab = np.zeros(2000)
+    f = np.ones(7)
+    rc = lib.orc_contnm_one(1, f.ctypes.data_as(C.c_void_p), 800., 270., wk.ctypes.data_as(C.c_void_p), 1e24, 22,
+                            100., 900., 97., 904., 808, ab.ctypes.data_as(C.c_void_p))
+    assert rc != 0
+
+
+def test_modm_selection_counts_and_totals():
+    # every O2 line passes the cutoff (modm.f90:384 has I.NE.7), others only inside 25 cm-1
+    case = harness.make_case(n_filler=256, nlay=4, wn=np.array([0.5, 10.0, 40.0, 54.0]), irt=3)
+    ref = harness.run_oracle(case)
+    ls = case["ls"]
+    pr = case["prof"]
+    # logical lines per molecule (coupling records are not lines)
+    for iw, w in enumerate(case["wn"]):
+        for k in range(4):
+            ratio = (pr["p"][k, 0] / (1.3806503E-16 * pr["t"][k, 0])) * 1e3 / ((1013.25 / (1.3806503E-16 * 296.)) * 1e3)
+            cnt = 0
+            for i in range(39):
+                n = int(ls.nblm[i])
+                if n == 0 or pr["wkl"][i, k, 0] == 0:
+                    continue
+                j = 0
+                while j < n:
+                    xg = ls.xg[i, j]
+                    xnu = ls.xnu0[i, j] + ls.deltnu[i, j] * ratio
+                    if i + 1 == 7 or not abs(w - xnu) > 25.0:
+                        cnt += 1
+                    j += 2 if xg in (-1., -3., -5.) else 1
+            assert ref["sel_count"][iw, k] == cnt
+    # O = sum of parts (modm.f90:265-269)
+    tot = ref["o_by_mol"].sum(axis=1) + ref["oc"].sum(axis=1) + ref["o_clw"] + ref["odxsec"]
+    assert np.allclose(tot, ref["o"], rtol=1e-13)
+    assert np.all(ref["o"] > 0)
+
+
+def test_modm_zero_amount_molecule_is_skipped_and_line_coupling_scales():
+    wn = np.linspace(1.6, 2.4, 9)
+    case = harness.make_case(n_filler=128, nlay=3, wn=wn, irt=3)
+    base = harness.run_oracle(case)
+    case0 = dict(case)
+    prof = {k: (v.copy() if hasattr(v, "copy") else v) for k, v in case["prof"].items()}
+    prof["wkl"][6] = 0.0                       # no O2: W_SPECIES == 0 -> skipped (modm.f90:318-321)
+    case0["prof"] = prof
+    no_o2 = harness.run_oracle(case0)
+    assert np.all(no_o2["o_by_mol"][:, 6, :] == 0)
+    assert np.all(no_o2["sel_count"] < base["sel_count"])
+    # SCLCPL scales the first-order coupling of the O2 band (modm.f90:358-361)
+    c2 = dict(case)
+    c2["sclcpl"] = 0.0
+    nolc = harness.run_oracle(c2)
+    assert not np.allclose(nolc["o_by_mol"][:, 6, 0], base["o_by_mol"][:, 6, 0], rtol=1e-6)
+
+
+def test_oracle_o0_and_o2_builds_agree():
+    case = harness.make_case(n_filler=128, nlay=6, wn=np.linspace(0.3, 20.0, 24), irt=1, clw=True)
+    a = harness.run_oracle(case, opt="O0")
+    b = harness.run_oracle(case, opt="O2")
+    assert np.array_equal(a["sel_hash"], b["sel_hash"])
+    assert harness.rel_diff(a["o"], b["o"]) < 1e-13
+    assert np.max(np.abs(a["tb"] - b["tb"])) < 1e-9
