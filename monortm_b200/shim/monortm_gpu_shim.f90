@@ -1,0 +1,151 @@
+!  monortm_gpu_shim.f90 -- ISO_C_BINDING shim between the unchanged monoRTM Fortran host
+!  (monortm.f90, monortm_sub.F90, lblatm.f90, lnfl_mod.f90) and libmonortm_b200.so.
+!
+!  It replaces the three calls of src/monortm.f90:557-574 (MODM, CALCTMR, RTM).  The host keeps
+!  reading MONORTM.IN / MONORTM_PROF.IN / TAPE3 and writing MONORTM.OUT exactly as before.
+!
+!  Kinds: the parity build linuxGNUdbl compiles with -fdefault-real-8 -fdefault-integer-8
+!  (build/makefile.common:195-198), so default REAL == c_double and default INTEGER == c_int64_t;
+!  brd_mol_flg is integer*4 in lnfl_mod itself.  Build the host with the same flags and link
+!  -lmonortm_b200 (see INTEGRATION.md).
+!
+!  NOTE: this file cannot be compiled in the authoring environment (no Fortran compiler); it is
+!  delivered as source and its argument marshalling is exercised through the ctypes/C++ callers,
+!  which pass the same column-major arrays.
+module monortm_gpu_shim
+  use, intrinsic :: iso_c_binding
+  implicit none
+  private
+  public :: mrtm_gpu_init, mrtm_gpu_stage_lines, mrtm_gpu_modm, mrtm_gpu_calctmr, mrtm_gpu_rtm, mrtm_gpu_done
+
+  type(c_ptr), save :: ctx = c_null_ptr
+
+  type, bind(c) :: mrtm_opts
+     integer(c_int32_t) :: use_global_range = 0
+     integer(c_int32_t) :: reserved0 = 0
+     real(c_double)     :: v1_global = 0, v2_global = 0
+     integer(c_int64_t) :: iw0 = 0
+     type(c_ptr)        :: sel_count = c_null_ptr
+     type(c_ptr)        :: sel_hash = c_null_ptr
+     type(c_ptr)        :: stream = c_null_ptr
+  end type mrtm_opts
+
+  interface
+     integer(c_int) function c_mrtm_init(device, ctx) bind(c, name="mrtm_init")
+       import :: c_int, c_ptr
+       integer(c_int), value :: device
+       type(c_ptr) :: ctx
+     end function
+     integer(c_int) function c_mrtm_free(ctx) bind(c, name="mrtm_free")
+       import :: c_int, c_ptr
+       type(c_ptr), value :: ctx
+     end function
+     function c_mrtm_last_error(ctx) bind(c, name="mrtm_last_error") result(p)
+       import :: c_ptr
+       type(c_ptr), value :: ctx
+       type(c_ptr) :: p
+     end function
+     integer(c_int) function c_mrtm_stage_lines(ctx, nblm, iim, iso, xnu0, deltnu, e, alps, alpf, x, xg, s0, &
+          rmol, sdep, brd_flg, brd_tmp, brd_hw, brd_shft) bind(c, name="mrtm_stage_lines")
+       import :: c_int, c_ptr, c_int64_t, c_double, c_int32_t
+       type(c_ptr), value :: ctx
+       integer(c_int64_t) :: nblm(*), iso(*)
+       integer(c_int64_t), value :: iim
+       real(c_double) :: xnu0(*), deltnu(*), e(*), alps(*), alpf(*), x(*), xg(*), s0(*), rmol(*), sdep(*)
+       integer(c_int32_t) :: brd_flg(*)
+       real(c_double) :: brd_tmp(*), brd_hw(*), brd_shft(*)
+     end function
+     integer(c_int) function c_mrtm_modm(ctx, nwn, wn, dvset, nlay, p, t, clw, o, o_by_mol, oc, o_clw, odxsec, &
+          nmol, wkl, wbrodl, sclcpl, sclhw, y0res, cntnm, ixsect, ibrd, scor, opts) bind(c, name="mrtm_modm")
+       import :: c_int, c_ptr, c_int64_t, c_double
+       type(c_ptr), value :: ctx
+       integer(c_int64_t), value :: nwn, nlay, nmol, ixsect, ibrd
+       real(c_double), value :: dvset, sclcpl, sclhw, y0res
+       real(c_double) :: wn(*), p(*), t(*), clw(*), o(*), o_by_mol(*), oc(*), o_clw(*), odxsec(*)
+       real(c_double) :: wkl(*), wbrodl(*), cntnm(7), scor(*)
+       type(c_ptr), value :: opts
+     end function
+     integer(c_int) function c_mrtm_calctmr(ctx, nlayrs, nwn, wn, t, tz, o, tmr) bind(c, name="mrtm_calctmr")
+       import :: c_int, c_ptr, c_int64_t, c_double
+       type(c_ptr), value :: ctx
+       integer(c_int64_t), value :: nlayrs, nwn
+       real(c_double) :: wn(*), t(*), tz(*), o(*), tmr(*)
+     end function
+     integer(c_int) function c_mrtm_rtm(ctx, iout, irt, nwn, wn, nlay, t, tz, o, tmpsfc, rup, trtot, rdn, &
+          reflc, emiss, rad, tb, idu) bind(c, name="mrtm_rtm")
+       import :: c_int, c_ptr, c_int64_t, c_double
+       type(c_ptr), value :: ctx
+       integer(c_int64_t), value :: iout, irt, nwn, nlay, idu
+       real(c_double) :: wn(*), t(*), tz(*), o(*), tmpsfc, rup(*), trtot(*), rdn(*), reflc(*), emiss(*), rad(*), tb(*)
+     end function
+  end interface
+
+contains
+
+  subroutine check(rc, where)
+    integer(c_int), intent(in) :: rc
+    character(*), intent(in) :: where
+    if (rc /= 0) then
+       write(*,*) 'monortm_b200: error ', rc, ' in ', where
+       stop 'monortm_b200 GPU hot path failed'       ! the reference STOPs on every error path
+    end if
+  end subroutine check
+
+  subroutine mrtm_gpu_init(device)
+    integer, intent(in) :: device
+    if (.not. c_associated(ctx)) call check(c_mrtm_init(int(device, c_int), ctx), 'mrtm_init')
+  end subroutine
+
+  !  call once, right after GET_LNFL has filled the lnfl_mod module arrays (modm.f90:187-190)
+  subroutine mrtm_gpu_stage_lines()
+    use lnfl_mod, only: NBLM, ISO, XNU0, DELTNU, E, ALPS, ALPF, X, XG, S0, RMOL, SDEP, &
+                        brd_mol_flg, brd_mol_tmp, brd_mol_hw, brd_mol_shft
+    call check(c_mrtm_stage_lines(ctx, NBLM, int(size(XNU0, 2), c_int64_t), ISO, XNU0, DELTNU, E, ALPS, ALPF, X, XG, &
+         S0, RMOL, SDEP, brd_mol_flg, brd_mol_tmp, brd_mol_hw, brd_mol_shft), 'mrtm_stage_lines')
+  end subroutine
+
+  !  drop-in for CALL MODM(...) (src/monortm.f90:557-561).  tips_2003 stays on this side.
+  !  O, O_CLW, ODXSEC are (nwn, mxlay) and O_BY_MOL, OC (nwn, mxmol, mxlay) in the driver
+  !  (src/monortm.f90:352-353): pass contiguous (nwn,nlay) / (nwn,mxmol,nlay) sections.
+  subroutine mrtm_gpu_modm(nwn, wn, dvset, nlay, p, t, clw, o, o_by_mol, oc, o_clw, odxsec, nmol, wkl, wbrodl, &
+       sclcpl, sclhw, y0res, cntnm7, ixsect, ibrd)
+    integer, intent(in) :: nwn, nlay, nmol, ixsect, ibrd
+    real*8, intent(in) :: wn(*)
+    real, intent(in) :: dvset, p(*), t(*), clw(*), wkl(39, *), wbrodl(*), sclcpl, sclhw, y0res, cntnm7(7)
+    real :: o(nwn, *), o_by_mol(nwn, 39, *), oc(nwn, 39, *), o_clw(nwn, *), odxsec(nwn, *)
+    real, allocatable :: scor(:, :, :)
+    integer :: k
+    allocate(scor(42, 9, nlay))
+    scor = 0.
+    do k = 1, nlay
+       call tips_2003(nmol, t(k), scor(:, :, k))          ! src/modm.f90:250
+    end do
+    call check(c_mrtm_modm(ctx, int(nwn, c_int64_t), wn, dvset, int(nlay, c_int64_t), p, t, clw, o, o_by_mol, oc, &
+         o_clw, odxsec, int(nmol, c_int64_t), wkl, wbrodl, sclcpl, sclhw, y0res, cntnm7, &
+         int(ixsect, c_int64_t), int(ibrd, c_int64_t), scor, c_null_ptr), 'mrtm_modm')
+    deallocate(scor)
+  end subroutine
+
+  subroutine mrtm_gpu_calctmr(nlayrs, nwn, wn, t, tz, o, tmr)
+    integer, intent(in) :: nlayrs, nwn
+    real*8, intent(in) :: wn(*)
+    real, intent(in) :: t(*), tz(0:*), o(nwn, *)
+    real :: tmr(*)
+    call check(c_mrtm_calctmr(ctx, int(nlayrs, c_int64_t), int(nwn, c_int64_t), wn, t, tz, o, tmr), 'mrtm_calctmr')
+  end subroutine
+
+  subroutine mrtm_gpu_rtm(iout, irt, nwn, wn, nlay, t, tz, o, tmpsfc, rup, trtot, rdn, reflc, emiss, rad, tb, idu)
+    integer, intent(in) :: iout, irt, nwn, nlay, idu
+    real*8, intent(in) :: wn(*)
+    real, intent(in) :: t(*), tz(0:*), o(nwn, *), reflc(*), emiss(*)
+    real :: tmpsfc, rup(*), trtot(*), rdn(*), rad(*), tb(*)
+    call check(c_mrtm_rtm(ctx, int(iout, c_int64_t), int(irt, c_int64_t), int(nwn, c_int64_t), wn, &
+         int(nlay, c_int64_t), t, tz, o, tmpsfc, rup, trtot, rdn, reflc, emiss, rad, tb, int(idu, c_int64_t)), 'mrtm_rtm')
+  end subroutine
+
+  subroutine mrtm_gpu_done()
+    if (c_associated(ctx)) call check(c_mrtm_free(ctx), 'mrtm_free')
+    ctx = c_null_ptr
+  end subroutine
+
+end module monortm_gpu_shim
