@@ -45,6 +45,7 @@ struct mrtm_ctx {
     std::vector<void*> table_allocs;
     int32_t* tips_row_dev = nullptr;
     int* errflag_dev = nullptr;
+    DevBuf b_vtmax;
     DevBuf b_layer, b_scorc, b_absrb, b_planes, b_o, b_obm, b_oc, b_in[16], b_out[16], b_sel[2], b_tmps;
     mrtm_stats st;
     size_t planes_budget = (size_t)8 << 30;
@@ -171,7 +172,7 @@ extern "C" int mrtm_free(mrtm_ctx* ctx)
     cudaStreamSynchronize(ctx->stream);
     free_lines(ctx);
     for (void* p : ctx->table_allocs) cudaFree(p);
-    DevBuf* bufs[] = {&ctx->b_layer, &ctx->b_scorc, &ctx->b_absrb, &ctx->b_planes, &ctx->b_o, &ctx->b_obm, &ctx->b_oc, &ctx->b_sel[0], &ctx->b_sel[1], &ctx->b_tmps};
+    DevBuf* bufs[] = {&ctx->b_vtmax, &ctx->b_layer, &ctx->b_scorc, &ctx->b_absrb, &ctx->b_planes, &ctx->b_o, &ctx->b_obm, &ctx->b_oc, &ctx->b_sel[0], &ctx->b_sel[1], &ctx->b_tmps};
     for (DevBuf* b : bufs) if (b->p) cudaFree(b->p);
     for (auto& b : ctx->b_in) if (b.p) cudaFree(b.p);
     for (auto& b : ctx->b_out) if (b.p) cudaFree(b.p);
@@ -207,7 +208,7 @@ extern "C" int mrtm_stage_lines(mrtm_ctx* ctx, const int64_t nblm[MRTM_MXMOL], i
     d.n_pad = (int32_t)h.n_pad;
     auto& own = ctx->line_allocs;
 #define UPV(F) if ((rc = upload(ctx, h.F, own, &d.F))) return rc;
-    UPV(mol) UPV(iso) UPV(xf) UPV(cls) UPV(sidx) UPV(lcidx) UPV(brdidx)
+    UPV(mol) UPV(iso) UPV(xf) UPV(cls) UPV(sidx) UPV(lcidx) UPV(brdidx) UPV(segidx)
     UPV(xnu0) UPV(s0adj) UPV(e) UPV(alpf) UPV(alps) UPV(x) UPV(deltnu) UPV(sdep) UPV(mass)
     UPV(lc) UPV(lc_self) UPV(brd) UPV(scor_index)
 #undef UPV
@@ -292,11 +293,11 @@ struct RunDesc {
     int64_t iw0;
 };
 
-template <int F>
+template <int F, int NT>
 static void launch_lines(const LinesArgs& la, dim3 grid, bool sel, cudaStream_t s)
 {
-    if (sel) lines_kernel<F, true><<<grid, 128, 0, s>>>(la);
-    else lines_kernel<F, false><<<grid, 128, 0, s>>>(la);
+    if (sel) lines_kernel<F, true, NT><<<grid, NT, 0, s>>>(la);
+    else lines_kernel<F, false, NT><<<grid, NT, 0, s>>>(la);
 }
 
 static int run_device(mrtm_ctx* ctx, const RunDesc& r, cudaStream_t s)
@@ -354,6 +355,7 @@ static int run_device(mrtm_ctx* ctx, const RunDesc& r, cudaStream_t s)
         if ((rc = ensure(ctx, ctx->b_scorc, (size_t)B * nlay * std::max(1, (int)ctx->ld.nsi) * 8))) return rc;
         if ((rc = ensure(ctx, ctx->b_absrb, (size_t)B * nlay * 3 * nptabs_pad * 8))) return rc;
         if ((rc = ensure(ctx, ctx->b_planes, (size_t)B * nlay * D_NPLANES * (size_t)n_pad * 8))) return rc;
+        if ((rc = ensure(ctx, ctx->b_vtmax, (size_t)B * nlay * std::max<size_t>(1, h.segments.size()) * 8))) return rc;
         CU(cudaMemsetAsync(ctx->errflag_dev, 0, sizeof(int), s));
         st.nominal_evals = (double)h.n * (double)nlay * (double)nwn * (double)r.nprof;
         st.inwindow_evals = -1.;
@@ -406,6 +408,9 @@ static int run_device(mrtm_ctx* ctx, const RunDesc& r, cudaStream_t s)
             da.y0res = r.y0res;
             da.ibrd = (int32_t)r.ibrd;
             da.planes = (double*)ctx->b_planes.p;
+            da.vtmax = (unsigned long long*)ctx->b_vtmax.p;
+            da.nseg = (int32_t)h.segments.size();
+            CU(cudaMemsetAsync(ctx->b_vtmax.p, 0, (size_t)Lb * std::max<size_t>(1, h.segments.size()) * 8, s));
             CU(cudaEventRecord(ctx->ev[0], s));
             derive_kernel<<<dim3((unsigned)((n_pad + 255) / 256), (unsigned)Lb), 256, 0, s>>>(da);
             CU(cudaEventRecord(ctx->ev[1], s));
@@ -427,6 +432,7 @@ static int run_device(mrtm_ctx* ctx, const RunDesc& r, cudaStream_t s)
             la.key = ctx->ld.key;
             la.planes = (const double*)ctx->b_planes.p;
             la.lay = (const LayerDev*)ctx->b_layer.p;
+            la.vtmax = (const unsigned long long*)ctx->b_vtmax.p;
             la.absrb = (const double*)ctx->b_absrb.p;
             la.nptabs = nptabs;
             la.nptabs_pad = nptabs_pad;
@@ -447,12 +453,16 @@ static int run_device(mrtm_ctx* ctx, const RunDesc& r, cudaStream_t s)
             la.sel_hash = r.sel_hash ? r.sel_hash + (size_t)b0 * nwn * nlay : nullptr;
             la.errflag = ctx->errflag_dev;
             const bool sel = (r.sel_count != nullptr) || (r.sel_hash != nullptr);
-            const int F = (nwn >= 2048) ? 4 : ((nwn >= 512) ? 2 : 1);
-            dim3 grid((unsigned)((nwn + 128 * F - 1) / (128 * F)), (unsigned)nlay, (unsigned)nb);
+            // frequencies per CTA: 128 threads x F (512 on dense grids, smaller tiles for short channel lists)
+            static const int force_nt = std::getenv("MRTM_LINES_NT") ? std::atoi(std::getenv("MRTM_LINES_NT")) : 0;
+            const int NTsel = force_nt ? force_nt : 128;   // 256-thread CTAs measured 4% slower on the dense sweep
+            const int F = (NTsel == 256 || nwn >= 2048) ? 4 : ((nwn >= 512) ? 2 : 1);
+            dim3 grid((unsigned)((nwn + NTsel * F - 1) / (NTsel * F)), (unsigned)nlay, (unsigned)nb);
             CU(cudaEventRecord(ctx->ev[2], s));
-            if (F == 4) launch_lines<4>(la, grid, sel, s);
-            else if (F == 2) launch_lines<2>(la, grid, sel, s);
-            else launch_lines<1>(la, grid, sel, s);
+            if (NTsel == 256) launch_lines<4, 256>(la, grid, sel, s);
+            else if (F == 4) launch_lines<4, 128>(la, grid, sel, s);
+            else if (F == 2) launch_lines<2, 128>(la, grid, sel, s);
+            else launch_lines<1, 128>(la, grid, sel, s);
             CU(cudaEventRecord(ctx->ev[3], s));
             st.kernel_launches++;
             CU(cudaGetLastError());

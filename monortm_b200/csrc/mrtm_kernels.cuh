@@ -16,7 +16,7 @@ namespace mrtm {
 // static line planes (device pointers)
 struct LinesDev {
     int32_t n, n_pad;
-    const int32_t *mol, *iso, *xf, *cls, *sidx, *lcidx, *brdidx;
+    const int32_t *mol, *iso, *xf, *cls, *sidx, *lcidx, *brdidx, *segidx;
     const double *xnu0, *s0adj, *e, *alpf, *alps, *x, *deltnu, *sdep, *mass;
     const unsigned long long* key;
     const double* lc;          // [nlc][16]
@@ -335,6 +335,8 @@ struct DeriveArgs {
     double sclcpl, sclhw, y0res;
     int32_t ibrd, pad;
     double* planes;           // [L][D_NPLANES][n_pad]
+    unsigned long long* vtmax; // [L][nseg]: max over the segment of VT (bits of a non-negative double), 0 = no Voigt-capable line
+    int32_t nseg, pad2;
 };
 
 __global__ void __launch_bounds__(256) derive_kernel(DeriveArgs a)
@@ -443,7 +445,9 @@ __global__ void __launch_bounds__(256) derive_kernel(DeriveArgs a)
     pl[(size_t)D_P4 * np + q] = p4;
     pl[(size_t)D_H * np + q] = hwhm_c;
     pl[(size_t)D_AD * np + q] = hwhm_d;
-    pl[(size_t)D_VT * np + q] = (zeta > 0.99) ? -1.0 : 100. * hwhm_d;
+    const double vt = (zeta > 0.99) ? -1.0 : 100. * hwhm_d;
+    pl[(size_t)D_VT * np + q] = vt;
+    if (vt >= 0.) atomicMax(a.vtmax + (size_t)L * a.nseg + a.ln.segidx[q], (unsigned long long)__double_as_longlong(vt));
     pl[(size_t)D_STILD * np + q] = stild;
     pl[(size_t)D_AIP * np + q] = aip;
     pl[(size_t)D_BIP * np + q] = bip;
@@ -469,6 +473,7 @@ struct LinesArgs {
     const unsigned long long* key;
     const double* planes;         // [L][D_NPLANES][n_pad]
     const LayerDev* lay;          // [L]
+    const unsigned long long* vtmax;   // [L][nseg]
     // continuum
     const double* absrb;          // [L][3][nptabs_pad]
     int32_t nptabs, nptabs_pad;
@@ -594,15 +599,31 @@ __device__ __forceinline__ double rcp3(double x)
 constexpr int kTile = 256;      // lines per smem tile
 constexpr int kStages = 2;
 
-// lines_kernel, version 2: line-parameter tiles (XNU, H2, CN, P3 planes) are streamed into shared
-// memory with TMA bulk copies, double buffered on mbarriers; per segment the sorted static centres
-// are binary-searched for the window and for the three narrow bands in which per-thread tests are
-// needed (window edges, the WN+Xnu<=25 boundary, the Voigt zone); everything between the bands runs
-// in branch-free interior loops (one or two Lorentzians per line, pedestal summed separately).
-template <int F, bool SEL>
-__global__ void __launch_bounds__(128, MRTM_LINES_MINB) lines_kernel(LinesArgs a)
+// per-segment work descriptor built once per CTA (in parallel) in shared memory
+struct SegWork {
+    int q0, q1;        // lines that can be inside the 25 cm-1 window of some frequency of the CTA
+    int eb, ec;        // [q0,eb) and [ec,q1): window-edge bands (per-thread window test)
+    int n0, n1;        // [n0,n1): band where WN+Xnu<=25 flips; < n0: both resonances for every thread
+    int v0, v1;        // [v0,v1): Voigt zone
+    int nbp;           // sub-range break points bp[0..nbp-1]
+    int bp[10];
+    int t0, ntile;     // TMA tile origin (32-byte aligned) and tile count; ntile==0: nothing to stream
+    int next;          // next segment with ntile>0, or -1
+    int active;        // W_species != 0
+};
+
+// lines_kernel, version 3.  CTA = (NT*F frequencies, one layer, one profile); each thread owns F
+// (frequency, layer) accumulators.
+//  * prologue: all window / band searches of all segments run in parallel (one search per thread)
+//  * line-parameter tiles (XNU, H2, CN, P3) stream through shared memory with TMA bulk copies, double
+//    buffered on mbarriers, prefetching across segment boundaries
+//  * interior ranges run branch-free (4 lines share one reciprocal); the three narrow bands (window
+//    edges, the WN+Xnu<=25 boundary, the Voigt zone) run loops specialised per test combination with the
+//    reference's exact per-(line,frequency) tests (modm.f90:384, 427, 746)
+template <int F, bool SEL, int NT>
+__global__ void __launch_bounds__(NT, (MRTM_LINES_MINB * 128) / NT) lines_kernel(LinesArgs a)
 {
-    constexpr int NT = 128;
+    constexpr int NW = NT / 32;
     const int tid = threadIdx.x;
     const int k = blockIdx.y;                     // layer within profile
     const int prof = blockIdx.z;
@@ -618,7 +639,10 @@ __global__ void __launch_bounds__(128, MRTM_LINES_MINB) lines_kernel(LinesArgs a
 
     __shared__ __align__(128) double s_tile[kStages][4][kTile];
     __shared__ __align__(8) uint64_t s_bar[kStages];
-    __shared__ double s_lo[NT / 32], s_hi[NT / 32];
+    __shared__ double s_lo[NW], s_hi[NW];
+    __shared__ double s_ped[2][NW];
+    __shared__ SegWork s_work[kMaxSegments];
+    __shared__ int s_first;
 
     // this thread's frequencies (strided so global accesses coalesce)
     const int base = blockIdx.x * (NT * F);
@@ -644,12 +668,89 @@ __global__ void __launch_bounds__(128, MRTM_LINES_MINB) lines_kernel(LinesArgs a
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
-    wlo = fmin(fmin(s_lo[0], s_lo[1]), fmin(s_lo[2], s_lo[3]));
-    whi = fmax(fmax(s_hi[0], s_hi[1]), fmax(s_hi[2], s_hi[3]));
+#pragma unroll
+    for (int i = 0; i < NW; i++) { wlo = fmin(wlo, s_lo[i]); whi = fmax(whi, s_hi[i]); }
     const double sm = ly.shift_margin;
-    const double winL = wlo - kDELTNUC - sm, winR = whi + kDELTNUC + sm;
     const double rp = ly.rp, rp2 = ly.rp2;
+    const int nseg = a.nseg;
+
+    // ---- prologue: one binary search per thread over (segment, field) tasks ----------------------
+    for (int task = tid; task < nseg * 8; task += NT) {
+        const int s = task >> 3, w = task & 7;
+        const Segment sg = a.seg[s];
+        const int cls = sg.cls;
+        const bool tma_cls = (cls == CLS_PED) || (cls == CLS_O2) || (cls == CLS_O2_LC35);
+        const bool has_win = (cls == CLS_PED) || (cls == CLS_O2) || (cls == CLS_GENERAL && sg.mol != 7);
+        int r;
+        switch (w) {
+        case 0: r = has_win ? lower_bound_d(a.xnu0, sg.begin, sg.end, wlo - kDELTNUC - sm) : sg.begin; break;
+        case 1: r = has_win ? upper_bound_d(a.xnu0, sg.begin, sg.end, whi + kDELTNUC + sm) : sg.end; break;
+        case 2: r = (has_win && tma_cls) ? upper_bound_d(a.xnu0, sg.begin, sg.end, whi - kDELTNUC + sm) : sg.begin; break;
+        case 3: r = (has_win && tma_cls) ? lower_bound_d(a.xnu0, sg.begin, sg.end, wlo + kDELTNUC - sm) : sg.end; break;
+        case 4: r = (has_win && tma_cls) ? lower_bound_d(a.xnu0, sg.begin, sg.end, kDELTNUC - whi - sm) : sg.end; break;
+        case 5: r = (has_win && tma_cls) ? upper_bound_d(a.xnu0, sg.begin, sg.end, kDELTNUC - wlo + sm + 1e-9) : sg.end; break;
+        default: {
+            // Voigt zone: where a frequency can come within max(100*HWHM_D) of a centre (modm.f90:427); the
+            // maximum is over the lines of this (layer, segment) that are not Lorentz-only (zeta <= 0.99)
+            const unsigned long long vbits = a.vtmax[(size_t)L * nseg + s];
+            if (tma_cls && vbits != 0ull) {
+                const double vb = __longlong_as_double((long long)vbits) * (1. + 1e-12) + sm + 1e-9;
+                r = (w == 6) ? lower_bound_d(a.xnu0, sg.begin, sg.end, wlo - vb) : upper_bound_d(a.xnu0, sg.begin, sg.end, whi + vb);
+            } else {
+                r = sg.begin;      // empty zone after clipping
+            }
+        } break;
+        }
+        (&s_work[s].q0)[w] = r;
+    }
+    __syncthreads();
+    for (int s = tid; s < nseg; s += NT) {
+        SegWork& wk = s_work[s];
+        const Segment sg = a.seg[s];
+        const int cls = sg.cls;
+        const bool tma_cls = (cls == CLS_PED) || (cls == CLS_O2) || (cls == CLS_O2_LC35);
+        const int q0 = wk.q0, q1 = wk.q1 > wk.q0 ? wk.q1 : wk.q0;
+        wk.q1 = q1;
+        int c[6] = {wk.eb, wk.ec, wk.n0, wk.n1, wk.v0, wk.v1};
+        for (int i = 0; i < 6; i++) c[i] = c[i] < q0 ? q0 : (c[i] > q1 ? q1 : c[i]);
+        wk.eb = c[0]; wk.ec = c[1]; wk.n0 = c[2]; wk.n1 = c[3]; wk.v0 = c[4]; wk.v1 = c[5];
+        for (int i = 1; i < 6; i++) { int v = c[i], j = i - 1; while (j >= 0 && c[j] > v) { c[j + 1] = c[j]; j--; } c[j + 1] = v; }
+        int nbp = 0;
+        wk.bp[nbp++] = q0;
+        for (int i = 0; i < 6; i++) if (c[i] > wk.bp[nbp - 1]) wk.bp[nbp++] = c[i];
+        if (q1 > wk.bp[nbp - 1]) wk.bp[nbp++] = q1;
+        wk.nbp = nbp;
+        wk.active = (ly.wk[sg.mol - 1] != 0.) ? 1 : 0;           // W_SPECIES == 0: molecule skipped (:318-321)
+        wk.t0 = q0 & ~3;
+        wk.ntile = (tma_cls && wk.active && q1 > wk.t0) ? (q1 - wk.t0 + kTile - 1) / kTile : 0;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        int nxt = -1;
+        for (int s = nseg - 1; s >= 0; s--) {
+            s_work[s].next = nxt;
+            if (s_work[s].ntile > 0) nxt = s;
+        }
+        s_first = nxt;
+    }
+    __syncthreads();
+
     uint32_t phase_bits = 0;    // per-stage mbarrier phase parity (bit i = stage i)
+    int ped_buf = 0;            // alternates per tile over the whole kernel (s_ped double buffer)
+    int gtile = 0;              // global tile counter: stage of a tile = gtile & 1
+
+    auto issue = [&](int s, int t, int st) {      // one elected thread: TMA one tile of segment s into stage st
+        const int qs = s_work[s].t0 + t * kTile;
+        int n = a.n_pad - qs;
+        n = n > kTile ? kTile : n;
+        const uint32_t bytes = (uint32_t)n * 8u;
+        mbar_expect_tx(&s_bar[st], 4u * bytes);
+        tma_load_1d(&s_tile[st][0][0], pXNU + qs, bytes, &s_bar[st]);
+        tma_load_1d(&s_tile[st][1][0], pH2 + qs, bytes, &s_bar[st]);
+        tma_load_1d(&s_tile[st][2][0], pCN + qs, bytes, &s_bar[st]);
+        tma_load_1d(&s_tile[st][3][0], pP3 + qs, bytes, &s_bar[st]);
+    };
+    if (tid == 0 && s_first >= 0) issue(s_first, 0, 0);
 
     double osum[F], sf[F];
     long long cnt[F];
@@ -684,13 +785,14 @@ __global__ void __launch_bounds__(128, MRTM_LINES_MINB) lines_kernel(LinesArgs a
         return pl[(size_t)D_STILD * a.n_pad + q] * sls;
     };
 
-    for (int s = 0; s < a.nseg; s++) {
+    for (int s = 0; s < nseg; s++) {
         const Segment sg = a.seg[s];
         if (sg.mol != cur_mol) {
             finish_mol(cur_mol);
             cur_mol = sg.mol;
         }
-        if (ly.wk[sg.mol - 1] == 0.) continue;            // W_SPECIES == 0: molecule skipped (:318-321)
+        const SegWork& wk = s_work[s];
+        if (!wk.active) continue;
         const int cls = sg.cls;
         if (SEL && sg.mol == 7) {                          // every O2 line passes modm.f90:384
 #pragma unroll
@@ -700,57 +802,18 @@ __global__ void __launch_bounds__(128, MRTM_LINES_MINB) lines_kernel(LinesArgs a
             const bool has_win = (cls != CLS_O2_LC35);
             const bool force_both = (cls == CLS_O2_LC35);
             const bool count_sel = SEL && (cls == CLS_PED);
-            // ---- sub-ranges (warp-uniform): bp[] ascending, mode per sub-range
-            int q0 = sg.begin, q1 = sg.end;
-            int eb = sg.begin, ec = sg.end;              // [q0,eb) and [ec,q1): window-edge bands
-            int n0 = sg.end, n1 = sg.end;                // [n0,n1): WN+Xnu<=25 boundary band; < n0: both resonances
-            if (has_win) {
-                q0 = lower_bound_d(a.xnu0, sg.begin, sg.end, winL);
-                q1 = upper_bound_d(a.xnu0, sg.begin, sg.end, winR);
-                eb = upper_bound_d(a.xnu0, q0, q1, whi - kDELTNUC + sm);
-                ec = lower_bound_d(a.xnu0, q0, q1, wlo + kDELTNUC - sm);
-                n0 = lower_bound_d(a.xnu0, q0, q1, kDELTNUC - whi - sm);
-                n1 = upper_bound_d(a.xnu0, q0, q1, kDELTNUC - wlo + sm + 1e-9);
-            }
-            const double vb = sg.vfac * ly.sqrt_t + sm + 1e-9;
-            const int v0 = lower_bound_d(a.xnu0, q0, q1, wlo - vb);
-            const int v1 = upper_bound_d(a.xnu0, q0, q1, whi + vb);
-            int bp[10];
-            int nbp = 0;
-            bp[nbp++] = q0;
-            {
-                int c[6] = {eb, ec, n0, n1, v0, v1};
-                // insertion sort of the 6 candidates, clipped to [q0,q1]
-                for (int i = 0; i < 6; i++) { c[i] = c[i] < q0 ? q0 : (c[i] > q1 ? q1 : c[i]); }
-                for (int i = 1; i < 6; i++) { int v = c[i], j = i - 1; while (j >= 0 && c[j] > v) { c[j + 1] = c[j]; j--; } c[j + 1] = v; }
-                for (int i = 0; i < 6; i++) if (c[i] > bp[nbp - 1]) bp[nbp++] = c[i];
-            }
-            if (q1 > bp[nbp - 1]) bp[nbp++] = q1;
-            const int nsub = nbp - 1;
-
-            // ---- stream [q0,q1) through the double-buffered tile pipeline
-            const int t0 = q0 & ~3;                       // 32-byte aligned tile origin
-            const int ntile = (q1 > t0) ? (q1 - t0 + kTile - 1) / kTile : 0;
-            auto issue = [&](int t) {
-                const int st = t % kStages;
-                const int qs = t0 + t * kTile;
-                int n = a.n_pad - qs;
-                n = n > kTile ? kTile : n;
-                const uint32_t bytes = (uint32_t)n * 8u;
-                mbar_expect_tx(&s_bar[st], 4u * bytes);
-                tma_load_1d(&s_tile[st][0][0], pXNU + qs, bytes, &s_bar[st]);
-                tma_load_1d(&s_tile[st][1][0], pH2 + qs, bytes, &s_bar[st]);
-                tma_load_1d(&s_tile[st][2][0], pCN + qs, bytes, &s_bar[st]);
-                tma_load_1d(&s_tile[st][3][0], pP3 + qs, bytes, &s_bar[st]);
-            };
-            if (ntile > 0 && tid == 0) issue(0);
+            const int eb = wk.eb, ec = wk.ec, n0 = wk.n0, n1 = wk.n1, v0 = wk.v0, v1 = wk.v1;
+            const int nsub = wk.nbp - 1, t0 = wk.t0, ntile = wk.ntile;
             double psum[F];
 #pragma unroll
             for (int f = 0; f < F; f++) psum[f] = 0.;
             double pacc = 0.;                              // pedestal total of the interior ranges (uniform)
-            for (int t = 0; t < ntile; t++) {
-                const int st = t % kStages;
-                if (t + 1 < ntile && tid == 0) issue(t + 1);
+            for (int t = 0; t < ntile; t++, gtile++) {
+                const int st = gtile & 1;
+                if (tid == 0) {                            // prefetch the next tile (possibly of the next segment)
+                    if (t + 1 < ntile) issue(s, t + 1, st ^ 1);
+                    else if (wk.next >= 0) issue(wk.next, 0, st ^ 1);
+                }
                 mbar_wait(&s_bar[st], (phase_bits >> st) & 1u);
                 phase_bits ^= (1u << st);
                 const double* __restrict__ tX = s_tile[st][0];
@@ -758,50 +821,75 @@ __global__ void __launch_bounds__(128, MRTM_LINES_MINB) lines_kernel(LinesArgs a
                 const double* __restrict__ tC = s_tile[st][2];
                 const double* __restrict__ tP = s_tile[st][3];
                 const int tb = t0 + t * kTile, te = tb + kTile;
+                double pmine = 0.;                          // this thread's share of the tile's interior pedestals
                 for (int u = 0; u < nsub; u++) {
-                    int lo = bp[u] > tb ? bp[u] : tb;
-                    int hi = bp[u + 1] < te ? bp[u + 1] : te;
+                    const int x = wk.bp[u];
+                    int lo = x > tb ? x : tb;
+                    int hi = wk.bp[u + 1] < te ? wk.bp[u + 1] : te;
                     if (lo >= hi) continue;
-                    const int x = bp[u];
-                    const bool edge = has_win && ((x < eb) || (x >= ec));
-                    const bool mixedneg = has_win && (x >= n0) && (x < n1);
-                    const bool vz = (x >= v0) && (x < v1);
-                    if (edge || mixedneg || vz) {
-                        // ---- predicated loop: exact per-thread window / resonance / Voigt tests
-                        for (int q = lo; q < hi; q++) {
-                            const int j = q - tb;
-                            const double xnu = tX[j], h2 = tH[j], cn = tC[j], ped = tP[j];
-                            const double vt = pVT[q];
-#pragma unroll
-                            for (int f = 0; f < F; f++) {
-                                const double dm = wn[f] - xnu;                      // WN-Xnu
-                                const double sp = wn[f] + xnu;                      // WN+Xnu
-                                const bool inwin = !has_win || !(fabs(dm) > kDELTNUC);
-                                if (count_sel && inwin) { cnt[f]++; hsh[f] += a.key[q]; }
-                                if (inwin && fabs(dm) <= vt) {                      // Voigt branch (:427), rare
-                                    sf[f] += voigt_term(sg.mol, q, wn[f], xnu);
-                                } else {
-                                    const bool neg = force_both || (sp <= kDELTNUC);     // DIFF <= 0
-                                    const double r1 = rcp3(fma(dm, dm, h2));
-                                    const double r2 = rcp3(fma(sp, sp, h2));
-                                    double val = cn * (r1 + (neg ? r2 : 0.)) - (neg ? 2. * ped : ped);
-                                    sf[f] += inwin ? val : 0.;
-                                }
-                            }
+                    int mode = 0;           // bit0 window-edge test, bit1 per-thread resonance test, bit2 Voigt test
+                    if (has_win && ((x < eb) || (x >= ec))) mode |= 1;
+                    if (has_win && (x >= n0) && (x < n1)) mode |= 2;
+                    if ((x >= v0) && (x < v1)) mode |= 4;
+                    const bool negall = force_both || (x < n0);
+                    if (mode != 0) {
+                        // ---- predicated loops, specialised per test combination
+                        switch (mode) {
+#define MRTM_PRED(M)                                                                                              \
+    case M:                                                                                                       \
+        for (int q = lo; q < hi; q++) {                                                                           \
+            const int j = q - tb;                                                                                 \
+            const double xnu = tX[j], h2 = tH[j], cn = tC[j], ped = tP[j];                                        \
+            const double vt = ((M)&4) ? pVT[q] : -1.0;                                                            \
+            _Pragma("unroll") for (int f = 0; f < F; f++)                                                         \
+            {                                                                                                     \
+                const double dm = wn[f] - xnu;                                                                    \
+                const bool inwin = ((M)&1) ? !(fabs(dm) > kDELTNUC) : true;                                       \
+                if (count_sel && inwin) { cnt[f]++; hsh[f] += a.key[q]; }                                         \
+                if (((M)&4) && inwin && fabs(dm) <= vt) {                                                         \
+                    sf[f] += voigt_term(sg.mol, q, wn[f], xnu);                                                   \
+                } else {                                                                                          \
+                    double val;                                                                                   \
+                    if ((M)&2) {                                                                                  \
+                        const double sp = wn[f] + xnu;                                                            \
+                        const bool neg = (sp <= kDELTNUC);                                                        \
+                        const double r1 = rcp3(fma(dm, dm, h2)), r2 = rcp3(fma(sp, sp, h2));                      \
+                        val = cn * (r1 + (neg ? r2 : 0.)) - (neg ? 2. * ped : ped);                               \
+                    } else if (negall) {                                                                          \
+                        const double sp = wn[f] + xnu;                                                            \
+                        const double aa = fma(dm, dm, h2), bb = fma(sp, sp, h2);                                  \
+                        val = fma(cn * (aa + bb), rcp3(aa * bb), -2. * ped);                                      \
+                    } else {                                                                                      \
+                        val = fma(cn, rcp3(fma(dm, dm, h2)), -ped);                                               \
+                    }                                                                                             \
+                    sf[f] += inwin ? val : 0.;                                                                    \
+                }                                                                                                 \
+            }                                                                                                     \
+        }                                                                                                         \
+        break;
+                            MRTM_PRED(1) MRTM_PRED(2) MRTM_PRED(3) MRTM_PRED(4) MRTM_PRED(5) MRTM_PRED(6) MRTM_PRED(7)
+#undef MRTM_PRED
+                        default: break;
                         }
-                    } else if (force_both || x < n0) {
+                        continue;
+                    }
+                    if (count_sel) {
+                        unsigned long long hs = 0ull;
+                        for (int q = lo; q < hi; q++) hs += a.key[q];
+#pragma unroll
+                        for (int f = 0; f < F; f++) { cnt[f] += hi - lo; hsh[f] += hs; }
+                    }
+                    // this thread's share of the interior pedestals of the tile (reduced across the CTA below)
+                    {
+                        const double w = negall ? 2. : 1.;          // pedestal counted for both resonances (:749)
+                        for (int q = lo + tid; q < hi; q += NT) pmine = fma(w, tP[q - tb], pmine);
+                    }
+                    if (negall) {
                         // ---- interior, both resonances: cn*(1/a+1/b) = cn*(a+b)/(a*b), one reciprocal
-                        if (count_sel) {
-                            unsigned long long hs = 0ull;
-                            for (int q = lo; q < hi; q++) hs += a.key[q];
-#pragma unroll
-                            for (int f = 0; f < F; f++) { cnt[f] += hi - lo; hsh[f] += hs; }
-                        }
 MRTM_UNROLL(MRTM_UNROLL_BOTH)
                         for (int q = lo; q < hi; q++) {
                             const int j = q - tb;
                             const double xnu = tX[j], h2 = tH[j], cn = tC[j];
-                            pacc += 2. * tP[j];                     // pedestal counted for both (modm.f90:749)
 #pragma unroll
                             for (int f = 0; f < F; f++) {
                                 const double dm = wn[f] - xnu, sp = wn[f] + xnu;
@@ -811,18 +899,29 @@ MRTM_UNROLL(MRTM_UNROLL_BOTH)
                             }
                         }
                     } else {
-                        // ---- interior, single resonance (modm.f90:751)
-                        if (count_sel) {
-                            unsigned long long hs = 0ull;
-                            for (int q = lo; q < hi; q++) hs += a.key[q];
+                        // ---- interior, single resonance (modm.f90:751): four lines share one reciprocal,
+                        // sum c_i/a_i = N/(a1 a2 a3 a4), N = (c1 a2 + c2 a1)(a3 a4) + (c3 a4 + c4 a3)(a1 a2);
+                        // 21 FP64 ops + 1 MUFU per 4 evaluations
+                        int q = lo;
+                        for (; q + 4 <= hi; q += 4) {
+                            const int j = q - tb;
+                            const double x1 = tX[j], x2 = tX[j + 1], x3 = tX[j + 2], x4 = tX[j + 3];
+                            const double g1 = tH[j], g2 = tH[j + 1], g3 = tH[j + 2], g4 = tH[j + 3];
+                            const double c1 = tC[j], c2 = tC[j + 1], c3 = tC[j + 2], c4 = tC[j + 3];
 #pragma unroll
-                            for (int f = 0; f < F; f++) { cnt[f] += hi - lo; hsh[f] += hs; }
+                            for (int f = 0; f < F; f++) {
+                                const double d1 = wn[f] - x1, d2 = wn[f] - x2, d3 = wn[f] - x3, d4 = wn[f] - x4;
+                                const double a1 = fma(d1, d1, g1), a2 = fma(d2, d2, g2);
+                                const double a3 = fma(d3, d3, g3), a4 = fma(d4, d4, g4);
+                                const double p12 = a1 * a2, p34 = a3 * a4;
+                                const double n12 = fma(c1, a2, c2 * a1), n34 = fma(c3, a4, c4 * a3);
+                                const double r = rcp3(p12 * p34);
+                                psum[f] = fma(fma(n12, p34, n34 * p12), r, psum[f]);
+                            }
                         }
-MRTM_UNROLL(MRTM_UNROLL_SINGLE)
-                        for (int q = lo; q < hi; q++) {
+                        for (; q < hi; q++) {
                             const int j = q - tb;
                             const double xnu = tX[j], h2 = tH[j], cn = tC[j];
-                            pacc += tP[j];
 #pragma unroll
                             for (int f = 0; f < F; f++) {
                                 const double dm = wn[f] - xnu;
@@ -831,12 +930,19 @@ MRTM_UNROLL(MRTM_UNROLL_SINGLE)
                         }
                     }
                 }
-                __syncthreads();       // all reads of this stage done before it is refilled
+                // CTA-wide sum of the interior pedestals of this tile (uniform result)
+#pragma unroll
+                for (int off = 16; off > 0; off >>= 1) pmine += __shfl_xor_sync(0xffffffffu, pmine, off);
+                if ((tid & 31) == 0) s_ped[ped_buf][tid >> 5] = pmine;
+                __syncthreads();       // all reads of this stage done before it is refilled; s_ped visible
+#pragma unroll
+                for (int i = 0; i < NW; i++) pacc += s_ped[ped_buf][i];
+                ped_buf ^= 1;
             }
 #pragma unroll
             for (int f = 0; f < F; f++) sf[f] += psum[f] - pacc;
         } else if (cls == CLS_O2_LC1) {
-            for (int q = sg.begin; q < sg.end; q++) {
+            for (int q = wk.q0; q < wk.q1; q++) {
                 const double xnu = pXNU[q], h2 = pH2[q], cg = pP3[q], cq = pP4[q], vt = pVT[q];
 #pragma unroll
                 for (int f = 0; f < F; f++) {
@@ -851,12 +957,7 @@ MRTM_UNROLL(MRTM_UNROLL_SINGLE)
                 }
             }
         } else {   // CLS_GENERAL: faithful case tree per (line, frequency)
-            int q0 = sg.begin, q1 = sg.end;
-            if (sg.mol != 7) {
-                q0 = lower_bound_d(a.xnu0, sg.begin, sg.end, winL);
-                q1 = upper_bound_d(a.xnu0, sg.begin, sg.end, winR);
-            }
-            for (int q = q0; q < q1; q++) {
+            for (int q = wk.q0; q < wk.q1; q++) {
                 const double xnu = pXNU[q], vt = pVT[q];
                 const double hw = pl[(size_t)D_H * a.n_pad + q], ad = pl[(size_t)D_AD * a.n_pad + q];
                 const double st = pl[(size_t)D_STILD * a.n_pad + q];

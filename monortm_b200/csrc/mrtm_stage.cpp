@@ -142,7 +142,7 @@ int stage_lines_host(const int64_t nblm[MRTM_MXMOL], int64_t iim, const int64_t*
     auto rs_i = [&](std::vector<int32_t>& v) { v.assign(out.n_pad, 0); };
     auto rs_d = [&](std::vector<double>& v) { v.assign(out.n_pad, 0.0); };
     rs_i(out.mol); rs_i(out.iso); rs_i(out.xf); rs_i(out.cls); rs_i(out.sidx); rs_i(out.lcidx);
-    rs_i(out.brdidx); rs_i(out.rec);
+    rs_i(out.brdidx); rs_i(out.rec); rs_i(out.segidx);
     rs_d(out.xnu0); rs_d(out.s0adj); rs_d(out.e); rs_d(out.alpf); rs_d(out.alps); rs_d(out.x);
     rs_d(out.deltnu); rs_d(out.sdep); rs_d(out.mass);
     out.key.assign(out.n_pad, 0);
@@ -213,6 +213,7 @@ int stage_lines_host(const int64_t nblm[MRTM_MXMOL], int64_t iim, const int64_t*
             out.error = "too many (molecule,class) segments";
             return MRTM_EARG;
         }
+        for (int64_t u = q; u < q1; u++) out.segidx[u] = (int32_t)out.segments.size();
         out.segments.push_back(s);
         if (out.mol_slot[s.mol - 1] < 0) {
             if ((int)out.slot_mol.size() >= kMaxSlots) {

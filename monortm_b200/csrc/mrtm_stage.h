@@ -8,7 +8,7 @@ struct HostLines {
     int64_t n = 0;       // logical lines
     int64_t n_pad = 0;   // padded plane length (multiple of 8, >= n+8)
     // static per-line planes, staged order = (molecule asc, class asc, xnu0 asc [stable])
-    std::vector<int32_t> mol, iso, xf, cls, sidx, lcidx, brdidx, rec;
+    std::vector<int32_t> mol, iso, xf, cls, sidx, lcidx, brdidx, rec, segidx;
     std::vector<double> xnu0, s0adj, e, alpf, alps, x, deltnu, sdep, mass;
     std::vector<uint64_t> key;
     // compact line-coupling table: 16 doubles per coupled line: A[4],B[4] foreign, A2[4],B2[4] self
