@@ -28,25 +28,28 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 NLAY = 100
-N_FILLER = 4096
+N_FILLER = 65536                  # TAPE3-synth "full-like" list; --n-filler 4096 = "fast-like"
 DV = 5.5e-5
 NWN_GLOBAL_FULL = 1000000
 FLOP_PER_INWINDOW_EVAL = 12.0     # Lorentz, no coupling, hoisted per-(line,layer) terms
+FLOP_PER_FAR_EXPANSION = 59.0     # 11 set-up + 12 x (mul + fma + add) for the 14-term Taylor series
 
 
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--nwn-per-gpu", type=int, default=int(os.environ.get("MRTM_BENCH_NWN", 16384)))
-    ap.add_argument("--cpu-sample-nwn", type=int, default=24)
+    ap.add_argument("--n-filler", type=int, default=N_FILLER, help="synthetic filler lines (65536 full-like, 4096 fast-like)")
+    ap.add_argument("--cpu-sample-nwn", type=int, default=32)
+    ap.add_argument("--direct-steps", type=int, default=3, help="extra steps timed with line_mode=1 (direct evaluation)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
 
 
-def build_inputs(nwn, rank, world):
+def build_inputs(nwn, rank, world, n_filler=N_FILLER):
     """Synthetic C3 shard: a contiguous block of `nwn` frequencies of the GLOBAL 1e6-point grid, centred
     in this rank's 1/world-th of the grid; one 100-layer profile.  v1, v2 are the global range."""
     import harness
@@ -55,7 +58,7 @@ def build_inputs(nwn, rank, world):
     part = NWN_GLOBAL_FULL // world
     iw0 = rank * part + max(0, (part - nwn) // 2)
     wn = DV * np.arange(iw0 + 1, iw0 + nwn + 1, dtype=np.float64)
-    ls = harness.synthetic_store(N_FILLER, v1=v1, v2=v2)
+    ls = harness.synthetic_store(n_filler, v1=v1, v2=v2)
     prof = synth.synthetic_profiles(1, NLAY, seed0=1000, clw_layers=False, nmol=22)
     scor = api.scor_for_layers(22, prof["t"])
     return dict(wn=wn, ls=ls, prof=prof, scor=scor, v1=v1, v2=v2, iw0=iw0,
@@ -63,38 +66,55 @@ def build_inputs(nwn, rank, world):
 
 
 class ClockSampler(threading.Thread):
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+    """SM clock / power / throttle reasons sampled DURING the timed region through NVML (10 ms period;
+    `nvidia-smi` polling is too slow for a sub-second timed region)."""
 
     def __init__(self, gpu):
         super().__init__(daemon=True)
-        self.gpu, self.rows, self.stop_flag = gpu, [], False
+        self.gpu, self.rows, self.stop_flag, self.err = gpu, [], False, None
+        self.max_mhz = None
 
     def run(self):
-        while not self.stop_flag:
-            try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
-                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
-                for ln in out.strip().split("\n"):
-                    f = [x.strip() for x in ln.split(",")]
-                    if len(f) >= 9:
-                        self.rows.append(f)
-            except Exception:
-                pass
-            time.sleep(0.2)
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = int(vis.split(",")[self.gpu]) if vis and vis.split(",")[0].isdigit() else self.gpu
+            h = nv.nvmlDeviceGetHandleByIndex(idx)
+            self.max_mhz = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+            R = {"hw_slowdown": nv.nvmlClocksThrottleReasonHwSlowdown,
+                 "hw_thermal_slowdown": nv.nvmlClocksThrottleReasonHwThermalSlowdown,
+                 "sw_thermal_slowdown": nv.nvmlClocksThrottleReasonSwThermalSlowdown,
+                 "sw_power_cap": nv.nvmlClocksThrottleReasonSwPowerCap}
+            while not self.stop_flag:
+                mhz = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+                pw = nv.nvmlDeviceGetPowerUsage(h) / 1000.0
+                rs = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                self.rows.append((float(mhz), pw, [k for k, bit in R.items() if rs & bit]))
+                time.sleep(0.01)
+        except Exception as e:          # fall back to nvidia-smi polling
+            self.err = repr(e)
+            q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+                 "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+            while not self.stop_flag:
+                try:
+                    out = subprocess.run(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
+                                         capture_output=True, text=True, timeout=5).stdout.strip().split("\n")[0]
+                    f = [x.strip() for x in out.split(",")]
+                    self.max_mhz = float(f[1])
+                    names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+                    self.rows.append((float(f[0]), float(f[2]), [n for n, v in zip(names, f[3:7]) if v.lower().startswith("active")]))
+                except Exception:
+                    pass
+                time.sleep(0.1)
 
     def summary(self):
         if not self.rows:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unsampled"]}
-        sm = sorted(float(r[1]) for r in self.rows)
-        reasons = set()
-        for r in self.rows:
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.rows[0][2]), "reasons": sorted(reasons),
-                "samples": len(self.rows), "power_w_max": max(float(r[3]) for r in self.rows)}
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["unsampled"], "sampler_error": self.err}
+        sm = sorted(r[0] for r in self.rows)
+        reasons = sorted({x for r in self.rows for x in r[2]})
+        return {"sm_mhz": sm[len(sm) // 2], "sm_min_mhz": sm[0], "sm_max_mhz": self.max_mhz, "reasons": reasons,
+                "samples": len(self.rows), "power_w_max": max(r[1] for r in self.rows)}
 
 
 def cpu_sample(inp, nwn_sample, opt="O0"):
@@ -127,8 +147,8 @@ def logical_lines(ls):
 
 
 def _farm_worker(args):
-    nwn, rank, world, lo, hi = args
-    inp = build_inputs(nwn, rank, world)
+    nwn, rank, world, lo, hi, n_filler = args
+    inp = build_inputs(nwn, rank, world, n_filler)
     sub = dict(inp)
     sub["wn"] = inp["wn"][lo:hi]
     sub["emiss"], sub["reflc"] = inp["emiss"][lo:hi], inp["reflc"][lo:hi]
@@ -147,8 +167,8 @@ def run_reference(args):
     nwn = args.nwn_per_gpu
     per = max(2, args.cpu_sample_nwn // 4)
     stride = max(per, (nwn - per) // max(cores, 1))
-    chunks = [(nwn, 0, args.gpus, (c * stride) % (nwn - per), (c * stride) % (nwn - per) + per) for c in range(cores)]
-    build_inputs(nwn, 0, args.gpus)          # build/cached once before forking
+    chunks = [(nwn, 0, args.gpus, (c * stride) % (nwn - per), (c * stride) % (nwn - per) + per, args.n_filler) for c in range(cores)]
+    build_inputs(nwn, 0, args.gpus, args.n_filler)          # build/cached once before forking
     times = []
     nominal = 0.0
     with mp.get_context("fork").Pool(cores) as pool:
@@ -174,8 +194,9 @@ def run_reference(args):
 def workload_config(args):
     return {"workload": "C3 dense monochromatic sweep 0-55 cm-1 (wn_i=5.5e-5*i), frequency-sharded: %d frequencies/GPU "
                         "(a contiguous block centred in each rank's 1/N of the global 1e6-point grid) x %d layers x TAPE3-synth "
-                        "fast-like line list (%d filler + physical seed lines), IRT=1, MODM+CALCTMR+RTM per step"
-                        % (args.nwn_per_gpu, NLAY, N_FILLER),
+                        "%s line list (%d filler + physical seed lines), IRT=1, MODM+CALCTMR+RTM per step"
+                        % (args.nwn_per_gpu, NLAY, "full-like" if args.n_filler >= 65536 else "fast-like", args.n_filler),
+            "n_filler": args.n_filler,
             "nwn_per_gpu": args.nwn_per_gpu, "nlay": NLAY, "sharding": "frequency", "parallelism": "freq-shard x%d" % args.gpus,
             "l2": "L2 flushed (256 MiB write) between timed steps"}
 
@@ -201,7 +222,7 @@ def main():
     dev = torch.device("cuda", local)
 
     nwn = args.nwn_per_gpu
-    inp = build_inputs(nwn, rank, world)
+    inp = build_inputs(nwn, rank, world, args.n_filler)
     sess = api.Session(local)
     nlines = sess.stage_lines(inp["ls"])
     pr = inp["prof"]
@@ -221,8 +242,9 @@ def main():
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     stream = torch.cuda.current_stream()
 
-    def step_dev():
-        sess.profiles_dev(1, nwn, NLAY, 22, 0.0, ptrs, inp["v1"], inp["v2"], inp["iw0"], inp["irt"], stream=stream.cuda_stream)
+    def step_dev(line_mode=0):
+        sess.profiles_dev(1, nwn, NLAY, 22, 0.0, ptrs, inp["v1"], inp["v2"], inp["iw0"], inp["irt"], stream=stream.cuda_stream,
+                          line_mode=line_mode)
         if world > 1:
             dist.all_gather_into_tensor(gathered, outs)
 
@@ -239,7 +261,7 @@ def main():
     sampler = ClockSampler(local)
     sampler.start()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    lines_ms, rt_ms, derive_ms = [], [], []
+    lines_ms, rt_ms, derive_ms, far_exp, direct_ev = [], [], [], [], []
     barrier()
     t_wall0 = time.time()
     for i in range(args.steps):
@@ -249,6 +271,7 @@ def main():
         ev[i][1].record(stream)
         st = sess.stats()
         lines_ms.append(st["last_lines_kernel_ms"]); rt_ms.append(st["last_rt_kernel_ms"]); derive_ms.append(st["last_derive_kernel_ms"])
+        far_exp.append(st["far_expansions"]); direct_ev.append(st["direct_evals"])
     barrier()
     t_wall = time.time() - t_wall0
     dev_ms = sum(a.elapsed_time(b) for a, b in ev)
@@ -259,6 +282,27 @@ def main():
     ms_per_step = float(tmax.item()) / args.steps
     nominal_per_step = float(nlines) * NLAY * nwn * world
     value = nominal_per_step / (ms_per_step * 1e-3)
+
+    # ---- the same steps with every in-window triple evaluated directly (line_mode=1): the classic
+    # per-(line,layer,frequency) kernel, reported beside the default path
+    direct = None
+    if args.direct_steps > 0:
+        step_dev(1)
+        barrier()
+        evd = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.direct_steps)]
+        dl = []
+        for i in range(args.direct_steps):
+            flush.zero_()
+            evd[i][0].record(stream)
+            step_dev(1)
+            evd[i][1].record(stream)
+            dl.append(sess.stats()["last_lines_kernel_ms"])
+        barrier()
+        dms = torch.tensor([sum(a.elapsed_time(b) for a, b in evd) / args.direct_steps], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(dms, op=dist.ReduceOp.MAX)
+        direct = {"ms_per_step": float(dms.item()), "lines_kernel_ms": float(np.mean(dl)),
+                  "value": nominal_per_step / (float(dms.item()) * 1e-3)}
 
     # ---- e2e: host buffers through mrtm_profiles (pinned inputs, H2D + D2H inside the timed region)
     def pin(a):
@@ -306,7 +350,11 @@ def main():
         fp64_peak = sess.fp64_peak_tflops()
         lk_ms = float(np.mean(lines_ms))
         inwin_per_launch = inwin_frac * float(nlines) * NLAY * nwn
-        achieved = inwin_per_launch * FLOP_PER_INWINDOW_EVAL / (lk_ms * 1e-3) / 1e12
+        # algorithmic flops of one launch of the default path: far-field expansions + directly evaluated triples
+        far_n, dir_n = float(np.mean(far_exp)), float(np.mean(direct_ev))
+        flops_launch = far_n * FLOP_PER_FAR_EXPANSION + dir_n * FLOP_PER_INWINDOW_EVAL
+        achieved = flops_launch / (lk_ms * 1e-3) / 1e12
+        equiv_direct = inwin_per_launch * FLOP_PER_INWINDOW_EVAL / (lk_ms * 1e-3) / 1e12
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -330,13 +378,28 @@ def main():
             "roofline": {"bound": "fp64", "kernel": "lines_kernel", "achieved": achieved, "peak": fp64_peak,
                          "unit": "TFLOP/s", "frac": achieved / fp64_peak if fp64_peak else None, "traffic": None,
                          "peak_source": "measured live: mrtm_fp64_peak DFMA probe (MEASURED_PEAKS.json has no FP64 figure)",
-                         "flop_per_inwindow_eval": FLOP_PER_INWINDOW_EVAL, "kernel_ms": lk_ms,
-                         "share_of_step": lk_ms / ms_per_step},
+                         "flop_per_direct_eval": FLOP_PER_INWINDOW_EVAL, "flop_per_far_expansion": FLOP_PER_FAR_EXPANSION,
+                         "far_expansions_per_launch": far_n, "direct_evals_per_launch": dir_n,
+                         "inwindow_evals_per_launch": inwin_per_launch,
+                         "equivalent_direct_tflops": equiv_direct,
+                         "note": "achieved counts the flops the expansion algorithm needs (DESIGN.md 3); equivalent_direct_tflops "
+                                 "is 12 flop x every in-window triple / kernel time, i.e. what a per-triple kernel would have to "
+                                 "sustain for the same time (may exceed the FP64 peak)",
+                         "kernel_ms": lk_ms, "share_of_step": lk_ms / ms_per_step},
             "roofline_rt": {"bound": "hbm", "kernel": "rt_kernel", "achieved": rt_bytes / (rt_k_ms * 1e-3) / 1e9 if rt_k_ms else None,
                             "peak": hbm_peak, "unit": "GB/s", "frac": (rt_bytes / (rt_k_ms * 1e-3) / 1e9) / hbm_peak if rt_k_ms else None,
                             "kernel_ms": rt_k_ms, "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s"},
             "derive_kernel_ms": float(np.mean(derive_ms)),
         }
+        if direct:
+            d_ach = inwin_per_launch * FLOP_PER_INWINDOW_EVAL / (direct["lines_kernel_ms"] * 1e-3) / 1e12
+            line["direct_path"] = {"what": "same step with mrtm_opts.line_mode=1: every in-window (line,layer,frequency) triple "
+                                           "evaluated per frequency, no far-field expansion", "steps": args.direct_steps,
+                                   "value": direct["value"], "unit": "evals/s", "ms_per_step": direct["ms_per_step"],
+                                   "lines_kernel_ms": direct["lines_kernel_ms"],
+                                   "roofline": {"bound": "fp64", "achieved": d_ach, "peak": fp64_peak, "unit": "TFLOP/s",
+                                                "frac": d_ach / fp64_peak if fp64_peak else None,
+                                                "flop_per_inwindow_eval": FLOP_PER_INWINDOW_EVAL}}
         if not args.no_cpu_baseline:
             dt, nominal, inwin = cpu_sample(inp, args.cpu_sample_nwn)
             line["cpu_baseline"] = {"value": nominal / dt, "unit": "evals/s", "cores": 1, "kind": "port",

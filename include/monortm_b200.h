@@ -60,7 +60,12 @@ typedef struct mrtm_opts {
      * global grid passes the global v1, v2 and its 0-based offset iw0 here.
      * use_global_range == 0 -> v1 = wn[0], v2 = wn[nwn-1], iw0 = 0. */
     int32_t use_global_range;
-    int32_t reserved0;
+    /* Line-shape evaluation mode.  0 (default): lines whose poles are far from a frequency tile are
+     * summed through a 14-term Taylor expansion about the tile centre (truncation <= ~2e-13 of the
+     * line's own contribution), everything else -- near lines, window edges, the Voigt zone -- is
+     * evaluated per (line, frequency) like the reference does.  1: every in-window triple is
+     * evaluated directly (no expansion); same results to rounding, used for verification. */
+    int32_t line_mode;
     double v1_global, v2_global;
     int64_t iw0;
     /* Verification: when non-NULL (host, (nwn,nlay)) the line kernel also returns, per
@@ -163,6 +168,9 @@ typedef struct mrtm_stats {
     double last_derive_kernel_ms;
     double nominal_evals;        /* (logical line, layer, frequency) triples of the last call */
     double inwindow_evals;       /* triples that pass modm.f90:384 (needs opts->sel_count) else -1 */
+    double far_expansions;       /* far-field Taylor expansions (line x resonance x frequency tile x layer) of the last call */
+    double direct_evals;         /* (line, layer, frequency) triples evaluated directly by the last call */
+    double last_prep_ms;         /* layer_prep + continuum kernels of the last call */
 } mrtm_stats;
 int mrtm_get_stats(mrtm_ctx *ctx, mrtm_stats *st);
 int mrtm_reset_stats(mrtm_ctx *ctx);

@@ -21,7 +21,7 @@ c_uint64_p = C.POINTER(C.c_uint64)
 class MrtmOpts(C.Structure):
     _fields_ = [
         ("use_global_range", C.c_int32),
-        ("reserved0", C.c_int32),
+        ("line_mode", C.c_int32),
         ("v1_global", C.c_double),
         ("v2_global", C.c_double),
         ("iw0", C.c_int64),
@@ -40,6 +40,9 @@ class MrtmStats(C.Structure):
         ("last_derive_kernel_ms", C.c_double),
         ("nominal_evals", C.c_double),
         ("inwindow_evals", C.c_double),
+        ("far_expansions", C.c_double),
+        ("direct_evals", C.c_double),
+        ("last_prep_ms", C.c_double),
     ]
 
 

@@ -110,8 +110,9 @@ class Session:
         return v.value
 
     @staticmethod
-    def _opts(v1=None, v2=None, iw0=0, sel=None):
+    def _opts(v1=None, v2=None, iw0=0, sel=None, line_mode=0):
         o = MrtmOpts()
+        o.line_mode = int(line_mode)
         if v1 is not None:
             o.use_global_range = 1
             o.v1_global, o.v2_global, o.iw0 = float(v1), float(v2), int(iw0)
@@ -123,7 +124,7 @@ class Session:
     # ---- MODM ---------------------------------------------------------------------------------
     def modm(self, wn, dvset, p, t, clw, nmol, wkl, wbrodl, scor, cntnm=CNTNM_ALL_ONE,
              sclcpl=1.0, sclhw=1.0, y0res=0.0, ixsect=0, odxsec=None, ibrd=0,
-             want_by_mol=True, selection=False, global_range=None):
+             want_by_mol=True, selection=False, global_range=None, line_mode=0):
         """Returns dict(o, o_by_mol, oc, o_clw, odxsec[, sel_count, sel_hash]); shapes as in
         src/monortm.f90:352-353 with mxlay -> nlay."""
         wn = _f(wn)
@@ -140,7 +141,7 @@ class Session:
         if selection:
             sel = (np.zeros((nwn, nlay), np.int64, order="F"), np.zeros((nwn, nlay), np.uint64, order="F"))
         gr = global_range or (None, None, 0)
-        opts = self._opts(gr[0], gr[1], gr[2], sel)
+        opts = self._opts(gr[0], gr[1], gr[2], sel, line_mode)
         c7 = _f(np.array(cntnm, dtype=np.float64), (7,))
         self._check(self.lib.mrtm_modm(self.h, nwn, _ptr(wn), float(dvset), nlay, _ptr(p), _ptr(t), _ptr(clw),
                                        _ptr(o), _ptr(obm), _ptr(oc), _ptr(o_clw), _ptr(odx), int(nmol),
@@ -176,7 +177,7 @@ class Session:
     # ---- fused batched path ---------------------------------------------------------------------
     def profiles(self, wn, dvset, prof, scor, irt, tmpsfc, emiss, reflc, cntnm=CNTNM_ALL_ONE, iout=1, idu=1,
                  sclcpl=1.0, sclhw=1.0, y0res=0.0, ibrd=0, want_o=False, want_otot_by_mol=False,
-                 selection=False, global_range=None):
+                 selection=False, global_range=None, line_mode=0):
         """prof: dict from synth.synthetic_profiles / profio (arrays with trailing profile dim)."""
         wn = _f(wn)
         nwn, nlay, nprof, nmol = wn.shape[0], int(prof["nlay"]), int(prof["nprof"]), int(prof["nmol"])
@@ -193,7 +194,7 @@ class Session:
         if selection:
             sel = (np.zeros((nwn, nlay, nprof), np.int64, order="F"), np.zeros((nwn, nlay, nprof), np.uint64, order="F"))
         gr = global_range or (None, None, 0)
-        opts = self._opts(gr[0], gr[1], gr[2], sel)
+        opts = self._opts(gr[0], gr[1], gr[2], sel, line_mode)
         c7 = _f(np.array(cntnm, dtype=np.float64), (7,))
         self._check(self.lib.mrtm_profiles(
             self.h, nprof, nwn, _ptr(wn), float(dvset), nlay, _ptr(p), _ptr(t), _ptr(tz), _ptr(clw), nmol,
@@ -211,10 +212,10 @@ class Session:
         return outs
 
     def profiles_dev(self, nprof, nwn, nlay, nmol, dvset, ptrs, v1, v2, iw0, irt, cntnm=CNTNM_ALL_ONE, iout=1,
-                     idu=1, sclcpl=1.0, sclhw=1.0, y0res=0.0, ibrd=0, stream=None):
+                     idu=1, sclcpl=1.0, sclhw=1.0, y0res=0.0, ibrd=0, stream=None, line_mode=0):
         """Device-resident path.  ptrs: dict of integer device addresses (e.g. torch tensor.data_ptr()):
         wn,p,t,tz,clw,wkl,wbrodl,scor(or 0),tmpsfc,emiss,reflc,rad,tb,tmr,trtot,rup,rdn,o(or 0)."""
-        opts = self._opts(v1, v2, iw0)
+        opts = self._opts(v1, v2, iw0, line_mode=line_mode)
         if stream is not None:
             opts.stream = C.c_void_p(int(stream))
         c7 = _f(np.array(cntnm, dtype=np.float64), (7,))

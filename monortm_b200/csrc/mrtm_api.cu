@@ -45,6 +45,8 @@ struct mrtm_ctx {
     std::vector<void*> table_allocs;
     int32_t* tips_row_dev = nullptr;
     int* errflag_dev = nullptr;
+    unsigned long long* counters_dev = nullptr;   // [2] far expansions, direct evaluations
+    double ff_ratio = 10.0;                       // far-field pole-distance ratio (MRTM_FF_RATIO; 0 = direct only)
     DevBuf b_vtmax;
     DevBuf b_layer, b_scorc, b_absrb, b_planes, b_o, b_obm, b_oc, b_in[16], b_out[16], b_sel[2], b_tmps;
     mrtm_stats st;
@@ -142,6 +144,10 @@ extern "C" int mrtm_init(int device, mrtm_ctx** out)
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return set_err(nullptr, MRTM_ECUDA, "cudaStreamCreate failed"); }
     for (auto& ev : ctx->ev) cudaEventCreate(&ev);
     if (const char* s = std::getenv("MRTM_PLANES_GB")) ctx->planes_budget = (size_t)(std::atof(s) * (double)(1ull << 30));
+    if (const char* s = std::getenv("MRTM_FF_RATIO")) {
+        double v = std::atof(s);
+        ctx->ff_ratio = (v <= 0.) ? 0. : std::max(v, 4.0);
+    }
     // continuum + TIPS tables -> HBM (about 190 KB)
     int rc;
 #define UP(NAME, FIELD) if ((rc = upload_arr(ctx, NAME, sizeof(NAME) / sizeof(double), ctx->table_allocs, &ctx->tb.FIELD))) { *out = ctx; return rc; }
@@ -154,6 +160,8 @@ extern "C" int mrtm_init(int device, mrtm_ctx** out)
     ctx->tips.row = nullptr;
     if (cudaMalloc(&ctx->errflag_dev, sizeof(int)) != cudaSuccess) { *out = ctx; return set_err(ctx, MRTM_ENOMEM, "cudaMalloc errflag"); }
     cudaMemset(ctx->errflag_dev, 0, sizeof(int));
+    if (cudaMalloc(&ctx->counters_dev, 2 * sizeof(unsigned long long)) != cudaSuccess) { *out = ctx; return set_err(ctx, MRTM_ENOMEM, "cudaMalloc counters"); }
+    cudaMemset(ctx->counters_dev, 0, 2 * sizeof(unsigned long long));
     *out = ctx;
     return MRTM_OK;
 }
@@ -177,6 +185,7 @@ extern "C" int mrtm_free(mrtm_ctx* ctx)
     for (auto& b : ctx->b_in) if (b.p) cudaFree(b.p);
     for (auto& b : ctx->b_out) if (b.p) cudaFree(b.p);
     if (ctx->errflag_dev) cudaFree(ctx->errflag_dev);
+    if (ctx->counters_dev) cudaFree(ctx->counters_dev);
     for (auto& ev : ctx->ev) cudaEventDestroy(ev);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -215,6 +224,9 @@ extern "C" int mrtm_stage_lines(mrtm_ctx* ctx, const int64_t nblm[MRTM_MXMOL], i
     {
         std::vector<unsigned long long> k(h.key.begin(), h.key.end());
         if ((rc = upload(ctx, k, own, &d.key))) return rc;
+        std::vector<unsigned long long> kp(k.size() + 1, 0ull);
+        for (size_t i = 0; i < k.size(); i++) kp[i + 1] = kp[i] + k[i];
+        if ((rc = upload(ctx, kp, own, &d.keypre))) return rc;
     }
     d.nsi = (int32_t)h.scor_index.size();
     {
@@ -291,13 +303,20 @@ struct RunDesc {
     bool do_lines, do_tmr, do_rtm;
     double v1, v2;
     int64_t iw0;
+    int line_mode;                  // mrtm_opts.line_mode
 };
 
 template <int F, int NT>
 static void launch_lines(const LinesArgs& la, dim3 grid, bool sel, cudaStream_t s)
 {
-    if (sel) lines_kernel<F, true, NT><<<grid, NT, 0, s>>>(la);
-    else lines_kernel<F, false, NT><<<grid, NT, 0, s>>>(la);
+    const size_t dyn = sizeof(double) * kStages * 4 * kTile + (size_t)std::max(la.nseg, 1) * sizeof(SegWork);
+    if (sel) {
+        cudaFuncSetAttribute(lines_kernel<F, true, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+        lines_kernel<F, true, NT><<<grid, NT, dyn, s>>>(la);
+    } else {
+        cudaFuncSetAttribute(lines_kernel<F, false, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+        lines_kernel<F, false, NT><<<grid, NT, dyn, s>>>(la);
+    }
 }
 
 static int run_device(mrtm_ctx* ctx, const RunDesc& r, cudaStream_t s)
@@ -357,6 +376,7 @@ static int run_device(mrtm_ctx* ctx, const RunDesc& r, cudaStream_t s)
         if ((rc = ensure(ctx, ctx->b_planes, (size_t)B * nlay * D_NPLANES * (size_t)n_pad * 8))) return rc;
         if ((rc = ensure(ctx, ctx->b_vtmax, (size_t)B * nlay * std::max<size_t>(1, h.segments.size()) * 8))) return rc;
         CU(cudaMemsetAsync(ctx->errflag_dev, 0, sizeof(int), s));
+        CU(cudaMemsetAsync(ctx->counters_dev, 0, 2 * sizeof(unsigned long long), s));
         st.nominal_evals = (double)h.n * (double)nlay * (double)nwn * (double)r.nprof;
         st.inwindow_evals = -1.;
     }
@@ -430,6 +450,9 @@ static int run_device(mrtm_ctx* ctx, const RunDesc& r, cudaStream_t s)
             la.xf_s = ctx->ld.xf;
             la.sdep_s = ctx->ld.sdep;
             la.key = ctx->ld.key;
+            la.keypre = ctx->ld.keypre;
+            la.ff_ratio = (r.line_mode == 1) ? 0. : ctx->ff_ratio;
+            la.counters = ctx->counters_dev;
             la.planes = (const double*)ctx->b_planes.p;
             la.lay = (const LayerDev*)ctx->b_layer.p;
             la.vtmax = (const unsigned long long*)ctx->b_vtmax.p;
@@ -455,12 +478,12 @@ static int run_device(mrtm_ctx* ctx, const RunDesc& r, cudaStream_t s)
             const bool sel = (r.sel_count != nullptr) || (r.sel_hash != nullptr);
             // frequencies per CTA: 128 threads x F (512 on dense grids, smaller tiles for short channel lists)
             static const int force_nt = std::getenv("MRTM_LINES_NT") ? std::atoi(std::getenv("MRTM_LINES_NT")) : 0;
-            const int NTsel = force_nt ? force_nt : 128;   // 256-thread CTAs measured 4% slower on the dense sweep
-            const int F = (NTsel == 256 || nwn >= 2048) ? 4 : ((nwn >= 512) ? 2 : 1);
+            (void)force_nt;
+            const int NTsel = 128;                         // 256-thread CTAs measured 4% slower on the dense sweep
+            const int F = (nwn >= 2048) ? 4 : ((nwn >= 512) ? 2 : 1);
             dim3 grid((unsigned)((nwn + NTsel * F - 1) / (NTsel * F)), (unsigned)nlay, (unsigned)nb);
             CU(cudaEventRecord(ctx->ev[2], s));
-            if (NTsel == 256) launch_lines<4, 256>(la, grid, sel, s);
-            else if (F == 4) launch_lines<4, 128>(la, grid, sel, s);
+            if (F == 4) launch_lines<4, 128>(la, grid, sel, s);
             else if (F == 2) launch_lines<2, 128>(la, grid, sel, s);
             else launch_lines<1, 128>(la, grid, sel, s);
             CU(cudaEventRecord(ctx->ev[3], s));
@@ -508,8 +531,12 @@ static int run_device(mrtm_ctx* ctx, const RunDesc& r, cudaStream_t s)
     }
     if (r.do_lines) {
         int flag = 0;
+        unsigned long long cnt[2] = {0ull, 0ull};
         CU(cudaMemcpyAsync(&flag, ctx->errflag_dev, sizeof(int), cudaMemcpyDeviceToHost, s));
+        CU(cudaMemcpyAsync(cnt, ctx->counters_dev, sizeof cnt, cudaMemcpyDeviceToHost, s));
         CU(cudaStreamSynchronize(s));
+        st.far_expansions = (double)cnt[0];
+        st.direct_evals = (double)cnt[1];
         if (flag & 1) return set_err(ctx, MRTM_ETIPS, mrtm_strerror(MRTM_ETIPS));
         if (flag & 2) return set_err(ctx, MRTM_ESDVOIGT, mrtm_strerror(MRTM_ESDVOIGT));
     }
@@ -558,6 +585,7 @@ extern "C" int mrtm_modm(mrtm_ctx* ctx, int64_t nwn, const double* wn, double dv
     r.sclcpl = sclcpl; r.sclhw = sclhw; r.y0res = y0res; r.ibrd = ibrd;
     for (int i = 0; i < 7; i++) r.cntnm[i] = cntnm[i];
     r.do_lines = true;
+    r.line_mode = opts ? opts->line_mode : 0;
     fill_range(r, wn, opts);
     int rc;
     const size_t fl = (size_t)nwn * nlay * 8, fml = (size_t)nwn * MRTM_MXMOL * nlay * 8;
@@ -680,6 +708,7 @@ extern "C" int mrtm_profiles_dev(mrtm_ctx* ctx, int64_t nprof, int64_t nwn, cons
     r.rad = rad_dev; r.tb = tb_dev; r.tmr = tmr_dev; r.trtot = trtot_dev; r.rup = rup_dev; r.rdn = rdn_dev;
     r.o = o_dev;
     r.do_lines = true; r.do_tmr = true; r.do_rtm = true;
+    r.line_mode = opts->line_mode;
     r.v1 = opts->v1_global; r.v2 = opts->v2_global; r.iw0 = opts->iw0;
     return run_device(ctx, r, s);
 }
@@ -705,6 +734,7 @@ extern "C" int mrtm_profiles(mrtm_ctx* ctx, int64_t nprof, int64_t nwn, const do
     r.sclcpl = sclcpl; r.sclhw = sclhw; r.y0res = y0res; r.ibrd = ibrd; r.irt = irt; r.iout = iout; r.idu = idu;
     for (int i = 0; i < 7; i++) r.cntnm[i] = cntnm[i];
     r.do_lines = true; r.do_tmr = true; r.do_rtm = true;
+    r.line_mode = opts ? opts->line_mode : 0;
     fill_range(r, wn, opts);
     int rc;
     const size_t L = (size_t)nprof * nlay;

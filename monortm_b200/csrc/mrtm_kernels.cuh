@@ -19,6 +19,7 @@ struct LinesDev {
     const int32_t *mol, *iso, *xf, *cls, *sidx, *lcidx, *brdidx, *segidx;
     const double *xnu0, *s0adj, *e, *alpf, *alps, *x, *deltnu, *sdep, *mass;
     const unsigned long long* key;
+    const unsigned long long* keypre;   // [n_pad+1]
     const double* lc;          // [nlc][16]
     const int32_t* lc_self;    // [nlc]
     const double* brd;         // [nbrd][28]
@@ -471,6 +472,9 @@ struct LinesArgs {
     const int32_t *mol_s, *xf_s;  // static per line
     const double* sdep_s;
     const unsigned long long* key;
+    const unsigned long long* keypre;   // [n_pad+1] prefix sums of key (selection hash of a whole range)
+    double ff_ratio;              // far-field expansion: poles >= ff_ratio tile half-widths away; 0 = direct only
+    unsigned long long* counters; // [2] far-field expansions, direct (line,frequency) evaluations (may be null)
     const double* planes;         // [L][D_NPLANES][n_pad]
     const LayerDev* lay;          // [L]
     const unsigned long long* vtmax;   // [L][nseg]
@@ -492,7 +496,7 @@ __device__ __forceinline__ int lower_bound_d(const double* a, int lo, int hi, do
 {   // first index in [lo,hi) with a[i] >= v
     while (lo < hi) {
         int mid = (lo + hi) >> 1;
-        if (a[mid] < v) lo = mid + 1; else hi = mid;
+        if (__ldg(a + mid) < v) lo = mid + 1; else hi = mid;
     }
     return lo;
 }
@@ -500,7 +504,7 @@ __device__ __forceinline__ int upper_bound_d(const double* a, int lo, int hi, do
 {   // first index in [lo,hi) with a[i] > v
     while (lo < hi) {
         int mid = (lo + hi) >> 1;
-        if (a[mid] <= v) lo = mid + 1; else hi = mid;
+        if (__ldg(a + mid) <= v) lo = mid + 1; else hi = mid;
     }
     return lo;
 }
@@ -588,42 +592,101 @@ __device__ __forceinline__ double rcp3(double x)
 #ifndef MRTM_LINES_MINB
 #define MRTM_LINES_MINB 4
 #endif
-#ifndef MRTM_UNROLL_SINGLE
-#define MRTM_UNROLL_SINGLE 4
-#endif
 #ifndef MRTM_UNROLL_BOTH
 #define MRTM_UNROLL_BOTH 2
 #endif
 #define MRTM_PRAGMA(x) _Pragma(#x)
 #define MRTM_UNROLL(n) MRTM_PRAGMA(unroll n)
-constexpr int kTile = 256;      // lines per smem tile
-constexpr int kStages = 2;
+constexpr int kTile = 128;      // lines per smem tile
+constexpr int kStages = 8;      // tile ring: up to kStages-1 TMA jobs in flight ahead of the consumer
+constexpr int kFarK = 14;       // Taylor terms of the far-field expansion (degree kFarK-1)
+constexpr int kMaxBp = 12;      // break points per segment
+constexpr int kMaxRun = 6;      // direct runs per segment
+
+// sub-range mode bits
+constexpr int M_EDGE = 1;       // per-(line,frequency) window test |WN-Xnu| > 25 (modm.f90:384)
+constexpr int M_NEG = 2;        // per-(line,frequency) test WN+Xnu <= 25 (modm.f90:746)
+constexpr int M_VOIGT = 4;      // per-(line,frequency) test |WN-Xnu| <= 100*HWHM_D (modm.f90:427)
+constexpr int M_NEAR = 8;       // direct evaluation (a pole of the line is too close to the tile to expand)
 
 // per-segment work descriptor built once per CTA (in parallel) in shared memory
 struct SegWork {
+    // searched fields, in the order of the prologue tasks (kept contiguous)
     int q0, q1;        // lines that can be inside the 25 cm-1 window of some frequency of the CTA
-    int eb, ec;        // [q0,eb) and [ec,q1): window-edge bands (per-thread window test)
-    int n0, n1;        // [n0,n1): band where WN+Xnu<=25 flips; < n0: both resonances for every thread
+    int eb, ec;        // [q0,eb) and [ec,q1): window-edge bands
+    int n0, n1;        // [n0,n1): band where WN+Xnu<=25 flips; < n0: both resonances for every frequency
     int v0, v1;        // [v0,v1): Voigt zone
-    int nbp;           // sub-range break points bp[0..nbp-1]
-    int bp[10];
-    int t0, ntile;     // TMA tile origin (32-byte aligned) and tile count; ntile==0: nothing to stream
-    int next;          // next segment with ntile>0, or -1
-    int active;        // W_species != 0
+    int z0;            // < z0: the negative-frequency pole -Xnu is near the tile
+    int f0, f1;        // [f0,f1): the pole +Xnu is near the tile
+    // derived
+    int nbp;                     // break points bp[0..nbp-1]; sub-range u = [bp[u], bp[u+1])
+    int bp[kMaxBp];
+    unsigned char mode[kMaxBp];  // mode bits of sub-range u; 0 = far field (Taylor expansion)
+    int nrun;                    // maximal runs of consecutive direct (mode != 0) sub-ranges
+    int run_lo[kMaxRun], run_hi[kMaxRun], run_t0[kMaxRun], run_nt[kMaxRun];
+    int active;                  // W_species != 0
+    int tma;                     // class streams its direct runs through shared memory
+    int has_far;
 };
+constexpr int kSegTasks = 11;
 
-// lines_kernel, version 3.  CTA = (NT*F frequencies, one layer, one profile); each thread owns F
+// One far-field term: w/((D+t)^2+h2) (+ optional pedestal) expanded in s = t/h about the tile centre,
+//   sum_k b_k s^k,  b_0 = w*u, b_1 = al*b_0, b_k = al*b_{k-1} + be*b_{k-2},  u = 1/(D^2+h2), al = -2*D*h*u, be = -h^2*u.
+// The poles of the term sit at distance sqrt(D^2+h2) >= ratio*h from the centre, so the series converges like ratio^-k.
+__device__ __forceinline__ void far_accum(double D, double h2, double w, double ped, double m2h, double mhh, double (&A)[kFarK])
+{
+    const double u = rcp3(fma(D, D, h2));
+    const double al = (D * m2h) * u, be = mhh * u;
+    double b0 = w * u;
+    double b1 = al * b0;
+    A[0] += b0 - ped;
+    A[1] += b1;
+#pragma unroll
+    for (int k = 2; k < kFarK; k++) {
+        const double b2 = fma(al, b1, be * b0);
+        A[k] += b2;
+        b0 = b1;
+        b1 = b2;
+    }
+}
+// first-order line mixing (modm.f90:777-786): (g + c*(D+t))/((D+t)^2+h2), c = +-cq
+__device__ __forceinline__ void far_accum_mix(double D, double h2, double cg, double cq, double hh, double m2h, double mhh, double (&A)[kFarK])
+{
+    const double u = rcp3(fma(D, D, h2));
+    const double al = (D * m2h) * u, be = mhh * u;
+    const double g1 = fma(cq, D, cg), g2 = cq * hh;
+    double b0 = u;
+    double b1 = al * b0;
+    A[0] = fma(g1, b0, A[0]);
+    A[1] = fma(g1, b1, fma(g2, b0, A[1]));
+#pragma unroll
+    for (int k = 2; k < kFarK; k++) {
+        const double b2 = fma(al, b1, be * b0);
+        A[k] = fma(g1, b2, fma(g2, b1, A[k]));
+        b0 = b1;
+        b1 = b2;
+    }
+}
+
+// lines_kernel, version 4.  CTA = (NT*F frequencies, one layer, one profile); each thread owns F
 // (frequency, layer) accumulators.
-//  * prologue: all window / band searches of all segments run in parallel (one search per thread)
-//  * line-parameter tiles (XNU, H2, CN, P3) stream through shared memory with TMA bulk copies, double
-//    buffered on mbarriers, prefetching across segment boundaries
-//  * interior ranges run branch-free (4 lines share one reciprocal); the three narrow bands (window
-//    edges, the WN+Xnu<=25 boundary, the Voigt zone) run loops specialised per test combination with the
-//    reference's exact per-(line,frequency) tests (modm.f90:384, 427, 746)
+//  * prologue: all window / band / near-zone searches of all segments run in parallel (one per thread)
+//  * far field: a line whose poles (+-Xnu +- i*HWHM) are at least ff_ratio tile half-widths away from the tile
+//    centre is not evaluated per frequency; its Lorentz terms are expanded in a kFarK-term Taylor series about
+//    the tile centre (one line per thread, coalesced loads), the coefficients are summed over the CTA and every
+//    frequency evaluates the polynomial once per molecule.  Truncation error <= ~(K+1)*ratio^-K of the line's own
+//    contribution (1.6e-13 for ratio 10, K 14).  The window test stays exact: only lines that are inside the
+//    25 cm-1 window of EVERY frequency of the tile (proved with margins) take this path.
+//  * near field: line-parameter tiles (XNU, H2, CN, P3) of the remaining runs stream through shared memory with
+//    TMA bulk copies, double buffered on mbarriers, prefetching across runs and segments; interior ranges run
+//    branch-free (4 lines share one reciprocal); the narrow bands (window edges, the WN+Xnu<=25 boundary, the
+//    Voigt zone) run loops specialised per test combination with the reference's exact per-(line,frequency)
+//    tests (modm.f90:384, 427, 746)
 template <int F, bool SEL, int NT>
 __global__ void __launch_bounds__(NT, (MRTM_LINES_MINB * 128) / NT) lines_kernel(LinesArgs a)
 {
     constexpr int NW = NT / 32;
+    constexpr int CH = NT / 8;                    // chunk of the two-stage coefficient reduction
     const int tid = threadIdx.x;
     const int k = blockIdx.y;                     // layer within profile
     const int prof = blockIdx.z;
@@ -637,12 +700,15 @@ __global__ void __launch_bounds__(NT, (MRTM_LINES_MINB * 128) / NT) lines_kernel
     const double* __restrict__ pP4 = pl + (size_t)D_P4 * a.n_pad;
     const double* __restrict__ pVT = pl + (size_t)D_VT * a.n_pad;
 
-    __shared__ __align__(128) double s_tile[kStages][4][kTile];
     __shared__ __align__(8) uint64_t s_bar[kStages];
     __shared__ double s_lo[NW], s_hi[NW];
     __shared__ double s_ped[2][NW];
-    __shared__ SegWork s_work[kMaxSegments];
-    __shared__ int s_first;
+    __shared__ double s_red[kFarK][NT];
+    __shared__ double s_red2[kFarK][8];
+    __shared__ double s_coef[kFarK];
+    extern __shared__ __align__(128) unsigned char s_dyn[];
+    double (*s_tile)[4][kTile] = reinterpret_cast<double (*)[4][kTile]>(s_dyn);      // [kStages][4][kTile]
+    SegWork* s_work = reinterpret_cast<SegWork*>(s_dyn + sizeof(double) * kStages * 4 * kTile);
 
     // this thread's frequencies (strided so global accesses coalesce)
     const int base = blockIdx.x * (NT * F);
@@ -673,13 +739,19 @@ __global__ void __launch_bounds__(NT, (MRTM_LINES_MINB * 128) / NT) lines_kernel
     const double sm = ly.shift_margin;
     const double rp = ly.rp, rp2 = ly.rp2;
     const int nseg = a.nseg;
+    // tile centre / half width (CTA uniform): expansion variable s = (WN - cen)/hh in [-1,1]
+    const double cen = 0.5 * (wlo + whi), hh = 0.5 * (whi - wlo);
+    const double hinv = hh > 0. ? 1. / hh : 0.;
+    const bool ff = a.ff_ratio > 0.;
+    const double Rn = a.ff_ratio * hh;
 
     // ---- prologue: one binary search per thread over (segment, field) tasks ----------------------
-    for (int task = tid; task < nseg * 8; task += NT) {
-        const int s = task >> 3, w = task & 7;
+    for (int task = tid; task < nseg * kSegTasks; task += NT) {
+        const int s = task / kSegTasks, w = task - s * kSegTasks;
         const Segment sg = a.seg[s];
         const int cls = sg.cls;
         const bool tma_cls = (cls == CLS_PED) || (cls == CLS_O2) || (cls == CLS_O2_LC35);
+        const bool exp_cls = tma_cls || (cls == CLS_O2_LC1);      // classes with a far-field path
         const bool has_win = (cls == CLS_PED) || (cls == CLS_O2) || (cls == CLS_GENERAL && sg.mol != 7);
         int r;
         switch (w) {
@@ -689,17 +761,21 @@ __global__ void __launch_bounds__(NT, (MRTM_LINES_MINB * 128) / NT) lines_kernel
         case 3: r = (has_win && tma_cls) ? lower_bound_d(a.xnu0, sg.begin, sg.end, wlo + kDELTNUC - sm) : sg.end; break;
         case 4: r = (has_win && tma_cls) ? lower_bound_d(a.xnu0, sg.begin, sg.end, kDELTNUC - whi - sm) : sg.end; break;
         case 5: r = (has_win && tma_cls) ? upper_bound_d(a.xnu0, sg.begin, sg.end, kDELTNUC - wlo + sm + 1e-9) : sg.end; break;
-        default: {
+        case 6:
+        case 7: {
             // Voigt zone: where a frequency can come within max(100*HWHM_D) of a centre (modm.f90:427); the
             // maximum is over the lines of this (layer, segment) that are not Lorentz-only (zeta <= 0.99)
             const unsigned long long vbits = a.vtmax[(size_t)L * nseg + s];
-            if (tma_cls && vbits != 0ull) {
+            if (exp_cls && vbits != 0ull) {
                 const double vb = __longlong_as_double((long long)vbits) * (1. + 1e-12) + sm + 1e-9;
                 r = (w == 6) ? lower_bound_d(a.xnu0, sg.begin, sg.end, wlo - vb) : upper_bound_d(a.xnu0, sg.begin, sg.end, whi + vb);
             } else {
                 r = sg.begin;      // empty zone after clipping
             }
         } break;
+        case 8: r = (ff && exp_cls) ? lower_bound_d(a.xnu0, sg.begin, sg.end, Rn - cen + sm) : sg.end; break;
+        case 9: r = (ff && exp_cls) ? lower_bound_d(a.xnu0, sg.begin, sg.end, cen - Rn - sm) : sg.begin; break;
+        default: r = (ff && exp_cls) ? upper_bound_d(a.xnu0, sg.begin, sg.end, cen + Rn + sm) : sg.end; break;
         }
         (&s_work[s].q0)[w] = r;
     }
@@ -709,38 +785,77 @@ __global__ void __launch_bounds__(NT, (MRTM_LINES_MINB * 128) / NT) lines_kernel
         const Segment sg = a.seg[s];
         const int cls = sg.cls;
         const bool tma_cls = (cls == CLS_PED) || (cls == CLS_O2) || (cls == CLS_O2_LC35);
+        const bool has_win = tma_cls && (cls != CLS_O2_LC35);
+        const bool force_both = (cls == CLS_O2_LC35) || (cls == CLS_O2_LC1);
         const int q0 = wk.q0, q1 = wk.q1 > wk.q0 ? wk.q1 : wk.q0;
         wk.q1 = q1;
-        int c[6] = {wk.eb, wk.ec, wk.n0, wk.n1, wk.v0, wk.v1};
-        for (int i = 0; i < 6; i++) c[i] = c[i] < q0 ? q0 : (c[i] > q1 ? q1 : c[i]);
+        int c[9] = {wk.eb, wk.ec, wk.n0, wk.n1, wk.v0, wk.v1, wk.z0, wk.f0, wk.f1};
+        for (int i = 0; i < 9; i++) c[i] = c[i] < q0 ? q0 : (c[i] > q1 ? q1 : c[i]);
         wk.eb = c[0]; wk.ec = c[1]; wk.n0 = c[2]; wk.n1 = c[3]; wk.v0 = c[4]; wk.v1 = c[5];
-        for (int i = 1; i < 6; i++) { int v = c[i], j = i - 1; while (j >= 0 && c[j] > v) { c[j + 1] = c[j]; j--; } c[j + 1] = v; }
+        wk.z0 = c[6]; wk.f0 = c[7]; wk.f1 = c[8];
+        for (int i = 1; i < 9; i++) { int v = c[i], j = i - 1; while (j >= 0 && c[j] > v) { c[j + 1] = c[j]; j--; } c[j + 1] = v; }
         int nbp = 0;
         wk.bp[nbp++] = q0;
-        for (int i = 0; i < 6; i++) if (c[i] > wk.bp[nbp - 1]) wk.bp[nbp++] = c[i];
+        for (int i = 0; i < 9; i++) if (c[i] > wk.bp[nbp - 1]) wk.bp[nbp++] = c[i];
         if (q1 > wk.bp[nbp - 1]) wk.bp[nbp++] = q1;
         wk.nbp = nbp;
         wk.active = (ly.wk[sg.mol - 1] != 0.) ? 1 : 0;           // W_SPECIES == 0: molecule skipped (:318-321)
-        wk.t0 = q0 & ~3;
-        wk.ntile = (tma_cls && wk.active && q1 > wk.t0) ? (q1 - wk.t0 + kTile - 1) / kTile : 0;
-    }
-    __syncthreads();
-    if (tid == 0) {
-        int nxt = -1;
-        for (int s = nseg - 1; s >= 0; s--) {
-            s_work[s].next = nxt;
-            if (s_work[s].ntile > 0) nxt = s;
+        wk.tma = tma_cls ? 1 : 0;
+        // modes and direct runs
+        int nrun = 0, has_far = 0;
+        bool open = false;
+        for (int u = 0; u + 1 < nbp; u++) {
+            const int x = wk.bp[u];
+            int mode = 0;
+            if (has_win && ((x < wk.eb) || (x >= wk.ec))) mode |= M_EDGE;
+            if (has_win && (x >= wk.n0) && (x < wk.n1)) mode |= M_NEG;
+            if ((x >= wk.v0) && (x < wk.v1)) mode |= M_VOIGT;
+            const bool second = force_both || (has_win && x < wk.n1);      // the negative-frequency term can be present
+            if (((x >= wk.f0) && (x < wk.f1)) || (second && x < wk.z0)) mode |= M_NEAR;
+            if (!(tma_cls || cls == CLS_O2_LC1)) mode |= M_NEAR;            // CLS_GENERAL: always direct
+            wk.mode[u] = (unsigned char)mode;
+            if (mode != 0) {
+                if (open) {
+                    wk.run_hi[nrun - 1] = wk.bp[u + 1];
+                } else {
+                    wk.run_lo[nrun] = x;
+                    wk.run_hi[nrun] = wk.bp[u + 1];
+                    nrun++;
+                    open = true;
+                }
+            } else {
+                has_far = 1;
+                open = false;
+            }
         }
-        s_first = nxt;
+        for (int r = 0; r < nrun; r++) {
+            wk.run_t0[r] = wk.run_lo[r] & ~3;
+            wk.run_nt[r] = (wk.run_hi[r] - wk.run_t0[r] + kTile - 1) / kTile;
+        }
+        wk.nrun = (wk.active) ? nrun : 0;
+        wk.has_far = (wk.active) ? has_far : 0;
     }
     __syncthreads();
 
-    uint32_t phase_bits = 0;    // per-stage mbarrier phase parity (bit i = stage i)
-    int ped_buf = 0;            // alternates per tile over the whole kernel (s_ped double buffer)
-    int gtile = 0;              // global tile counter: stage of a tile = gtile & 1
-
-    auto issue = [&](int s, int t, int st) {      // one elected thread: TMA one tile of segment s into stage st
-        const int qs = s_work[s].t0 + t * kTile;
+    // ---- TMA tile jobs: (segment, run, tile) in consumption order; thread 0 keeps a cursor one job ahead
+    auto advance = [&](int& js, int& jr, int& jt) -> bool {
+        jt++;
+        while (js < nseg) {
+            const SegWork& w = s_work[js];
+            if (w.tma && jr < w.nrun) {
+                if (jt < w.run_nt[jr]) return true;
+                jr++;
+                jt = 0;
+                continue;
+            }
+            js++;
+            jr = 0;
+            jt = 0;
+        }
+        return false;
+    };
+    auto issue = [&](int js, int jr, int jt, int st) {      // one elected thread: TMA one tile into stage st
+        const int qs = s_work[js].run_t0[jr] + jt * kTile;
         int n = a.n_pad - qs;
         n = n > kTile ? kTile : n;
         const uint32_t bytes = (uint32_t)n * 8u;
@@ -750,7 +865,17 @@ __global__ void __launch_bounds__(NT, (MRTM_LINES_MINB * 128) / NT) lines_kernel
         tma_load_1d(&s_tile[st][2][0], pCN + qs, bytes, &s_bar[st]);
         tma_load_1d(&s_tile[st][3][0], pP3 + qs, bytes, &s_bar[st]);
     };
-    if (tid == 0 && s_first >= 0) issue(s_first, 0, 0);
+    int pjs = 0, pjr = 0, pjt = -1;      // prefetch cursor (thread 0 only)
+    bool more = true;
+    if (tid == 0) {
+        for (int i = 0; i < kStages - 1 && more; i++) {
+            more = advance(pjs, pjr, pjt);
+            if (more) issue(pjs, pjr, pjt, i);
+        }
+    }
+
+    int ped_buf = 0;            // alternates per tile over the whole kernel (s_ped double buffer)
+    int gtile = 0;              // global tile counter: stage = gtile % kStages, mbarrier parity = (gtile / kStages) & 1
 
     double osum[F], sf[F];
     long long cnt[F];
@@ -763,6 +888,12 @@ __global__ void __launch_bounds__(NT, (MRTM_LINES_MINB * 128) / NT) lines_kernel
 
     int err = 0;
     int cur_mol = 0;
+    long long n_far = 0, n_direct = 0;      // work counters (thread 0 reports them)
+    int nvalid = 0;
+    if (a.counters) {
+        const int rem = a.nwn - base;
+        nvalid = rem < NT * F ? rem : NT * F;
+    }
     auto finish_mol = [&](int mol) {
         if (mol <= 0) return;
         const double w = ly.wk[mol - 1];
@@ -790,6 +921,82 @@ __global__ void __launch_bounds__(NT, (MRTM_LINES_MINB * 128) / NT) lines_kernel
         if (sg.mol != cur_mol) {
             finish_mol(cur_mol);
             cur_mol = sg.mol;
+            // ---- far field of every segment of this molecule ---------------------------------------
+            bool any_far = false;
+            int s_end = s;
+            for (; s_end < nseg && a.seg[s_end].mol == cur_mol; s_end++) any_far |= (s_work[s_end].has_far != 0);
+            if (any_far) {
+                double A[kFarK];
+#pragma unroll
+                for (int i = 0; i < kFarK; i++) A[i] = 0.;
+                const double m2h = -2. * hh, mhh = -hh * hh;
+                for (int s2 = s; s2 < s_end; s2++) {
+                    const SegWork& wk = s_work[s2];
+                    if (!wk.has_far) continue;
+                    const int cls2 = a.seg[s2].cls;
+                    const bool force_both = (cls2 == CLS_O2_LC35) || (cls2 == CLS_O2_LC1);
+                    const bool count_sel = SEL && (cls2 == CLS_PED);
+                    for (int u = 0; u + 1 < wk.nbp; u++) {
+                        if (wk.mode[u] != 0) continue;
+                        const int lo = wk.bp[u], hi = wk.bp[u + 1];
+                        const bool both = force_both || (lo < wk.n0);
+                        if (count_sel) {
+                            const unsigned long long hs = a.keypre[hi] - a.keypre[lo];
+#pragma unroll
+                            for (int f = 0; f < F; f++) { cnt[f] += hi - lo; hsh[f] += hs; }
+                        }
+                        if (a.counters) n_far += (long long)(hi - lo) * (both ? 2 : 1);
+                        // one line per thread, coalesced read-only loads, next line's parameters in flight
+                        int q = lo + tid;
+                        double xnu = 0., h2 = 1., c3 = 0., c4 = 0.;
+                        const double* __restrict__ pA = (cls2 == CLS_O2_LC1) ? pP3 : pCN;
+                        const double* __restrict__ pB = (cls2 == CLS_O2_LC1) ? pP4 : pP3;
+                        if (q < hi) { xnu = __ldg(pXNU + q); h2 = __ldg(pH2 + q); c3 = __ldg(pA + q); c4 = __ldg(pB + q); }
+                        while (q < hi) {
+                            const int qn = q + NT;
+                            double xnu_n = 0., h2_n = 1., c3_n = 0., c4_n = 0.;
+                            if (qn < hi) { xnu_n = __ldg(pXNU + qn); h2_n = __ldg(pH2 + qn); c3_n = __ldg(pA + qn); c4_n = __ldg(pB + qn); }
+                            if (cls2 == CLS_O2_LC1) {
+                                far_accum_mix(cen - xnu, h2, c3, c4, hh, m2h, mhh, A);
+                                far_accum_mix(cen + xnu, h2, c3, -c4, hh, m2h, mhh, A);
+                            } else if (both) {
+                                far_accum(cen - xnu, h2, c3, c4, m2h, mhh, A);
+                                far_accum(cen + xnu, h2, c3, c4, m2h, mhh, A);
+                            } else {
+                                far_accum(cen - xnu, h2, c3, c4, m2h, mhh, A);
+                            }
+                            xnu = xnu_n; h2 = h2_n; c3 = c3_n; c4 = c4_n;
+                            q = qn;
+                        }
+                    }
+                }
+                // CTA-wide sums of the coefficients in a fixed order (deterministic)
+#pragma unroll
+                for (int i = 0; i < kFarK; i++) s_red[i][tid] = A[i];
+                __syncthreads();
+                if (tid < kFarK * 8) {
+                    const int i = tid >> 3, part = tid & 7;
+                    double t = 0.;
+                    for (int j = 0; j < CH; j++) t += s_red[i][part * CH + ((j + tid) & (CH - 1))];
+                    s_red2[i][part] = t;
+                }
+                __syncthreads();
+                if (tid < kFarK) {
+                    double t = 0.;
+#pragma unroll
+                    for (int j = 0; j < 8; j++) t += s_red2[tid][j];
+                    s_coef[tid] = t;
+                }
+                __syncthreads();
+#pragma unroll
+                for (int f = 0; f < F; f++) {
+                    const double sv = (wn[f] - cen) * hinv;
+                    double p = s_coef[kFarK - 1];
+#pragma unroll
+                    for (int i = kFarK - 2; i >= 0; i--) p = fma(p, sv, s_coef[i]);
+                    sf[f] += p;
+                }
+            }
         }
         const SegWork& wk = s_work[s];
         if (!wk.active) continue;
@@ -799,42 +1006,42 @@ __global__ void __launch_bounds__(NT, (MRTM_LINES_MINB * 128) / NT) lines_kernel
             for (int f = 0; f < F; f++) { cnt[f] += sg.count_all; hsh[f] += sg.hash_all; }
         }
         if (cls == CLS_PED || cls == CLS_O2 || cls == CLS_O2_LC35) {
-            const bool has_win = (cls != CLS_O2_LC35);
             const bool force_both = (cls == CLS_O2_LC35);
             const bool count_sel = SEL && (cls == CLS_PED);
-            const int eb = wk.eb, ec = wk.ec, n0 = wk.n0, n1 = wk.n1, v0 = wk.v0, v1 = wk.v1;
-            const int nsub = wk.nbp - 1, t0 = wk.t0, ntile = wk.ntile;
+            const int n0 = wk.n0;
+            const int nsub = wk.nbp - 1;
             double psum[F];
 #pragma unroll
             for (int f = 0; f < F; f++) psum[f] = 0.;
             double pacc = 0.;                              // pedestal total of the interior ranges (uniform)
-            for (int t = 0; t < ntile; t++, gtile++) {
-                const int st = gtile & 1;
-                if (tid == 0) {                            // prefetch the next tile (possibly of the next segment)
-                    if (t + 1 < ntile) issue(s, t + 1, st ^ 1);
-                    else if (wk.next >= 0) issue(wk.next, 0, st ^ 1);
-                }
-                mbar_wait(&s_bar[st], (phase_bits >> st) & 1u);
-                phase_bits ^= (1u << st);
-                const double* __restrict__ tX = s_tile[st][0];
-                const double* __restrict__ tH = s_tile[st][1];
-                const double* __restrict__ tC = s_tile[st][2];
-                const double* __restrict__ tP = s_tile[st][3];
-                const int tb = t0 + t * kTile, te = tb + kTile;
-                double pmine = 0.;                          // this thread's share of the tile's interior pedestals
-                for (int u = 0; u < nsub; u++) {
-                    const int x = wk.bp[u];
-                    int lo = x > tb ? x : tb;
-                    int hi = wk.bp[u + 1] < te ? wk.bp[u + 1] : te;
-                    if (lo >= hi) continue;
-                    int mode = 0;           // bit0 window-edge test, bit1 per-thread resonance test, bit2 Voigt test
-                    if (has_win && ((x < eb) || (x >= ec))) mode |= 1;
-                    if (has_win && (x >= n0) && (x < n1)) mode |= 2;
-                    if ((x >= v0) && (x < v1)) mode |= 4;
-                    const bool negall = force_both || (x < n0);
-                    if (mode != 0) {
-                        // ---- predicated loops, specialised per test combination
-                        switch (mode) {
+            for (int r = 0; r < wk.nrun; r++) {
+                const int rlo = wk.run_lo[r], rhi = wk.run_hi[r], t0 = wk.run_t0[r], ntile = wk.run_nt[r];
+                for (int t = 0; t < ntile; t++, gtile++) {
+                    const int st = gtile % kStages;
+                    if (tid == 0 && more) {        // refill the stage the previous tile released
+                        more = advance(pjs, pjr, pjt);
+                        if (more) issue(pjs, pjr, pjt, (gtile + kStages - 1) % kStages);
+                    }
+                    mbar_wait(&s_bar[st], (uint32_t)(gtile / kStages) & 1u);
+                    const double* __restrict__ tX = s_tile[st][0];
+                    const double* __restrict__ tH = s_tile[st][1];
+                    const double* __restrict__ tC = s_tile[st][2];
+                    const double* __restrict__ tP = s_tile[st][3];
+                    const int tb = t0 + t * kTile;
+                    const int tlo = tb > rlo ? tb : rlo;
+                    const int thi = (tb + kTile) < rhi ? (tb + kTile) : rhi;
+                    double pmine = 0.;                          // this thread's share of the tile's interior pedestals
+                    for (int u = 0; u < nsub; u++) {
+                        const int x = wk.bp[u];
+                        const int mode = wk.mode[u];
+                        int lo = x > tlo ? x : tlo;
+                        int hi = wk.bp[u + 1] < thi ? wk.bp[u + 1] : thi;
+                        if (lo >= hi || mode == 0) continue;
+                        const bool negall = force_both || (x < n0);
+                        if (a.counters) n_direct += (long long)(hi - lo) * nvalid;
+                        if ((mode & 7) != 0) {
+                            // ---- predicated loops, specialised per test combination
+                            switch (mode & 7) {
 #define MRTM_PRED(M)                                                                                              \
     case M:                                                                                                       \
         for (int q = lo; q < hi; q++) {                                                                           \
@@ -867,96 +1074,100 @@ __global__ void __launch_bounds__(NT, (MRTM_LINES_MINB * 128) / NT) lines_kernel
             }                                                                                                     \
         }                                                                                                         \
         break;
-                            MRTM_PRED(1) MRTM_PRED(2) MRTM_PRED(3) MRTM_PRED(4) MRTM_PRED(5) MRTM_PRED(6) MRTM_PRED(7)
+                                MRTM_PRED(1) MRTM_PRED(2) MRTM_PRED(3) MRTM_PRED(4) MRTM_PRED(5) MRTM_PRED(6) MRTM_PRED(7)
 #undef MRTM_PRED
-                        default: break;
+                            default: break;
+                            }
+                            continue;
                         }
-                        continue;
-                    }
-                    if (count_sel) {
-                        unsigned long long hs = 0ull;
-                        for (int q = lo; q < hi; q++) hs += a.key[q];
+                        if (count_sel) {
+                            const unsigned long long hs = a.keypre[hi] - a.keypre[lo];
 #pragma unroll
-                        for (int f = 0; f < F; f++) { cnt[f] += hi - lo; hsh[f] += hs; }
-                    }
-                    // this thread's share of the interior pedestals of the tile (reduced across the CTA below)
-                    {
-                        const double w = negall ? 2. : 1.;          // pedestal counted for both resonances (:749)
-                        for (int q = lo + tid; q < hi; q += NT) pmine = fma(w, tP[q - tb], pmine);
-                    }
-                    if (negall) {
-                        // ---- interior, both resonances: cn*(1/a+1/b) = cn*(a+b)/(a*b), one reciprocal
+                            for (int f = 0; f < F; f++) { cnt[f] += hi - lo; hsh[f] += hs; }
+                        }
+                        // this thread's share of the interior pedestals of the tile (reduced across the CTA below)
+                        {
+                            const double w = negall ? 2. : 1.;          // pedestal counted for both resonances (:749)
+                            for (int q = lo + tid; q < hi; q += NT) pmine = fma(w, tP[q - tb], pmine);
+                        }
+                        if (negall) {
+                            // ---- interior, both resonances: cn*(1/a+1/b) = cn*(a+b)/(a*b), one reciprocal
 MRTM_UNROLL(MRTM_UNROLL_BOTH)
-                        for (int q = lo; q < hi; q++) {
-                            const int j = q - tb;
-                            const double xnu = tX[j], h2 = tH[j], cn = tC[j];
+                            for (int q = lo; q < hi; q++) {
+                                const int j = q - tb;
+                                const double xnu = tX[j], h2 = tH[j], cn = tC[j];
 #pragma unroll
-                            for (int f = 0; f < F; f++) {
-                                const double dm = wn[f] - xnu, sp = wn[f] + xnu;
-                                const double aa = fma(dm, dm, h2), bb = fma(sp, sp, h2);
-                                const double r = rcp3(aa * bb);
-                                psum[f] = fma(cn * (aa + bb), r, psum[f]);
+                                for (int f = 0; f < F; f++) {
+                                    const double dm = wn[f] - xnu, sp = wn[f] + xnu;
+                                    const double aa = fma(dm, dm, h2), bb = fma(sp, sp, h2);
+                                    const double r = rcp3(aa * bb);
+                                    psum[f] = fma(cn * (aa + bb), r, psum[f]);
+                                }
                             }
-                        }
-                    } else {
-                        // ---- interior, single resonance (modm.f90:751): four lines share one reciprocal,
-                        // sum c_i/a_i = N/(a1 a2 a3 a4), N = (c1 a2 + c2 a1)(a3 a4) + (c3 a4 + c4 a3)(a1 a2);
-                        // 21 FP64 ops + 1 MUFU per 4 evaluations
-                        int q = lo;
-                        for (; q + 4 <= hi; q += 4) {
-                            const int j = q - tb;
-                            const double x1 = tX[j], x2 = tX[j + 1], x3 = tX[j + 2], x4 = tX[j + 3];
-                            const double g1 = tH[j], g2 = tH[j + 1], g3 = tH[j + 2], g4 = tH[j + 3];
-                            const double c1 = tC[j], c2 = tC[j + 1], c3 = tC[j + 2], c4 = tC[j + 3];
+                        } else {
+                            // ---- interior, single resonance (modm.f90:751): four lines share one reciprocal,
+                            // sum c_i/a_i = N/(a1 a2 a3 a4), N = (c1 a2 + c2 a1)(a3 a4) + (c3 a4 + c4 a3)(a1 a2);
+                            // 21 FP64 ops + 1 MUFU per 4 evaluations
+                            int q = lo;
+                            for (; q + 4 <= hi; q += 4) {
+                                const int j = q - tb;
+                                const double x1 = tX[j], x2 = tX[j + 1], x3 = tX[j + 2], x4 = tX[j + 3];
+                                const double g1 = tH[j], g2 = tH[j + 1], g3 = tH[j + 2], g4 = tH[j + 3];
+                                const double c1 = tC[j], c2 = tC[j + 1], c3 = tC[j + 2], c4 = tC[j + 3];
 #pragma unroll
-                            for (int f = 0; f < F; f++) {
-                                const double d1 = wn[f] - x1, d2 = wn[f] - x2, d3 = wn[f] - x3, d4 = wn[f] - x4;
-                                const double a1 = fma(d1, d1, g1), a2 = fma(d2, d2, g2);
-                                const double a3 = fma(d3, d3, g3), a4 = fma(d4, d4, g4);
-                                const double p12 = a1 * a2, p34 = a3 * a4;
-                                const double n12 = fma(c1, a2, c2 * a1), n34 = fma(c3, a4, c4 * a3);
-                                const double r = rcp3(p12 * p34);
-                                psum[f] = fma(fma(n12, p34, n34 * p12), r, psum[f]);
+                                for (int f = 0; f < F; f++) {
+                                    const double d1 = wn[f] - x1, d2 = wn[f] - x2, d3 = wn[f] - x3, d4 = wn[f] - x4;
+                                    const double a1 = fma(d1, d1, g1), a2 = fma(d2, d2, g2);
+                                    const double a3 = fma(d3, d3, g3), a4 = fma(d4, d4, g4);
+                                    const double p12 = a1 * a2, p34 = a3 * a4;
+                                    const double n12 = fma(c1, a2, c2 * a1), n34 = fma(c3, a4, c4 * a3);
+                                    const double r = rcp3(p12 * p34);
+                                    psum[f] = fma(fma(n12, p34, n34 * p12), r, psum[f]);
+                                }
                             }
-                        }
-                        for (; q < hi; q++) {
-                            const int j = q - tb;
-                            const double xnu = tX[j], h2 = tH[j], cn = tC[j];
+                            for (; q < hi; q++) {
+                                const int j = q - tb;
+                                const double xnu = tX[j], h2 = tH[j], cn = tC[j];
 #pragma unroll
-                            for (int f = 0; f < F; f++) {
-                                const double dm = wn[f] - xnu;
-                                psum[f] = fma(cn, rcp3(fma(dm, dm, h2)), psum[f]);
+                                for (int f = 0; f < F; f++) {
+                                    const double dm = wn[f] - xnu;
+                                    psum[f] = fma(cn, rcp3(fma(dm, dm, h2)), psum[f]);
+                                }
                             }
                         }
                     }
+                    // CTA-wide sum of the interior pedestals of this tile (uniform result)
+#pragma unroll
+                    for (int off = 16; off > 0; off >>= 1) pmine += __shfl_xor_sync(0xffffffffu, pmine, off);
+                    if ((tid & 31) == 0) s_ped[ped_buf][tid >> 5] = pmine;
+                    __syncthreads();       // all reads of this stage done before it is refilled; s_ped visible
+#pragma unroll
+                    for (int i = 0; i < NW; i++) pacc += s_ped[ped_buf][i];
+                    ped_buf ^= 1;
                 }
-                // CTA-wide sum of the interior pedestals of this tile (uniform result)
-#pragma unroll
-                for (int off = 16; off > 0; off >>= 1) pmine += __shfl_xor_sync(0xffffffffu, pmine, off);
-                if ((tid & 31) == 0) s_ped[ped_buf][tid >> 5] = pmine;
-                __syncthreads();       // all reads of this stage done before it is refilled; s_ped visible
-#pragma unroll
-                for (int i = 0; i < NW; i++) pacc += s_ped[ped_buf][i];
-                ped_buf ^= 1;
             }
 #pragma unroll
             for (int f = 0; f < F; f++) sf[f] += psum[f] - pacc;
         } else if (cls == CLS_O2_LC1) {
-            for (int q = wk.q0; q < wk.q1; q++) {
-                const double xnu = pXNU[q], h2 = pH2[q], cg = pP3[q], cq = pP4[q], vt = pVT[q];
+            for (int r = 0; r < wk.nrun; r++) {
+                if (a.counters) n_direct += (long long)(wk.run_hi[r] - wk.run_lo[r]) * nvalid;
+                for (int q = wk.run_lo[r]; q < wk.run_hi[r]; q++) {
+                    const double xnu = pXNU[q], h2 = pH2[q], cg = pP3[q], cq = pP4[q], vt = pVT[q];
 #pragma unroll
-                for (int f = 0; f < F; f++) {
-                    const double dm = wn[f] - xnu, sp = wn[f] + xnu;
-                    if (fabs(dm) <= vt) {
-                        sf[f] += voigt_term(sg.mol, q, wn[f], xnu);
-                    } else {
-                        const double r1 = rcp3(fma(dm, dm, h2));
-                        const double r2 = rcp3(fma(sp, sp, h2));
-                        sf[f] += fma(cq, dm, cg) * r1 + fma(-cq, sp, cg) * r2;
+                    for (int f = 0; f < F; f++) {
+                        const double dm = wn[f] - xnu, sp = wn[f] + xnu;
+                        if (fabs(dm) <= vt) {
+                            sf[f] += voigt_term(sg.mol, q, wn[f], xnu);
+                        } else {
+                            const double r1 = rcp3(fma(dm, dm, h2));
+                            const double r2 = rcp3(fma(sp, sp, h2));
+                            sf[f] += fma(cq, dm, cg) * r1 + fma(-cq, sp, cg) * r2;
+                        }
                     }
                 }
             }
         } else {   // CLS_GENERAL: faithful case tree per (line, frequency)
+            if (a.counters) n_direct += (long long)(wk.q1 - wk.q0) * nvalid;
             for (int q = wk.q0; q < wk.q1; q++) {
                 const double xnu = pXNU[q], vt = pVT[q];
                 const double hw = pl[(size_t)D_H * a.n_pad + q], ad = pl[(size_t)D_AD * a.n_pad + q];
@@ -976,6 +1187,10 @@ MRTM_UNROLL(MRTM_UNROLL_BOTH)
     }
     finish_mol(cur_mol);
     if (err) atomicOr(a.errflag, 2);
+    if (a.counters && tid == 0) {
+        atomicAdd(a.counters + 0, (unsigned long long)n_far);
+        atomicAdd(a.counters + 1, (unsigned long long)n_direct);
+    }
 
     // ---- epilogue: continuum, cloud, totals ---------------------------------------------------
     const double* ab = a.absrb + (size_t)L * 3 * a.nptabs_pad;

@@ -17,7 +17,20 @@ TB_ATOL = 1e-5      # north_star: brightness temperatures within 1e-5 K
 
 def check_case(case, od_rtol=OD_RTOL):
     ref = harness.run_oracle(case)
+    # the direct mode (every in-window triple evaluated) must meet the same bars and agree with the default
+    # mode (far-field expansion) far inside the tolerance
+    direct = harness.run_gpu(case, line_mode=1)
+    _check_against(ref, direct, od_rtol)
     gpu = harness.run_gpu(case)
+    _check_against(ref, gpu, od_rtol)
+    assert np.array_equal(gpu["sel_hash"], direct["sel_hash"])
+    assert harness.rel_diff(gpu["o"], direct["o"]) < 1e-11
+    assert np.max(np.abs(gpu["tb"] - direct["tb"])) < 1e-7
+    assert direct["stats"]["far_expansions"] == 0
+    return ref, gpu
+
+
+def _check_against(ref, gpu, od_rtol):
     # selected line set: bit exact (count and order-independent hash of (molecule, record) pairs)
     assert np.array_equal(gpu["sel_count"], ref["sel_count"])
     assert np.array_equal(gpu["sel_hash"], ref["sel_hash"])
@@ -33,7 +46,6 @@ def check_case(case, od_rtol=OD_RTOL):
         assert harness.rel_diff(gpu[k], ref[k], floor=1e-300) < 1e-8, k
     assert gpu["tmpsfc"] == ref["tmpsfc"]
     assert gpu["stats"]["kernel_launches"] >= 4
-    return ref, gpu
 
 
 def test_c1_channels_downwelling():
@@ -90,3 +102,14 @@ def test_large_frequency_tiles():
     wn = 5.5e-5 * np.arange(1, 2600 + 1) * 300.0
     case = harness.make_case(n_filler=192, nlay=6, wn=wn, irt=1)
     check_case(case)
+
+
+def test_dense_grid_far_field_expansion():
+    """C3-like dense grid (5.5e-5 cm-1 spacing): most in-window lines take the far-field Taylor path; the
+    result must still match the oracle to 1e-9 and the direct mode to 1e-11, selection bit-exact."""
+    for i0 in (1, 13400, 400000):          # next to zero frequency, across the 22 GHz line, mid-band
+        wn = 5.5e-5 * np.arange(i0, i0 + 1536)
+        case = harness.make_case(n_filler=1536, nlay=6, wn=wn, irt=1, line_kw=dict(n_co2=4, n_generic_lc=4))
+        ref, gpu = check_case(case)
+        assert gpu["stats"]["far_expansions"] > 0
+        assert gpu["stats"]["direct_evals"] < 0.2 * ref["sel_count"].sum()
