@@ -47,7 +47,10 @@ struct mrtm_ctx {
     int* errflag_dev = nullptr;
     unsigned long long* counters_dev = nullptr;   // [2] far expansions, direct evaluations
     double ff_ratio = 10.0;                       // far-field pole-distance ratio (MRTM_FF_RATIO; 0 = direct only)
-    DevBuf b_vtmax;
+    DevBuf b_vtmax;                               // [0] sm_max bits, [1..nseg] vtmax per segment
+    DevBuf b_lvoigt;                              // [L] per-layer "has Voigt-capable lines" flag
+    DevBuf b_plan[kMaxLevels], b_hdr[kMaxLevels], b_coef[kMaxLevels];
+    int ff_levels = 2, ff_S = 8;                  // far-field hierarchy (MRTM_FF_LEVELS 1..3, MRTM_FF_S)
     DevBuf b_layer, b_scorc, b_absrb, b_planes, b_o, b_obm, b_oc, b_in[16], b_out[16], b_sel[2], b_tmps;
     mrtm_stats st;
     size_t planes_budget = (size_t)8 << 30;
@@ -144,6 +147,8 @@ extern "C" int mrtm_init(int device, mrtm_ctx** out)
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return set_err(nullptr, MRTM_ECUDA, "cudaStreamCreate failed"); }
     for (auto& ev : ctx->ev) cudaEventCreate(&ev);
     if (const char* s = std::getenv("MRTM_PLANES_GB")) ctx->planes_budget = (size_t)(std::atof(s) * (double)(1ull << 30));
+    if (const char* s = std::getenv("MRTM_FF_LEVELS")) ctx->ff_levels = std::min(std::max(std::atoi(s), 1), kMaxLevels);
+    if (const char* s = std::getenv("MRTM_FF_S")) ctx->ff_S = std::min(std::max(std::atoi(s), 2), 64);
     if (const char* s = std::getenv("MRTM_FF_RATIO")) {
         double v = std::atof(s);
         ctx->ff_ratio = (v <= 0.) ? 0. : std::max(v, 4.0);
@@ -180,8 +185,13 @@ extern "C" int mrtm_free(mrtm_ctx* ctx)
     cudaStreamSynchronize(ctx->stream);
     free_lines(ctx);
     for (void* p : ctx->table_allocs) cudaFree(p);
-    DevBuf* bufs[] = {&ctx->b_vtmax, &ctx->b_layer, &ctx->b_scorc, &ctx->b_absrb, &ctx->b_planes, &ctx->b_o, &ctx->b_obm, &ctx->b_oc, &ctx->b_sel[0], &ctx->b_sel[1], &ctx->b_tmps};
+    DevBuf* bufs[] = {&ctx->b_lvoigt, &ctx->b_vtmax, &ctx->b_layer, &ctx->b_scorc, &ctx->b_absrb, &ctx->b_planes, &ctx->b_o, &ctx->b_obm, &ctx->b_oc, &ctx->b_sel[0], &ctx->b_sel[1], &ctx->b_tmps};
     for (DevBuf* b : bufs) if (b->p) cudaFree(b->p);
+    for (int i = 0; i < kMaxLevels; i++) {
+        if (ctx->b_plan[i].p) cudaFree(ctx->b_plan[i].p);
+        if (ctx->b_hdr[i].p) cudaFree(ctx->b_hdr[i].p);
+        if (ctx->b_coef[i].p) cudaFree(ctx->b_coef[i].p);
+    }
     for (auto& b : ctx->b_in) if (b.p) cudaFree(b.p);
     for (auto& b : ctx->b_out) if (b.p) cudaFree(b.p);
     if (ctx->errflag_dev) cudaFree(ctx->errflag_dev);
@@ -309,7 +319,7 @@ struct RunDesc {
 template <int F, int NT>
 static void launch_lines(const LinesArgs& la, dim3 grid, bool sel, cudaStream_t s)
 {
-    const size_t dyn = sizeof(double) * kStages * 4 * kTile + (size_t)std::max(la.nseg, 1) * sizeof(SegWork);
+    const size_t dyn = sizeof(double) * kStages * 4 * kTile + 2 * (size_t)std::max(la.nseg, 1) * sizeof(SegWork);
     if (sel) {
         cudaFuncSetAttribute(lines_kernel<F, true, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
         lines_kernel<F, true, NT><<<grid, NT, dyn, s>>>(la);
@@ -374,7 +384,7 @@ static int run_device(mrtm_ctx* ctx, const RunDesc& r, cudaStream_t s)
         if ((rc = ensure(ctx, ctx->b_scorc, (size_t)B * nlay * std::max(1, (int)ctx->ld.nsi) * 8))) return rc;
         if ((rc = ensure(ctx, ctx->b_absrb, (size_t)B * nlay * 3 * nptabs_pad * 8))) return rc;
         if ((rc = ensure(ctx, ctx->b_planes, (size_t)B * nlay * D_NPLANES * (size_t)n_pad * 8))) return rc;
-        if ((rc = ensure(ctx, ctx->b_vtmax, (size_t)B * nlay * std::max<size_t>(1, h.segments.size()) * 8))) return rc;
+        if ((rc = ensure(ctx, ctx->b_vtmax, (1 + std::max<size_t>(1, h.segments.size())) * 8))) return rc;
         CU(cudaMemsetAsync(ctx->errflag_dev, 0, sizeof(int), s));
         CU(cudaMemsetAsync(ctx->counters_dev, 0, 2 * sizeof(unsigned long long), s));
         st.nominal_evals = (double)h.n * (double)nlay * (double)nwn * (double)r.nprof;
@@ -407,6 +417,8 @@ static int run_device(mrtm_ctx* ctx, const RunDesc& r, cudaStream_t s)
             pa.scor_index = ctx->ld.scor_index;
             pa.scorc = (double*)ctx->b_scorc.p;
             pa.errflag = ctx->errflag_dev;
+            pa.sm_max_bits = (unsigned long long*)ctx->b_vtmax.p;
+            CU(cudaMemsetAsync(ctx->b_vtmax.p, 0, (1 + std::max<size_t>(1, h.segments.size())) * 8, s));
             layer_prep_kernel<<<(unsigned)((Lb + 127) / 128), 128, 0, s>>>(pa);
             st.kernel_launches++;
 
@@ -428,9 +440,11 @@ static int run_device(mrtm_ctx* ctx, const RunDesc& r, cudaStream_t s)
             da.y0res = r.y0res;
             da.ibrd = (int32_t)r.ibrd;
             da.planes = (double*)ctx->b_planes.p;
-            da.vtmax = (unsigned long long*)ctx->b_vtmax.p;
+            da.vtmax = (unsigned long long*)ctx->b_vtmax.p + 1;
             da.nseg = (int32_t)h.segments.size();
-            CU(cudaMemsetAsync(ctx->b_vtmax.p, 0, (size_t)Lb * std::max<size_t>(1, h.segments.size()) * 8, s));
+            if ((rc = ensure(ctx, ctx->b_lvoigt, (size_t)Lb * sizeof(int)))) return rc;
+            CU(cudaMemsetAsync(ctx->b_lvoigt.p, 0, (size_t)Lb * sizeof(int), s));
+            da.layer_voigt = (int*)ctx->b_lvoigt.p;
             CU(cudaEventRecord(ctx->ev[0], s));
             derive_kernel<<<dim3((unsigned)((n_pad + 255) / 256), (unsigned)Lb), 256, 0, s>>>(da);
             CU(cudaEventRecord(ctx->ev[1], s));
@@ -453,9 +467,9 @@ static int run_device(mrtm_ctx* ctx, const RunDesc& r, cudaStream_t s)
             la.keypre = ctx->ld.keypre;
             la.ff_ratio = (r.line_mode == 1) ? 0. : ctx->ff_ratio;
             la.counters = ctx->counters_dev;
+            la.layer_voigt = (const int*)ctx->b_lvoigt.p;
             la.planes = (const double*)ctx->b_planes.p;
             la.lay = (const LayerDev*)ctx->b_layer.p;
-            la.vtmax = (const unsigned long long*)ctx->b_vtmax.p;
             la.absrb = (const double*)ctx->b_absrb.p;
             la.nptabs = nptabs;
             la.nptabs_pad = nptabs_pad;
@@ -477,12 +491,69 @@ static int run_device(mrtm_ctx* ctx, const RunDesc& r, cudaStream_t s)
             la.errflag = ctx->errflag_dev;
             const bool sel = (r.sel_count != nullptr) || (r.sel_hash != nullptr);
             // frequencies per CTA: 128 threads x F (512 on dense grids, smaller tiles for short channel lists)
-            static const int force_nt = std::getenv("MRTM_LINES_NT") ? std::atoi(std::getenv("MRTM_LINES_NT")) : 0;
-            (void)force_nt;
             const int NTsel = 128;                         // 256-thread CTAs measured 4% slower on the dense sweep
             const int F = (nwn >= 2048) ? 4 : ((nwn >= 512) ? 2 : 1);
-            dim3 grid((unsigned)((nwn + NTsel * F - 1) / (NTsel * F)), (unsigned)nlay, (unsigned)nb);
+            const int T0 = NTsel * F;
+            dim3 grid((unsigned)((nwn + T0 - 1) / T0), (unsigned)nlay, (unsigned)nb);
             CU(cudaEventRecord(ctx->ev[2], s));
+            // ---- plans (layer independent) and the upper levels of the far-field hierarchy
+            const int nseg_i = (int)h.segments.size();
+            const int nslot = std::max<int>(1, (int)h.slot_mol.size());
+            int nlev = 1;
+            int64_t ntiles[kMaxLevels], tfreq[kMaxLevels];
+            ntiles[0] = grid.x;
+            tfreq[0] = T0;
+            if (la.ff_ratio > 0.)
+                while (nlev < ctx->ff_levels && ntiles[nlev - 1] > 1) {
+                    tfreq[nlev] = tfreq[nlev - 1] * ctx->ff_S;
+                    ntiles[nlev] = (nwn + tfreq[nlev] - 1) / tfreq[nlev];
+                    nlev++;
+                }
+            la.nlev = nlev;
+            la.S = ctx->ff_S;
+            la.nslot = nslot;
+            for (int lv = 0; lv < nlev; lv++) {
+                if ((rc = ensure(ctx, ctx->b_plan[lv], (size_t)ntiles[lv] * std::max(nseg_i, 1) * sizeof(SegWork)))) return rc;
+                if ((rc = ensure(ctx, ctx->b_hdr[lv], (size_t)ntiles[lv] * sizeof(TileHdr)))) return rc;
+                if (lv >= 1 && (rc = ensure(ctx, ctx->b_coef[lv], (size_t)ntiles[lv] * Lb * nslot * kFarK * 8))) return rc;
+                PlanArgs pl;
+                std::memset(&pl, 0, sizeof pl);
+                pl.nwn = (int32_t)nwn;
+                pl.tile_freqs = (int32_t)tfreq[lv];
+                pl.nseg = nseg_i;
+                pl.wn = r.wn;
+                pl.seg = ctx->seg_dev;
+                pl.xnu0 = ctx->ld.xnu0;
+                pl.sm_max_bits = (const unsigned long long*)ctx->b_vtmax.p;
+                pl.vtmax_seg = (const unsigned long long*)ctx->b_vtmax.p + 1;
+                pl.ff_ratio = la.ff_ratio;
+                pl.out = (SegWork*)ctx->b_plan[lv].p;
+                pl.hdr = (TileHdr*)ctx->b_hdr[lv].p;
+                plan_kernel<<<(unsigned)ntiles[lv], 128, (size_t)std::max(nseg_i, 1) * sizeof(SegWork), s>>>(pl);
+                st.kernel_launches++;
+                la.plan[lv] = (const SegWork*)ctx->b_plan[lv].p;
+                la.hdr[lv] = (const TileHdr*)ctx->b_hdr[lv].p;
+                la.coef[lv] = (const double*)ctx->b_coef[lv].p;
+            }
+            for (int lv = 1; lv < nlev; lv++) {
+                FarArgs fa;
+                std::memset(&fa, 0, sizeof fa);
+                fa.nlay = (int32_t)nlay;
+                fa.nseg = nseg_i;
+                fa.n_pad = n_pad;
+                fa.nslot = nslot;
+                fa.seg = ctx->seg_dev;
+                fa.plan = la.plan[lv];
+                fa.hdr = la.hdr[lv];
+                fa.pplan = (lv + 1 < nlev) ? la.plan[lv + 1] : nullptr;
+                fa.S = ctx->ff_S;
+                fa.planes = la.planes;
+                fa.lay = la.lay;
+                fa.coef = (double*)ctx->b_coef[lv].p;
+                fa.counters = ctx->counters_dev;
+                far_kernel<<<dim3((unsigned)ntiles[lv], (unsigned)nlay, (unsigned)nb), 128, 2 * (size_t)std::max(nseg_i, 1) * sizeof(SegWork), s>>>(fa);
+                st.kernel_launches++;
+            }
             if (F == 4) launch_lines<4, 128>(la, grid, sel, s);
             else if (F == 2) launch_lines<2, 128>(la, grid, sel, s);
             else launch_lines<1, 128>(la, grid, sel, s);

@@ -148,6 +148,53 @@ __device__ __noinline__ double sdvoigt(double deltnu, double alphal, double alph
     return v.re * anorm1;
 }
 
+// Real part of Humlicek region I (modm.f90:1105-1106, s = |x|+y >= 15): Re[t*.5641896/(.5+t*t)], t = (y,-x)
+__device__ __forceinline__ double hum1_re(double x, double y)
+{
+    const double dre = .5 + (y * y - x * x), dim = -2. * (x * y);
+    return (.5641896 * (y * dre - x * dim)) / (dre * dre + dim * dim);
+}
+__device__ __forceinline__ double w4_re(double x, double y)
+{
+    if (!(fabs(x) + y < 15.)) return hum1_re(x, y);
+    return w4(x, y).re;
+}
+
+// The Voigt branch (modm.f90:427-431 -> LSF_SDVOIGT :567-704) for the line classes the line kernel
+// streams: kind 0 generic molecule without coupling (Voigt pedestal at 25 cm-1, :588-599), 1 O2 without
+// coupling (:618-626), 2 O2 XF=-3/-5 (:650-653), 3 O2 XF=-1 first-order mixing (:642-649).
+// Returns STILD*SLS.  Same Humlicek regions and constants as SDVOIGT/W4; the three profile values share
+// one reciprocal of the Doppler width, and the far ones (s >= 15) take region I inline.
+__device__ __noinline__ double voigt_lines_term(int kind, double wn, double xnu, const double* __restrict__ pl, int n_pad, int q,
+                                                double sdep, double rp, double rp2, int* err)
+{
+    const double hw = pl[(size_t)D_H * n_pad + q], ad = pl[(size_t)D_AD * n_pad + q], stild = pl[(size_t)D_STILD * n_pad + q];
+    const double dm = wn - xnu, sp = wn + xnu;
+    const bool second = (kind >= 2) || ((sp - kDELTNUC) <= 0.);
+    double y1 = 1., y2 = 1.;
+    if (kind == 3) {
+        const double aip = pl[(size_t)D_AIP * n_pad + q], bip = pl[(size_t)D_BIP * n_pad + q];
+        y1 = (1. + (aip * (1 / hw) * rp * dm) + (bip * rp2));
+        y2 = (1. - (aip * (1 / hw) * rp * sp) + (bip * rp2));
+    }
+    const double nped = (kind == 0) ? (second ? 2. : 1.) : 0.;
+    const double zeta = hw / (hw + ad);
+    if (fabs(sdep) > 1.0e-4 || !(zeta < 1.0)) {      // speed dependence / degenerate Doppler width: the general routine
+        double sls = y1 * sdvoigt(dm, hw, ad, sdep, err);
+        if (second) sls += y2 * sdvoigt(sp, hw, ad, sdep, err);
+        if (nped != 0.) sls -= nped * sdvoigt(kDELTNUC, hw, ad, sdep, err);
+        return stild * sls;
+    }
+    const double inv = 1. / ad;
+    const double sl2 = 0.8325546111576977;         // sqrt(log(2))
+    const double y = sl2 * (hw * inv);
+    const double anorm = 0.46971863934982516 * inv;       // sqrt(log(2)/PI) with the reference's 13-digit PI
+    double sls = y1 * w4_re(sl2 * (dm * inv), y);
+    if (second) sls += y2 * w4_re(sl2 * (sp * inv), y);
+    if (nped != 0.) sls -= nped * w4_re(sl2 * (kDELTNUC * inv), y);
+    return stild * (sls * anorm);
+}
+
 // XLORENTZ(z)/HWHM: the Lorentz profile with the reference's truncated PI (modm.f90:888-895)
 __device__ __forceinline__ double lorentz_profile(double d, double hwhm)
 {

@@ -35,7 +35,7 @@ struct Segment {          // contiguous run of staged lines of one (molecule, cl
     int32_t cls;
     int32_t begin, end;   // [begin,end) in staged order
     int32_t count_all;    // = end-begin
-    int32_t pad;
+    int32_t slot;         // compact index of the molecule among the molecules that own lines
     uint64_t hash_all;    // sum of line keys (for O2 every line passes modm.f90:384)
     double vfac;          // 100*HWHM_D upper bound factor: vthr <= vfac*sqrt(T)
 };

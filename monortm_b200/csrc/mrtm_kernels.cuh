@@ -59,6 +59,7 @@ struct LayerPrepArgs {
     const int32_t* scor_index;
     double* scorc;             // [L][nsi]
     int* errflag;              // bit0: TIPS range/partition-sum failure
+    unsigned long long* sm_max_bits;   // max over the batch of shift_margin (bits of a non-negative double)
 };
 
 // AtoB, tips_2003.f90:4610-4700 (4-point Lagrange, 3-point at the table ends)
@@ -158,6 +159,7 @@ __global__ void layer_prep_kernel(LayerPrepArgs a)
         sm += sr * a.max_abs_brd_dshift * (1. + 1e-9);
     }
     o.shift_margin = sm;
+    if (a.sm_max_bits) atomicMax(a.sm_max_bits, (unsigned long long)__double_as_longlong(sm));   // sm >= 0
     // CONTNM scalars (P0=1013, T0=296 there: contnm.f90:86)
     {
         const double cp0 = 1013., ct0 = 296., xlosmt = 2.68675E+19;
@@ -336,7 +338,8 @@ struct DeriveArgs {
     double sclcpl, sclhw, y0res;
     int32_t ibrd, pad;
     double* planes;           // [L][D_NPLANES][n_pad]
-    unsigned long long* vtmax; // [L][nseg]: max over the segment of VT (bits of a non-negative double), 0 = no Voigt-capable line
+    unsigned long long* vtmax; // [nseg]: max over the segment and the batch's layers of VT/|Xnu| (bits of a non-negative double), 0 = no Voigt-capable line
+    int* layer_voigt;          // [L] set to 1 when some line of the layer can take the Voigt branch (zeta <= 0.99)
     int32_t nseg, pad2;
 };
 
@@ -448,7 +451,16 @@ __global__ void __launch_bounds__(256) derive_kernel(DeriveArgs a)
     pl[(size_t)D_AD * np + q] = hwhm_d;
     const double vt = (zeta > 0.99) ? -1.0 : 100. * hwhm_d;
     pl[(size_t)D_VT * np + q] = vt;
-    if (vt >= 0.) atomicMax(a.vtmax + (size_t)L * a.nseg + a.ln.segidx[q], (unsigned long long)__double_as_longlong(vt));
+    if (vt >= 0.) {
+        // 100*HWHM_D is proportional to |Xnu| (modm.f90:453): keep the largest ratio per segment; most threads
+        // find the running maximum already at or above their value
+        if (fabs(xnu) > 1e-9) {
+            unsigned long long* addr = a.vtmax + a.ln.segidx[q];
+            const unsigned long long bits = (unsigned long long)__double_as_longlong(vt / fabs(xnu));
+            if (bits > *(volatile unsigned long long*)addr) atomicMax(addr, bits);
+        }
+        if (*(volatile int*)(a.layer_voigt + L) == 0) a.layer_voigt[L] = 1;
+    }
     pl[(size_t)D_STILD * np + q] = stild;
     pl[(size_t)D_AIP * np + q] = aip;
     pl[(size_t)D_BIP * np + q] = bip;
@@ -462,6 +474,9 @@ __global__ void __launch_bounds__(256) derive_kernel(DeriveArgs a)
 // centre (modm.f90:384).  Epilogue fuses RFT (:257), the continuum interpolation + RADFN
 // (:218-230), cloud liquid water (:264) and the total (:265-269).
 // =============================================================================================
+struct SegWork;
+struct TileHdr;
+constexpr int kMaxLevels = 3;   // far-field hierarchy: level 0 = the line kernel's own tiles
 struct LinesArgs {
     int32_t nwn, nlay;            // frequencies in this call/chunk, layers per profile
     int32_t nseg, n_pad;
@@ -477,7 +492,13 @@ struct LinesArgs {
     unsigned long long* counters; // [2] far-field expansions, direct (line,frequency) evaluations (may be null)
     const double* planes;         // [L][D_NPLANES][n_pad]
     const LayerDev* lay;          // [L]
-    const unsigned long long* vtmax;   // [L][nseg]
+    // far-field hierarchy: level 0 = this kernel's tiles, level lv tiles are S^lv times wider
+    int32_t nlev, S;
+    const SegWork* plan[kMaxLevels];    // [ntiles_lv][nseg]
+    const TileHdr* hdr[kMaxLevels];     // [ntiles_lv]
+    const double* coef[kMaxLevels];     // lv >= 1: [tile][L][slot][kFarK] from far_kernel
+    int32_t nslot, pad0;
+    const int* layer_voigt;             // [L] 0: every line of the layer is Lorentz-only (zeta > 0.99)
     // continuum
     const double* absrb;          // [L][3][nptabs_pad]
     int32_t nptabs, nptabs_pad;
@@ -559,6 +580,10 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes)
 {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
 {
     uint32_t done;
@@ -598,7 +623,8 @@ __device__ __forceinline__ double rcp3(double x)
 #define MRTM_PRAGMA(x) _Pragma(#x)
 #define MRTM_UNROLL(n) MRTM_PRAGMA(unroll n)
 constexpr int kTile = 128;      // lines per smem tile
-constexpr int kStages = 8;      // tile ring: up to kStages-1 TMA jobs in flight ahead of the consumer
+constexpr int kStages = 8;      // tile ring
+constexpr int kPrefetch = 5;    // TMA jobs in flight ahead of the consumer; a warp may run kStages-kPrefetch tiles ahead of the slowest
 constexpr int kFarK = 14;       // Taylor terms of the far-field expansion (degree kFarK-1)
 constexpr int kMaxBp = 12;      // break points per segment
 constexpr int kMaxRun = 6;      // direct runs per segment
@@ -609,10 +635,12 @@ constexpr int M_NEG = 2;        // per-(line,frequency) test WN+Xnu <= 25 (modm.
 constexpr int M_VOIGT = 4;      // per-(line,frequency) test |WN-Xnu| <= 100*HWHM_D (modm.f90:427)
 constexpr int M_NEAR = 8;       // direct evaluation (a pole of the line is too close to the tile to expand)
 
-// per-segment work descriptor built once per CTA (in parallel) in shared memory
+// Classification of one (molecule, class) segment against one frequency tile.  It does not depend on
+// the layer: the margins are maxima over the layers of the batch (shift margin, 100*HWHM_D), so one
+// plan serves every layer and every profile of a call.
 struct SegWork {
-    // searched fields, in the order of the prologue tasks (kept contiguous)
-    int q0, q1;        // lines that can be inside the 25 cm-1 window of some frequency of the CTA
+    // searched fields, in the order of the plan tasks (kept contiguous)
+    int q0, q1;        // lines that can be inside the 25 cm-1 window of some frequency of the tile
     int eb, ec;        // [q0,eb) and [ec,q1): window-edge bands
     int n0, n1;        // [n0,n1): band where WN+Xnu<=25 flips; < n0: both resonances for every frequency
     int v0, v1;        // [v0,v1): Voigt zone
@@ -624,12 +652,162 @@ struct SegWork {
     unsigned char mode[kMaxBp];  // mode bits of sub-range u; 0 = far field (Taylor expansion)
     int nrun;                    // maximal runs of consecutive direct (mode != 0) sub-ranges
     int run_lo[kMaxRun], run_hi[kMaxRun], run_t0[kMaxRun], run_nt[kMaxRun];
-    int active;                  // W_species != 0
     int tma;                     // class streams its direct runs through shared memory
     int has_far;
 };
 constexpr int kSegTasks = 11;
+struct TileHdr {
+    double wlo, whi;             // frequency extent of the tile
+};
 
+// =============================================================================================
+// plan_kernel: one CTA per frequency tile of one hierarchy level.  All window / band / near-zone
+// searches of all segments run in parallel (one binary search per thread), then one thread per
+// segment orders the break points, assigns the sub-range modes and the direct runs.
+// =============================================================================================
+struct PlanArgs {
+    int32_t nwn, tile_freqs, nseg, pad;
+    const double* wn;
+    const Segment* seg;
+    const double* xnu0;
+    const unsigned long long* sm_max_bits;    // max shift margin over the layers of the batch (bits of a double)
+    const unsigned long long* vtmax_seg;      // [nseg] max 100*HWHM_D/|Xnu| of Voigt-capable lines (bits), 0 = none
+    double ff_ratio;
+    SegWork* out;                             // [ntiles][nseg]
+    TileHdr* hdr;                             // [ntiles]
+};
+
+__global__ void __launch_bounds__(128) plan_kernel(PlanArgs a)
+{
+    constexpr int NT = 128;
+    extern __shared__ __align__(128) unsigned char s_dyn[];
+    SegWork* s_work = reinterpret_cast<SegWork*>(s_dyn);
+    __shared__ double s_lo[4], s_hi[4];
+    const int tid = threadIdx.x;
+    const int tile = blockIdx.x;
+    const int i0 = tile * a.tile_freqs;
+    const int i1 = min(i0 + a.tile_freqs, a.nwn);
+    double wlo = 1e300, whi = -1e300;
+    for (int i = i0 + tid; i < i1; i += NT) {
+        const double w = a.wn[i];
+        wlo = fmin(wlo, w);
+        whi = fmax(whi, w);
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        wlo = fmin(wlo, __shfl_xor_sync(0xffffffffu, wlo, off));
+        whi = fmax(whi, __shfl_xor_sync(0xffffffffu, whi, off));
+    }
+    if ((tid & 31) == 0) { s_lo[tid >> 5] = wlo; s_hi[tid >> 5] = whi; }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 4; i++) { wlo = fmin(wlo, s_lo[i]); whi = fmax(whi, s_hi[i]); }
+    if (tid == 0) { a.hdr[tile].wlo = wlo; a.hdr[tile].whi = whi; }
+    const double sm = __longlong_as_double((long long)*a.sm_max_bits);
+    const int nseg = a.nseg;
+    const double cen = 0.5 * (wlo + whi), hh = 0.5 * (whi - wlo);
+    const bool ff = a.ff_ratio > 0.;
+    const double Rn = a.ff_ratio * hh;
+
+    for (int task = tid; task < nseg * kSegTasks; task += NT) {
+        const int s = task / kSegTasks, w = task - s * kSegTasks;
+        const Segment sg = a.seg[s];
+        const int cls = sg.cls;
+        const bool tma_cls = (cls == CLS_PED) || (cls == CLS_O2) || (cls == CLS_O2_LC35);
+        const bool exp_cls = tma_cls || (cls == CLS_O2_LC1);      // classes with a far-field path
+        const bool has_win = (cls == CLS_PED) || (cls == CLS_O2) || (cls == CLS_GENERAL && sg.mol != 7);
+        int r;
+        switch (w) {
+        case 0: r = has_win ? lower_bound_d(a.xnu0, sg.begin, sg.end, wlo - kDELTNUC - sm) : sg.begin; break;
+        case 1: r = has_win ? upper_bound_d(a.xnu0, sg.begin, sg.end, whi + kDELTNUC + sm) : sg.end; break;
+        case 2: r = (has_win && tma_cls) ? upper_bound_d(a.xnu0, sg.begin, sg.end, whi - kDELTNUC + sm) : sg.begin; break;
+        case 3: r = (has_win && tma_cls) ? lower_bound_d(a.xnu0, sg.begin, sg.end, wlo + kDELTNUC - sm) : sg.end; break;
+        case 4: r = (has_win && tma_cls) ? lower_bound_d(a.xnu0, sg.begin, sg.end, kDELTNUC - whi - sm) : sg.end; break;
+        case 5: r = (has_win && tma_cls) ? upper_bound_d(a.xnu0, sg.begin, sg.end, kDELTNUC - wlo + sm + 1e-9) : sg.end; break;
+        case 6:
+        case 7: {
+            // Voigt zone: where a frequency can come within max(100*HWHM_D) of a centre (modm.f90:427); the
+            // maximum is over the lines of the segment that are not Lorentz-only (zeta <= 0.99) in some layer
+            const unsigned long long vbits = a.vtmax_seg[s];
+            if (exp_cls && vbits != 0ull) {
+                // 100*HWHM_D <= rate*|Xnu| and a line of the zone has |Xnu| <= max|WN| + 1
+                const double vb = __longlong_as_double((long long)vbits) * (fmax(fabs(wlo), fabs(whi)) + 1.0) * (1. + 1e-9) + sm + 1e-9;
+                r = (w == 6) ? lower_bound_d(a.xnu0, sg.begin, sg.end, wlo - vb) : upper_bound_d(a.xnu0, sg.begin, sg.end, whi + vb);
+            } else {
+                r = sg.begin;      // empty zone after clipping
+            }
+        } break;
+        case 8: r = (ff && exp_cls) ? lower_bound_d(a.xnu0, sg.begin, sg.end, Rn - cen + sm) : sg.end; break;
+        case 9: r = (ff && exp_cls) ? lower_bound_d(a.xnu0, sg.begin, sg.end, cen - Rn - sm) : sg.begin; break;
+        default: r = (ff && exp_cls) ? upper_bound_d(a.xnu0, sg.begin, sg.end, cen + Rn + sm) : sg.end; break;
+        }
+        (&s_work[s].q0)[w] = r;
+    }
+    __syncthreads();
+    for (int s = tid; s < nseg; s += NT) {
+        SegWork& wk = s_work[s];
+        const Segment sg = a.seg[s];
+        const int cls = sg.cls;
+        const bool tma_cls = (cls == CLS_PED) || (cls == CLS_O2) || (cls == CLS_O2_LC35);
+        const bool has_win = tma_cls && (cls != CLS_O2_LC35);
+        const bool force_both = (cls == CLS_O2_LC35) || (cls == CLS_O2_LC1);
+        const int q0 = wk.q0, q1 = wk.q1 > wk.q0 ? wk.q1 : wk.q0;
+        wk.q1 = q1;
+        int c[9] = {wk.eb, wk.ec, wk.n0, wk.n1, wk.v0, wk.v1, wk.z0, wk.f0, wk.f1};
+        for (int i = 0; i < 9; i++) c[i] = c[i] < q0 ? q0 : (c[i] > q1 ? q1 : c[i]);
+        wk.eb = c[0]; wk.ec = c[1]; wk.n0 = c[2]; wk.n1 = c[3]; wk.v0 = c[4]; wk.v1 = c[5];
+        wk.z0 = c[6]; wk.f0 = c[7]; wk.f1 = c[8];
+        for (int i = 1; i < 9; i++) { int v = c[i], j = i - 1; while (j >= 0 && c[j] > v) { c[j + 1] = c[j]; j--; } c[j + 1] = v; }
+        int nbp = 0;
+        wk.bp[nbp++] = q0;
+        for (int i = 0; i < 9; i++) if (c[i] > wk.bp[nbp - 1]) wk.bp[nbp++] = c[i];
+        if (q1 > wk.bp[nbp - 1]) wk.bp[nbp++] = q1;
+        wk.nbp = nbp;
+        wk.tma = tma_cls ? 1 : 0;
+        int nrun = 0, has_far = 0;
+        bool open = false;
+        for (int u = 0; u + 1 < nbp; u++) {
+            const int x = wk.bp[u];
+            int mode = 0;
+            if (has_win && ((x < wk.eb) || (x >= wk.ec))) mode |= M_EDGE;
+            if (has_win && (x >= wk.n0) && (x < wk.n1)) mode |= M_NEG;
+            if ((x >= wk.v0) && (x < wk.v1)) mode |= M_VOIGT;
+            const bool second = force_both || (has_win && x < wk.n1);      // the negative-frequency term can be present
+            if (((x >= wk.f0) && (x < wk.f1)) || (second && x < wk.z0)) mode |= M_NEAR;
+            if (!(tma_cls || cls == CLS_O2_LC1)) mode |= M_NEAR;            // CLS_GENERAL: always direct
+            wk.mode[u] = (unsigned char)mode;
+            if (mode != 0) {
+                if (open) {
+                    wk.run_hi[nrun - 1] = wk.bp[u + 1];
+                } else {
+                    wk.run_lo[nrun] = x;
+                    wk.run_hi[nrun] = wk.bp[u + 1];
+                    nrun++;
+                    open = true;
+                }
+            } else {
+                has_far = 1;
+                open = false;
+            }
+        }
+        for (int r = 0; r < nrun; r++) {
+            wk.run_t0[r] = wk.run_lo[r] & ~3;
+            wk.run_nt[r] = (wk.run_hi[r] - wk.run_t0[r] + kTile - 1) / kTile;
+        }
+        wk.nrun = nrun;
+        wk.has_far = has_far;
+    }
+    __syncthreads();
+    {   // plan -> HBM
+        const int nw = nseg * (int)(sizeof(SegWork) / 4);
+        const int* src = reinterpret_cast<const int*>(s_work);
+        int* dst = reinterpret_cast<int*>(a.out + (size_t)tile * nseg);
+        for (int i = tid; i < nw; i += NT) dst[i] = src[i];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// far field
 // One far-field term: w/((D+t)^2+h2) (+ optional pedestal) expanded in s = t/h about the tile centre,
 //   sum_k b_k s^k,  b_0 = w*u, b_1 = al*b_0, b_k = al*b_{k-1} + be*b_{k-2},  u = 1/(D^2+h2), al = -2*D*h*u, be = -h^2*u.
 // The poles of the term sit at distance sqrt(D^2+h2) >= ratio*h from the centre, so the series converges like ratio^-k.
@@ -668,29 +846,198 @@ __device__ __forceinline__ void far_accum_mix(double D, double h2, double cg, do
     }
 }
 
-// lines_kernel, version 4.  CTA = (NT*F frequencies, one layer, one profile); each thread owns F
+// the far (mode 0) sub-ranges of a segment at this level, minus the ones the parent level already
+// expanded (the parent's far set is a subset of the child's by construction of the margins)
+template <class Fn>
+__device__ __forceinline__ void for_each_far_piece(const SegWork& wk, const SegWork* pk, Fn fn)
+{
+    for (int u = 0; u + 1 < wk.nbp; u++) {
+        if (wk.mode[u] != 0) continue;
+        const int lo = wk.bp[u], hi = wk.bp[u + 1];
+        int cur = lo;
+        if (pk) {
+            for (int v = 0; v + 1 < pk->nbp && cur < hi; v++) {
+                if (pk->mode[v] != 0) continue;
+                const int pa = pk->bp[v], pb = pk->bp[v + 1];
+                if (pb <= cur) continue;
+                if (pa >= hi) break;
+                if (pa > cur) fn(cur, pa, lo);
+                cur = pb > cur ? pb : cur;
+            }
+        }
+        if (cur < hi) fn(cur, hi, lo);
+    }
+}
+
+// Taylor coefficients of the far lines of one segment, one line per thread (coalesced read-only loads,
+// the next line's parameters in flight), accumulated into the thread's A[]
+template <int NT>
+__device__ __forceinline__ void far_pass_segment(const SegWork& wk, const SegWork* pk, int cls, int tid,
+                                                 const double* __restrict__ pXNU, const double* __restrict__ pH2,
+                                                 const double* __restrict__ pA, const double* __restrict__ pB,
+                                                 double cen, double hh, double (&A)[kFarK], long long& n_far)
+{
+    const double m2h = -2. * hh, mhh = -hh * hh;
+    const bool force_both = (cls == CLS_O2_LC35) || (cls == CLS_O2_LC1);
+    const bool mix = (cls == CLS_O2_LC1);
+    for_each_far_piece(wk, pk, [&](int lo, int hi, int sub_lo) {
+        const bool both = force_both || (sub_lo < wk.n0);
+        n_far += (long long)(hi - lo) * (both ? 2 : 1);
+        int q = lo + tid;
+        double xnu = 0., h2 = 1., c3 = 0., c4 = 0.;
+        if (q < hi) { xnu = __ldg(pXNU + q); h2 = __ldg(pH2 + q); c3 = __ldg(pA + q); c4 = __ldg(pB + q); }
+        while (q < hi) {
+            const int qn = q + NT;
+            double xnu_n = 0., h2_n = 1., c3_n = 0., c4_n = 0.;
+            if (qn < hi) { xnu_n = __ldg(pXNU + qn); h2_n = __ldg(pH2 + qn); c3_n = __ldg(pA + qn); c4_n = __ldg(pB + qn); }
+            if (mix) {
+                far_accum_mix(cen - xnu, h2, c3, c4, hh, m2h, mhh, A);
+                far_accum_mix(cen + xnu, h2, c3, -c4, hh, m2h, mhh, A);
+            } else if (both) {
+                far_accum(cen - xnu, h2, c3, c4, m2h, mhh, A);
+                far_accum(cen + xnu, h2, c3, c4, m2h, mhh, A);
+            } else {
+                far_accum(cen - xnu, h2, c3, c4, m2h, mhh, A);
+            }
+            xnu = xnu_n; h2 = h2_n; c3 = c3_n; c4 = c4_n;
+            q = qn;
+        }
+    });
+}
+
+// CTA-wide sums of the per-thread coefficients in a fixed order (deterministic); result in s_coef[kFarK]
+template <int NT>
+__device__ __forceinline__ void reduce_coefs(const double (&A)[kFarK], int tid, double (*s_red)[NT], double (*s_red2)[8], double* s_coef)
+{
+    constexpr int CH = NT / 8;
+#pragma unroll
+    for (int i = 0; i < kFarK; i++) s_red[i][tid] = A[i];
+    __syncthreads();
+    if (tid < kFarK * 8) {
+        const int i = tid >> 3, part = tid & 7;
+        double t = 0.;
+        for (int j = 0; j < CH; j++) t += s_red[i][part * CH + ((j + tid) & (CH - 1))];
+        s_red2[i][part] = t;
+    }
+    __syncthreads();
+    if (tid < kFarK) {
+        double t = 0.;
+#pragma unroll
+        for (int j = 0; j < 8; j++) t += s_red2[tid][j];
+        s_coef[tid] = t;
+    }
+    __syncthreads();
+}
+
+// =============================================================================================
+// far_kernel: hierarchy levels >= 1.  CTA = (level tile, layer, profile).  Expands the lines that are
+// far at this level but not at the parent level and writes, per molecule slot, the kFarK Taylor
+// coefficients about the level tile's centre; lines_kernel adds the polynomial per frequency.
+// =============================================================================================
+struct FarArgs {
+    int32_t nlay, nseg, n_pad, nslot;
+    const Segment* seg;
+    const SegWork* plan;      // [ntiles][nseg] this level
+    const TileHdr* hdr;
+    const SegWork* pplan;     // parent level or null
+    int32_t S, pad;           // tiles of this level per parent tile
+    const double* planes;
+    const LayerDev* lay;
+    double* coef;             // [tile][L][slot][kFarK]
+    unsigned long long* counters;
+};
+
+__global__ void __launch_bounds__(128) far_kernel(FarArgs a)
+{
+    constexpr int NT = 128;
+    extern __shared__ __align__(128) unsigned char s_dyn[];
+    SegWork* s_work = reinterpret_cast<SegWork*>(s_dyn);
+    SegWork* s_pwork = s_work + a.nseg;
+    __shared__ double s_red[kFarK][NT];
+    __shared__ double s_red2[kFarK][8];
+    __shared__ double s_coef[kFarK];
+    const int tid = threadIdx.x;
+    const int tile = blockIdx.x;
+    const int64_t Ltot = (int64_t)gridDim.y * gridDim.z;
+    const int64_t L = (int64_t)blockIdx.z * a.nlay + blockIdx.y;
+    const LayerDev& ly = a.lay[L];
+    const double* pl = a.planes + (size_t)L * D_NPLANES * a.n_pad;
+    const double* __restrict__ pXNU = pl + (size_t)D_XNU * a.n_pad;
+    const double* __restrict__ pH2 = pl + (size_t)D_H2 * a.n_pad;
+    const double* __restrict__ pCN = pl + (size_t)D_CN * a.n_pad;
+    const double* __restrict__ pP3 = pl + (size_t)D_P3 * a.n_pad;
+    const double* __restrict__ pP4 = pl + (size_t)D_P4 * a.n_pad;
+    const int nseg = a.nseg;
+    {
+        const int nw = nseg * (int)(sizeof(SegWork) / 4);
+        const int* src = reinterpret_cast<const int*>(a.plan + (size_t)tile * nseg);
+        int* dst = reinterpret_cast<int*>(s_work);
+        for (int i = tid; i < nw; i += NT) dst[i] = src[i];
+        if (a.pplan) {
+            const int* psrc = reinterpret_cast<const int*>(a.pplan + (size_t)(tile / a.S) * nseg);
+            int* pdst = reinterpret_cast<int*>(s_pwork);
+            for (int i = tid; i < nw; i += NT) pdst[i] = psrc[i];
+        }
+    }
+    __syncthreads();
+    const TileHdr th = a.hdr[tile];
+    const double cen = 0.5 * (th.wlo + th.whi), hh = 0.5 * (th.whi - th.wlo);
+    double* out = a.coef + ((size_t)tile * Ltot + L) * a.nslot * kFarK;
+    long long n_far = 0;
+    int s = 0;
+    while (s < nseg) {
+        const int mol = a.seg[s].mol, slot = a.seg[s].slot;
+        int s_end = s;
+        bool any_far = false;
+        for (; s_end < nseg && a.seg[s_end].mol == mol; s_end++) any_far |= (s_work[s_end].has_far != 0);
+        const bool active = ly.wk[mol - 1] != 0.;
+        if (any_far && active) {
+            double A[kFarK];
+#pragma unroll
+            for (int i = 0; i < kFarK; i++) A[i] = 0.;
+            for (int s2 = s; s2 < s_end; s2++) {
+                if (!s_work[s2].has_far) continue;
+                const int cls2 = a.seg[s2].cls;
+                const bool mix = (cls2 == CLS_O2_LC1);
+                far_pass_segment<NT>(s_work[s2], a.pplan ? &s_pwork[s2] : nullptr, cls2, tid, pXNU, pH2, mix ? pP3 : pCN, mix ? pP4 : pP3,
+                                     cen, hh, A, n_far);
+            }
+            reduce_coefs<NT>(A, tid, s_red, s_red2, s_coef);
+            if (tid < kFarK) out[(size_t)slot * kFarK + tid] = s_coef[tid];
+        } else {
+            if (tid < kFarK) out[(size_t)slot * kFarK + tid] = 0.;
+        }
+        s = s_end;
+    }
+    if (a.counters && tid == 0) atomicAdd(a.counters + 0, (unsigned long long)n_far);
+}
+
+// =============================================================================================
+// lines_kernel, version 5.  CTA = (NT*F frequencies, one layer, one profile); each thread owns F
 // (frequency, layer) accumulators.
-//  * prologue: all window / band / near-zone searches of all segments run in parallel (one per thread)
+//  * the tile's plan (plan_kernel) is copied from HBM: no searches here
 //  * far field: a line whose poles (+-Xnu +- i*HWHM) are at least ff_ratio tile half-widths away from the tile
 //    centre is not evaluated per frequency; its Lorentz terms are expanded in a kFarK-term Taylor series about
 //    the tile centre (one line per thread, coalesced loads), the coefficients are summed over the CTA and every
-//    frequency evaluates the polynomial once per molecule.  Truncation error <= ~(K+1)*ratio^-K of the line's own
-//    contribution (1.6e-13 for ratio 10, K 14).  The window test stays exact: only lines that are inside the
-//    25 cm-1 window of EVERY frequency of the tile (proved with margins) take this path.
+//    frequency evaluates the polynomial once per molecule.  Lines that are already far from the 8x (64x) wider
+//    parent tiles were expanded once per parent tile by far_kernel; their polynomials are added here.
+//    Truncation error <= ~(K+1)*ratio^-K of the line's own contribution (1.6e-13 for ratio 10, K 14).  The
+//    window test stays exact: only lines that are inside the 25 cm-1 window of EVERY frequency of the tile
+//    (proved with margins) take this path.
 //  * near field: line-parameter tiles (XNU, H2, CN, P3) of the remaining runs stream through shared memory with
-//    TMA bulk copies, double buffered on mbarriers, prefetching across runs and segments; interior ranges run
-//    branch-free (4 lines share one reciprocal); the narrow bands (window edges, the WN+Xnu<=25 boundary, the
-//    Voigt zone) run loops specialised per test combination with the reference's exact per-(line,frequency)
-//    tests (modm.f90:384, 427, 746)
+//    TMA bulk copies on an 8-stage mbarrier ring; interior ranges run branch-free (4 lines share one
+//    reciprocal); the narrow bands (window edges, the WN+Xnu<=25 boundary, the Voigt zone) run loops
+//    specialised per test combination with the reference's exact per-(line,frequency) tests (modm.f90:384, 427, 746)
+// =============================================================================================
 template <int F, bool SEL, int NT>
 __global__ void __launch_bounds__(NT, (MRTM_LINES_MINB * 128) / NT) lines_kernel(LinesArgs a)
 {
     constexpr int NW = NT / 32;
-    constexpr int CH = NT / 8;                    // chunk of the two-stage coefficient reduction
     const int tid = threadIdx.x;
     const int k = blockIdx.y;                     // layer within profile
     const int prof = blockIdx.z;
     const int64_t L = (int64_t)prof * a.nlay + k;
+    const int64_t Ltot = (int64_t)gridDim.y * gridDim.z;
     const LayerDev& ly = a.lay[L];
     const double* pl = a.planes + (size_t)L * D_NPLANES * a.n_pad;
     const double* __restrict__ pXNU = pl + (size_t)D_XNU * a.n_pad;
@@ -700,149 +1047,58 @@ __global__ void __launch_bounds__(NT, (MRTM_LINES_MINB * 128) / NT) lines_kernel
     const double* __restrict__ pP4 = pl + (size_t)D_P4 * a.n_pad;
     const double* __restrict__ pVT = pl + (size_t)D_VT * a.n_pad;
 
-    __shared__ __align__(8) uint64_t s_bar[kStages];
-    __shared__ double s_lo[NW], s_hi[NW];
-    __shared__ double s_ped[2][NW];
+    __shared__ __align__(8) uint64_t s_bar[kStages];      // stage filled (TMA transaction bytes)
+    __shared__ __align__(8) uint64_t s_empty[kStages];    // stage released (one arrival per warp)
     __shared__ double s_red[kFarK][NT];
     __shared__ double s_red2[kFarK][8];
     __shared__ double s_coef[kFarK];
+    __shared__ unsigned char s_act[kMaxSegments];
     extern __shared__ __align__(128) unsigned char s_dyn[];
     double (*s_tile)[4][kTile] = reinterpret_cast<double (*)[4][kTile]>(s_dyn);      // [kStages][4][kTile]
     SegWork* s_work = reinterpret_cast<SegWork*>(s_dyn + sizeof(double) * kStages * 4 * kTile);
+    SegWork* s_pwork = s_work + a.nseg;           // parent level's plan (a.nlev > 1)
+
+    const int nseg = a.nseg;
+    {
+        const int nw = nseg * (int)(sizeof(SegWork) / 4);
+        const int* src = reinterpret_cast<const int*>(a.plan[0] + (size_t)blockIdx.x * nseg);
+        int* dst = reinterpret_cast<int*>(s_work);
+        for (int i = tid; i < nw; i += NT) dst[i] = src[i];
+        if (a.nlev > 1) {
+            const int* psrc = reinterpret_cast<const int*>(a.plan[1] + (size_t)(blockIdx.x / a.S) * nseg);
+            int* pdst = reinterpret_cast<int*>(s_pwork);
+            for (int i = tid; i < nw; i += NT) pdst[i] = psrc[i];
+        }
+        for (int s = tid; s < nseg; s += NT) s_act[s] = (ly.wk[a.seg[s].mol - 1] != 0.) ? 1 : 0;   // W_SPECIES == 0: skipped (:318-321)
+    }
+    if (tid == 0) {
+        for (int i = 0; i < kStages; i++) { mbar_init(&s_bar[i], 1); mbar_init(&s_empty[i], NW); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
 
     // this thread's frequencies (strided so global accesses coalesce)
     const int base = blockIdx.x * (NT * F);
     double wn[F];
     bool valid[F];
-    double wlo = 1e300, whi = -1e300;
 #pragma unroll
     for (int f = 0; f < F; f++) {
         int iw = base + f * NT + tid;
         valid[f] = iw < a.nwn;
         wn[f] = a.wn[valid[f] ? iw : (a.nwn - 1)];
-        wlo = fmin(wlo, wn[f]);
-        whi = fmax(whi, wn[f]);
     }
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) {
-        wlo = fmin(wlo, __shfl_xor_sync(0xffffffffu, wlo, off));
-        whi = fmax(whi, __shfl_xor_sync(0xffffffffu, whi, off));
-    }
-    if ((tid & 31) == 0) { s_lo[tid >> 5] = wlo; s_hi[tid >> 5] = whi; }
-    if (tid == 0) {
-        for (int i = 0; i < kStages; i++) mbar_init(&s_bar[i], 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
-#pragma unroll
-    for (int i = 0; i < NW; i++) { wlo = fmin(wlo, s_lo[i]); whi = fmax(whi, s_hi[i]); }
-    const double sm = ly.shift_margin;
     const double rp = ly.rp, rp2 = ly.rp2;
-    const int nseg = a.nseg;
     // tile centre / half width (CTA uniform): expansion variable s = (WN - cen)/hh in [-1,1]
-    const double cen = 0.5 * (wlo + whi), hh = 0.5 * (whi - wlo);
+    const TileHdr th = a.hdr[0][blockIdx.x];
+    const double cen = 0.5 * (th.wlo + th.whi), hh = 0.5 * (th.whi - th.wlo);
     const double hinv = hh > 0. ? 1. / hh : 0.;
-    const bool ff = a.ff_ratio > 0.;
-    const double Rn = a.ff_ratio * hh;
-
-    // ---- prologue: one binary search per thread over (segment, field) tasks ----------------------
-    for (int task = tid; task < nseg * kSegTasks; task += NT) {
-        const int s = task / kSegTasks, w = task - s * kSegTasks;
-        const Segment sg = a.seg[s];
-        const int cls = sg.cls;
-        const bool tma_cls = (cls == CLS_PED) || (cls == CLS_O2) || (cls == CLS_O2_LC35);
-        const bool exp_cls = tma_cls || (cls == CLS_O2_LC1);      // classes with a far-field path
-        const bool has_win = (cls == CLS_PED) || (cls == CLS_O2) || (cls == CLS_GENERAL && sg.mol != 7);
-        int r;
-        switch (w) {
-        case 0: r = has_win ? lower_bound_d(a.xnu0, sg.begin, sg.end, wlo - kDELTNUC - sm) : sg.begin; break;
-        case 1: r = has_win ? upper_bound_d(a.xnu0, sg.begin, sg.end, whi + kDELTNUC + sm) : sg.end; break;
-        case 2: r = (has_win && tma_cls) ? upper_bound_d(a.xnu0, sg.begin, sg.end, whi - kDELTNUC + sm) : sg.begin; break;
-        case 3: r = (has_win && tma_cls) ? lower_bound_d(a.xnu0, sg.begin, sg.end, wlo + kDELTNUC - sm) : sg.end; break;
-        case 4: r = (has_win && tma_cls) ? lower_bound_d(a.xnu0, sg.begin, sg.end, kDELTNUC - whi - sm) : sg.end; break;
-        case 5: r = (has_win && tma_cls) ? upper_bound_d(a.xnu0, sg.begin, sg.end, kDELTNUC - wlo + sm + 1e-9) : sg.end; break;
-        case 6:
-        case 7: {
-            // Voigt zone: where a frequency can come within max(100*HWHM_D) of a centre (modm.f90:427); the
-            // maximum is over the lines of this (layer, segment) that are not Lorentz-only (zeta <= 0.99)
-            const unsigned long long vbits = a.vtmax[(size_t)L * nseg + s];
-            if (exp_cls && vbits != 0ull) {
-                const double vb = __longlong_as_double((long long)vbits) * (1. + 1e-12) + sm + 1e-9;
-                r = (w == 6) ? lower_bound_d(a.xnu0, sg.begin, sg.end, wlo - vb) : upper_bound_d(a.xnu0, sg.begin, sg.end, whi + vb);
-            } else {
-                r = sg.begin;      // empty zone after clipping
-            }
-        } break;
-        case 8: r = (ff && exp_cls) ? lower_bound_d(a.xnu0, sg.begin, sg.end, Rn - cen + sm) : sg.end; break;
-        case 9: r = (ff && exp_cls) ? lower_bound_d(a.xnu0, sg.begin, sg.end, cen - Rn - sm) : sg.begin; break;
-        default: r = (ff && exp_cls) ? upper_bound_d(a.xnu0, sg.begin, sg.end, cen + Rn + sm) : sg.end; break;
-        }
-        (&s_work[s].q0)[w] = r;
-    }
-    __syncthreads();
-    for (int s = tid; s < nseg; s += NT) {
-        SegWork& wk = s_work[s];
-        const Segment sg = a.seg[s];
-        const int cls = sg.cls;
-        const bool tma_cls = (cls == CLS_PED) || (cls == CLS_O2) || (cls == CLS_O2_LC35);
-        const bool has_win = tma_cls && (cls != CLS_O2_LC35);
-        const bool force_both = (cls == CLS_O2_LC35) || (cls == CLS_O2_LC1);
-        const int q0 = wk.q0, q1 = wk.q1 > wk.q0 ? wk.q1 : wk.q0;
-        wk.q1 = q1;
-        int c[9] = {wk.eb, wk.ec, wk.n0, wk.n1, wk.v0, wk.v1, wk.z0, wk.f0, wk.f1};
-        for (int i = 0; i < 9; i++) c[i] = c[i] < q0 ? q0 : (c[i] > q1 ? q1 : c[i]);
-        wk.eb = c[0]; wk.ec = c[1]; wk.n0 = c[2]; wk.n1 = c[3]; wk.v0 = c[4]; wk.v1 = c[5];
-        wk.z0 = c[6]; wk.f0 = c[7]; wk.f1 = c[8];
-        for (int i = 1; i < 9; i++) { int v = c[i], j = i - 1; while (j >= 0 && c[j] > v) { c[j + 1] = c[j]; j--; } c[j + 1] = v; }
-        int nbp = 0;
-        wk.bp[nbp++] = q0;
-        for (int i = 0; i < 9; i++) if (c[i] > wk.bp[nbp - 1]) wk.bp[nbp++] = c[i];
-        if (q1 > wk.bp[nbp - 1]) wk.bp[nbp++] = q1;
-        wk.nbp = nbp;
-        wk.active = (ly.wk[sg.mol - 1] != 0.) ? 1 : 0;           // W_SPECIES == 0: molecule skipped (:318-321)
-        wk.tma = tma_cls ? 1 : 0;
-        // modes and direct runs
-        int nrun = 0, has_far = 0;
-        bool open = false;
-        for (int u = 0; u + 1 < nbp; u++) {
-            const int x = wk.bp[u];
-            int mode = 0;
-            if (has_win && ((x < wk.eb) || (x >= wk.ec))) mode |= M_EDGE;
-            if (has_win && (x >= wk.n0) && (x < wk.n1)) mode |= M_NEG;
-            if ((x >= wk.v0) && (x < wk.v1)) mode |= M_VOIGT;
-            const bool second = force_both || (has_win && x < wk.n1);      // the negative-frequency term can be present
-            if (((x >= wk.f0) && (x < wk.f1)) || (second && x < wk.z0)) mode |= M_NEAR;
-            if (!(tma_cls || cls == CLS_O2_LC1)) mode |= M_NEAR;            // CLS_GENERAL: always direct
-            wk.mode[u] = (unsigned char)mode;
-            if (mode != 0) {
-                if (open) {
-                    wk.run_hi[nrun - 1] = wk.bp[u + 1];
-                } else {
-                    wk.run_lo[nrun] = x;
-                    wk.run_hi[nrun] = wk.bp[u + 1];
-                    nrun++;
-                    open = true;
-                }
-            } else {
-                has_far = 1;
-                open = false;
-            }
-        }
-        for (int r = 0; r < nrun; r++) {
-            wk.run_t0[r] = wk.run_lo[r] & ~3;
-            wk.run_nt[r] = (wk.run_hi[r] - wk.run_t0[r] + kTile - 1) / kTile;
-        }
-        wk.nrun = (wk.active) ? nrun : 0;
-        wk.has_far = (wk.active) ? has_far : 0;
-    }
     __syncthreads();
 
-    // ---- TMA tile jobs: (segment, run, tile) in consumption order; thread 0 keeps a cursor one job ahead
+    // ---- TMA tile jobs: (segment, run, tile) in consumption order; thread 0 keeps a cursor ahead of the consumer
     auto advance = [&](int& js, int& jr, int& jt) -> bool {
         jt++;
         while (js < nseg) {
             const SegWork& w = s_work[js];
-            if (w.tma && jr < w.nrun) {
+            if (w.tma && s_act[js] && jr < w.nrun) {
                 if (jt < w.run_nt[jr]) return true;
                 jr++;
                 jt = 0;
@@ -868,13 +1124,12 @@ __global__ void __launch_bounds__(NT, (MRTM_LINES_MINB * 128) / NT) lines_kernel
     int pjs = 0, pjr = 0, pjt = -1;      // prefetch cursor (thread 0 only)
     bool more = true;
     if (tid == 0) {
-        for (int i = 0; i < kStages - 1 && more; i++) {
+        for (int i = 0; i < kPrefetch && more; i++) {
             more = advance(pjs, pjr, pjt);
             if (more) issue(pjs, pjr, pjt, i);
         }
     }
 
-    int ped_buf = 0;            // alternates per tile over the whole kernel (s_ped double buffer)
     int gtile = 0;              // global tile counter: stage = gtile % kStages, mbarrier parity = (gtile / kStages) & 1
 
     double osum[F], sf[F];
@@ -887,7 +1142,8 @@ __global__ void __launch_bounds__(NT, (MRTM_LINES_MINB * 128) / NT) lines_kernel
     for (int f = 0; f < F; f++) rft[f] = wn[f] * tanh((ly.radct * wn[f]) / (2 * ly.t));   // modm.f90:257
 
     int err = 0;
-    int cur_mol = 0;
+    // a layer without Voigt-capable lines runs its Voigt zones as plain near-field ranges
+    const int vmode_mask = a.layer_voigt[L] ? 0xff : (0xff & ~M_VOIGT);
     long long n_far = 0, n_direct = 0;      // work counters (thread 0 reports them)
     int nvalid = 0;
     if (a.counters) {
@@ -909,283 +1165,285 @@ __global__ void __launch_bounds__(NT, (MRTM_LINES_MINB * 128) / NT) lines_kernel
         }
     };
 
-    // slow path shared by the predicated loops: the Voigt branch of modm.f90:427-431
-    auto voigt_term = [&](int mol, int q, double w, double xnu) -> double {
-        double sls = lsf_general(mol, a.xf_s[q], rp, rp2, pl[(size_t)D_AIP * a.n_pad + q], pl[(size_t)D_BIP * a.n_pad + q],
-                                 pl[(size_t)D_H * a.n_pad + q], w, xnu, pl[(size_t)D_AD * a.n_pad + q], a.sdep_s[q], true, &err);
-        return pl[(size_t)D_STILD * a.n_pad + q] * sls;
-    };
-
-    for (int s = 0; s < nseg; s++) {
-        const Segment sg = a.seg[s];
-        if (sg.mol != cur_mol) {
-            finish_mol(cur_mol);
-            cur_mol = sg.mol;
-            // ---- far field of every segment of this molecule ---------------------------------------
-            bool any_far = false;
-            int s_end = s;
-            for (; s_end < nseg && a.seg[s_end].mol == cur_mol; s_end++) any_far |= (s_work[s_end].has_far != 0);
-            if (any_far) {
-                double A[kFarK];
+    // ---- molecules in order; per molecule: near field (direct) of its segments, far field, one CTA reduction
+    int s = 0;
+    while (s < nseg) {
+        const int mol = a.seg[s].mol, slot = a.seg[s].slot;
+        int s_end = s;
+        bool any_far = false, any_run = false;
+        for (; s_end < nseg && a.seg[s_end].mol == mol; s_end++) {
+            any_far |= (s_work[s_end].has_far != 0);
+            any_run |= (s_work[s_end].nrun != 0);
+        }
+        if (!s_act[s]) {            // W_SPECIES == 0: molecule skipped (modm.f90:318-321)
+            finish_mol(mol);
+            s = s_end;
+            continue;
+        }
+        double pmine = 0.;          // this thread's share of the pedestals of the interior direct ranges
+        for (int sd = s; sd < s_end; sd++) {
+            const Segment sg = a.seg[sd];
+            const SegWork& wk = s_work[sd];
+            const int cls = sg.cls;
+            if (SEL && sg.mol == 7) {                          // every O2 line passes modm.f90:384
 #pragma unroll
-                for (int i = 0; i < kFarK; i++) A[i] = 0.;
-                const double m2h = -2. * hh, mhh = -hh * hh;
-                for (int s2 = s; s2 < s_end; s2++) {
-                    const SegWork& wk = s_work[s2];
-                    if (!wk.has_far) continue;
-                    const int cls2 = a.seg[s2].cls;
-                    const bool force_both = (cls2 == CLS_O2_LC35) || (cls2 == CLS_O2_LC1);
-                    const bool count_sel = SEL && (cls2 == CLS_PED);
-                    for (int u = 0; u + 1 < wk.nbp; u++) {
-                        if (wk.mode[u] != 0) continue;
-                        const int lo = wk.bp[u], hi = wk.bp[u + 1];
-                        const bool both = force_both || (lo < wk.n0);
-                        if (count_sel) {
-                            const unsigned long long hs = a.keypre[hi] - a.keypre[lo];
+                for (int f = 0; f < F; f++) { cnt[f] += sg.count_all; hsh[f] += sg.hash_all; }
+            }
+            if (cls == CLS_PED || cls == CLS_O2 || cls == CLS_O2_LC35) {
+                const bool force_both = (cls == CLS_O2_LC35);
+                const bool count_sel = SEL && (cls == CLS_PED);
+                const int n0 = wk.n0;
+                const int nsub = wk.nbp - 1;
+                double psum[F];
 #pragma unroll
-                            for (int f = 0; f < F; f++) { cnt[f] += hi - lo; hsh[f] += hs; }
-                        }
-                        if (a.counters) n_far += (long long)(hi - lo) * (both ? 2 : 1);
-                        // one line per thread, coalesced read-only loads, next line's parameters in flight
-                        int q = lo + tid;
-                        double xnu = 0., h2 = 1., c3 = 0., c4 = 0.;
-                        const double* __restrict__ pA = (cls2 == CLS_O2_LC1) ? pP3 : pCN;
-                        const double* __restrict__ pB = (cls2 == CLS_O2_LC1) ? pP4 : pP3;
-                        if (q < hi) { xnu = __ldg(pXNU + q); h2 = __ldg(pH2 + q); c3 = __ldg(pA + q); c4 = __ldg(pB + q); }
-                        while (q < hi) {
-                            const int qn = q + NT;
-                            double xnu_n = 0., h2_n = 1., c3_n = 0., c4_n = 0.;
-                            if (qn < hi) { xnu_n = __ldg(pXNU + qn); h2_n = __ldg(pH2 + qn); c3_n = __ldg(pA + qn); c4_n = __ldg(pB + qn); }
-                            if (cls2 == CLS_O2_LC1) {
-                                far_accum_mix(cen - xnu, h2, c3, c4, hh, m2h, mhh, A);
-                                far_accum_mix(cen + xnu, h2, c3, -c4, hh, m2h, mhh, A);
-                            } else if (both) {
-                                far_accum(cen - xnu, h2, c3, c4, m2h, mhh, A);
-                                far_accum(cen + xnu, h2, c3, c4, m2h, mhh, A);
-                            } else {
-                                far_accum(cen - xnu, h2, c3, c4, m2h, mhh, A);
+                for (int f = 0; f < F; f++) psum[f] = 0.;
+                for (int r = 0; r < wk.nrun; r++) {
+                    const int rlo = wk.run_lo[r], rhi = wk.run_hi[r], t0 = wk.run_t0[r], ntile = wk.run_nt[r];
+                    for (int t = 0; t < ntile; t++, gtile++) {
+                        const int st = gtile % kStages;
+                        if (tid == 0 && more) {        // keep kPrefetch jobs in flight
+                            more = advance(pjs, pjr, pjt);
+                            if (more) {
+                                const int gj = gtile + kPrefetch, sj = gj % kStages;
+                                if (gj >= kStages) mbar_wait(&s_empty[sj], (uint32_t)(gj / kStages - 1) & 1u);   // every warp left tile gj-kStages
+                                issue(pjs, pjr, pjt, sj);
                             }
-                            xnu = xnu_n; h2 = h2_n; c3 = c3_n; c4 = c4_n;
-                            q = qn;
+                        }
+                        mbar_wait(&s_bar[st], (uint32_t)(gtile / kStages) & 1u);
+                        const double* __restrict__ tX = s_tile[st][0];
+                        const double* __restrict__ tH = s_tile[st][1];
+                        const double* __restrict__ tC = s_tile[st][2];
+                        const double* __restrict__ tP = s_tile[st][3];
+                        const int tb = t0 + t * kTile;
+                        const int tlo = tb > rlo ? tb : rlo;
+                        const int thi = (tb + kTile) < rhi ? (tb + kTile) : rhi;
+                        for (int u = 0; u < nsub; u++) {
+                            const int x = wk.bp[u];
+                            const int mode = wk.mode[u] & vmode_mask;
+                            int lo = x > tlo ? x : tlo;
+                            int hi = wk.bp[u + 1] < thi ? wk.bp[u + 1] : thi;
+                            if (lo >= hi || wk.mode[u] == 0) continue;
+                            const bool negall = force_both || (x < n0);
+                            if (a.counters) n_direct += (long long)(hi - lo) * nvalid;
+                            if ((mode & 7) != 0) {
+                                // ---- band loops: the reference's exact per-(line,frequency) tests
+                                const bool edge = (mode & M_EDGE) != 0, negtest = (mode & M_NEG) != 0, vz = (mode & M_VOIGT) != 0;
+                                if (!vz) {
+                                    if (negall || negtest) {
+                                        for (int q = lo; q < hi; q++) {
+                                            const int j = q - tb;
+                                            const double xnu = tX[j], h2 = tH[j], cn = tC[j], ped = tP[j];
+#pragma unroll
+                                            for (int f = 0; f < F; f++) {
+                                                const double dm = wn[f] - xnu, sp = wn[f] + xnu;
+                                                const bool inwin = edge ? !(fabs(dm) > kDELTNUC) : true;
+                                                if (count_sel && inwin) { cnt[f]++; hsh[f] += a.key[q]; }
+                                                const bool neg = negall || (sp <= kDELTNUC);
+                                                const double r1 = rcp3(fma(dm, dm, h2)), r2 = rcp3(fma(sp, sp, h2));
+                                                const double val = cn * (r1 + (neg ? r2 : 0.)) - (neg ? 2. * ped : ped);
+                                                sf[f] += inwin ? val : 0.;
+                                            }
+                                        }
+                                    } else {
+                                        for (int q = lo; q < hi; q++) {
+                                            const int j = q - tb;
+                                            const double xnu = tX[j], h2 = tH[j], cn = tC[j], ped = tP[j];
+#pragma unroll
+                                            for (int f = 0; f < F; f++) {
+                                                const double dm = wn[f] - xnu;
+                                                const bool inwin = !(fabs(dm) > kDELTNUC);
+                                                if (count_sel && inwin) { cnt[f]++; hsh[f] += a.key[q]; }
+                                                const double val = fma(cn, rcp3(fma(dm, dm, h2)), -ped);
+                                                sf[f] += inwin ? val : 0.;
+                                            }
+                                        }
+                                    }
+                                    continue;
+                                }
+                                const int vkind = (cls == CLS_PED) ? 0 : ((cls == CLS_O2) ? 1 : 2);
+                                for (int q = lo; q < hi; q++) {
+                                    const int j = q - tb;
+                                    const double xnu = tX[j], h2 = tH[j], cn = tC[j], ped = tP[j];
+                                    const double vt = __ldg(pVT + q);
+                                    unsigned vmask = 0u;
+#pragma unroll
+                                    for (int f = 0; f < F; f++) {
+                                        const double dm = wn[f] - xnu, sp = wn[f] + xnu;
+                                        const bool inwin = edge ? !(fabs(dm) > kDELTNUC) : true;
+                                        if (count_sel && inwin) { cnt[f]++; hsh[f] += a.key[q]; }
+                                        const bool isv = inwin && (fabs(dm) <= vt);
+                                        const bool neg = negall || (negtest && (sp <= kDELTNUC));
+                                        const double r1 = rcp3(fma(dm, dm, h2)), r2 = rcp3(fma(sp, sp, h2));
+                                        const double val = cn * (r1 + (neg ? r2 : 0.)) - (neg ? 2. * ped : ped);
+                                        sf[f] += (inwin && !isv) ? val : 0.;
+                                        vmask |= isv ? (1u << f) : 0u;
+                                    }
+                                    if (vmask) {                    // Voigt branch of modm.f90:427-431
+#pragma unroll
+                                        for (int f = 0; f < F; f++)
+                                            if (vmask & (1u << f)) sf[f] += voigt_lines_term(vkind, wn[f], xnu, pl, a.n_pad, q, a.sdep_s[q], rp, rp2, &err);
+                                    }
+                                }
+                                continue;
+                            }
+                            if (count_sel) {
+                                const unsigned long long hs = a.keypre[hi] - a.keypre[lo];
+#pragma unroll
+                                for (int f = 0; f < F; f++) { cnt[f] += hi - lo; hsh[f] += hs; }
+                            }
+                            // this thread's share of the interior pedestals (summed over the CTA with the far-field coefficients)
+                            {
+                                const double w = negall ? 2. : 1.;          // pedestal counted for both resonances (:749)
+                                for (int q = lo + tid; q < hi; q += NT) pmine = fma(w, tP[q - tb], pmine);
+                            }
+                            if (negall) {
+                                // ---- interior, both resonances: cn*(1/a+1/b) = cn*(a+b)/(a*b), one reciprocal
+MRTM_UNROLL(MRTM_UNROLL_BOTH)
+                                for (int q = lo; q < hi; q++) {
+                                    const int j = q - tb;
+                                    const double xnu = tX[j], h2 = tH[j], cn = tC[j];
+#pragma unroll
+                                    for (int f = 0; f < F; f++) {
+                                        const double dm = wn[f] - xnu, sp = wn[f] + xnu;
+                                        const double aa = fma(dm, dm, h2), bb = fma(sp, sp, h2);
+                                        const double r = rcp3(aa * bb);
+                                        psum[f] = fma(cn * (aa + bb), r, psum[f]);
+                                    }
+                                }
+                            } else {
+                                // ---- interior, single resonance (modm.f90:751): four lines share one reciprocal,
+                                // sum c_i/a_i = N/(a1 a2 a3 a4), N = (c1 a2 + c2 a1)(a3 a4) + (c3 a4 + c4 a3)(a1 a2);
+                                // 21 FP64 ops + 1 MUFU per 4 evaluations
+                                int q = lo;
+                                for (; q + 4 <= hi; q += 4) {
+                                    const int j = q - tb;
+                                    const double x1 = tX[j], x2 = tX[j + 1], x3 = tX[j + 2], x4 = tX[j + 3];
+                                    const double g1 = tH[j], g2 = tH[j + 1], g3 = tH[j + 2], g4 = tH[j + 3];
+                                    const double c1 = tC[j], c2 = tC[j + 1], c3 = tC[j + 2], c4 = tC[j + 3];
+#pragma unroll
+                                    for (int f = 0; f < F; f++) {
+                                        const double d1 = wn[f] - x1, d2 = wn[f] - x2, d3 = wn[f] - x3, d4 = wn[f] - x4;
+                                        const double a1 = fma(d1, d1, g1), a2 = fma(d2, d2, g2);
+                                        const double a3 = fma(d3, d3, g3), a4 = fma(d4, d4, g4);
+                                        const double p12 = a1 * a2, p34 = a3 * a4;
+                                        const double n12 = fma(c1, a2, c2 * a1), n34 = fma(c3, a4, c4 * a3);
+                                        const double r = rcp3(p12 * p34);
+                                        psum[f] = fma(fma(n12, p34, n34 * p12), r, psum[f]);
+                                    }
+                                }
+                                for (; q < hi; q++) {
+                                    const int j = q - tb;
+                                    const double xnu = tX[j], h2 = tH[j], cn = tC[j];
+#pragma unroll
+                                    for (int f = 0; f < F; f++) {
+                                        const double dm = wn[f] - xnu;
+                                        psum[f] = fma(cn, rcp3(fma(dm, dm, h2)), psum[f]);
+                                    }
+                                }
+                            }
+                        }
+                        // this warp has finished reading the stage
+                        __syncwarp();
+                        if ((tid & 31) == 0) mbar_arrive(&s_empty[st]);
+                    }
+                }
+#pragma unroll
+                for (int f = 0; f < F; f++) sf[f] += psum[f];
+            } else if (cls == CLS_O2_LC1) {
+                for (int r = 0; r < wk.nrun; r++) {
+                    if (a.counters) n_direct += (long long)(wk.run_hi[r] - wk.run_lo[r]) * nvalid;
+                    for (int q = wk.run_lo[r]; q < wk.run_hi[r]; q++) {
+                        const double xnu = pXNU[q], h2 = pH2[q], cg = pP3[q], cq = pP4[q], vt = pVT[q];
+#pragma unroll
+                        for (int f = 0; f < F; f++) {
+                            const double dm = wn[f] - xnu, sp = wn[f] + xnu;
+                            if (fabs(dm) <= vt) {
+                                sf[f] += voigt_lines_term(3, wn[f], xnu, pl, a.n_pad, q, a.sdep_s[q], rp, rp2, &err);
+                            } else {
+                                const double r1 = rcp3(fma(dm, dm, h2));
+                                const double r2 = rcp3(fma(sp, sp, h2));
+                                sf[f] += fma(cq, dm, cg) * r1 + fma(-cq, sp, cg) * r2;
+                            }
                         }
                     }
                 }
-                // CTA-wide sums of the coefficients in a fixed order (deterministic)
+            } else {   // CLS_GENERAL: faithful case tree per (line, frequency)
+                if (a.counters) n_direct += (long long)(wk.q1 - wk.q0) * nvalid;
+                for (int q = wk.q0; q < wk.q1; q++) {
+                    const double xnu = pXNU[q], vt = pVT[q];
+                    const double hw = pl[(size_t)D_H * a.n_pad + q], ad = pl[(size_t)D_AD * a.n_pad + q];
+                    const double st = pl[(size_t)D_STILD * a.n_pad + q];
+                    const double aip = pl[(size_t)D_AIP * a.n_pad + q], bip = pl[(size_t)D_BIP * a.n_pad + q];
+                    const int xf = a.xf_s[q];
 #pragma unroll
-                for (int i = 0; i < kFarK; i++) s_red[i][tid] = A[i];
-                __syncthreads();
-                if (tid < kFarK * 8) {
-                    const int i = tid >> 3, part = tid & 7;
-                    double t = 0.;
-                    for (int j = 0; j < CH; j++) t += s_red[i][part * CH + ((j + tid) & (CH - 1))];
-                    s_red2[i][part] = t;
+                    for (int f = 0; f < F; f++) {
+                        const double dm = wn[f] - xnu;
+                        if ((fabs(dm) > kDELTNUC) && (sg.mol != 7)) continue;          // modm.f90:384
+                        if (SEL && sg.mol != 7) { cnt[f]++; hsh[f] += a.key[q]; }
+                        const bool voigt = fabs(dm) <= vt;
+                        sf[f] += st * lsf_general(sg.mol, xf, rp, rp2, aip, bip, hw, wn[f], xnu, ad, a.sdep_s[q], voigt, &err);
+                    }
                 }
-                __syncthreads();
-                if (tid < kFarK) {
-                    double t = 0.;
+            }
+        }
+        // ---- far field of every segment of this molecule; the interior pedestals ride on coefficient 0
+        if (any_far || any_run) {
+            double A[kFarK];
 #pragma unroll
-                    for (int j = 0; j < 8; j++) t += s_red2[tid][j];
-                    s_coef[tid] = t;
+            for (int i = 0; i < kFarK; i++) A[i] = 0.;
+            A[0] = -pmine;
+            for (int s2 = s; s2 < s_end; s2++) {
+                const SegWork& wk = s_work[s2];
+                if (!wk.has_far) continue;
+                const int cls2 = a.seg[s2].cls;
+                const bool mix = (cls2 == CLS_O2_LC1);
+                if (SEL && cls2 == CLS_PED) {       // every far line (any level) is inside the window of every frequency
+                    for (int u = 0; u + 1 < wk.nbp; u++) {
+                        if (wk.mode[u] != 0) continue;
+                        const int lo = wk.bp[u], hi = wk.bp[u + 1];
+                        const unsigned long long hs = a.keypre[hi] - a.keypre[lo];
+#pragma unroll
+                        for (int f = 0; f < F; f++) { cnt[f] += hi - lo; hsh[f] += hs; }
+                    }
                 }
-                __syncthreads();
+                far_pass_segment<NT>(wk, a.nlev > 1 ? &s_pwork[s2] : nullptr, cls2, tid, pXNU, pH2, mix ? pP3 : pCN, mix ? pP4 : pP3,
+                                     cen, hh, A, n_far);
+            }
+            reduce_coefs<NT>(A, tid, s_red, s_red2, s_coef);
+#pragma unroll
+            for (int f = 0; f < F; f++) {
+                const double sv = (wn[f] - cen) * hinv;
+                double p = s_coef[kFarK - 1];
+#pragma unroll
+                for (int i = kFarK - 2; i >= 0; i--) p = fma(p, sv, s_coef[i]);
+                sf[f] += p;
+            }
+        }
+        // the parents' polynomials (lines expanded once per parent tile by far_kernel)
+        if (any_far) {
+            int ptile = blockIdx.x;
+            for (int lv = 1; lv < a.nlev; lv++) {
+                ptile /= a.S;
+                const TileHdr ph = a.hdr[lv][ptile];
+                const double pc = 0.5 * (ph.wlo + ph.whi), phh = 0.5 * (ph.whi - ph.wlo);
+                const double phinv = phh > 0. ? 1. / phh : 0.;
+                const double* __restrict__ cf = a.coef[lv] + (((size_t)ptile * Ltot + L) * a.nslot + slot) * kFarK;
+                double c[kFarK];
+#pragma unroll
+                for (int i = 0; i < kFarK; i++) c[i] = __ldg(cf + i);
 #pragma unroll
                 for (int f = 0; f < F; f++) {
-                    const double sv = (wn[f] - cen) * hinv;
-                    double p = s_coef[kFarK - 1];
+                    const double sv = (wn[f] - pc) * phinv;
+                    double p = c[kFarK - 1];
 #pragma unroll
-                    for (int i = kFarK - 2; i >= 0; i--) p = fma(p, sv, s_coef[i]);
+                    for (int i = kFarK - 2; i >= 0; i--) p = fma(p, sv, c[i]);
                     sf[f] += p;
                 }
             }
         }
-        const SegWork& wk = s_work[s];
-        if (!wk.active) continue;
-        const int cls = sg.cls;
-        if (SEL && sg.mol == 7) {                          // every O2 line passes modm.f90:384
-#pragma unroll
-            for (int f = 0; f < F; f++) { cnt[f] += sg.count_all; hsh[f] += sg.hash_all; }
-        }
-        if (cls == CLS_PED || cls == CLS_O2 || cls == CLS_O2_LC35) {
-            const bool force_both = (cls == CLS_O2_LC35);
-            const bool count_sel = SEL && (cls == CLS_PED);
-            const int n0 = wk.n0;
-            const int nsub = wk.nbp - 1;
-            double psum[F];
-#pragma unroll
-            for (int f = 0; f < F; f++) psum[f] = 0.;
-            double pacc = 0.;                              // pedestal total of the interior ranges (uniform)
-            for (int r = 0; r < wk.nrun; r++) {
-                const int rlo = wk.run_lo[r], rhi = wk.run_hi[r], t0 = wk.run_t0[r], ntile = wk.run_nt[r];
-                for (int t = 0; t < ntile; t++, gtile++) {
-                    const int st = gtile % kStages;
-                    if (tid == 0 && more) {        // refill the stage the previous tile released
-                        more = advance(pjs, pjr, pjt);
-                        if (more) issue(pjs, pjr, pjt, (gtile + kStages - 1) % kStages);
-                    }
-                    mbar_wait(&s_bar[st], (uint32_t)(gtile / kStages) & 1u);
-                    const double* __restrict__ tX = s_tile[st][0];
-                    const double* __restrict__ tH = s_tile[st][1];
-                    const double* __restrict__ tC = s_tile[st][2];
-                    const double* __restrict__ tP = s_tile[st][3];
-                    const int tb = t0 + t * kTile;
-                    const int tlo = tb > rlo ? tb : rlo;
-                    const int thi = (tb + kTile) < rhi ? (tb + kTile) : rhi;
-                    double pmine = 0.;                          // this thread's share of the tile's interior pedestals
-                    for (int u = 0; u < nsub; u++) {
-                        const int x = wk.bp[u];
-                        const int mode = wk.mode[u];
-                        int lo = x > tlo ? x : tlo;
-                        int hi = wk.bp[u + 1] < thi ? wk.bp[u + 1] : thi;
-                        if (lo >= hi || mode == 0) continue;
-                        const bool negall = force_both || (x < n0);
-                        if (a.counters) n_direct += (long long)(hi - lo) * nvalid;
-                        if ((mode & 7) != 0) {
-                            // ---- predicated loops, specialised per test combination
-                            switch (mode & 7) {
-#define MRTM_PRED(M)                                                                                              \
-    case M:                                                                                                       \
-        for (int q = lo; q < hi; q++) {                                                                           \
-            const int j = q - tb;                                                                                 \
-            const double xnu = tX[j], h2 = tH[j], cn = tC[j], ped = tP[j];                                        \
-            const double vt = ((M)&4) ? pVT[q] : -1.0;                                                            \
-            _Pragma("unroll") for (int f = 0; f < F; f++)                                                         \
-            {                                                                                                     \
-                const double dm = wn[f] - xnu;                                                                    \
-                const bool inwin = ((M)&1) ? !(fabs(dm) > kDELTNUC) : true;                                       \
-                if (count_sel && inwin) { cnt[f]++; hsh[f] += a.key[q]; }                                         \
-                if (((M)&4) && inwin && fabs(dm) <= vt) {                                                         \
-                    sf[f] += voigt_term(sg.mol, q, wn[f], xnu);                                                   \
-                } else {                                                                                          \
-                    double val;                                                                                   \
-                    if ((M)&2) {                                                                                  \
-                        const double sp = wn[f] + xnu;                                                            \
-                        const bool neg = (sp <= kDELTNUC);                                                        \
-                        const double r1 = rcp3(fma(dm, dm, h2)), r2 = rcp3(fma(sp, sp, h2));                      \
-                        val = cn * (r1 + (neg ? r2 : 0.)) - (neg ? 2. * ped : ped);                               \
-                    } else if (negall) {                                                                          \
-                        const double sp = wn[f] + xnu;                                                            \
-                        const double aa = fma(dm, dm, h2), bb = fma(sp, sp, h2);                                  \
-                        val = fma(cn * (aa + bb), rcp3(aa * bb), -2. * ped);                                      \
-                    } else {                                                                                      \
-                        val = fma(cn, rcp3(fma(dm, dm, h2)), -ped);                                               \
-                    }                                                                                             \
-                    sf[f] += inwin ? val : 0.;                                                                    \
-                }                                                                                                 \
-            }                                                                                                     \
-        }                                                                                                         \
-        break;
-                                MRTM_PRED(1) MRTM_PRED(2) MRTM_PRED(3) MRTM_PRED(4) MRTM_PRED(5) MRTM_PRED(6) MRTM_PRED(7)
-#undef MRTM_PRED
-                            default: break;
-                            }
-                            continue;
-                        }
-                        if (count_sel) {
-                            const unsigned long long hs = a.keypre[hi] - a.keypre[lo];
-#pragma unroll
-                            for (int f = 0; f < F; f++) { cnt[f] += hi - lo; hsh[f] += hs; }
-                        }
-                        // this thread's share of the interior pedestals of the tile (reduced across the CTA below)
-                        {
-                            const double w = negall ? 2. : 1.;          // pedestal counted for both resonances (:749)
-                            for (int q = lo + tid; q < hi; q += NT) pmine = fma(w, tP[q - tb], pmine);
-                        }
-                        if (negall) {
-                            // ---- interior, both resonances: cn*(1/a+1/b) = cn*(a+b)/(a*b), one reciprocal
-MRTM_UNROLL(MRTM_UNROLL_BOTH)
-                            for (int q = lo; q < hi; q++) {
-                                const int j = q - tb;
-                                const double xnu = tX[j], h2 = tH[j], cn = tC[j];
-#pragma unroll
-                                for (int f = 0; f < F; f++) {
-                                    const double dm = wn[f] - xnu, sp = wn[f] + xnu;
-                                    const double aa = fma(dm, dm, h2), bb = fma(sp, sp, h2);
-                                    const double r = rcp3(aa * bb);
-                                    psum[f] = fma(cn * (aa + bb), r, psum[f]);
-                                }
-                            }
-                        } else {
-                            // ---- interior, single resonance (modm.f90:751): four lines share one reciprocal,
-                            // sum c_i/a_i = N/(a1 a2 a3 a4), N = (c1 a2 + c2 a1)(a3 a4) + (c3 a4 + c4 a3)(a1 a2);
-                            // 21 FP64 ops + 1 MUFU per 4 evaluations
-                            int q = lo;
-                            for (; q + 4 <= hi; q += 4) {
-                                const int j = q - tb;
-                                const double x1 = tX[j], x2 = tX[j + 1], x3 = tX[j + 2], x4 = tX[j + 3];
-                                const double g1 = tH[j], g2 = tH[j + 1], g3 = tH[j + 2], g4 = tH[j + 3];
-                                const double c1 = tC[j], c2 = tC[j + 1], c3 = tC[j + 2], c4 = tC[j + 3];
-#pragma unroll
-                                for (int f = 0; f < F; f++) {
-                                    const double d1 = wn[f] - x1, d2 = wn[f] - x2, d3 = wn[f] - x3, d4 = wn[f] - x4;
-                                    const double a1 = fma(d1, d1, g1), a2 = fma(d2, d2, g2);
-                                    const double a3 = fma(d3, d3, g3), a4 = fma(d4, d4, g4);
-                                    const double p12 = a1 * a2, p34 = a3 * a4;
-                                    const double n12 = fma(c1, a2, c2 * a1), n34 = fma(c3, a4, c4 * a3);
-                                    const double r = rcp3(p12 * p34);
-                                    psum[f] = fma(fma(n12, p34, n34 * p12), r, psum[f]);
-                                }
-                            }
-                            for (; q < hi; q++) {
-                                const int j = q - tb;
-                                const double xnu = tX[j], h2 = tH[j], cn = tC[j];
-#pragma unroll
-                                for (int f = 0; f < F; f++) {
-                                    const double dm = wn[f] - xnu;
-                                    psum[f] = fma(cn, rcp3(fma(dm, dm, h2)), psum[f]);
-                                }
-                            }
-                        }
-                    }
-                    // CTA-wide sum of the interior pedestals of this tile (uniform result)
-#pragma unroll
-                    for (int off = 16; off > 0; off >>= 1) pmine += __shfl_xor_sync(0xffffffffu, pmine, off);
-                    if ((tid & 31) == 0) s_ped[ped_buf][tid >> 5] = pmine;
-                    __syncthreads();       // all reads of this stage done before it is refilled; s_ped visible
-#pragma unroll
-                    for (int i = 0; i < NW; i++) pacc += s_ped[ped_buf][i];
-                    ped_buf ^= 1;
-                }
-            }
-#pragma unroll
-            for (int f = 0; f < F; f++) sf[f] += psum[f] - pacc;
-        } else if (cls == CLS_O2_LC1) {
-            for (int r = 0; r < wk.nrun; r++) {
-                if (a.counters) n_direct += (long long)(wk.run_hi[r] - wk.run_lo[r]) * nvalid;
-                for (int q = wk.run_lo[r]; q < wk.run_hi[r]; q++) {
-                    const double xnu = pXNU[q], h2 = pH2[q], cg = pP3[q], cq = pP4[q], vt = pVT[q];
-#pragma unroll
-                    for (int f = 0; f < F; f++) {
-                        const double dm = wn[f] - xnu, sp = wn[f] + xnu;
-                        if (fabs(dm) <= vt) {
-                            sf[f] += voigt_term(sg.mol, q, wn[f], xnu);
-                        } else {
-                            const double r1 = rcp3(fma(dm, dm, h2));
-                            const double r2 = rcp3(fma(sp, sp, h2));
-                            sf[f] += fma(cq, dm, cg) * r1 + fma(-cq, sp, cg) * r2;
-                        }
-                    }
-                }
-            }
-        } else {   // CLS_GENERAL: faithful case tree per (line, frequency)
-            if (a.counters) n_direct += (long long)(wk.q1 - wk.q0) * nvalid;
-            for (int q = wk.q0; q < wk.q1; q++) {
-                const double xnu = pXNU[q], vt = pVT[q];
-                const double hw = pl[(size_t)D_H * a.n_pad + q], ad = pl[(size_t)D_AD * a.n_pad + q];
-                const double st = pl[(size_t)D_STILD * a.n_pad + q];
-                const double aip = pl[(size_t)D_AIP * a.n_pad + q], bip = pl[(size_t)D_BIP * a.n_pad + q];
-                const int xf = a.xf_s[q];
-#pragma unroll
-                for (int f = 0; f < F; f++) {
-                    const double dm = wn[f] - xnu;
-                    if ((fabs(dm) > kDELTNUC) && (sg.mol != 7)) continue;          // modm.f90:384
-                    if (SEL && sg.mol != 7) { cnt[f]++; hsh[f] += a.key[q]; }
-                    const bool voigt = fabs(dm) <= vt;
-                    sf[f] += st * lsf_general(sg.mol, xf, rp, rp2, aip, bip, hw, wn[f], xnu, ad, a.sdep_s[q], voigt, &err);
-                }
-            }
-        }
+        finish_mol(mol);
+        s = s_end;
     }
-    finish_mol(cur_mol);
     if (err) atomicOr(a.errflag, 2);
     if (a.counters && tid == 0) {
         atomicAdd(a.counters + 0, (unsigned long long)n_far);

@@ -214,7 +214,6 @@ int stage_lines_host(const int64_t nblm[MRTM_MXMOL], int64_t iim, const int64_t*
             return MRTM_EARG;
         }
         for (int64_t u = q; u < q1; u++) out.segidx[u] = (int32_t)out.segments.size();
-        out.segments.push_back(s);
         if (out.mol_slot[s.mol - 1] < 0) {
             if ((int)out.slot_mol.size() >= kMaxSlots) {
                 out.error = "more than kMaxSlots molecules own lines";
@@ -223,6 +222,8 @@ int stage_lines_host(const int64_t nblm[MRTM_MXMOL], int64_t iim, const int64_t*
             out.mol_slot[s.mol - 1] = (int32_t)out.slot_mol.size();
             out.slot_mol.push_back(s.mol);
         }
+        s.slot = out.mol_slot[s.mol - 1];
+        out.segments.push_back(s);
         q = q1;
     }
     return MRTM_OK;
