@@ -46,11 +46,11 @@ struct mrtm_ctx {
     int32_t* tips_row_dev = nullptr;
     int* errflag_dev = nullptr;
     unsigned long long* counters_dev = nullptr;   // [2] far expansions, direct evaluations
-    double ff_ratio = 10.0;                       // far-field pole-distance ratio (MRTM_FF_RATIO; 0 = direct only)
+    double ff_ratio = 8.0;                        // far-field pole-distance ratio (MRTM_FF_RATIO; 0 = direct only)
     DevBuf b_vtmax;                               // [0] sm_max bits, [1..nseg] vtmax per segment
     DevBuf b_lvoigt;                              // [L] per-layer "has Voigt-capable lines" flag
-    DevBuf b_plan[kMaxLevels], b_hdr[kMaxLevels], b_coef[kMaxLevels];
-    int ff_levels = 2, ff_S = 8;                  // far-field hierarchy (MRTM_FF_LEVELS 1..3, MRTM_FF_S)
+    DevBuf b_plan[kMaxLevels], b_hdr[kMaxLevels], b_coef[kMaxLevels], b_pieces[kMaxLevels];
+    int ff_levels = 3, ff_S = 8;                  // far-field hierarchy (MRTM_FF_LEVELS 1..3, MRTM_FF_S)
     DevBuf b_layer, b_scorc, b_absrb, b_planes, b_o, b_obm, b_oc, b_in[16], b_out[16], b_sel[2], b_tmps;
     mrtm_stats st;
     size_t planes_budget = (size_t)8 << 30;
@@ -191,6 +191,7 @@ extern "C" int mrtm_free(mrtm_ctx* ctx)
         if (ctx->b_plan[i].p) cudaFree(ctx->b_plan[i].p);
         if (ctx->b_hdr[i].p) cudaFree(ctx->b_hdr[i].p);
         if (ctx->b_coef[i].p) cudaFree(ctx->b_coef[i].p);
+        if (ctx->b_pieces[i].p) cudaFree(ctx->b_pieces[i].p);
     }
     for (auto& b : ctx->b_in) if (b.p) cudaFree(b.p);
     for (auto& b : ctx->b_out) if (b.p) cudaFree(b.p);
@@ -229,7 +230,7 @@ extern "C" int mrtm_stage_lines(mrtm_ctx* ctx, const int64_t nblm[MRTM_MXMOL], i
 #define UPV(F) if ((rc = upload(ctx, h.F, own, &d.F))) return rc;
     UPV(mol) UPV(iso) UPV(xf) UPV(cls) UPV(sidx) UPV(lcidx) UPV(brdidx) UPV(segidx)
     UPV(xnu0) UPV(s0adj) UPV(e) UPV(alpf) UPV(alps) UPV(x) UPV(deltnu) UPV(sdep) UPV(mass)
-    UPV(lc) UPV(lc_self) UPV(brd) UPV(scor_index)
+    UPV(lc) UPV(lc_self) UPV(brd) UPV(scor_index) UPV(slot_mol)
 #undef UPV
     {
         std::vector<unsigned long long> k(h.key.begin(), h.key.end());
@@ -319,14 +320,17 @@ struct RunDesc {
 template <int F, int NT>
 static void launch_lines(const LinesArgs& la, dim3 grid, bool sel, cudaStream_t s)
 {
-    const size_t dyn = sizeof(double) * kStages * 4 * kTile + 2 * (size_t)std::max(la.nseg, 1) * sizeof(SegWork);
+    // near field (direct), Voigt branch, then polynomial + continuum + totals
+    const size_t dyn = sizeof(double) * kStages * 4 * kTile + (size_t)std::max(la.nseg, 1) * sizeof(SegWork);
     if (sel) {
-        cudaFuncSetAttribute(lines_kernel<F, true, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
-        lines_kernel<F, true, NT><<<grid, NT, dyn, s>>>(la);
+        cudaFuncSetAttribute(near_kernel<F, true, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+        near_kernel<F, true, NT><<<grid, NT, dyn, s>>>(la);
     } else {
-        cudaFuncSetAttribute(lines_kernel<F, false, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
-        lines_kernel<F, false, NT><<<grid, NT, dyn, s>>>(la);
+        cudaFuncSetAttribute(near_kernel<F, false, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+        near_kernel<F, false, NT><<<grid, NT, dyn, s>>>(la);
     }
+    voigt_kernel<F, NT><<<grid, NT, 0, s>>>(la);
+    final_kernel<F, NT><<<grid, NT, 0, s>>>(la);
 }
 
 static int run_device(mrtm_ctx* ctx, const RunDesc& r, cudaStream_t s)
@@ -492,13 +496,16 @@ static int run_device(mrtm_ctx* ctx, const RunDesc& r, cudaStream_t s)
             const bool sel = (r.sel_count != nullptr) || (r.sel_hash != nullptr);
             // frequencies per CTA: 128 threads x F (512 on dense grids, smaller tiles for short channel lists)
             const int NTsel = 128;                         // 256-thread CTAs measured 4% slower on the dense sweep
-            const int F = (nwn >= 2048) ? 4 : ((nwn >= 512) ? 2 : 1);
+            static const int force_f = std::getenv("MRTM_LINES_F") ? std::atoi(std::getenv("MRTM_LINES_F")) : 0;
+            const int F = (force_f == 1 || force_f == 2 || force_f == 4) ? force_f : ((nwn >= 2048) ? 4 : ((nwn >= 512) ? 2 : 1));
             const int T0 = NTsel * F;
             dim3 grid((unsigned)((nwn + T0 - 1) / T0), (unsigned)nlay, (unsigned)nb);
             CU(cudaEventRecord(ctx->ev[2], s));
             // ---- plans (layer independent) and the upper levels of the far-field hierarchy
             const int nseg_i = (int)h.segments.size();
-            const int nslot = std::max<int>(1, (int)h.slot_mol.size());
+            // per-molecule outputs need one far-field coefficient set per molecule; otherwise one set serves all
+            const bool combined = (r.o_by_mol == nullptr);
+            const int nslot = combined ? 1 : (int)h.slot_mol.size();
             int nlev = 1;
             int64_t ntiles[kMaxLevels], tfreq[kMaxLevels];
             ntiles[0] = grid.x;
@@ -512,10 +519,11 @@ static int run_device(mrtm_ctx* ctx, const RunDesc& r, cudaStream_t s)
             la.nlev = nlev;
             la.S = ctx->ff_S;
             la.nslot = nslot;
-            for (int lv = 0; lv < nlev; lv++) {
+            for (int lv = nlev - 1; lv >= 0; lv--) {       // top level first: a level's far work list excludes its parent's
+                if ((rc = ensure(ctx, ctx->b_pieces[lv], (size_t)ntiles[lv] * std::max(nseg_i, 1) * kPiecePerSeg * sizeof(FarPiece)))) return rc;
                 if ((rc = ensure(ctx, ctx->b_plan[lv], (size_t)ntiles[lv] * std::max(nseg_i, 1) * sizeof(SegWork)))) return rc;
                 if ((rc = ensure(ctx, ctx->b_hdr[lv], (size_t)ntiles[lv] * sizeof(TileHdr)))) return rc;
-                if (lv >= 1 && (rc = ensure(ctx, ctx->b_coef[lv], (size_t)ntiles[lv] * Lb * nslot * kFarK * 8))) return rc;
+                if (la.ff_ratio > 0. && (rc = ensure(ctx, ctx->b_coef[lv], (size_t)ntiles[lv] * Lb * std::max(nslot, 1) * kFarK * 8))) return rc;
                 PlanArgs pl;
                 std::memset(&pl, 0, sizeof pl);
                 pl.nwn = (int32_t)nwn;
@@ -529,31 +537,41 @@ static int run_device(mrtm_ctx* ctx, const RunDesc& r, cudaStream_t s)
                 pl.ff_ratio = la.ff_ratio;
                 pl.out = (SegWork*)ctx->b_plan[lv].p;
                 pl.hdr = (TileHdr*)ctx->b_hdr[lv].p;
-                plan_kernel<<<(unsigned)ntiles[lv], 128, (size_t)std::max(nseg_i, 1) * sizeof(SegWork), s>>>(pl);
+                pl.pplan = (lv + 1 < nlev) ? (const SegWork*)ctx->b_plan[lv + 1].p : nullptr;
+                pl.S = ctx->ff_S;
+                pl.pieces = (FarPiece*)ctx->b_pieces[lv].p;
+                plan_kernel<<<(unsigned)ntiles[lv], 128, (size_t)std::max(nseg_i, 1) * (sizeof(SegWork) + kPiecePerSeg * sizeof(FarPiece)), s>>>(pl);
                 st.kernel_launches++;
                 la.plan[lv] = (const SegWork*)ctx->b_plan[lv].p;
                 la.hdr[lv] = (const TileHdr*)ctx->b_hdr[lv].p;
-                la.coef[lv] = (const double*)ctx->b_coef[lv].p;
+                la.coef[lv] = (la.ff_ratio > 0.) ? (const double*)ctx->b_coef[lv].p : nullptr;
             }
-            for (int lv = 1; lv < nlev; lv++) {
-                FarArgs fa;
-                std::memset(&fa, 0, sizeof fa);
-                fa.nlay = (int32_t)nlay;
-                fa.nseg = nseg_i;
-                fa.n_pad = n_pad;
-                fa.nslot = nslot;
-                fa.seg = ctx->seg_dev;
-                fa.plan = la.plan[lv];
-                fa.hdr = la.hdr[lv];
-                fa.pplan = (lv + 1 < nlev) ? la.plan[lv + 1] : nullptr;
-                fa.S = ctx->ff_S;
-                fa.planes = la.planes;
-                fa.lay = la.lay;
-                fa.coef = (double*)ctx->b_coef[lv].p;
-                fa.counters = ctx->counters_dev;
-                far_kernel<<<dim3((unsigned)ntiles[lv], (unsigned)nlay, (unsigned)nb), 128, 2 * (size_t)std::max(nseg_i, 1) * sizeof(SegWork), s>>>(fa);
-                st.kernel_launches++;
-            }
+            la.slot_mol = ctx->ld.slot_mol;
+            if (la.ff_ratio > 0.)
+                for (int lv = nlev - 1; lv >= 0; lv--) {      // top level first: each level folds its parent's polynomial in
+                    FarArgs fa;
+                    std::memset(&fa, 0, sizeof fa);
+                    fa.nlay = (int32_t)nlay;
+                    fa.nseg = nseg_i;
+                    fa.n_pad = n_pad;
+                    fa.nslot = nslot;
+                    fa.seg = ctx->seg_dev;
+                    fa.pieces = (const FarPiece*)ctx->b_pieces[lv].p;
+                    fa.hdr = la.hdr[lv];
+                    if (lv + 1 < nlev) {
+                        fa.phdr = la.hdr[lv + 1];
+                        fa.pcoef = la.coef[lv + 1];
+                    }
+                    fa.S = ctx->ff_S;
+                    fa.combined = combined ? 1 : 0;
+                    fa.planes = la.planes;
+                    fa.lay = la.lay;
+                    fa.coef = (double*)ctx->b_coef[lv].p;
+                    fa.counters = ctx->counters_dev;
+                    far_kernel<<<dim3((unsigned)ntiles[lv], (unsigned)nlay, (unsigned)nb), 128, (size_t)std::max(nseg_i, 1) * kPiecePerSeg * sizeof(FarPiece), s>>>(fa);
+                    st.kernel_launches++;
+                }
+            st.kernel_launches += 2;       // voigt_kernel, final_kernel (near_kernel is counted below)
             if (F == 4) launch_lines<4, 128>(la, grid, sel, s);
             else if (F == 2) launch_lines<2, 128>(la, grid, sel, s);
             else launch_lines<1, 128>(la, grid, sel, s);

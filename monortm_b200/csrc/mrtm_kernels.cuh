@@ -25,6 +25,7 @@ struct LinesDev {
     const double* brd;         // [nbrd][28]
     int32_t nsi;               // compact scor slots
     const int32_t* scor_index; // [nsi] -> (mol-1)+(iso-1)*42
+    const int32_t* slot_mol;   // [nslot] molecule of each compact slot (ascending)
 };
 
 struct ContTablesDev {
@@ -499,6 +500,7 @@ struct LinesArgs {
     const double* coef[kMaxLevels];     // lv >= 1: [tile][L][slot][kFarK] from far_kernel
     int32_t nslot, pad0;
     const int* layer_voigt;             // [L] 0: every line of the layer is Lorentz-only (zeta > 0.99)
+    const int32_t* slot_mol;            // [nslot]
     // continuum
     const double* absrb;          // [L][3][nptabs_pad]
     int32_t nptabs, nptabs_pad;
@@ -652,13 +654,49 @@ struct SegWork {
     unsigned char mode[kMaxBp];  // mode bits of sub-range u; 0 = far field (Taylor expansion)
     int nrun;                    // maximal runs of consecutive direct (mode != 0) sub-ranges
     int run_lo[kMaxRun], run_hi[kMaxRun], run_t0[kMaxRun], run_nt[kMaxRun];
+    int run_off[kMaxRun];        // near_kernel (stage-all mode): offset of the run in the CTA's staging area
+    int run_u0[kMaxRun], run_u1[kMaxRun];   // sub-ranges [u0,u1) that make up the run
     int tma;                     // class streams its direct runs through shared memory
     int has_far;
 };
 constexpr int kSegTasks = 11;
 struct TileHdr {
     double wlo, whi;             // frequency extent of the tile
+    int total_lines;             // lines (padded to 4 per run) of all direct runs of the streamed classes
+    int npieces, nunits;         // far-field work list of the tile: pieces, and work units of the non-mixing pieces
+    int nterms;                  // Taylor expansions of the non-mixing pieces (statistics)
 };
+// One contiguous range of lines that far_kernel expands for a tile: far at this level and not at the parent level.
+constexpr int kPiecePerSeg = 12;
+struct FarPiece {
+    int lo, n;                   // lines [lo, lo+n)
+    int off;                     // first work unit of the piece in the tile's unit numbering (non-mixing pieces); a unit is
+                                 // one line with both resonances, or two adjacent single-resonance lines
+    int info;                    // segment | both << 16 | mix << 17
+};
+
+// the far (mode 0) sub-ranges of a segment at this level, minus the ones the parent level already
+// expanded (the parent's far set is a subset of the child's by construction of the margins)
+template <class Fn>
+__device__ __forceinline__ void for_each_far_piece(const SegWork& wk, const SegWork* pk, Fn fn)
+{
+    for (int u = 0; u + 1 < wk.nbp; u++) {
+        if (wk.mode[u] != 0) continue;
+        const int lo = wk.bp[u], hi = wk.bp[u + 1];
+        int cur = lo;
+        if (pk) {
+            for (int v = 0; v + 1 < pk->nbp && cur < hi; v++) {
+                if (pk->mode[v] != 0) continue;
+                const int pa = pk->bp[v], pb = pk->bp[v + 1];
+                if (pb <= cur) continue;
+                if (pa >= hi) break;
+                if (pa > cur) fn(cur, pa, lo);
+                cur = pb > cur ? pb : cur;
+            }
+        }
+        if (cur < hi) fn(cur, hi, lo);
+    }
+}
 
 // =============================================================================================
 // plan_kernel: one CTA per frequency tile of one hierarchy level.  All window / band / near-zone
@@ -675,6 +713,9 @@ struct PlanArgs {
     double ff_ratio;
     SegWork* out;                             // [ntiles][nseg]
     TileHdr* hdr;                             // [ntiles]
+    const SegWork* pplan;                     // parent level's plan (computed first) or null
+    int32_t S, pad2;                          // tiles of this level per parent tile
+    FarPiece* pieces;                         // [ntiles][nseg*kPiecePerSeg]
 };
 
 __global__ void __launch_bounds__(128) plan_kernel(PlanArgs a)
@@ -779,9 +820,12 @@ __global__ void __launch_bounds__(128) plan_kernel(PlanArgs a)
             if (mode != 0) {
                 if (open) {
                     wk.run_hi[nrun - 1] = wk.bp[u + 1];
+                    wk.run_u1[nrun - 1] = u + 1;
                 } else {
                     wk.run_lo[nrun] = x;
                     wk.run_hi[nrun] = wk.bp[u + 1];
+                    wk.run_u0[nrun] = u;
+                    wk.run_u1[nrun] = u + 1;
                     nrun++;
                     open = true;
                 }
@@ -793,9 +837,68 @@ __global__ void __launch_bounds__(128) plan_kernel(PlanArgs a)
         for (int r = 0; r < nrun; r++) {
             wk.run_t0[r] = wk.run_lo[r] & ~3;
             wk.run_nt[r] = (wk.run_hi[r] - wk.run_t0[r] + kTile - 1) / kTile;
+            wk.run_off[r] = 0;
         }
         wk.nrun = nrun;
         wk.has_far = has_far;
+    }
+    __syncthreads();
+    if (tid == 0) {      // staging offsets of the direct runs (near_kernel, stage-all mode)
+        int tot = 0;
+        for (int s = 0; s < nseg; s++) {
+            SegWork& w = s_work[s];
+            if (!w.tma) continue;
+            for (int r = 0; r < w.nrun; r++) {
+                w.run_off[r] = tot;
+                tot += ((w.run_hi[r] - w.run_t0[r]) + 3) & ~3;
+            }
+        }
+        a.hdr[tile].total_lines = tot;
+    }
+    // far-field work list: per segment the far sub-ranges minus the parent's, then one term numbering per tile
+    __shared__ int s_npc[kMaxSegments];
+    FarPiece* s_pc = reinterpret_cast<FarPiece*>(s_work + nseg);      // [nseg][kPiecePerSeg]
+    for (int s = tid; s < nseg; s += NT) {
+        const SegWork& wk = s_work[s];
+        const SegWork* pk = a.pplan ? a.pplan + (size_t)(tile / a.S) * nseg + s : nullptr;
+        const int cls = a.seg[s].cls;
+        const bool force_both = (cls == CLS_O2_LC35) || (cls == CLS_O2_LC1);
+        const int mix = (cls == CLS_O2_LC1) ? 1 : 0;
+        int n = 0;
+        if (wk.has_far)
+            for_each_far_piece(wk, pk, [&](int lo, int hi, int sub_lo) {
+                if (n < kPiecePerSeg) {
+                    FarPiece fp;
+                    fp.lo = lo;
+                    fp.n = hi - lo;
+                    fp.off = 0;
+                    fp.info = s | ((force_both || (sub_lo < wk.n0)) ? (1 << 16) : 0) | (mix << 17);
+                    s_pc[s * kPiecePerSeg + n] = fp;
+                }
+                n++;
+            });
+        s_npc[s] = n < kPiecePerSeg ? n : kPiecePerSeg;       // cannot overflow: <= 5 far sub-ranges, <= 5 parent cuts
+    }
+    __syncthreads();
+    if (tid == 0) {
+        FarPiece* dst = a.pieces + (size_t)tile * nseg * kPiecePerSeg;
+        int np = 0, nu = 0, nt = 0;
+        for (int pass = 0; pass < 2; pass++)          // non-mixing pieces first (they share the unit numbering)
+            for (int s = 0; s < nseg; s++)
+                for (int i = 0; i < s_npc[s]; i++) {
+                    FarPiece fp = s_pc[s * kPiecePerSeg + i];
+                    if (((fp.info >> 17) & 1) != pass) continue;
+                    fp.off = nu;
+                    if (pass == 0) {
+                        const bool both = (fp.info >> 16) & 1;
+                        nu += both ? fp.n : (fp.n + 1) / 2;
+                        nt += both ? 2 * fp.n : fp.n;
+                    }
+                    dst[np++] = fp;
+                }
+        a.hdr[tile].npieces = np;
+        a.hdr[tile].nunits = nu;
+        a.hdr[tile].nterms = nt;
     }
     __syncthreads();
     {   // plan -> HBM
@@ -827,6 +930,24 @@ __device__ __forceinline__ void far_accum(double D, double h2, double w, double 
         b1 = b2;
     }
 }
+// two independent terms interleaved (instruction-level parallelism for the two recurrences)
+__device__ __forceinline__ void far_accum2(double D1, double h21, double w1, double p1, double D2, double h22, double w2, double p2,
+                                           double m2h, double mhh, double (&A)[kFarK])
+{
+    const double u1 = rcp3(fma(D1, D1, h21)), u2 = rcp3(fma(D2, D2, h22));
+    const double al1 = (D1 * m2h) * u1, be1 = mhh * u1, al2 = (D2 * m2h) * u2, be2 = mhh * u2;
+    double b01 = w1 * u1, b02 = w2 * u2;
+    double b11 = al1 * b01, b12 = al2 * b02;
+    A[0] += (b01 - p1) + (b02 - p2);
+    A[1] += b11 + b12;
+#pragma unroll
+    for (int k = 2; k < kFarK; k++) {
+        const double b21 = fma(al1, b11, be1 * b01), b22 = fma(al2, b12, be2 * b02);
+        A[k] += b21 + b22;
+        b01 = b11; b11 = b21;
+        b02 = b12; b12 = b22;
+    }
+}
 // first-order line mixing (modm.f90:777-786): (g + c*(D+t))/((D+t)^2+h2), c = +-cq
 __device__ __forceinline__ void far_accum_mix(double D, double h2, double cg, double cq, double hh, double m2h, double mhh, double (&A)[kFarK])
 {
@@ -844,65 +965,6 @@ __device__ __forceinline__ void far_accum_mix(double D, double h2, double cg, do
         b0 = b1;
         b1 = b2;
     }
-}
-
-// the far (mode 0) sub-ranges of a segment at this level, minus the ones the parent level already
-// expanded (the parent's far set is a subset of the child's by construction of the margins)
-template <class Fn>
-__device__ __forceinline__ void for_each_far_piece(const SegWork& wk, const SegWork* pk, Fn fn)
-{
-    for (int u = 0; u + 1 < wk.nbp; u++) {
-        if (wk.mode[u] != 0) continue;
-        const int lo = wk.bp[u], hi = wk.bp[u + 1];
-        int cur = lo;
-        if (pk) {
-            for (int v = 0; v + 1 < pk->nbp && cur < hi; v++) {
-                if (pk->mode[v] != 0) continue;
-                const int pa = pk->bp[v], pb = pk->bp[v + 1];
-                if (pb <= cur) continue;
-                if (pa >= hi) break;
-                if (pa > cur) fn(cur, pa, lo);
-                cur = pb > cur ? pb : cur;
-            }
-        }
-        if (cur < hi) fn(cur, hi, lo);
-    }
-}
-
-// Taylor coefficients of the far lines of one segment, one line per thread (coalesced read-only loads,
-// the next line's parameters in flight), accumulated into the thread's A[]
-template <int NT>
-__device__ __forceinline__ void far_pass_segment(const SegWork& wk, const SegWork* pk, int cls, int tid,
-                                                 const double* __restrict__ pXNU, const double* __restrict__ pH2,
-                                                 const double* __restrict__ pA, const double* __restrict__ pB,
-                                                 double cen, double hh, double (&A)[kFarK], long long& n_far)
-{
-    const double m2h = -2. * hh, mhh = -hh * hh;
-    const bool force_both = (cls == CLS_O2_LC35) || (cls == CLS_O2_LC1);
-    const bool mix = (cls == CLS_O2_LC1);
-    for_each_far_piece(wk, pk, [&](int lo, int hi, int sub_lo) {
-        const bool both = force_both || (sub_lo < wk.n0);
-        n_far += (long long)(hi - lo) * (both ? 2 : 1);
-        int q = lo + tid;
-        double xnu = 0., h2 = 1., c3 = 0., c4 = 0.;
-        if (q < hi) { xnu = __ldg(pXNU + q); h2 = __ldg(pH2 + q); c3 = __ldg(pA + q); c4 = __ldg(pB + q); }
-        while (q < hi) {
-            const int qn = q + NT;
-            double xnu_n = 0., h2_n = 1., c3_n = 0., c4_n = 0.;
-            if (qn < hi) { xnu_n = __ldg(pXNU + qn); h2_n = __ldg(pH2 + qn); c3_n = __ldg(pA + qn); c4_n = __ldg(pB + qn); }
-            if (mix) {
-                far_accum_mix(cen - xnu, h2, c3, c4, hh, m2h, mhh, A);
-                far_accum_mix(cen + xnu, h2, c3, -c4, hh, m2h, mhh, A);
-            } else if (both) {
-                far_accum(cen - xnu, h2, c3, c4, m2h, mhh, A);
-                far_accum(cen + xnu, h2, c3, c4, m2h, mhh, A);
-            } else {
-                far_accum(cen - xnu, h2, c3, c4, m2h, mhh, A);
-            }
-            xnu = xnu_n; h2 = h2_n; c3 = c3_n; c4 = c4_n;
-            q = qn;
-        }
-    });
 }
 
 // CTA-wide sums of the per-thread coefficients in a fixed order (deterministic); result in s_coef[kFarK]
@@ -929,18 +991,41 @@ __device__ __forceinline__ void reduce_coefs(const double (&A)[kFarK], int tid, 
     __syncthreads();
 }
 
+// binomial coefficients C(j,k), j,k < kFarK (polynomial translation between hierarchy levels)
+struct BinomTable {
+    double c[kFarK][kFarK];
+    constexpr BinomTable() : c{}
+    {
+        for (int j = 0; j < kFarK; j++)
+            for (int k = 0; k < kFarK; k++) {
+                double v = 0.;
+                if (k <= j) {
+                    v = 1.;
+                    for (int i = 1; i <= k; i++) v = v * (double)(j - k + i) / (double)i;
+                }
+                c[j][k] = v;
+            }
+    }
+};
+__constant__ BinomTable c_binom = BinomTable();
+
 // =============================================================================================
-// far_kernel: hierarchy levels >= 1.  CTA = (level tile, layer, profile).  Expands the lines that are
-// far at this level but not at the parent level and writes, per molecule slot, the kFarK Taylor
-// coefficients about the level tile's centre; lines_kernel adds the polynomial per frequency.
+// far_kernel: one launch per hierarchy level, top level first.  CTA = (level tile, layer, profile).
+// Expands the lines that are far at this level but not at the parent level in kFarK Taylor terms about
+// the tile centre, adds the parent tile's polynomial re-expanded about this centre (exact polynomial
+// translation), and writes one coefficient set per molecule slot.  After the level-0 launch every line
+// that is far from a level-0 tile -- at whatever level it was expanded -- is contained in that tile's
+// coefficients; final_kernel evaluates them once per frequency.
 // =============================================================================================
 struct FarArgs {
     int32_t nlay, nseg, n_pad, nslot;
     const Segment* seg;
-    const SegWork* plan;      // [ntiles][nseg] this level
+    const FarPiece* pieces;   // [ntiles][nseg*kPiecePerSeg] work list of this level (plan_kernel)
     const TileHdr* hdr;
-    const SegWork* pplan;     // parent level or null
-    int32_t S, pad;           // tiles of this level per parent tile
+    const TileHdr* phdr;      // parent level or null
+    const double* pcoef;      // parent's coefficients [ptile][L][slot][kFarK]
+    int32_t S;                // tiles of this level per parent tile
+    int32_t combined;         // 1: one coefficient set, lines weighted by their molecule's column amount (nslot == 1)
     const double* planes;
     const LayerDev* lay;
     double* coef;             // [tile][L][slot][kFarK]
@@ -951,11 +1036,12 @@ __global__ void __launch_bounds__(128) far_kernel(FarArgs a)
 {
     constexpr int NT = 128;
     extern __shared__ __align__(128) unsigned char s_dyn[];
-    SegWork* s_work = reinterpret_cast<SegWork*>(s_dyn);
-    SegWork* s_pwork = s_work + a.nseg;
+    FarPiece* s_pc = reinterpret_cast<FarPiece*>(s_dyn);        // the tile's work list
     __shared__ double s_red[kFarK][NT];
     __shared__ double s_red2[kFarK][8];
     __shared__ double s_coef[kFarK];
+    __shared__ double s_pcoef[kMaxSlots * kFarK];       // the parent tile's coefficients
+    __shared__ double s_w[kMaxSegments];                // column amount of each segment's molecule
     const int tid = threadIdx.x;
     const int tile = blockIdx.x;
     const int64_t Ltot = (int64_t)gridDim.y * gridDim.z;
@@ -968,76 +1054,182 @@ __global__ void __launch_bounds__(128) far_kernel(FarArgs a)
     const double* __restrict__ pP3 = pl + (size_t)D_P3 * a.n_pad;
     const double* __restrict__ pP4 = pl + (size_t)D_P4 * a.n_pad;
     const int nseg = a.nseg;
+    const int ptile = tile / a.S;
+    const TileHdr th = a.hdr[tile];
+    const int np = th.npieces;
     {
-        const int nw = nseg * (int)(sizeof(SegWork) / 4);
-        const int* src = reinterpret_cast<const int*>(a.plan + (size_t)tile * nseg);
-        int* dst = reinterpret_cast<int*>(s_work);
+        const int nw = np * (int)(sizeof(FarPiece) / 4);
+        const int* src = reinterpret_cast<const int*>(a.pieces + (size_t)tile * nseg * kPiecePerSeg);
+        int* dst = reinterpret_cast<int*>(s_pc);
         for (int i = tid; i < nw; i += NT) dst[i] = src[i];
-        if (a.pplan) {
-            const int* psrc = reinterpret_cast<const int*>(a.pplan + (size_t)(tile / a.S) * nseg);
-            int* pdst = reinterpret_cast<int*>(s_pwork);
-            for (int i = tid; i < nw; i += NT) pdst[i] = psrc[i];
+        if (a.pcoef) {
+            const double* pin = a.pcoef + ((size_t)ptile * Ltot + L) * a.nslot * kFarK;
+            for (int i = tid; i < a.nslot * kFarK; i += NT) s_pcoef[i] = pin[i];
         }
+        for (int s = tid; s < nseg; s += NT) s_w[s] = ly.wk[a.seg[s].mol - 1];
     }
     __syncthreads();
-    const TileHdr th = a.hdr[tile];
     const double cen = 0.5 * (th.wlo + th.whi), hh = 0.5 * (th.whi - th.wlo);
-    double* out = a.coef + ((size_t)tile * Ltot + L) * a.nslot * kFarK;
-    long long n_far = 0;
-    int s = 0;
-    while (s < nseg) {
-        const int mol = a.seg[s].mol, slot = a.seg[s].slot;
-        int s_end = s;
-        bool any_far = false;
-        for (; s_end < nseg && a.seg[s_end].mol == mol; s_end++) any_far |= (s_work[s_end].has_far != 0);
-        const bool active = ly.wk[mol - 1] != 0.;
-        if (any_far && active) {
-            double A[kFarK];
-#pragma unroll
-            for (int i = 0; i < kFarK; i++) A[i] = 0.;
-            for (int s2 = s; s2 < s_end; s2++) {
-                if (!s_work[s2].has_far) continue;
-                const int cls2 = a.seg[s2].cls;
-                const bool mix = (cls2 == CLS_O2_LC1);
-                far_pass_segment<NT>(s_work[s2], a.pplan ? &s_pwork[s2] : nullptr, cls2, tid, pXNU, pH2, mix ? pP3 : pCN, mix ? pP4 : pP3,
-                                     cen, hh, A, n_far);
-            }
-            reduce_coefs<NT>(A, tid, s_red, s_red2, s_coef);
-            if (tid < kFarK) out[(size_t)slot * kFarK + tid] = s_coef[tid];
-        } else {
-            if (tid < kFarK) out[(size_t)slot * kFarK + tid] = 0.;
-        }
-        s = s_end;
+    const double m2h = -2. * hh, mhh = -hh * hh;
+    double alpha = 0., beta = 0.;       // parent variable s_p = alpha + beta*s
+    if (a.pcoef) {
+        const TileHdr ph = a.phdr[ptile];
+        const double pc = 0.5 * (ph.wlo + ph.whi), phh = 0.5 * (ph.whi - ph.wlo);
+        if (phh > 0.) { alpha = (cen - pc) / phh; beta = hh / phh; }
     }
-    if (a.counters && tid == 0) atomicAdd(a.counters + 0, (unsigned long long)n_far);
+    double* out = a.coef + ((size_t)tile * Ltot + L) * a.nslot * kFarK;
+    const double* pin = a.pcoef ? s_pcoef : nullptr;
+    // coefficient tid of the parent's polynomial p(alpha + beta*s) re-expanded in s:
+    // beta^tid * sum_{j>=tid} c_j C(j,tid) alpha^(j-tid)
+    auto translated = [&](const double* pcf) -> double {
+        double acc = 0.;
+        for (int j = kFarK - 1; j >= tid; j--) acc = fma(acc, alpha, pcf[j] * c_binom.c[j][tid]);
+        double bk = 1.;
+        for (int i = 0; i < tid; i++) bk *= beta;
+        return acc * bk;
+    };
+    // number of leading non-mixing pieces
+    int npm = 0;
+    while (npm < np && !((s_pc[npm].info >> 17) & 1)) npm++;
+
+    // work units [vbeg,vend) of the non-mixing pieces [pbeg,pend): one unit (two independent recurrences) per thread
+    // and step, the next unit's line parameters already loading
+    auto accumulate = [&](int pbeg, int pend, int vbeg, int vend, bool weighted, double (&A)[kFarK]) {
+        auto fetch = [&](int v, int& pi, double& D1, double& g1, double& w1, double& p1, double& D2, double& g2, double& w2, double& p2) {
+            D1 = 1.; g1 = 1.; w1 = 0.; p1 = 0.; D2 = 1.; g2 = 1.; w2 = 0.; p2 = 0.;
+            if (v >= vend) return;
+            while (pi + 1 < pend && v >= s_pc[pi + 1].off) pi++;
+            const FarPiece fp = s_pc[pi];
+            const int kk = v - fp.off;
+            const double ws = weighted ? s_w[fp.info & 0xffff] : 1.;
+            if ((fp.info >> 16) & 1) {                    // both resonances of one line: cen - xnu and cen + xnu
+                const int q = fp.lo + kk;
+                const double xnu = __ldg(pXNU + q);
+                g1 = g2 = __ldg(pH2 + q);
+                w1 = w2 = ws * __ldg(pCN + q);
+                p1 = p2 = ws * __ldg(pP3 + q);
+                D1 = cen - xnu;
+                D2 = cen + xnu;
+            } else {                                      // two adjacent single-resonance lines
+                const int q = fp.lo + 2 * kk;
+                D1 = cen - __ldg(pXNU + q);
+                g1 = __ldg(pH2 + q);
+                w1 = ws * __ldg(pCN + q);
+                p1 = ws * __ldg(pP3 + q);
+                if (2 * kk + 1 < fp.n) {
+                    D2 = cen - __ldg(pXNU + q + 1);
+                    g2 = __ldg(pH2 + q + 1);
+                    w2 = ws * __ldg(pCN + q + 1);
+                    p2 = ws * __ldg(pP3 + q + 1);
+                }
+            }
+        };
+        int pi = pbeg;
+        int v = vbeg + tid;
+        double D1, g1, w1, p1, D2, g2, w2, p2;
+        fetch(v, pi, D1, g1, w1, p1, D2, g2, w2, p2);
+        while (v < vend) {
+            const int vn = v + NT;
+            double D1n, g1n, w1n, p1n, D2n, g2n, w2n, p2n;
+            fetch(vn, pi, D1n, g1n, w1n, p1n, D2n, g2n, w2n, p2n);
+            far_accum2(D1, g1, w1, p1, D2, g2, w2, p2, m2h, mhh, A);
+            D1 = D1n; g1 = g1n; w1 = w1n; p1 = p1n;
+            D2 = D2n; g2 = g2n; w2 = w2n; p2 = p2n;
+            v = vn;
+        }
+    };
+    // first-order mixing pieces [pbeg,pend): few lines, one line (both resonances) per thread and step
+    auto accumulate_mix = [&](int pbeg, int pend, bool weighted, double (&A)[kFarK]) {
+        for (int pi = pbeg; pi < pend; pi++) {
+            const FarPiece fp = s_pc[pi];
+            const double ws = weighted ? s_w[fp.info & 0xffff] : 1.;
+            for (int q = fp.lo + tid; q < fp.lo + fp.n; q += NT) {
+                const double xnu = __ldg(pXNU + q), h2 = __ldg(pH2 + q), cg = ws * __ldg(pP3 + q), cq = ws * __ldg(pP4 + q);
+                far_accum_mix(cen - xnu, h2, cg, cq, hh, m2h, mhh, A);
+                far_accum_mix(cen + xnu, h2, cg, -cq, hh, m2h, mhh, A);
+            }
+        }
+    };
+
+    if (a.combined) {
+        // one coefficient set for all molecules: every line enters with its molecule's column amount W
+        // (o = RFT * sum_mol W_mol*SF_mol, modm.f90:436-438, 265-267)
+        double A[kFarK];
+#pragma unroll
+        for (int i = 0; i < kFarK; i++) A[i] = 0.;
+        if (np > 0) {
+            accumulate(0, npm, 0, th.nunits, true, A);
+            accumulate_mix(npm, np, true, A);
+            reduce_coefs<NT>(A, tid, s_red, s_red2, s_coef);
+        }
+        if (tid < kFarK) {
+            double v = (np > 0) ? s_coef[tid] : 0.;
+            if (pin) v += translated(pin);
+            out[tid] = v;
+        }
+    } else {
+        // one coefficient set per molecule slot; the pieces of a molecule are contiguous in both lists
+        int s = 0;
+        while (s < nseg) {
+            const int mol = a.seg[s].mol, slot = a.seg[s].slot;
+            int s_end = s;
+            while (s_end < nseg && a.seg[s_end].mol == mol) s_end++;
+            int pb = 0, pe, mb = npm, me;
+            while (pb < npm && (s_pc[pb].info & 0xffff) < s) pb++;
+            pe = pb;
+            while (pe < npm && (s_pc[pe].info & 0xffff) < s_end) pe++;
+            while (mb < np && (s_pc[mb].info & 0xffff) < s) mb++;
+            me = mb;
+            while (me < np && (s_pc[me].info & 0xffff) < s_end) me++;
+            const bool active = ly.wk[mol - 1] != 0.;
+            const bool work = active && (pe > pb || me > mb);
+            if (work) {
+                double A[kFarK];
+#pragma unroll
+                for (int i = 0; i < kFarK; i++) A[i] = 0.;
+                if (pe > pb) {
+                    const FarPiece last = s_pc[pe - 1];
+                    accumulate(pb, pe, s_pc[pb].off, last.off + ((((last.info >> 16) & 1)) ? last.n : (last.n + 1) / 2), false, A);
+                }
+                accumulate_mix(mb, me, false, A);
+                reduce_coefs<NT>(A, tid, s_red, s_red2, s_coef);
+            }
+            if (tid < kFarK) {
+                double v = work ? s_coef[tid] : 0.;
+                if (pin && active) v += translated(pin + (size_t)slot * kFarK);
+                out[(size_t)slot * kFarK + tid] = v;
+            }
+            __syncthreads();        // s_coef is reused by the next molecule
+            s = s_end;
+        }
+    }
+    if (a.counters && tid == 0) {
+        long long n_far = th.nterms;
+        for (int pi = npm; pi < np; pi++) n_far += 2ll * s_pc[pi].n;
+        atomicAdd(a.counters + 0, (unsigned long long)n_far);
+    }
 }
 
 // =============================================================================================
-// lines_kernel, version 5.  CTA = (NT*F frequencies, one layer, one profile); each thread owns F
-// (frequency, layer) accumulators.
-//  * the tile's plan (plan_kernel) is copied from HBM: no searches here
-//  * far field: a line whose poles (+-Xnu +- i*HWHM) are at least ff_ratio tile half-widths away from the tile
-//    centre is not evaluated per frequency; its Lorentz terms are expanded in a kFarK-term Taylor series about
-//    the tile centre (one line per thread, coalesced loads), the coefficients are summed over the CTA and every
-//    frequency evaluates the polynomial once per molecule.  Lines that are already far from the 8x (64x) wider
-//    parent tiles were expanded once per parent tile by far_kernel; their polynomials are added here.
-//    Truncation error <= ~(K+1)*ratio^-K of the line's own contribution (1.6e-13 for ratio 10, K 14).  The
-//    window test stays exact: only lines that are inside the 25 cm-1 window of EVERY frequency of the tile
-//    (proved with margins) take this path.
-//  * near field: line-parameter tiles (XNU, H2, CN, P3) of the remaining runs stream through shared memory with
-//    TMA bulk copies on an 8-stage mbarrier ring; interior ranges run branch-free (4 lines share one
-//    reciprocal); the narrow bands (window edges, the WN+Xnu<=25 boundary, the Voigt zone) run loops
-//    specialised per test combination with the reference's exact per-(line,frequency) tests (modm.f90:384, 427, 746)
+// near_kernel: the per-(line,layer,frequency) evaluations that remain after the far field is taken
+// out.  CTA = (NT*F frequencies, one layer, one profile); each thread owns F (frequency, layer)
+// accumulators.  The tile's plan (plan_kernel) is copied from HBM: no searches here.
+//  * line-parameter tiles (XNU, H2, CN, P3) of the direct runs stream through shared memory with TMA bulk
+//    copies on an 8-stage mbarrier ring; all threads read the same line -> smem broadcast
+//  * interior ranges run branch-free (4 lines share one reciprocal); the narrow bands (window edges, the
+//    WN+Xnu<=25 boundary, the Voigt zone) run loops with the reference's exact per-(line,frequency) tests
+//    (modm.f90:384, 427, 746); (line,frequency) pairs on the Voigt branch are left to voigt_kernel
+//  * writes sum_mol W_mol*SF_mol (direct part, without RFT) to O and, when per-molecule outputs are
+//    requested, W_mol*SF_mol to O_BY_MOL; final_kernel completes them
 // =============================================================================================
 template <int F, bool SEL, int NT>
-__global__ void __launch_bounds__(NT, (MRTM_LINES_MINB * 128) / NT) lines_kernel(LinesArgs a)
+__global__ void __launch_bounds__(NT, (MRTM_LINES_MINB * 128) / NT) near_kernel(LinesArgs a)
 {
     constexpr int NW = NT / 32;
     const int tid = threadIdx.x;
     const int k = blockIdx.y;                     // layer within profile
     const int prof = blockIdx.z;
     const int64_t L = (int64_t)prof * a.nlay + k;
-    const int64_t Ltot = (int64_t)gridDim.y * gridDim.z;
     const LayerDev& ly = a.lay[L];
     const double* pl = a.planes + (size_t)L * D_NPLANES * a.n_pad;
     const double* __restrict__ pXNU = pl + (size_t)D_XNU * a.n_pad;
@@ -1047,16 +1239,13 @@ __global__ void __launch_bounds__(NT, (MRTM_LINES_MINB * 128) / NT) lines_kernel
     const double* __restrict__ pP4 = pl + (size_t)D_P4 * a.n_pad;
     const double* __restrict__ pVT = pl + (size_t)D_VT * a.n_pad;
 
-    __shared__ __align__(8) uint64_t s_bar[kStages];      // stage filled (TMA transaction bytes)
-    __shared__ __align__(8) uint64_t s_empty[kStages];    // stage released (one arrival per warp)
-    __shared__ double s_red[kFarK][NT];
-    __shared__ double s_red2[kFarK][8];
-    __shared__ double s_coef[kFarK];
+    __shared__ __align__(8) uint64_t s_bar[kStages];
+    __shared__ __align__(8) uint64_t s_all_bar;
+    __shared__ double s_ped[2][NW];
     __shared__ unsigned char s_act[kMaxSegments];
     extern __shared__ __align__(128) unsigned char s_dyn[];
     double (*s_tile)[4][kTile] = reinterpret_cast<double (*)[4][kTile]>(s_dyn);      // [kStages][4][kTile]
     SegWork* s_work = reinterpret_cast<SegWork*>(s_dyn + sizeof(double) * kStages * 4 * kTile);
-    SegWork* s_pwork = s_work + a.nseg;           // parent level's plan (a.nlev > 1)
 
     const int nseg = a.nseg;
     {
@@ -1064,15 +1253,11 @@ __global__ void __launch_bounds__(NT, (MRTM_LINES_MINB * 128) / NT) lines_kernel
         const int* src = reinterpret_cast<const int*>(a.plan[0] + (size_t)blockIdx.x * nseg);
         int* dst = reinterpret_cast<int*>(s_work);
         for (int i = tid; i < nw; i += NT) dst[i] = src[i];
-        if (a.nlev > 1) {
-            const int* psrc = reinterpret_cast<const int*>(a.plan[1] + (size_t)(blockIdx.x / a.S) * nseg);
-            int* pdst = reinterpret_cast<int*>(s_pwork);
-            for (int i = tid; i < nw; i += NT) pdst[i] = psrc[i];
-        }
         for (int s = tid; s < nseg; s += NT) s_act[s] = (ly.wk[a.seg[s].mol - 1] != 0.) ? 1 : 0;   // W_SPECIES == 0: skipped (:318-321)
     }
     if (tid == 0) {
-        for (int i = 0; i < kStages; i++) { mbar_init(&s_bar[i], 1); mbar_init(&s_empty[i], NW); }
+        for (int i = 0; i < kStages; i++) mbar_init(&s_bar[i], 1);
+        mbar_init(&s_all_bar, 32);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
 
@@ -1087,11 +1272,12 @@ __global__ void __launch_bounds__(NT, (MRTM_LINES_MINB * 128) / NT) lines_kernel
         wn[f] = a.wn[valid[f] ? iw : (a.nwn - 1)];
     }
     const double rp = ly.rp, rp2 = ly.rp2;
-    // tile centre / half width (CTA uniform): expansion variable s = (WN - cen)/hh in [-1,1]
-    const TileHdr th = a.hdr[0][blockIdx.x];
-    const double cen = 0.5 * (th.wlo + th.whi), hh = 0.5 * (th.whi - th.wlo);
-    const double hinv = hh > 0. ? 1. / hh : 0.;
     __syncthreads();
+    // Staging: when all direct runs of the CTA fit the tile memory (the usual case with the far field on) they
+    // are staged at once -- one mbarrier wait, no per-tile hand-shake; otherwise tiles stream through the ring.
+    constexpr int kCap = kStages * kTile;
+    const bool stage_all = a.hdr[0][blockIdx.x].total_lines <= kCap;
+    double* s_all = reinterpret_cast<double*>(s_dyn);       // [4][kCap] in stage-all mode
 
     // ---- TMA tile jobs: (segment, run, tile) in consumption order; thread 0 keeps a cursor ahead of the consumer
     auto advance = [&](int& js, int& jr, int& jt) -> bool {
@@ -1121,14 +1307,51 @@ __global__ void __launch_bounds__(NT, (MRTM_LINES_MINB * 128) / NT) lines_kernel
         tma_load_1d(&s_tile[st][2][0], pCN + qs, bytes, &s_bar[st]);
         tma_load_1d(&s_tile[st][3][0], pP3 + qs, bytes, &s_bar[st]);
     };
+    int ped_buf = 0;            // alternates per reduction (s_ped double buffer)
     int pjs = 0, pjr = 0, pjt = -1;      // prefetch cursor (thread 0 only)
-    bool more = true;
-    if (tid == 0) {
-        for (int i = 0; i < kPrefetch && more; i++) {
+    bool more = !stage_all;
+    if (stage_all) {
+        // every lane of warp 0 announces and issues the copies of its own segments (barrier count 32)
+        if (tid < 32) {
+            uint32_t mybytes = 0;
+            for (int s = tid; s < nseg; s += 32) {
+                const SegWork& w = s_work[s];
+                if (!(w.tma && s_act[s])) continue;
+                for (int r = 0; r < w.nrun; r++) mybytes += (uint32_t)(((w.run_hi[r] - w.run_t0[r]) + 3) & ~3) * 32u;
+            }
+            mbar_expect_tx(&s_all_bar, mybytes);
+            for (int s = tid; s < nseg; s += 32) {
+                const SegWork& w = s_work[s];
+                if (!(w.tma && s_act[s])) continue;
+                for (int r = 0; r < w.nrun; r++) {
+                    const int qs = w.run_t0[r], off = w.run_off[r];
+                    const uint32_t bytes = (uint32_t)(((w.run_hi[r] - qs) + 3) & ~3) * 8u;
+                    tma_load_1d(s_all + 0 * kCap + off, pXNU + qs, bytes, &s_all_bar);
+                    tma_load_1d(s_all + 1 * kCap + off, pH2 + qs, bytes, &s_all_bar);
+                    tma_load_1d(s_all + 2 * kCap + off, pCN + qs, bytes, &s_all_bar);
+                    tma_load_1d(s_all + 3 * kCap + off, pP3 + qs, bytes, &s_all_bar);
+                }
+            }
+        }
+        mbar_wait(&s_all_bar, 0u);
+    } else if (tid == 0) {
+        for (int i = 0; i < kStages - 1 && more; i++) {
             more = advance(pjs, pjr, pjt);
             if (more) issue(pjs, pjr, pjt, i);
         }
     }
+    double ped_mol = 0., ped_w = 0.;     // stage-all mode: this thread's share of the interior pedestals (molecule / weighted total)
+    auto cta_sum = [&](double v) -> double {
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+        if ((tid & 31) == 0) s_ped[ped_buf][tid >> 5] = v;
+        __syncthreads();
+        double t = 0.;
+#pragma unroll
+        for (int i = 0; i < NW; i++) t += s_ped[ped_buf][i];
+        ped_buf ^= 1;
+        return t;
+    };
 
     int gtile = 0;              // global tile counter: stage = gtile % kStages, mbarrier parity = (gtile / kStages) & 1
 
@@ -1137,25 +1360,33 @@ __global__ void __launch_bounds__(NT, (MRTM_LINES_MINB * 128) / NT) lines_kernel
     unsigned long long hsh[F];
 #pragma unroll
     for (int f = 0; f < F; f++) { osum[f] = 0.; sf[f] = 0.; cnt[f] = 0; hsh[f] = 0ull; }
-    double rft[F];
-#pragma unroll
-    for (int f = 0; f < F; f++) rft[f] = wn[f] * tanh((ly.radct * wn[f]) / (2 * ly.t));   // modm.f90:257
 
     int err = 0;
-    // a layer without Voigt-capable lines runs its Voigt zones as plain near-field ranges
-    const int vmode_mask = a.layer_voigt[L] ? 0xff : (0xff & ~M_VOIGT);
-    long long n_far = 0, n_direct = 0;      // work counters (thread 0 reports them)
+    long long n_direct = 0;      // work counter (thread 0 reports it)
     int nvalid = 0;
     if (a.counters) {
         const int rem = a.nwn - base;
         nvalid = rem < NT * F ? rem : NT * F;
     }
+    // a layer without Voigt-capable lines runs its Voigt zones as plain near-field ranges
+    const int vmode_mask = a.layer_voigt[L] ? 0xff : (0xff & ~M_VOIGT);
+    int cur_mol = 0;
     auto finish_mol = [&](int mol) {
         if (mol <= 0) return;
         const double w = ly.wk[mol - 1];
+        if (stage_all) {
+            if (a.o_by_mol) {           // per-molecule outputs: close the pedestal sum per molecule
+                const double pacc = cta_sum(ped_mol);
+#pragma unroll
+                for (int f = 0; f < F; f++) sf[f] -= pacc;
+            } else {
+                ped_w = fma(w, ped_mol, ped_w);
+            }
+            ped_mol = 0.;
+        }
 #pragma unroll
         for (int f = 0; f < F; f++) {
-            double ol = (w == 0.) ? 0. : rft[f] * (w * sf[f]);        // modm.f90:436-438
+            const double ol = (w == 0.) ? 0. : (w * sf[f]);            // W*SF; RFT is applied by final_kernel (modm.f90:436-438)
             osum[f] = osum[f] + ol;                                    // :265-267 (molecule order)
             if (a.o_by_mol && valid[f]) {
                 int iw = base + f * NT + tid;
@@ -1165,289 +1396,399 @@ __global__ void __launch_bounds__(NT, (MRTM_LINES_MINB * 128) / NT) lines_kernel
         }
     };
 
-    // ---- molecules in order; per molecule: near field (direct) of its segments, far field, one CTA reduction
-    int s = 0;
-    while (s < nseg) {
-        const int mol = a.seg[s].mol, slot = a.seg[s].slot;
-        int s_end = s;
-        bool any_far = false, any_run = false;
-        for (; s_end < nseg && a.seg[s_end].mol == mol; s_end++) {
-            any_far |= (s_work[s_end].has_far != 0);
-            any_run |= (s_work[s_end].nrun != 0);
+    for (int s = 0; s < nseg; s++) {
+        const Segment sg = a.seg[s];
+        if (sg.mol != cur_mol) {
+            finish_mol(cur_mol);
+            cur_mol = sg.mol;
         }
-        if (!s_act[s]) {            // W_SPECIES == 0: molecule skipped (modm.f90:318-321)
-            finish_mol(mol);
-            s = s_end;
-            continue;
-        }
-        double pmine = 0.;          // this thread's share of the pedestals of the interior direct ranges
-        for (int sd = s; sd < s_end; sd++) {
-            const Segment sg = a.seg[sd];
-            const SegWork& wk = s_work[sd];
-            const int cls = sg.cls;
-            if (SEL && sg.mol == 7) {                          // every O2 line passes modm.f90:384
+        const SegWork& wk = s_work[s];
+        if (!s_act[s]) continue;
+        const int cls = sg.cls;
+        if (SEL) {
+            if (sg.mol == 7) {                             // every O2 line passes modm.f90:384
 #pragma unroll
                 for (int f = 0; f < F; f++) { cnt[f] += sg.count_all; hsh[f] += sg.hash_all; }
-            }
-            if (cls == CLS_PED || cls == CLS_O2 || cls == CLS_O2_LC35) {
-                const bool force_both = (cls == CLS_O2_LC35);
-                const bool count_sel = SEL && (cls == CLS_PED);
-                const int n0 = wk.n0;
-                const int nsub = wk.nbp - 1;
-                double psum[F];
+            } else if (cls == CLS_PED) {                   // every far line (any level) is inside the window of every frequency
+                for (int u = 0; u + 1 < wk.nbp; u++) {
+                    if (wk.mode[u] != 0) continue;
+                    const int lo = wk.bp[u], hi = wk.bp[u + 1];
+                    const unsigned long long hs = a.keypre[hi] - a.keypre[lo];
 #pragma unroll
-                for (int f = 0; f < F; f++) psum[f] = 0.;
-                for (int r = 0; r < wk.nrun; r++) {
-                    const int rlo = wk.run_lo[r], rhi = wk.run_hi[r], t0 = wk.run_t0[r], ntile = wk.run_nt[r];
-                    for (int t = 0; t < ntile; t++, gtile++) {
+                    for (int f = 0; f < F; f++) { cnt[f] += hi - lo; hsh[f] += hs; }
+                }
+            }
+        }
+        if (cls == CLS_PED || cls == CLS_O2 || cls == CLS_O2_LC35) {
+            const bool force_both = (cls == CLS_O2_LC35);
+            const bool count_sel = SEL && (cls == CLS_PED);
+            const int n0 = wk.n0;
+            double psum[F];
+#pragma unroll
+            for (int f = 0; f < F; f++) psum[f] = 0.;
+            double pacc = 0.;                              // pedestal total of the interior ranges (uniform)
+            for (int r = 0; r < wk.nrun; r++) {
+                const int rlo = wk.run_lo[r], rhi = wk.run_hi[r], t0 = wk.run_t0[r];
+                const int ntile = stage_all ? 1 : wk.run_nt[r];
+                for (int t = 0; t < ntile; t++) {
+                    const double *tX, *tH, *tC, *tP;
+                    int tb, thi;
+                    if (stage_all) {
+                        const int off = wk.run_off[r];
+                        tX = s_all + off; tH = s_all + kCap + off; tC = s_all + 2 * kCap + off; tP = s_all + 3 * kCap + off;
+                        tb = t0;
+                        thi = rhi;
+                    } else {
                         const int st = gtile % kStages;
-                        if (tid == 0 && more) {        // keep kPrefetch jobs in flight
+                        if (tid == 0 && more) {        // refill the stage the previous tile released
                             more = advance(pjs, pjr, pjt);
-                            if (more) {
-                                const int gj = gtile + kPrefetch, sj = gj % kStages;
-                                if (gj >= kStages) mbar_wait(&s_empty[sj], (uint32_t)(gj / kStages - 1) & 1u);   // every warp left tile gj-kStages
-                                issue(pjs, pjr, pjt, sj);
-                            }
+                            if (more) issue(pjs, pjr, pjt, (gtile + kStages - 1) % kStages);
                         }
                         mbar_wait(&s_bar[st], (uint32_t)(gtile / kStages) & 1u);
-                        const double* __restrict__ tX = s_tile[st][0];
-                        const double* __restrict__ tH = s_tile[st][1];
-                        const double* __restrict__ tC = s_tile[st][2];
-                        const double* __restrict__ tP = s_tile[st][3];
-                        const int tb = t0 + t * kTile;
-                        const int tlo = tb > rlo ? tb : rlo;
-                        const int thi = (tb + kTile) < rhi ? (tb + kTile) : rhi;
-                        for (int u = 0; u < nsub; u++) {
-                            const int x = wk.bp[u];
-                            const int mode = wk.mode[u] & vmode_mask;
-                            int lo = x > tlo ? x : tlo;
-                            int hi = wk.bp[u + 1] < thi ? wk.bp[u + 1] : thi;
-                            if (lo >= hi || wk.mode[u] == 0) continue;
-                            const bool negall = force_both || (x < n0);
-                            if (a.counters) n_direct += (long long)(hi - lo) * nvalid;
-                            if ((mode & 7) != 0) {
-                                // ---- band loops: the reference's exact per-(line,frequency) tests
-                                const bool edge = (mode & M_EDGE) != 0, negtest = (mode & M_NEG) != 0, vz = (mode & M_VOIGT) != 0;
-                                if (!vz) {
-                                    if (negall || negtest) {
-                                        for (int q = lo; q < hi; q++) {
-                                            const int j = q - tb;
-                                            const double xnu = tX[j], h2 = tH[j], cn = tC[j], ped = tP[j];
-#pragma unroll
-                                            for (int f = 0; f < F; f++) {
-                                                const double dm = wn[f] - xnu, sp = wn[f] + xnu;
-                                                const bool inwin = edge ? !(fabs(dm) > kDELTNUC) : true;
-                                                if (count_sel && inwin) { cnt[f]++; hsh[f] += a.key[q]; }
-                                                const bool neg = negall || (sp <= kDELTNUC);
-                                                const double r1 = rcp3(fma(dm, dm, h2)), r2 = rcp3(fma(sp, sp, h2));
-                                                const double val = cn * (r1 + (neg ? r2 : 0.)) - (neg ? 2. * ped : ped);
-                                                sf[f] += inwin ? val : 0.;
-                                            }
-                                        }
-                                    } else {
-                                        for (int q = lo; q < hi; q++) {
-                                            const int j = q - tb;
-                                            const double xnu = tX[j], h2 = tH[j], cn = tC[j], ped = tP[j];
-#pragma unroll
-                                            for (int f = 0; f < F; f++) {
-                                                const double dm = wn[f] - xnu;
-                                                const bool inwin = !(fabs(dm) > kDELTNUC);
-                                                if (count_sel && inwin) { cnt[f]++; hsh[f] += a.key[q]; }
-                                                const double val = fma(cn, rcp3(fma(dm, dm, h2)), -ped);
-                                                sf[f] += inwin ? val : 0.;
-                                            }
-                                        }
-                                    }
-                                    continue;
-                                }
-                                const int vkind = (cls == CLS_PED) ? 0 : ((cls == CLS_O2) ? 1 : 2);
+                        tX = s_tile[st][0]; tH = s_tile[st][1]; tC = s_tile[st][2]; tP = s_tile[st][3];
+                        tb = t0 + t * kTile;
+                        thi = (tb + kTile) < rhi ? (tb + kTile) : rhi;
+                        gtile++;
+                    }
+                    const int tlo = tb > rlo ? tb : rlo;
+                    double pmine = 0.;                          // this thread's share of the tile's interior pedestals
+                    for (int u = wk.run_u0[r]; u < wk.run_u1[r]; u++) {
+                        const int x = wk.bp[u];
+                        const int mode = wk.mode[u] & vmode_mask;
+                        int lo = x > tlo ? x : tlo;
+                        int hi = wk.bp[u + 1] < thi ? wk.bp[u + 1] : thi;
+                        if (lo >= hi || wk.mode[u] == 0) continue;
+                        const bool negall = force_both || (x < n0);
+                        if (a.counters) n_direct += (long long)(hi - lo) * nvalid;
+                        if ((mode & 7) != 0) {
+                            // ---- band loops: the reference's exact per-(line,frequency) tests
+                            const bool edge = (mode & M_EDGE) != 0, negtest = (mode & M_NEG) != 0, vz = (mode & M_VOIGT) != 0;
+                            if (negall || negtest) {
                                 for (int q = lo; q < hi; q++) {
                                     const int j = q - tb;
                                     const double xnu = tX[j], h2 = tH[j], cn = tC[j], ped = tP[j];
-                                    const double vt = __ldg(pVT + q);
-                                    unsigned vmask = 0u;
+                                    const double vt = vz ? __ldg(pVT + q) : -1.0;
 #pragma unroll
                                     for (int f = 0; f < F; f++) {
                                         const double dm = wn[f] - xnu, sp = wn[f] + xnu;
                                         const bool inwin = edge ? !(fabs(dm) > kDELTNUC) : true;
                                         if (count_sel && inwin) { cnt[f]++; hsh[f] += a.key[q]; }
-                                        const bool isv = inwin && (fabs(dm) <= vt);
-                                        const bool neg = negall || (negtest && (sp <= kDELTNUC));
+                                        const bool take = inwin && !(fabs(dm) <= vt);      // Voigt-branch pairs: voigt_kernel
+                                        const bool neg = negall || (sp <= kDELTNUC);
                                         const double r1 = rcp3(fma(dm, dm, h2)), r2 = rcp3(fma(sp, sp, h2));
                                         const double val = cn * (r1 + (neg ? r2 : 0.)) - (neg ? 2. * ped : ped);
-                                        sf[f] += (inwin && !isv) ? val : 0.;
-                                        vmask |= isv ? (1u << f) : 0u;
-                                    }
-                                    if (vmask) {                    // Voigt branch of modm.f90:427-431
-#pragma unroll
-                                        for (int f = 0; f < F; f++)
-                                            if (vmask & (1u << f)) sf[f] += voigt_lines_term(vkind, wn[f], xnu, pl, a.n_pad, q, a.sdep_s[q], rp, rp2, &err);
-                                    }
-                                }
-                                continue;
-                            }
-                            if (count_sel) {
-                                const unsigned long long hs = a.keypre[hi] - a.keypre[lo];
-#pragma unroll
-                                for (int f = 0; f < F; f++) { cnt[f] += hi - lo; hsh[f] += hs; }
-                            }
-                            // this thread's share of the interior pedestals (summed over the CTA with the far-field coefficients)
-                            {
-                                const double w = negall ? 2. : 1.;          // pedestal counted for both resonances (:749)
-                                for (int q = lo + tid; q < hi; q += NT) pmine = fma(w, tP[q - tb], pmine);
-                            }
-                            if (negall) {
-                                // ---- interior, both resonances: cn*(1/a+1/b) = cn*(a+b)/(a*b), one reciprocal
-MRTM_UNROLL(MRTM_UNROLL_BOTH)
-                                for (int q = lo; q < hi; q++) {
-                                    const int j = q - tb;
-                                    const double xnu = tX[j], h2 = tH[j], cn = tC[j];
-#pragma unroll
-                                    for (int f = 0; f < F; f++) {
-                                        const double dm = wn[f] - xnu, sp = wn[f] + xnu;
-                                        const double aa = fma(dm, dm, h2), bb = fma(sp, sp, h2);
-                                        const double r = rcp3(aa * bb);
-                                        psum[f] = fma(cn * (aa + bb), r, psum[f]);
+                                        sf[f] += take ? val : 0.;
                                     }
                                 }
                             } else {
-                                // ---- interior, single resonance (modm.f90:751): four lines share one reciprocal,
-                                // sum c_i/a_i = N/(a1 a2 a3 a4), N = (c1 a2 + c2 a1)(a3 a4) + (c3 a4 + c4 a3)(a1 a2);
-                                // 21 FP64 ops + 1 MUFU per 4 evaluations
-                                int q = lo;
-                                for (; q + 4 <= hi; q += 4) {
+                                for (int q = lo; q < hi; q++) {
                                     const int j = q - tb;
-                                    const double x1 = tX[j], x2 = tX[j + 1], x3 = tX[j + 2], x4 = tX[j + 3];
-                                    const double g1 = tH[j], g2 = tH[j + 1], g3 = tH[j + 2], g4 = tH[j + 3];
-                                    const double c1 = tC[j], c2 = tC[j + 1], c3 = tC[j + 2], c4 = tC[j + 3];
-#pragma unroll
-                                    for (int f = 0; f < F; f++) {
-                                        const double d1 = wn[f] - x1, d2 = wn[f] - x2, d3 = wn[f] - x3, d4 = wn[f] - x4;
-                                        const double a1 = fma(d1, d1, g1), a2 = fma(d2, d2, g2);
-                                        const double a3 = fma(d3, d3, g3), a4 = fma(d4, d4, g4);
-                                        const double p12 = a1 * a2, p34 = a3 * a4;
-                                        const double n12 = fma(c1, a2, c2 * a1), n34 = fma(c3, a4, c4 * a3);
-                                        const double r = rcp3(p12 * p34);
-                                        psum[f] = fma(fma(n12, p34, n34 * p12), r, psum[f]);
-                                    }
-                                }
-                                for (; q < hi; q++) {
-                                    const int j = q - tb;
-                                    const double xnu = tX[j], h2 = tH[j], cn = tC[j];
+                                    const double xnu = tX[j], h2 = tH[j], cn = tC[j], ped = tP[j];
+                                    const double vt = vz ? __ldg(pVT + q) : -1.0;
 #pragma unroll
                                     for (int f = 0; f < F; f++) {
                                         const double dm = wn[f] - xnu;
-                                        psum[f] = fma(cn, rcp3(fma(dm, dm, h2)), psum[f]);
+                                        const bool inwin = edge ? !(fabs(dm) > kDELTNUC) : true;
+                                        if (count_sel && inwin) { cnt[f]++; hsh[f] += a.key[q]; }
+                                        const bool take = inwin && !(fabs(dm) <= vt);
+                                        const double val = fma(cn, rcp3(fma(dm, dm, h2)), -ped);
+                                        sf[f] += take ? val : 0.;
                                     }
                                 }
                             }
+                            continue;
                         }
-                        // this warp has finished reading the stage
-                        __syncwarp();
-                        if ((tid & 31) == 0) mbar_arrive(&s_empty[st]);
-                    }
-                }
+                        if (count_sel) {
+                            const unsigned long long hs = a.keypre[hi] - a.keypre[lo];
 #pragma unroll
-                for (int f = 0; f < F; f++) sf[f] += psum[f];
-            } else if (cls == CLS_O2_LC1) {
-                for (int r = 0; r < wk.nrun; r++) {
-                    if (a.counters) n_direct += (long long)(wk.run_hi[r] - wk.run_lo[r]) * nvalid;
-                    for (int q = wk.run_lo[r]; q < wk.run_hi[r]; q++) {
-                        const double xnu = pXNU[q], h2 = pH2[q], cg = pP3[q], cq = pP4[q], vt = pVT[q];
+                            for (int f = 0; f < F; f++) { cnt[f] += hi - lo; hsh[f] += hs; }
+                        }
+                        // this thread's share of the interior pedestals of the tile (reduced across the CTA below)
+                        {
+                            const double w = negall ? 2. : 1.;          // pedestal counted for both resonances (:749)
+                            for (int q = lo + tid; q < hi; q += NT) pmine = fma(w, tP[q - tb], pmine);
+                        }
+                        if (negall) {
+                            // ---- interior, both resonances: cn*(1/a+1/b) = cn*(a+b)/(a*b), one reciprocal
+MRTM_UNROLL(MRTM_UNROLL_BOTH)
+                            for (int q = lo; q < hi; q++) {
+                                const int j = q - tb;
+                                const double xnu = tX[j], h2 = tH[j], cn = tC[j];
 #pragma unroll
-                        for (int f = 0; f < F; f++) {
-                            const double dm = wn[f] - xnu, sp = wn[f] + xnu;
-                            if (fabs(dm) <= vt) {
-                                sf[f] += voigt_lines_term(3, wn[f], xnu, pl, a.n_pad, q, a.sdep_s[q], rp, rp2, &err);
-                            } else {
-                                const double r1 = rcp3(fma(dm, dm, h2));
-                                const double r2 = rcp3(fma(sp, sp, h2));
-                                sf[f] += fma(cq, dm, cg) * r1 + fma(-cq, sp, cg) * r2;
+                                for (int f = 0; f < F; f++) {
+                                    const double dm = wn[f] - xnu, sp = wn[f] + xnu;
+                                    const double aa = fma(dm, dm, h2), bb = fma(sp, sp, h2);
+                                    const double r = rcp3(aa * bb);
+                                    psum[f] = fma(cn * (aa + bb), r, psum[f]);
+                                }
+                            }
+                        } else {
+                            // ---- interior, single resonance (modm.f90:751): four lines share one reciprocal,
+                            // sum c_i/a_i = N/(a1 a2 a3 a4), N = (c1 a2 + c2 a1)(a3 a4) + (c3 a4 + c4 a3)(a1 a2);
+                            // 21 FP64 ops + 1 MUFU per 4 evaluations
+                            int q = lo;
+                            for (; q + 4 <= hi; q += 4) {
+                                const int j = q - tb;
+                                const double x1 = tX[j], x2 = tX[j + 1], x3 = tX[j + 2], x4 = tX[j + 3];
+                                const double g1 = tH[j], g2 = tH[j + 1], g3 = tH[j + 2], g4 = tH[j + 3];
+                                const double c1 = tC[j], c2 = tC[j + 1], c3 = tC[j + 2], c4 = tC[j + 3];
+#pragma unroll
+                                for (int f = 0; f < F; f++) {
+                                    const double d1 = wn[f] - x1, d2 = wn[f] - x2, d3 = wn[f] - x3, d4 = wn[f] - x4;
+                                    const double a1 = fma(d1, d1, g1), a2 = fma(d2, d2, g2);
+                                    const double a3 = fma(d3, d3, g3), a4 = fma(d4, d4, g4);
+                                    const double p12 = a1 * a2, p34 = a3 * a4;
+                                    const double n12 = fma(c1, a2, c2 * a1), n34 = fma(c3, a4, c4 * a3);
+                                    const double r = rcp3(p12 * p34);
+                                    psum[f] = fma(fma(n12, p34, n34 * p12), r, psum[f]);
+                                }
+                            }
+                            for (; q < hi; q++) {
+                                const int j = q - tb;
+                                const double xnu = tX[j], h2 = tH[j], cn = tC[j];
+#pragma unroll
+                                for (int f = 0; f < F; f++) {
+                                    const double dm = wn[f] - xnu;
+                                    psum[f] = fma(cn, rcp3(fma(dm, dm, h2)), psum[f]);
+                                }
                             }
                         }
                     }
+                    if (stage_all) {
+                        ped_mol += pmine;
+                    } else {
+                        // CTA-wide sum of the interior pedestals of this tile (uniform result); the barrier inside also
+                        // orders all reads of this stage before it is refilled
+                        pacc += cta_sum(pmine);
+                    }
                 }
-            } else {   // CLS_GENERAL: faithful case tree per (line, frequency)
-                if (a.counters) n_direct += (long long)(wk.q1 - wk.q0) * nvalid;
-                for (int q = wk.q0; q < wk.q1; q++) {
-                    const double xnu = pXNU[q], vt = pVT[q];
-                    const double hw = pl[(size_t)D_H * a.n_pad + q], ad = pl[(size_t)D_AD * a.n_pad + q];
-                    const double st = pl[(size_t)D_STILD * a.n_pad + q];
-                    const double aip = pl[(size_t)D_AIP * a.n_pad + q], bip = pl[(size_t)D_BIP * a.n_pad + q];
-                    const int xf = a.xf_s[q];
+            }
+#pragma unroll
+            for (int f = 0; f < F; f++) sf[f] += psum[f] - pacc;
+        } else if (cls == CLS_O2_LC1) {
+            for (int r = 0; r < wk.nrun; r++) {
+                if (a.counters) n_direct += (long long)(wk.run_hi[r] - wk.run_lo[r]) * nvalid;
+                for (int q = wk.run_lo[r]; q < wk.run_hi[r]; q++) {
+                    const double xnu = pXNU[q], h2 = pH2[q], cg = pP3[q], cq = pP4[q], vt = pVT[q];
+#pragma unroll
+                    for (int f = 0; f < F; f++) {
+                        const double dm = wn[f] - xnu, sp = wn[f] + xnu;
+                        const double r1 = rcp3(fma(dm, dm, h2));
+                        const double r2 = rcp3(fma(sp, sp, h2));
+                        const double val = fma(cq, dm, cg) * r1 + fma(-cq, sp, cg) * r2;
+                        sf[f] += (fabs(dm) <= vt) ? 0. : val;           // Voigt-branch pairs: voigt_kernel
+                    }
+                }
+            }
+        } else {   // CLS_GENERAL: faithful case tree per (line, frequency)
+            if (a.counters) n_direct += (long long)(wk.q1 - wk.q0) * nvalid;
+            for (int q = wk.q0; q < wk.q1; q++) {
+                const double xnu = pXNU[q], vt = pVT[q];
+                const double hw = pl[(size_t)D_H * a.n_pad + q], ad = pl[(size_t)D_AD * a.n_pad + q];
+                const double st = pl[(size_t)D_STILD * a.n_pad + q];
+                const double aip = pl[(size_t)D_AIP * a.n_pad + q], bip = pl[(size_t)D_BIP * a.n_pad + q];
+                const int xf = a.xf_s[q];
+#pragma unroll
+                for (int f = 0; f < F; f++) {
+                    const double dm = wn[f] - xnu;
+                    if ((fabs(dm) > kDELTNUC) && (sg.mol != 7)) continue;          // modm.f90:384
+                    if (SEL && sg.mol != 7) { cnt[f]++; hsh[f] += a.key[q]; }
+                    const bool voigt = fabs(dm) <= vt;
+                    sf[f] += st * lsf_general(sg.mol, xf, rp, rp2, aip, bip, hw, wn[f], xnu, ad, a.sdep_s[q], voigt, &err);
+                }
+            }
+        }
+    }
+    finish_mol(cur_mol);
+    if (stage_all && !a.o_by_mol) {       // one CTA reduction for the W-weighted interior pedestals of all molecules
+        const double pacc = cta_sum(ped_w);
+#pragma unroll
+        for (int f = 0; f < F; f++) osum[f] -= pacc;
+    }
+    if (err) atomicOr(a.errflag, 2);
+    if (a.counters && tid == 0) atomicAdd(a.counters + 1, (unsigned long long)n_direct);
+#pragma unroll
+    for (int f = 0; f < F; f++) {
+        if (!valid[f]) continue;
+        const int iw = base + f * NT + tid;
+        const size_t fl = (size_t)iw + (size_t)k * a.o_lds + (size_t)prof * a.o_prof;
+        a.o[fl] = osum[f];
+        if (SEL) {
+            if (a.sel_count) a.sel_count[fl] = cnt[f];
+            if (a.sel_hash) a.sel_hash[fl] = hsh[f];
+        }
+    }
+}
+
+// =============================================================================================
+// voigt_kernel: the Voigt branch (modm.f90:427-431).  CTA = (frequency tile, layer, profile); it leaves
+// at once when the layer has no Voigt-capable line.  For the lines of the plan's Voigt zones it applies
+// the reference's test |WN-Xnu| <= 100*HWHM_D per (line, frequency) and adds W*STILD*SLS of the pairs that
+// pass (near_kernel skipped exactly those) to O [and O_BY_MOL].
+// =============================================================================================
+template <int F, int NT>
+__global__ void __launch_bounds__(NT) voigt_kernel(LinesArgs a)
+{
+    const int tid = threadIdx.x;
+    const int k = blockIdx.y, prof = blockIdx.z;
+    const int64_t L = (int64_t)prof * a.nlay + k;
+    if (!a.layer_voigt[L]) return;
+    const LayerDev& ly = a.lay[L];
+    const double* pl = a.planes + (size_t)L * D_NPLANES * a.n_pad;
+    const double* __restrict__ pXNU = pl + (size_t)D_XNU * a.n_pad;
+    const double* __restrict__ pVT = pl + (size_t)D_VT * a.n_pad;
+    const SegWork* plan = a.plan[0] + (size_t)blockIdx.x * a.nseg;
+    constexpr int kVChunk = 256;
+    __shared__ double s_vt[kVChunk], s_x[kVChunk];
+    const int base = blockIdx.x * (NT * F);
+    double wn[F], vsum[F];
+    bool valid[F];
+#pragma unroll
+    for (int f = 0; f < F; f++) {
+        int iw = base + f * NT + tid;
+        valid[f] = iw < a.nwn;
+        wn[f] = a.wn[valid[f] ? iw : (a.nwn - 1)];
+        vsum[f] = 0.;
+    }
+    const double rp = ly.rp, rp2 = ly.rp2;
+    int err = 0;
+    bool any = false;
+    int s = 0;
+    while (s < a.nseg) {
+        const int mol = a.seg[s].mol;
+        const double w = ly.wk[mol - 1];
+        double msum[F];
+#pragma unroll
+        for (int f = 0; f < F; f++) msum[f] = 0.;
+        bool many = false;
+        int s_end = s;
+        for (; s_end < a.nseg && a.seg[s_end].mol == mol; s_end++) {
+            const int cls = a.seg[s_end].cls;
+            if (w == 0. || cls == CLS_GENERAL) continue;
+            const int v0 = plan[s_end].v0, v1 = plan[s_end].v1;
+            const int kind = (cls == CLS_PED) ? 0 : ((cls == CLS_O2) ? 1 : ((cls == CLS_O2_LC35) ? 2 : 3));
+            const bool has_win = (cls == CLS_PED) || (cls == CLS_O2);
+            for (int c0 = v0; c0 < v1; c0 += kVChunk) {          // zone lines staged through shared memory (coalesced loads)
+                const int n = min(kVChunk, v1 - c0);
+                __syncthreads();
+                for (int i = tid; i < n; i += NT) { s_vt[i] = __ldg(pVT + c0 + i); s_x[i] = __ldg(pXNU + c0 + i); }
+                __syncthreads();
+                for (int i = 0; i < n; i++) {
+                    const double vt = s_vt[i];
+                    if (!(vt >= 0.)) continue;
+                    const double xnu = s_x[i];
+                    const int q = c0 + i;
 #pragma unroll
                     for (int f = 0; f < F; f++) {
                         const double dm = wn[f] - xnu;
-                        if ((fabs(dm) > kDELTNUC) && (sg.mol != 7)) continue;          // modm.f90:384
-                        if (SEL && sg.mol != 7) { cnt[f]++; hsh[f] += a.key[q]; }
-                        const bool voigt = fabs(dm) <= vt;
-                        sf[f] += st * lsf_general(sg.mol, xf, rp, rp2, aip, bip, hw, wn[f], xnu, ad, a.sdep_s[q], voigt, &err);
+                        const bool inwin = has_win ? !(fabs(dm) > kDELTNUC) : true;
+                        if (inwin && fabs(dm) <= vt) {
+                            msum[f] += voigt_lines_term(kind, wn[f], xnu, pl, a.n_pad, q, a.sdep_s[q], rp, rp2, &err);
+                            many = true;
+                        }
                     }
                 }
             }
         }
-        // ---- far field of every segment of this molecule; the interior pedestals ride on coefficient 0
-        if (any_far || any_run) {
-            double A[kFarK];
-#pragma unroll
-            for (int i = 0; i < kFarK; i++) A[i] = 0.;
-            A[0] = -pmine;
-            for (int s2 = s; s2 < s_end; s2++) {
-                const SegWork& wk = s_work[s2];
-                if (!wk.has_far) continue;
-                const int cls2 = a.seg[s2].cls;
-                const bool mix = (cls2 == CLS_O2_LC1);
-                if (SEL && cls2 == CLS_PED) {       // every far line (any level) is inside the window of every frequency
-                    for (int u = 0; u + 1 < wk.nbp; u++) {
-                        if (wk.mode[u] != 0) continue;
-                        const int lo = wk.bp[u], hi = wk.bp[u + 1];
-                        const unsigned long long hs = a.keypre[hi] - a.keypre[lo];
-#pragma unroll
-                        for (int f = 0; f < F; f++) { cnt[f] += hi - lo; hsh[f] += hs; }
-                    }
-                }
-                far_pass_segment<NT>(wk, a.nlev > 1 ? &s_pwork[s2] : nullptr, cls2, tid, pXNU, pH2, mix ? pP3 : pCN, mix ? pP4 : pP3,
-                                     cen, hh, A, n_far);
-            }
-            reduce_coefs<NT>(A, tid, s_red, s_red2, s_coef);
+        if (many) {
+            any = true;
 #pragma unroll
             for (int f = 0; f < F; f++) {
-                const double sv = (wn[f] - cen) * hinv;
-                double p = s_coef[kFarK - 1];
-#pragma unroll
-                for (int i = kFarK - 2; i >= 0; i--) p = fma(p, sv, s_coef[i]);
-                sf[f] += p;
-            }
-        }
-        // the parents' polynomials (lines expanded once per parent tile by far_kernel)
-        if (any_far) {
-            int ptile = blockIdx.x;
-            for (int lv = 1; lv < a.nlev; lv++) {
-                ptile /= a.S;
-                const TileHdr ph = a.hdr[lv][ptile];
-                const double pc = 0.5 * (ph.wlo + ph.whi), phh = 0.5 * (ph.whi - ph.wlo);
-                const double phinv = phh > 0. ? 1. / phh : 0.;
-                const double* __restrict__ cf = a.coef[lv] + (((size_t)ptile * Ltot + L) * a.nslot + slot) * kFarK;
-                double c[kFarK];
-#pragma unroll
-                for (int i = 0; i < kFarK; i++) c[i] = __ldg(cf + i);
-#pragma unroll
-                for (int f = 0; f < F; f++) {
-                    const double sv = (wn[f] - pc) * phinv;
-                    double p = c[kFarK - 1];
-#pragma unroll
-                    for (int i = kFarK - 2; i >= 0; i--) p = fma(p, sv, c[i]);
-                    sf[f] += p;
+                const double ol = w * msum[f];
+                vsum[f] += ol;
+                if (a.o_by_mol && valid[f] && msum[f] != 0.) {
+                    int iw = base + f * NT + tid;
+                    a.o_by_mol[(size_t)iw + (size_t)(mol - 1) * a.obm_ldm + (size_t)L * a.obm_ldk] += ol;
                 }
             }
         }
-        finish_mol(mol);
         s = s_end;
     }
     if (err) atomicOr(a.errflag, 2);
-    if (a.counters && tid == 0) {
-        atomicAdd(a.counters + 0, (unsigned long long)n_far);
-        atomicAdd(a.counters + 1, (unsigned long long)n_direct);
+    if (any) {
+#pragma unroll
+        for (int f = 0; f < F; f++) {
+            if (!valid[f] || vsum[f] == 0.) continue;
+            const int iw = base + f * NT + tid;
+            a.o[(size_t)iw + (size_t)k * a.o_lds + (size_t)prof * a.o_prof] += vsum[f];
+        }
+    }
+}
+
+// =============================================================================================
+// final_kernel: per (frequency, layer): the far-field polynomial of the level-0 tile, RFT (modm.f90:257),
+// the continuum interpolation + RADFN (:218-230), cloud liquid water (:264) and the total (:265-269).
+// =============================================================================================
+template <int F, int NT>
+__global__ void __launch_bounds__(NT) final_kernel(LinesArgs a)
+{
+    const int tid = threadIdx.x;
+    const int k = blockIdx.y, prof = blockIdx.z;
+    const int64_t L = (int64_t)prof * a.nlay + k;
+    const int64_t Ltot = (int64_t)gridDim.y * gridDim.z;
+    const LayerDev& ly = a.lay[L];
+    __shared__ double s_coef[kFarK];
+    const int base = blockIdx.x * (NT * F);
+    double wn[F], sv[F];
+    bool valid[F];
+    const bool have_far = a.coef[0] != nullptr;
+    double cen = 0., hinv = 0.;
+    if (have_far) {
+        const TileHdr th = a.hdr[0][blockIdx.x];
+        const double hh = 0.5 * (th.whi - th.wlo);
+        cen = 0.5 * (th.wlo + th.whi);
+        hinv = hh > 0. ? 1. / hh : 0.;
+    }
+#pragma unroll
+    for (int f = 0; f < F; f++) {
+        int iw = base + f * NT + tid;
+        valid[f] = iw < a.nwn;
+        wn[f] = a.wn[valid[f] ? iw : (a.nwn - 1)];
+        sv[f] = (wn[f] - cen) * hinv;
+    }
+    const double* cf = have_far ? a.coef[0] + ((size_t)blockIdx.x * Ltot + L) * a.nslot * kFarK : nullptr;
+    double osum[F];
+    if (!a.o_by_mol) {
+        // one polynomial: sum over molecules of W_mol * coefficients (molecule order)
+        if (have_far && tid < kFarK) s_coef[tid] = cf[tid];        // far_kernel ran in combined mode (nslot == 1)
+        __syncthreads();
+#pragma unroll
+        for (int f = 0; f < F; f++) {
+            const int iw = base + f * NT + tid;
+            const size_t fl = (size_t)iw + (size_t)k * a.o_lds + (size_t)prof * a.o_prof;
+            double v = valid[f] ? a.o[fl] : 0.;
+            if (have_far) {
+                double p = s_coef[kFarK - 1];
+#pragma unroll
+                for (int i = kFarK - 2; i >= 0; i--) p = fma(p, sv[f], s_coef[i]);
+                v += p;
+            }
+            const double rft = wn[f] * tanh((ly.radct * wn[f]) / (2 * ly.t));   // modm.f90:257
+            osum[f] = rft * v;
+        }
+    } else {
+#pragma unroll
+        for (int f = 0; f < F; f++) osum[f] = 0.;
+        for (int sl = 0; sl < a.nslot; sl++) {
+            const int mol = a.slot_mol[sl];
+            const double w = ly.wk[mol - 1];
+            double c[kFarK];
+#pragma unroll
+            for (int i = 0; i < kFarK; i++) c[i] = have_far ? __ldg(cf + (size_t)sl * kFarK + i) : 0.;
+#pragma unroll
+            for (int f = 0; f < F; f++) {
+                if (!valid[f]) continue;
+                const int iw = base + f * NT + tid;
+                const size_t idx = (size_t)iw + (size_t)(mol - 1) * a.obm_ldm + (size_t)L * a.obm_ldk;
+                double p = c[kFarK - 1];
+#pragma unroll
+                for (int i = kFarK - 2; i >= 0; i--) p = fma(p, sv[f], c[i]);
+                const double rft = wn[f] * tanh((ly.radct * wn[f]) / (2 * ly.t));
+                const double ol = (w == 0.) ? 0. : rft * (a.o_by_mol[idx] + w * p);     // modm.f90:436-438
+                a.o_by_mol[idx] = ol;
+                osum[f] = osum[f] + ol;                                              // :265-267 (molecule order)
+            }
+        }
     }
 
     // ---- epilogue: continuum, cloud, totals ---------------------------------------------------
@@ -1485,12 +1826,8 @@ MRTM_UNROLL(MRTM_UNROLL_BOTH)
         double oclw = (ly.clw == 0.) ? 0. : odclw_tkc(wn[f], ly.t, ly.clw);   // modm.f90:264
         double odx = a.odxsec ? a.odxsec[fl] : 0.;
         double tot = osum[f] + odx + 0. + soc + oclw;                  // :268-269 (oc_rayl = 0 for V2 < 820)
-        if (a.o) a.o[fl] = tot;
+        a.o[fl] = tot;
         if (a.o_clw) a.o_clw[fl] = oclw;
-        if (SEL) {
-            if (a.sel_count) a.sel_count[fl] = cnt[f];
-            if (a.sel_hash) a.sel_hash[fl] = hsh[f];
-        }
     }
 }
 
