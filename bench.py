@@ -41,7 +41,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--nwn-per-gpu", type=int, default=int(os.environ.get("MRTM_BENCH_NWN", 16384)))
+    ap.add_argument("--nwn-per-gpu", type=int, default=int(os.environ.get("MRTM_BENCH_NWN", 125000)))
     ap.add_argument("--n-filler", type=int, default=N_FILLER, help="synthetic filler lines (65536 full-like, 4096 fast-like)")
     ap.add_argument("--cpu-sample-nwn", type=int, default=32)
     ap.add_argument("--direct-steps", type=int, default=3, help="extra steps timed with line_mode=1 (direct evaluation)")
