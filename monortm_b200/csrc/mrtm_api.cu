@@ -51,7 +51,7 @@ struct mrtm_ctx {
     DevBuf b_lvoigt;                              // [L] per-layer "has Voigt-capable lines" flag
     DevBuf b_plan[kMaxLevels], b_hdr[kMaxLevels], b_coef[kMaxLevels], b_pieces[kMaxLevels];
     int ff_levels = 3, ff_S = 8;                  // far-field hierarchy (MRTM_FF_LEVELS 1..3, MRTM_FF_S)
-    DevBuf b_layer, b_scorc, b_absrb, b_planes, b_o, b_obm, b_oc, b_in[16], b_out[16], b_sel[2], b_tmps;
+    DevBuf b_layer, b_scorc, b_absrb, b_planes, b_o, b_obm, b_oc, b_in[16], b_out[16], b_sel[2], b_tmps, b_fbeta;
     mrtm_stats st;
     size_t planes_budget = (size_t)8 << 30;
 };
@@ -185,7 +185,7 @@ extern "C" int mrtm_free(mrtm_ctx* ctx)
     cudaStreamSynchronize(ctx->stream);
     free_lines(ctx);
     for (void* p : ctx->table_allocs) cudaFree(p);
-    DevBuf* bufs[] = {&ctx->b_lvoigt, &ctx->b_vtmax, &ctx->b_layer, &ctx->b_scorc, &ctx->b_absrb, &ctx->b_planes, &ctx->b_o, &ctx->b_obm, &ctx->b_oc, &ctx->b_sel[0], &ctx->b_sel[1], &ctx->b_tmps};
+    DevBuf* bufs[] = {&ctx->b_lvoigt, &ctx->b_vtmax, &ctx->b_layer, &ctx->b_scorc, &ctx->b_absrb, &ctx->b_planes, &ctx->b_o, &ctx->b_obm, &ctx->b_oc, &ctx->b_sel[0], &ctx->b_sel[1], &ctx->b_tmps, &ctx->b_fbeta};
     for (DevBuf* b : bufs) if (b->p) cudaFree(b->p);
     for (int i = 0; i < kMaxLevels; i++) {
         if (ctx->b_plan[i].p) cudaFree(ctx->b_plan[i].p);
@@ -602,6 +602,15 @@ static int run_device(mrtm_ctx* ctx, const RunDesc& r, cudaStream_t s)
             ra.rad = off(r.rad); ra.tb = off(r.tb); ra.tmr = off(r.tmr);
             ra.trtot = off(r.trtot); ra.rup = off(r.rup); ra.rdn = off(r.rdn);
             CU(cudaEventRecord(ctx->ev[4], s));
+            {   // RADCN2/T per layer and level, once per batch
+                const int n_t = (int)(nb * nlay), n_tz = (int)(nb * (nlay + 1));
+                if ((rc = ensure(ctx, ctx->b_fbeta, (size_t)(n_t + n_tz) * 8))) return rc;
+                double* fb = (double*)ctx->b_fbeta.p;
+                rt_prep_kernel<<<(unsigned)((n_tz + 127) / 128), 128, 0, s>>>(n_t, ra.t, fb, n_tz, ra.tz, fb + n_t);
+                ra.fb = fb;
+                ra.fbz = fb + n_t;
+                st.kernel_launches++;
+            }
             rt_kernel<<<dim3((unsigned)((nwn + 127) / 128), (unsigned)nb), 128, 0, s>>>(ra);
             CU(cudaEventRecord(ctx->ev[5], s));
             st.kernel_launches++;

@@ -26,6 +26,17 @@ __device__ __forceinline__ double fast_rcp(double x)
     return r;
 }
 
+// reciprocal of a strictly positive normal double: MUFU seed (rel. err <= 2^-20) and one
+// third-order step r0*(1+e+e^2), e = 1-x*r0: error e^3 <= 2^-60, i.e. ~1 ulp after rounding.
+__device__ __forceinline__ double rcp3(double x)
+{
+    double r0;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r0) : "d"(x));
+    double e = fma(-x, r0, 1.0);
+    double t = fma(e, e, e);
+    return fma(r0, t, r0);
+}
+
 // ---- complex helpers ------------------------------------------------------------------------
 struct cplx {
     double re, im;
@@ -158,6 +169,38 @@ __device__ __forceinline__ double w4_re(double x, double y)
 {
     if (!(fabs(x) + y < 15.)) return hum1_re(x, y);
     return w4(x, y).re;
+}
+
+// Real part of W4 for voigt_kernel's staged lines: the same Humlicek regions, boundaries and constants as
+// W4 (modm.f90:1100-1130); the complex quotients are formed as a*conj(b)/|b|^2 with the ~1 ulp reciprocal
+// instead of IEEE divisions (the denominators are far from over/underflow for s < 15).
+__device__ __forceinline__ double cdiv_re(cplx a, cplx b)
+{
+    return (a.re * b.re + a.im * b.im) * rcp3(b.re * b.re + b.im * b.im);
+}
+__device__ __noinline__ double w4_re_near(double x, double y)
+{
+    const cplx t = cmk(y, -x);
+    const double s = fabs(x) + y;
+    if (!(s < 5.5)) {                    // region II
+        const cplx u = t * t;
+        return cdiv_re(t * (1.410474 + u * .5641896), .75 + u * (3. + u));
+    }
+    if (!(y < 0.195 * fabs(x) - 0.176))  // region III
+        return cdiv_re(16.4955 + t * (20.20933 + t * (11.96482 + t * (3.778987 + t * .5642236))),
+                       16.4955 + t * (38.82363 + t * (39.27121 + t * (21.69274 + t * (6.699398 + t)))));
+    const cplx u = t * t;                // region IV
+    const cplx num = t * (36183.31 - u * (3321.9905 - u * (1540.787 - u * (219.0313 - u * (35.76683 - u * (1.320522 - u * .56419))))));
+    const cplx den = 32066.6 - u * (24322.84 - u * (9022.228 - u * (2186.181 - u * (364.2191 - u * (61.57037 - u * (1.841439 - u))))));
+    return cexpd(u).re - cdiv_re(num, den);
+}
+__device__ __forceinline__ double w4_re_fast(double x, double y)
+{
+    if (!(fabs(x) + y < 15.)) {          // region I: Re[t*.5641896/(.5+t*t)]
+        const double dre = .5 + (y * y - x * x), dim = -2. * (x * y);
+        return (.5641896 * (y * dre - x * dim)) * rcp3(dre * dre + dim * dim);
+    }
+    return w4_re_near(x, y);
 }
 
 // The Voigt branch (modm.f90:427-431 -> LSF_SDVOIGT :567-704) for the line classes the line kernel

@@ -605,17 +605,6 @@ __device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src_gmem
                  ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
-// reciprocal of a strictly positive normal double: MUFU seed (rel. err <= 2^-20) and one
-// third-order step r0*(1+e+e^2), e = 1-x*r0: error e^3 <= 2^-60, i.e. ~1 ulp after rounding.
-__device__ __forceinline__ double rcp3(double x)
-{
-    double r0;
-    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r0) : "d"(x));
-    double e = fma(-x, r0, 1.0);
-    double t = fma(e, e, e);
-    return fma(r0, t, r0);
-}
-
 #ifndef MRTM_LINES_MINB
 #define MRTM_LINES_MINB 4
 #endif
@@ -627,7 +616,11 @@ __device__ __forceinline__ double rcp3(double x)
 constexpr int kTile = 128;      // lines per smem tile
 constexpr int kStages = 8;      // tile ring
 constexpr int kPrefetch = 5;    // TMA jobs in flight ahead of the consumer; a warp may run kStages-kPrefetch tiles ahead of the slowest
-constexpr int kFarK = 14;       // Taylor terms of the far-field expansion (degree kFarK-1)
+#ifndef MRTM_FARK
+#define MRTM_FARK 14
+#endif
+constexpr int kFarK = MRTM_FARK; // Taylor terms of the far-field expansion (degree kFarK-1); <= 16 (reduce_coefs)
+static_assert(kFarK >= 4 && kFarK <= 16, "kFarK out of range");
 constexpr int kMaxBp = 12;      // break points per segment
 constexpr int kMaxRun = 6;      // direct runs per segment
 
@@ -1637,9 +1630,17 @@ __global__ void __launch_bounds__(NT) voigt_kernel(LinesArgs a)
     const double* pl = a.planes + (size_t)L * D_NPLANES * a.n_pad;
     const double* __restrict__ pXNU = pl + (size_t)D_XNU * a.n_pad;
     const double* __restrict__ pVT = pl + (size_t)D_VT * a.n_pad;
+    const double* __restrict__ pH = pl + (size_t)D_H * a.n_pad;
+    const double* __restrict__ pAD = pl + (size_t)D_AD * a.n_pad;
+    const double* __restrict__ pST = pl + (size_t)D_STILD * a.n_pad;
+    const double* __restrict__ pAIP = pl + (size_t)D_AIP * a.n_pad;
+    const double* __restrict__ pBIP = pl + (size_t)D_BIP * a.n_pad;
     const SegWork* plan = a.plan[0] + (size_t)blockIdx.x * a.nseg;
-    constexpr int kVChunk = 256;
-    __shared__ double s_vt[kVChunk], s_x[kVChunk];
+    // Per zone line, once per CTA (amortised over the NT*F frequencies): everything of LSF_SDVOIGT/SDVOIGT that does
+    // not depend on the frequency -- 1/alphaD, y = sqrt(ln2)*alphaL/alphaD, STILD*sqrt(ln2/pi)/alphaD, the Voigt
+    // pedestal at 25 cm-1 (modm.f90:590) and the mixing factors (:595-596).
+    constexpr int kVChunk = 128;
+    __shared__ double s_vt[kVChunk], s_x[kVChunk], s_inv[kVChunk], s_y[kVChunk], s_c[kVChunk], s_pd[kVChunk], s_g[kVChunk], s_b[kVChunk];
     const int base = blockIdx.x * (NT * F);
     double wn[F], vsum[F];
     bool valid[F];
@@ -1651,6 +1652,7 @@ __global__ void __launch_bounds__(NT) voigt_kernel(LinesArgs a)
         vsum[f] = 0.;
     }
     const double rp = ly.rp, rp2 = ly.rp2;
+    const double sl2 = 0.8325546111576977;         // sqrt(log(2))
     int err = 0;
     bool any = false;
     int s = 0;
@@ -1668,22 +1670,57 @@ __global__ void __launch_bounds__(NT) voigt_kernel(LinesArgs a)
             const int v0 = plan[s_end].v0, v1 = plan[s_end].v1;
             const int kind = (cls == CLS_PED) ? 0 : ((cls == CLS_O2) ? 1 : ((cls == CLS_O2_LC35) ? 2 : 3));
             const bool has_win = (cls == CLS_PED) || (cls == CLS_O2);
-            for (int c0 = v0; c0 < v1; c0 += kVChunk) {          // zone lines staged through shared memory (coalesced loads)
+            for (int c0 = v0; c0 < v1; c0 += kVChunk) {
                 const int n = min(kVChunk, v1 - c0);
                 __syncthreads();
-                for (int i = tid; i < n; i += NT) { s_vt[i] = __ldg(pVT + c0 + i); s_x[i] = __ldg(pXNU + c0 + i); }
+                for (int i = tid; i < n; i += NT) {
+                    const int q = c0 + i;
+                    const double vt = __ldg(pVT + q);
+                    s_vt[i] = vt;
+                    s_x[i] = __ldg(pXNU + q);
+                    if (vt >= 0.) {
+                        const double hw = __ldg(pH + q), ad = __ldg(pAD + q);
+                        const double zeta = hw / (hw + ad);
+                        if (fabs(__ldg(a.sdep_s + q)) > 1.0e-4 || !(zeta < 1.0)) {
+                            s_inv[i] = -1.;        // speed dependence / degenerate Doppler width: the general routine per pair
+                        } else {
+                            const double inv = 1. / ad;
+                            const double y = sl2 * (hw * inv);
+                            s_inv[i] = inv;
+                            s_y[i] = y;
+                            s_c[i] = __ldg(pST + q) * (0.46971863934982516 * inv);   // sqrt(log(2)/PI), 13-digit PI
+                            s_pd[i] = (kind == 0) ? w4_re_fast(sl2 * (kDELTNUC * inv), y) : 0.;
+                            s_g[i] = (kind == 3) ? (__ldg(pAIP + q) * (1 / hw) * rp) : 0.;
+                            s_b[i] = (kind == 3) ? (__ldg(pBIP + q) * rp2) : 0.;
+                        }
+                    }
+                }
                 __syncthreads();
                 for (int i = 0; i < n; i++) {
                     const double vt = s_vt[i];
                     if (!(vt >= 0.)) continue;
                     const double xnu = s_x[i];
-                    const int q = c0 + i;
 #pragma unroll
                     for (int f = 0; f < F; f++) {
                         const double dm = wn[f] - xnu;
                         const bool inwin = has_win ? !(fabs(dm) > kDELTNUC) : true;
                         if (inwin && fabs(dm) <= vt) {
-                            msum[f] += voigt_lines_term(kind, wn[f], xnu, pl, a.n_pad, q, a.sdep_s[q], rp, rp2, &err);
+                            const double inv = s_inv[i];
+                            if (inv < 0.) {
+                                msum[f] += voigt_lines_term(kind, wn[f], xnu, pl, a.n_pad, c0 + i, a.sdep_s[c0 + i], rp, rp2, &err);
+                            } else {
+                                const double y = s_y[i], sp = wn[f] + xnu;
+                                const bool second = (kind >= 2) || ((sp - kDELTNUC) <= 0.);
+                                double sls = w4_re_fast(sl2 * (dm * inv), y);
+                                if (kind == 3) sls *= (1. + (s_g[i] * dm) + s_b[i]);
+                                if (second) {
+                                    double v2 = w4_re_fast(sl2 * (sp * inv), y);
+                                    if (kind == 3) v2 *= (1. - (s_g[i] * sp) + s_b[i]);
+                                    sls += v2;
+                                }
+                                if (kind == 0) sls -= (second ? 2. : 1.) * s_pd[i];
+                                msum[f] = fma(s_c[i], sls, msum[f]);
+                            }
                             many = true;
                         }
                     }
@@ -1861,6 +1898,7 @@ struct RtArgs {
     const double* wn;
     const double* o;  int64_t o_lds, o_prof;
     const double *t, *tz;          // (nlay,nprof), (nlay+1,nprof)
+    const double *fb, *fbz;        // RADCN2/T (nlay,nprof), RADCN2/TZ (nlay+1,nprof) from rt_prep_kernel
     double* tmpsfc;                // (nprof) device, in/out
     const double *emiss, *reflc;   // (nwn)
     double *rad, *tb, *tmr, *trtot, *rup, *rdn;   // (nwn,nprof), any may be null
@@ -1871,6 +1909,20 @@ __device__ __forceinline__ double bb_fn(double v, double fbeta)
     return kRADCN1 * (v * v * v) / (exp(v * fbeta) - 1.);
 }
 
+// fbeta = RADCN2/T of every layer and level (RTMmono.f90:183-185,199,215): frequency independent
+__global__ void rt_prep_kernel(int n_t, const double* t, double* fb, int n_tz, const double* tz, double* fbz)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_t) fb[i] = kRADCN2 / t[i];
+    if (i < n_tz) fbz[i] = kRADCN2 / tz[i];
+}
+
+// One pass from the top layer down serves the three reference loops: the downwelling sum (RTMmono.f90:207-219)
+// and CALCTMR's (:300-317) run in their own order, ODT by successive subtraction from the total exactly as written
+// there; the upwelling sum (:192-204) needs, for layer l, the optical depth above it, which the same pass carries
+// as a running sum from the top (the reference subtracts from the total going up: same value up to rounding).
+// Per (frequency, layer): Planck at the layer temperature and at one new level (the lower boundary becomes the
+// next layer's upper boundary), exp(-tau), and the two path transmittances: 5 exp instead of 8.
 __global__ void __launch_bounds__(128) rt_kernel(RtArgs a)
 {
     const int iw = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1878,45 +1930,40 @@ __global__ void __launch_bounds__(128) rt_kernel(RtArgs a)
     if (iw >= a.nwn) return;
     const double vv = a.wn[iw];
     const double* o = a.o + (size_t)prof * a.o_prof + iw;
-    const double* t = a.t + (size_t)prof * a.nlay;
-    const double* tz = a.tz + (size_t)prof * (a.nlay + 1);
+    const double* __restrict__ fb = a.fb + (size_t)prof * a.nlay;
+    const double* __restrict__ fbz = a.fbz + (size_t)prof * (a.nlay + 1);
     const size_t out = (size_t)iw + (size_t)prof * a.nwn;
 
     double odtot = 0.;
     for (int l = 0; l < a.nlay; l++) odtot = odtot + o[(size_t)l * a.o_lds];
 
-    double rup = 0., rdn = 0., sumexp = 0.;
-    if (a.do_rtm && a.irt != 3) {
-        double odt = odtot;
-        for (int l = 1; l <= a.nlay; l++) {
-            const double bb = bb_fn(vv, kRADCN2 / t[l - 1]);
-            const double bba = bb_fn(vv, kRADCN2 / tz[l]);
-            const double odvi = o[(size_t)(l - 1) * a.o_lds];
-            const double tri = exp(-odvi);
-            odt = odt - odvi;
-            const double trt = exp(-odt);
-            const double pade = 0.193 * odvi + 0.013 * (odvi * odvi);
-            rup = rup + trt * (1. - tri) * (bb + pade * bba) / (1. + pade);
+    const bool up = a.do_rtm && a.irt != 3;
+    const double c1v3 = kRADCN1 * (vv * vv * vv);
+    double rup = 0., rdn = 0.;
+    double odt = odtot;          // optical depth below the current layer after the subtraction (down loops)
+    double oda = 0.;             // optical depth above the current layer (up loop)
+    double bb_top = c1v3 / (exp(vv * __ldg(fbz + a.nlay)) - 1.);
+    for (int l = a.nlay; l >= 1; l--) {
+        const double odvi = o[(size_t)(l - 1) * a.o_lds];
+        const double bb = c1v3 / (exp(vv * __ldg(fb + l - 1)) - 1.);
+        const double bb_bot = c1v3 / (exp(vv * __ldg(fbz + l - 1)) - 1.);
+        odt = odt - odvi;
+        const double tri = exp(-odvi);
+        const double trt = exp(-odt);
+        const double pade = 0.193 * odvi + 0.013 * (odvi * odvi);
+        const double rden = 1. / (1. + pade);
+        const double emis = 1. - tri;
+        rdn = rdn + trt * emis * ((bb + pade * bb_bot) * rden);
+        if (up) {
+            const double tra = exp(-oda);
+            rup = rup + tra * emis * ((bb + pade * bb_top) * rden);
+            oda = oda + odvi;
         }
-    }
-    {
-        double odt = odtot;
-        for (int l = a.nlay; l >= 1; l--) {
-            const double bb = bb_fn(vv, kRADCN2 / t[l - 1]);
-            const double bba = bb_fn(vv, kRADCN2 / tz[l - 1]);
-            const double odvi = o[(size_t)(l - 1) * a.o_lds];
-            odt = odt - odvi;
-            const double tri = exp(-odvi);
-            const double trt = exp(-odt);
-            const double pade = 0.193 * odvi + 0.013 * (odvi * odvi);
-            rdn = rdn + trt * (1. - tri) * (bb + pade * bba) / (1. + pade);
-            const double beff = (bb + pade * bba) / (1. + pade);
-            sumexp = sumexp + beff * trt * (1 - tri);
-        }
+        bb_top = bb_bot;
     }
     const double trtot = exp(-odtot);
     if (a.do_tmr && a.tmr) {
-        double radtmr = sumexp / (1. - exp(-1 * odtot));
+        double radtmr = rdn / (1. - exp(-1 * odtot));
         double x = kRADCN1 * (vv * vv * vv) / radtmr + 1.;
         a.tmr[out] = kRADCN2 * vv / log(x);
     }
