@@ -49,8 +49,9 @@ struct mrtm_ctx {
     double ff_ratio = 8.0;                        // far-field pole-distance ratio (MRTM_FF_RATIO; 0 = direct only)
     DevBuf b_vtmax;                               // [0] sm_max bits, [1..nseg] vtmax per segment
     DevBuf b_lvoigt;                              // [L] per-layer "has Voigt-capable lines" flag
-    DevBuf b_plan[kMaxLevels], b_hdr[kMaxLevels], b_coef[kMaxLevels], b_pieces[kMaxLevels];
+    DevBuf b_plan[kMaxLevels], b_hdr[kMaxLevels], b_coef[kMaxLevels], b_pieces[kMaxLevels], b_npieces;
     int ff_levels = 3, ff_S = 8;                  // far-field hierarchy (MRTM_FF_LEVELS 1..3, MRTM_FF_S)
+    int use_near2 = 1;                            // per-warp re-planning near-field kernel (MRTM_NEAR2=0 disables)
     DevBuf b_layer, b_scorc, b_absrb, b_planes, b_o, b_obm, b_oc, b_in[16], b_out[16], b_sel[2], b_tmps, b_fbeta;
     mrtm_stats st;
     size_t planes_budget = (size_t)8 << 30;
@@ -148,6 +149,7 @@ extern "C" int mrtm_init(int device, mrtm_ctx** out)
     for (auto& ev : ctx->ev) cudaEventCreate(&ev);
     if (const char* s = std::getenv("MRTM_PLANES_GB")) ctx->planes_budget = (size_t)(std::atof(s) * (double)(1ull << 30));
     if (const char* s = std::getenv("MRTM_FF_LEVELS")) ctx->ff_levels = std::min(std::max(std::atoi(s), 1), kMaxLevels);
+    if (const char* s = std::getenv("MRTM_NEAR2")) ctx->use_near2 = std::atoi(s) != 0;
     if (const char* s = std::getenv("MRTM_FF_S")) ctx->ff_S = std::min(std::max(std::atoi(s), 2), 64);
     if (const char* s = std::getenv("MRTM_FF_RATIO")) {
         double v = std::atof(s);
@@ -185,7 +187,7 @@ extern "C" int mrtm_free(mrtm_ctx* ctx)
     cudaStreamSynchronize(ctx->stream);
     free_lines(ctx);
     for (void* p : ctx->table_allocs) cudaFree(p);
-    DevBuf* bufs[] = {&ctx->b_lvoigt, &ctx->b_vtmax, &ctx->b_layer, &ctx->b_scorc, &ctx->b_absrb, &ctx->b_planes, &ctx->b_o, &ctx->b_obm, &ctx->b_oc, &ctx->b_sel[0], &ctx->b_sel[1], &ctx->b_tmps, &ctx->b_fbeta};
+    DevBuf* bufs[] = {&ctx->b_lvoigt, &ctx->b_vtmax, &ctx->b_layer, &ctx->b_scorc, &ctx->b_absrb, &ctx->b_planes, &ctx->b_o, &ctx->b_obm, &ctx->b_oc, &ctx->b_sel[0], &ctx->b_sel[1], &ctx->b_tmps, &ctx->b_fbeta, &ctx->b_npieces};
     for (DevBuf* b : bufs) if (b->p) cudaFree(b->p);
     for (int i = 0; i < kMaxLevels; i++) {
         if (ctx->b_plan[i].p) cudaFree(ctx->b_plan[i].p);
@@ -322,6 +324,17 @@ static void launch_lines(const LinesArgs& la, dim3 grid, bool sel, cudaStream_t 
 {
     // near field (direct), Voigt branch, then polynomial + continuum + totals
     const size_t dyn = sizeof(double) * kStages * 4 * kTile + (size_t)std::max(la.nseg, 1) * sizeof(SegWork);
+    if (la.near_pieces) {       // tiles whose direct lines fit the staging area: per-warp re-planning kernel
+        const size_t dyn2 = sizeof(double) * 4 * (kNearCap + 8) + sizeof(unsigned short) * (NT / 32) * 2 * (kNearCap + 8) + kNearCap +
+                            sizeof(NearPiece) * kMaxNearPieces + (size_t)std::max(la.nseg, 1) * sizeof(SegWork);
+        if (sel) {
+            cudaFuncSetAttribute(near2_kernel<F, true, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn2);
+            near2_kernel<F, true, NT><<<grid, NT, dyn2, s>>>(la);
+        } else {
+            cudaFuncSetAttribute(near2_kernel<F, false, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn2);
+            near2_kernel<F, false, NT><<<grid, NT, dyn2, s>>>(la);
+        }
+    }
     if (sel) {
         cudaFuncSetAttribute(near_kernel<F, true, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
         near_kernel<F, true, NT><<<grid, NT, dyn, s>>>(la);
@@ -540,6 +553,11 @@ static int run_device(mrtm_ctx* ctx, const RunDesc& r, cudaStream_t s)
                 pl.pplan = (lv + 1 < nlev) ? (const SegWork*)ctx->b_plan[lv + 1].p : nullptr;
                 pl.S = ctx->ff_S;
                 pl.pieces = (FarPiece*)ctx->b_pieces[lv].p;
+                if (lv == 0 && la.ff_ratio > 0. && ctx->use_near2) {
+                    if ((rc = ensure(ctx, ctx->b_npieces, (size_t)ntiles[0] * kMaxNearPieces * sizeof(NearPiece)))) return rc;
+                    pl.near_pieces = (NearPiece*)ctx->b_npieces.p;
+                    la.near_pieces = pl.near_pieces;
+                }
                 plan_kernel<<<(unsigned)ntiles[lv], 128, (size_t)std::max(nseg_i, 1) * (sizeof(SegWork) + kPiecePerSeg * sizeof(FarPiece)), s>>>(pl);
                 st.kernel_launches++;
                 la.plan[lv] = (const SegWork*)ctx->b_plan[lv].p;

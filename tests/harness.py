@@ -207,7 +207,7 @@ def session():
     return _session
 
 
-def run_gpu(case, ip=0, by_mol=True, line_mode=0):
+def run_gpu(case, ip=0, by_mol=True, line_mode=0, selection=True):
     """MODM, CALCTMR and RTM through the C ABI (host buffers), one profile.
     line_mode 0 = default (far-field expansion where applicable), 1 = direct evaluation of every triple."""
     s = session()
@@ -216,7 +216,7 @@ def run_gpu(case, ip=0, by_mol=True, line_mode=0):
     s.reset_stats()
     m = s.modm(case["wn"], case["dvset"], pr["p"][:, ip], pr["t"][:, ip], pr["clw"][:, ip], case["nmol"],
                pr["wkl"][:, :, ip], pr["wbrodl"][:, ip], case["scor"][:, :, :, ip], cntnm=case["cntnm"],
-               ibrd=case["ibrd"], want_by_mol=by_mol, selection=True, line_mode=line_mode,
+               ibrd=case["ibrd"], want_by_mol=by_mol, selection=selection, line_mode=line_mode,
                sclcpl=case.get("sclcpl", 1.), sclhw=case.get("sclhw", 1.), y0res=case.get("y0res", 0.))
     tmr = s.calctmr(case["wn"], pr["t"][:, ip], pr["tz"][:, ip], m["o"])
     r = s.rtm(1, case["irt"], case["wn"], pr["t"][:, ip], pr["tz"][:, ip], m["o"], case["tmpsfc"],

@@ -27,6 +27,16 @@ def check_case(case, od_rtol=OD_RTOL):
     assert harness.rel_diff(gpu["o"], direct["o"]) < 1e-11
     assert np.max(np.abs(gpu["tb"] - direct["tb"])) < 1e-7
     assert direct["stats"]["far_expansions"] == 0
+    # the production variants: no selection instrumentation, with and without per-molecule outputs
+    # (one sum over all molecules, column amounts folded into the line strengths)
+    for by_mol in (True, False):
+        fast = harness.run_gpu(case, by_mol=by_mol, selection=False)
+        assert harness.rel_diff(fast["o"], ref["o"]) < od_rtol
+        assert harness.rel_diff(fast["o"], gpu["o"]) < 1e-11
+        assert np.max(np.abs(fast["tb"] - ref["tb"])) < TB_ATOL
+        if by_mol:
+            scale = np.abs(ref["o"])[:, None, :]
+            assert np.max(np.abs(fast["o_by_mol"] - ref["o_by_mol"]) / scale) < od_rtol
     return ref, gpu
 
 
