@@ -188,6 +188,55 @@ int mrtm_host_get_lnfl(const char *hfile, double v1, double v2, int64_t iim, int
 /* TIPS_2003 (src/tips_2003.f90:2-298): scor(42,9) = Q(296)/Q(T) for molecules 1..mol_max. */
 int mrtm_host_tips_2003(int64_t mol_max, double temp, double *scor);
 
+/* ---- host driver (PROGRAM MONORTM around the hot path, layer input IATM=0; no
+ * Fortran compiler needed).  The parsing / formatting entry points need no GPU. ------------------- */
+/* What RDLBLINP (src/monortm_sub.F90:33-423) returns through its arguments and COMMON blocks
+ * /MANE/ (DVSET), /BNDPRP/ (BNDEMI,BNDRFL), /profil_scal/, /CNTSCL/.  wn is malloc'ed by
+ * mrtm_host_read_control and released by mrtm_host_free_control. */
+typedef struct mrtm_control {
+    int64_t ihirac, icntnm, iemit, iplot, iatm, iod, ixsect, ispd, ibrd;   /* record 1.2 */
+    double cntnm[7];             /* applyCntnmCombo(ICNTNM) or record 1.2a (ICNTNM=6) */
+    double v1, v2, dvset;        /* record 1.3 (dvset = 0 in list mode) */
+    int64_t nwn;
+    double *wn;                  /* records 1.3.1/1.3.2 or V1 + (j-1)*DVSET */
+    double tmpbnd, bndemi[3], bndrfl[3];                                    /* record 1.4 */
+    int64_t nmol_scal;
+    char hmol_scal[64];
+    double xmol_scal[64];
+} mrtm_control;
+/* detail of the last failing mrtm_host_* call of this thread (the reference's STOP message) */
+const char *mrtm_host_last_error(void);
+/* RDLBLINP for records 1.1-1.4.  nwnmx <= 0 -> the reference's NWNMX = 80000 (src/RTMmono.f90:10). */
+int mrtm_host_read_control(const char *filein, int64_t nwnmx, mrtm_control *out);
+void mrtm_host_free_control(mrtm_control *c);
+/* GETPROFNUMBER, IATM=0 branch (src/monortm_sub.F90:894-907). */
+int mrtm_host_count_profiles(const char *fileprof, int64_t ixsect, int64_t *nprof);
+/* The MONORTM_PROF.IN block of PROGRAM MONORTM (src/monortm.f90:380-488) for the index-th
+ * (0-based) profile of the file, mixing ratios converted to column amounts (:423-483).
+ * p,t,clw,wbrodl (maxlay); altz,pz,tz (0:maxlay); wkl (39,maxlay). */
+int mrtm_host_read_profile(const char *fileprof, int64_t index, int64_t maxlay, int64_t *iform, int64_t *nlay,
+                           int64_t *nmol, int64_t *irt, double *secnt0, double *h1, double *h2, double *angle,
+                           double *p, double *t, double *clw, double *wbrodl, double *altz, double *pz,
+                           double *tz, double *wkl);
+/* EMISS_REFLEC (src/monortm_sub.F90:506-516) with EMISFN/REFLFN (:426-493); tables are read from
+ * <dir>in/EMISSION, <dir>in/REFLECTION when the first coefficient is negative (:319-336). */
+int mrtm_host_emiss_reflec(const mrtm_control *c, const char *dir, int64_t nwn, const double *wn,
+                           double *emiss, double *reflc);
+/* STOREOUT (src/monortm_sub.F90:519-787; formats 11/21/31 :780-783; IOD=1 writes the ODmono_*
+ * files next to fileout; the netCDF branch is not built).  Arguments as the reference's, arrays
+ * dimensioned o,odxsec (nwn,nlay), o_by_mol,oc (nwn,39,nlay), wkl (39,nlay) IN/OUT (:600).
+ * append == 0 truncates fileout (first profile), else appends. */
+int mrtm_host_storeout(const char *fileout, int append, int64_t nwn, const double *wn, double *wkl,
+                       const double *wbrodl, const double *rad, const double *tb, const double *trtot,
+                       int64_t npr, const double *o, const double *o_by_mol, const double *oc,
+                       const double *odxsec, const double *tmr, double wvcolmn, double clwcolmn,
+                       double tmpsfc, const double *reflc, const double *emiss, int64_t nlay, int64_t nmol,
+                       double angle, int64_t iod);
+/* PROGRAM MONORTM for IATM=0 (src/monortm.f90:283-588): reads MONORTM.IN, MONORTM_PROF.IN and
+ * TAPE3 in workdir, runs every profile through mrtm_profiles on `device`, writes MONORTM.OUT
+ * (+ MONORTM.LOG, ODmono_* with IOD=1).  Needs a GPU: there is no CPU path. */
+int mrtm_host_run_monortm(const char *workdir, int device, int64_t nwnmx, int verbose);
+
 #ifdef __cplusplus
 }
 #endif

@@ -46,6 +46,16 @@ class MrtmStats(C.Structure):
     ]
 
 
+class MrtmControl(C.Structure):
+    _fields_ = [(n, C.c_int64) for n in ("ihirac", "icntnm", "iemit", "iplot", "iatm", "iod", "ixsect", "ispd", "ibrd")] + [
+        ("cntnm", C.c_double * 7),
+        ("v1", C.c_double), ("v2", C.c_double), ("dvset", C.c_double),
+        ("nwn", C.c_int64), ("wn", c_double_p),
+        ("tmpbnd", C.c_double), ("bndemi", C.c_double * 3), ("bndrfl", C.c_double * 3),
+        ("nmol_scal", C.c_int64), ("hmol_scal", C.c_char * 64), ("xmol_scal", C.c_double * 64),
+    ]
+
+
 # every symbol include/monortm_b200.h declares: (restype, argtypes)
 _D, _I, _P = C.c_double, C.c_int64, C.c_void_p
 SIGNATURES = {
@@ -69,6 +79,16 @@ SIGNATURES = {
     "mrtm_fp64_peak": (C.c_int, [_P, c_double_p]),
     "mrtm_host_get_lnfl": (C.c_int, [C.c_char_p, _D, _D, _I] + [_P] * 16),
     "mrtm_host_tips_2003": (C.c_int, [_I, _D, _P]),
+    "mrtm_host_last_error": (C.c_char_p, []),
+    "mrtm_host_read_control": (C.c_int, [C.c_char_p, _I, C.POINTER(MrtmControl)]),
+    "mrtm_host_free_control": (None, [C.POINTER(MrtmControl)]),
+    "mrtm_host_count_profiles": (C.c_int, [C.c_char_p, _I, c_int64_p]),
+    "mrtm_host_read_profile": (C.c_int, [C.c_char_p, _I, _I, c_int64_p, c_int64_p, c_int64_p, c_int64_p,
+                                         c_double_p, c_double_p, c_double_p, c_double_p] + [_P] * 8),
+    "mrtm_host_emiss_reflec": (C.c_int, [C.POINTER(MrtmControl), C.c_char_p, _I, _P, _P, _P]),
+    "mrtm_host_storeout": (C.c_int, [C.c_char_p, C.c_int, _I, _P, _P, _P, _P, _P, _P, _I, _P, _P, _P, _P, _P,
+                                     _D, _D, _D, _P, _P, _I, _I, _D, _I]),
+    "mrtm_host_run_monortm": (C.c_int, [C.c_char_p, C.c_int, _I, C.c_int]),
 }
 
 _lib = None
