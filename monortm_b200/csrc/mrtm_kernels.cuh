@@ -2133,12 +2133,20 @@ MRTM_UNROLL(MRTM_UNROLL_BOTH)
 // voigt_kernel: the Voigt branch (modm.f90:427-431).  CTA = (frequency tile, layer, profile); it leaves
 // at once when the layer has no Voigt-capable line.  For the lines of the plan's Voigt zones it applies
 // the reference's test |WN-Xnu| <= 100*HWHM_D per (line, frequency) and adds W*STILD*SLS of the pairs that
-// pass (near_kernel skipped exactly those) to O [and O_BY_MOL].
+// pass (the near kernels skipped exactly those) to O [and O_BY_MOL].
+// Each warp owns a contiguous block of 32*F frequencies and walks it in F sub-blocks of 32.  Per sub-block
+// the lanes first cull the staged zone lines against the sub-block's frequency extent (one line per lane,
+// exact: the rounded difference WN-Xnu is monotone in WN) into a compact list, so the per-(line,frequency)
+// loop only visits lines whose zone reaches the sub-block.
 // =============================================================================================
+#ifndef MRTM_VOIGT_MINB
+#define MRTM_VOIGT_MINB 6
+#endif
 template <int F, int NT>
-__global__ void __launch_bounds__(NT) voigt_kernel(LinesArgs a)
+__global__ void __launch_bounds__(NT, MRTM_VOIGT_MINB) voigt_kernel(LinesArgs a)
 {
-    const int tid = threadIdx.x;
+    constexpr int NW = NT / 32;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int k = blockIdx.y, prof = blockIdx.z;
     const int64_t L = (int64_t)prof * a.nlay + k;
     if (!a.layer_voigt[L]) return;
@@ -2160,21 +2168,13 @@ __global__ void __launch_bounds__(NT) voigt_kernel(LinesArgs a)
     __shared__ double s_vt[kVCap], s_x[kVCap], s_inv[kVCap], s_y[kVCap], s_c[kVCap], s_pd[kVCap], s_g[kVCap], s_b[kVCap];
     __shared__ int s_q[kVCap];
     __shared__ unsigned char s_kind[kVCap], s_mol[kVCap];
+    __shared__ unsigned char s_list[NW][kVCap];
     __shared__ int s_zlo[kMaxSegments], s_zoff[kMaxSegments + 1];
-    const int base = blockIdx.x * (NT * F);
-    double wn[F], vsum[F], msum[F];
-    bool valid[F];
-#pragma unroll
-    for (int f = 0; f < F; f++) {
-        int iw = base + f * NT + tid;
-        valid[f] = iw < a.nwn;
-        wn[f] = a.wn[valid[f] ? iw : (a.nwn - 1)];
-        vsum[f] = 0.;
-        msum[f] = 0.;
-    }
+    const int base = blockIdx.x * (NT * F) + wid * (32 * F);
     const double rp = ly.rp, rp2 = ly.rp2;
     const double sl2 = 0.8325546111576977;         // sqrt(log(2))
     const bool by_mol = a.o_by_mol != nullptr;
+    const unsigned lt_mask = (1u << lane) - 1u;
     // zone directory: entry e of the CTA's zone list lies in segment s with s_zoff[s] <= e < s_zoff[s+1]
     if (tid == 0) {
         int tot = 0;
@@ -2192,24 +2192,7 @@ __global__ void __launch_bounds__(NT) voigt_kernel(LinesArgs a)
     const int total = s_zoff[a.nseg];
     if (total == 0) return;
     int err = 0;
-    int cur_mol = -1;
-    bool many = false;
-    auto flush_mol = [&]() {      // per-molecule outputs: close the molecule's sum
-        if (cur_mol > 0 && many) {
-            const double w = ly.wk[cur_mol - 1];
-#pragma unroll
-            for (int f = 0; f < F; f++) {
-                const double ol = w * msum[f];
-                vsum[f] += ol;
-                if (valid[f] && msum[f] != 0.) {
-                    const int iw = base + f * NT + tid;
-                    a.o_by_mol[(size_t)iw + (size_t)(cur_mol - 1) * a.obm_ldm + (size_t)L * a.obm_ldk] += ol;
-                }
-                msum[f] = 0.;
-            }
-        }
-        many = false;
-    };
+    unsigned char* lst = s_list[wid];
     for (int e0 = 0; e0 < total; e0 += kVCap) {
         const int n = min(kVCap, total - e0);
         if (e0 > 0) __syncthreads();
@@ -2246,26 +2229,63 @@ __global__ void __launch_bounds__(NT) voigt_kernel(LinesArgs a)
             }
         }
         __syncthreads();
-        for (int i = 0; i < n; i++) {
-            const double vt = s_vt[i];
-            if (!(vt >= 0.)) continue;
-            const int kind = s_kind[i];
-            if (by_mol && (int)s_mol[i] != cur_mol) {
-                flush_mol();
-                cur_mol = s_mol[i];
-            }
-            const double xnu = s_x[i];
-            const bool has_win = kind <= 1;
+        for (int f = 0; f < F; f++) {
+            const int iw = base + f * 32 + lane;
+            const bool valid = iw < a.nwn;
+            const double wn = a.wn[valid ? iw : (a.nwn - 1)];
+            double wA = valid ? wn : 1e300, wB = valid ? wn : -1e300;
 #pragma unroll
-            for (int f = 0; f < F; f++) {
-                const double dm = wn[f] - xnu;
-                const bool inwin = has_win ? !(fabs(dm) > kDELTNUC) : true;
-                if (inwin && fabs(dm) <= vt) {
+            for (int off = 16; off > 0; off >>= 1) {
+                wA = fmin(wA, __shfl_xor_sync(0xffffffffu, wA, off));
+                wB = fmax(wB, __shfl_xor_sync(0xffffffffu, wB, off));
+            }
+            if (wB < wA) break;                    // no frequency in this sub-block (nor in the following ones)
+            // cull: lines whose zone cannot reach [wA, wB] fail the test for every lane
+            int nl = 0;
+            for (int ib = 0; ib < n; ib += 32) {
+                const int i = ib + lane;
+                bool hit = false;
+                if (i < n) {
+                    const double vt = s_vt[i];
+                    if (vt >= 0.) {
+                        const double x = s_x[i];
+                        hit = !((wB - x) < -vt) && !((wA - x) > vt);
+                    }
+                }
+                const unsigned m = __ballot_sync(0xffffffffu, hit);
+                if (hit) lst[nl + __popc(m & lt_mask)] = (unsigned char)i;
+                nl += __popc(m);
+            }
+            __syncwarp();
+            double vsum = 0., msum = 0.;
+            int cur_mol = -1;
+            bool many = false;
+            auto flush_mol = [&]() {      // per-molecule outputs: close the molecule's sum
+                if (cur_mol > 0 && many) {
+                    const double ol = ly.wk[cur_mol - 1] * msum;
+                    vsum += ol;
+                    if (valid && msum != 0.)
+                        a.o_by_mol[(size_t)iw + (size_t)(cur_mol - 1) * a.obm_ldm + (size_t)L * a.obm_ldk] += ol;
+                    msum = 0.;
+                }
+                many = false;
+            };
+            for (int g = 0; g < nl; g++) {
+                const int i = lst[g];
+                const int kind = s_kind[i];
+                if (by_mol && (int)s_mol[i] != cur_mol) {
+                    flush_mol();
+                    cur_mol = s_mol[i];
+                }
+                const double xnu = s_x[i];
+                const double dm = wn - xnu;
+                const bool inwin = (kind <= 1) ? !(fabs(dm) > kDELTNUC) : true;
+                if (inwin && fabs(dm) <= s_vt[i]) {
                     const double inv = s_inv[i];
                     if (inv < 0.) {
-                        msum[f] = fma(s_c[i], voigt_lines_term(kind, wn[f], xnu, pl, a.n_pad, s_q[i], a.sdep_s[s_q[i]], rp, rp2, &err), msum[f]);
+                        msum = fma(s_c[i], voigt_lines_term(kind, wn, xnu, pl, a.n_pad, s_q[i], a.sdep_s[s_q[i]], rp, rp2, &err), msum);
                     } else {
-                        const double y = s_y[i], sp = wn[f] + xnu;
+                        const double y = s_y[i], sp = wn + xnu;
                         const bool second = (kind >= 2) || ((sp - kDELTNUC) <= 0.);
                         double sls = w4_re_fast(sl2 * (dm * inv), y);
                         if (kind == 3) sls *= (1. + (s_g[i] * dm) + s_b[i]);
@@ -2275,26 +2295,17 @@ __global__ void __launch_bounds__(NT) voigt_kernel(LinesArgs a)
                             sls += v2;
                         }
                         if (kind == 0) sls -= (second ? 2. : 1.) * s_pd[i];
-                        msum[f] = fma(s_c[i], sls, msum[f]);
+                        msum = fma(s_c[i], sls, msum);
                     }
                     many = true;
                 }
             }
+            if (by_mol) flush_mol(); else vsum = msum;
+            if (valid && vsum != 0.) a.o[(size_t)iw + (size_t)k * a.o_lds + (size_t)prof * a.o_prof] += vsum;
+            __syncwarp();                          // the list is rebuilt by the next sub-block
         }
     }
-    if (by_mol) {
-        flush_mol();
-    } else {
-#pragma unroll
-        for (int f = 0; f < F; f++) vsum[f] = msum[f];
-    }
     if (err) atomicOr(a.errflag, 2);
-#pragma unroll
-    for (int f = 0; f < F; f++) {
-        if (!valid[f] || vsum[f] == 0.) continue;
-        const int iw = base + f * NT + tid;
-        a.o[(size_t)iw + (size_t)k * a.o_lds + (size_t)prof * a.o_prof] += vsum[f];
-    }
 }
 
 // =============================================================================================
