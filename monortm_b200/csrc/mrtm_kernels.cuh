@@ -478,7 +478,7 @@ __global__ void __launch_bounds__(256) derive_kernel(DeriveArgs a)
 struct SegWork;
 struct TileHdr;
 struct NearPiece;
-constexpr int kMaxLevels = 3;   // far-field hierarchy: level 0 = the line kernel's own tiles
+constexpr int kMaxLevels = 4;   // far-field hierarchy: level 0 = the line kernel's own tiles
 struct LinesArgs {
     int32_t nwn, nlay;            // frequencies in this call/chunk, layers per profile
     int32_t nseg, n_pad;
@@ -670,6 +670,17 @@ struct NearPiece {
     int info;                    // segment | mode << 8 | negall << 16 | kind << 17 (0 PED, 1 O2, 2 O2_LC35)
 };
 constexpr int kMaxNearPieces = 192;
+#ifndef MRTM_NEAR2_CAP
+#define MRTM_NEAR2_CAP 640
+#endif
+#ifndef MRTM_NEAR2_MINB
+#define MRTM_NEAR2_MINB 5
+#endif
+#ifndef MRTM_FAR_MINB
+#define MRTM_FAR_MINB 6
+#endif
+constexpr int kNearCap = MRTM_NEAR2_CAP;        // staged lines per CTA of near2_kernel (tiles with more go to near_kernel)
+static_assert(kNearCap <= kStages * kTile && kNearCap % 32 == 0, "kNearCap");
 // One contiguous range of lines that far_kernel expands for a tile: far at this level and not at the parent level.
 constexpr int kPiecePerSeg = 12;
 struct FarPiece {
@@ -1065,7 +1076,7 @@ struct FarArgs {
     unsigned long long* counters;
 };
 
-__global__ void __launch_bounds__(128) far_kernel(FarArgs a)
+__global__ void __launch_bounds__(128, MRTM_FAR_MINB) far_kernel(FarArgs a)
 {
     constexpr int NT = 128;
     extern __shared__ __align__(128) unsigned char s_dyn[];
@@ -1262,7 +1273,7 @@ __global__ void __launch_bounds__(NT, (MRTM_LINES_MINB * 128) / NT) near_kernel(
     const int tid = threadIdx.x;
     if (a.near_pieces) {                          // near2_kernel took the tiles whose direct lines fit its staging area
         const TileHdr th0 = a.hdr[0][blockIdx.x];
-        if (th0.total_lines <= kStages * kTile && th0.nnear >= 0) return;
+        if (th0.total_lines <= kNearCap && th0.nnear >= 0) return;
     }
     const int k = blockIdx.y;                     // layer within profile
     const int prof = blockIdx.z;
@@ -1673,9 +1684,8 @@ MRTM_UNROLL(MRTM_UNROLL_BOTH)
 // One group of lists serves all molecules (line strengths pre-multiplied by the column amounts) unless
 // per-molecule outputs are requested.  No CTA barrier after the staging phase.
 // =============================================================================================
-constexpr int kNearCap = kStages * kTile;       // staged lines per CTA
 template <int F, bool SEL, int NT>
-__global__ void __launch_bounds__(NT, 3) near2_kernel(LinesArgs a)
+__global__ void __launch_bounds__(NT, MRTM_NEAR2_MINB) near2_kernel(LinesArgs a)
 {
     constexpr int NW = NT / 32;
     constexpr int kCap = kNearCap;
@@ -2140,7 +2150,7 @@ MRTM_UNROLL(MRTM_UNROLL_BOTH)
 // loop only visits lines whose zone reaches the sub-block.
 // =============================================================================================
 #ifndef MRTM_VOIGT_MINB
-#define MRTM_VOIGT_MINB 6
+#define MRTM_VOIGT_MINB 8
 #endif
 template <int F, int NT>
 __global__ void __launch_bounds__(NT, MRTM_VOIGT_MINB) voigt_kernel(LinesArgs a)
