@@ -46,11 +46,13 @@ struct mrtm_ctx {
     int32_t* tips_row_dev = nullptr;
     int* errflag_dev = nullptr;
     unsigned long long* counters_dev = nullptr;   // [2] far expansions, direct evaluations
+    double ffw_ratio = 8.0;                       // in-warp expansion ratio of near2_kernel (MRTM_FFW_RATIO)
     double ff_ratio = 8.0;                        // far-field pole-distance ratio (MRTM_FF_RATIO; 0 = direct only)
     DevBuf b_vtmax;                               // [0] sm_max bits, [1..nseg] vtmax per segment
     DevBuf b_lvoigt;                              // [L] per-layer "has Voigt-capable lines" flag
     DevBuf b_plan[kMaxLevels], b_hdr[kMaxLevels], b_coef[kMaxLevels], b_pieces[kMaxLevels], b_npieces;
-    int ff_levels = 3, ff_S = 8;                  // far-field hierarchy (MRTM_FF_LEVELS 1..3, MRTM_FF_S)
+    int64_t farw_min = 4096;                      // (tile, layer) pairs of a level from which far_warp_kernel takes it (MRTM_FARW_MIN)
+    int ff_levels = 3, ff_S = 6;                  // far-field hierarchy (MRTM_FF_LEVELS 1..3, MRTM_FF_S)
     int use_near2 = 1;                            // per-warp re-planning near-field kernel (MRTM_NEAR2=0 disables)
     DevBuf b_layer, b_scorc, b_absrb, b_planes, b_o, b_obm, b_oc, b_in[16], b_out[16], b_sel[2], b_tmps, b_fbeta;
     mrtm_stats st;
@@ -150,6 +152,8 @@ extern "C" int mrtm_init(int device, mrtm_ctx** out)
     if (const char* s = std::getenv("MRTM_PLANES_GB")) ctx->planes_budget = (size_t)(std::atof(s) * (double)(1ull << 30));
     if (const char* s = std::getenv("MRTM_FF_LEVELS")) ctx->ff_levels = std::min(std::max(std::atoi(s), 1), kMaxLevels);
     if (const char* s = std::getenv("MRTM_NEAR2")) ctx->use_near2 = std::atoi(s) != 0;
+    if (const char* s = std::getenv("MRTM_FFW_RATIO")) ctx->ffw_ratio = std::max(std::atof(s), 4.0);
+    if (const char* s = std::getenv("MRTM_FARW_MIN")) ctx->farw_min = std::atoll(s);
     if (const char* s = std::getenv("MRTM_FF_S")) ctx->ff_S = std::min(std::max(std::atoi(s), 2), 64);
     if (const char* s = std::getenv("MRTM_FF_RATIO")) {
         double v = std::atof(s);
@@ -483,6 +487,7 @@ static int run_device(mrtm_ctx* ctx, const RunDesc& r, cudaStream_t s)
             la.key = ctx->ld.key;
             la.keypre = ctx->ld.keypre;
             la.ff_ratio = (r.line_mode == 1) ? 0. : ctx->ff_ratio;
+            la.ffw_ratio = ctx->ffw_ratio;
             la.counters = ctx->counters_dev;
             la.layer_voigt = (const int*)ctx->b_lvoigt.p;
             la.planes = (const double*)ctx->b_planes.p;
@@ -586,7 +591,12 @@ static int run_device(mrtm_ctx* ctx, const RunDesc& r, cudaStream_t s)
                     fa.lay = la.lay;
                     fa.coef = (double*)ctx->b_coef[lv].p;
                     fa.counters = ctx->counters_dev;
-                    far_kernel<<<dim3((unsigned)ntiles[lv], (unsigned)nlay, (unsigned)nb), 128, (size_t)std::max(nseg_i, 1) * kPiecePerSeg * sizeof(FarPiece), s>>>(fa);
+                    // many small tiles (level 0 above all): one warp per (tile, layer); few large tiles: one CTA
+                    const size_t far_dyn = (size_t)std::max(nseg_i, 1) * kPiecePerSeg * sizeof(FarPiece);
+                    if (combined && ntiles[lv] * nlay * nb >= ctx->farw_min)
+                        far_warp_kernel<<<dim3((unsigned)ntiles[lv], (unsigned)((nlay + kFarWarps - 1) / kFarWarps), (unsigned)nb), 32 * kFarWarps, far_dyn, s>>>(fa);
+                    else
+                        far_kernel<<<dim3((unsigned)ntiles[lv], (unsigned)nlay, (unsigned)nb), 128, far_dyn, s>>>(fa);
                     st.kernel_launches++;
                 }
             st.kernel_launches += 2;       // voigt_kernel, final_kernel (near_kernel is counted below)

@@ -143,6 +143,8 @@ __global__ void layer_prep_kernel(LayerPrepArgs a)
     o.rectlc = xdiv(1.0, xsub(templc[ilc], templc[ilc - 1]));
     o.tmpdif = xsub(tt, templc[ilc - 1]);
     o.rt = xdiv(tt, kT0);
+    o.lnrt = log(o.rt);
+    o.dinvt = 1. / kT0 - 1. / tt;
     o.rhorat = xdiv(xn, xn0);
     for (int k = 0; k < 7; k++) o.rho_molec[k] = xdiv(xmul(o.rhorat, wk[k]), wtot);
     for (int m = 0; m < MRTM_MXMOL; m++) {
@@ -411,12 +413,13 @@ __global__ void __launch_bounds__(256) derive_kernel(DeriveArgs a)
     // INTENS
     const double xipsf = a.scorc[(size_t)L * a.ln.nsi + a.ln.sidx[q]];
     const double es = a.ln.e[q];
-    double s = a.ln.s0adj[q] * (exp(-radct * es / t) / exp(-radct * es / kT0)) * xipsf;
+    // exp(-c2 E/T)/exp(-c2 E/T0) as one exponential (modm.f90 INTENS)
+    double s = a.ln.s0adj[q] * exp(radct * es * ly.dinvt) * xipsf;
     double stild = s * ((1 + exp(-(radct * xnu / t))) / (xnu * (1 - exp(-(radct * xnu / kT0)))));
 
     // HALFWHM_C
     const double af = a.ln.alpf[q], as = a.ln.alps[q];
-    const double rtx = pow(ly.rt, a.ln.x[q]);
+    const double rtx = exp(a.ln.x[q] * ly.lnrt);         // (T/T0)^x with the layer's log(T/T0)
     const double alfa0i = af * rtx, hwhmsi = as * rtx;
     double hwhm_c = alfa0i * (rhorat - rho_self) + hwhmsi * rho_self;
     if (use_brd && brd) {
@@ -491,6 +494,7 @@ struct LinesArgs {
     const unsigned long long* key;
     const unsigned long long* keypre;   // [n_pad+1] prefix sums of key (selection hash of a whole range)
     double ff_ratio;              // far-field expansion: poles >= ff_ratio tile half-widths away; 0 = direct only
+    double ffw_ratio;             // the same ratio for near2_kernel's in-warp expansion about the warp's own block
     unsigned long long* counters; // [2] far-field expansions, direct (line,frequency) evaluations (may be null)
     const double* planes;         // [L][D_NPLANES][n_pad]
     const LayerDev* lay;          // [L]
@@ -1255,6 +1259,151 @@ __global__ void __launch_bounds__(128, MRTM_FAR_MINB) far_kernel(FarArgs a)
 }
 
 // =============================================================================================
+// far_warp_kernel: far_kernel for the levels with many small tiles (level 0 above all) in the combined
+// mode (one coefficient set for all molecules).  A WARP owns one (tile, layer): the four warps of a CTA
+// take four consecutive layers of the same tile and share its work list in shared memory; each lane walks
+// the tile's work units with stride 32, the coefficients are summed across the warp by shuffles (fixed
+// butterfly order: deterministic) -- no CTA barrier after the list is staged, and four times more units
+// per lane than far_kernel has per thread, which amortises the set-up, reduction and translation.
+// =============================================================================================
+#ifndef MRTM_FARW_MINB
+#define MRTM_FARW_MINB 5
+#endif
+constexpr int kFarWarps = 4;
+__global__ void __launch_bounds__(32 * kFarWarps, MRTM_FARW_MINB) far_warp_kernel(FarArgs a)
+{
+    constexpr int NT = 32 * kFarWarps;
+    extern __shared__ __align__(128) unsigned char s_dyn[];
+    FarPiece* s_pc = reinterpret_cast<FarPiece*>(s_dyn);        // the tile's work list
+    __shared__ double s_pcoef[kFarWarps][kFarK];                // the parent tile's coefficients, per layer
+    __shared__ double s_w[kFarWarps][kMaxSegments];             // column amount of each segment's molecule, per layer
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int tile = blockIdx.x;
+    const int nseg = a.nseg;
+    const TileHdr th = a.hdr[tile];
+    const int np = th.npieces;
+    {
+        const int nw = np * (int)(sizeof(FarPiece) / 4);
+        const int* src = reinterpret_cast<const int*>(a.pieces + (size_t)tile * nseg * kPiecePerSeg);
+        int* dst = reinterpret_cast<int*>(s_pc);
+        for (int i = tid; i < nw; i += NT) dst[i] = src[i];
+    }
+    __syncthreads();
+    const int k = blockIdx.y * kFarWarps + wid;
+    if (k >= a.nlay) return;                                    // no barrier follows
+    const int64_t Ltot = (int64_t)a.nlay * gridDim.z;
+    const int64_t L = (int64_t)blockIdx.z * a.nlay + k;
+    const LayerDev& ly = a.lay[L];
+    const double* pl = a.planes + (size_t)L * D_NPLANES * a.n_pad;
+    const double* __restrict__ pXNU = pl + (size_t)D_XNU * a.n_pad;
+    const double* __restrict__ pH2 = pl + (size_t)D_H2 * a.n_pad;
+    const double* __restrict__ pCN = pl + (size_t)D_CN * a.n_pad;
+    const double* __restrict__ pP3 = pl + (size_t)D_P3 * a.n_pad;
+    const double* __restrict__ pP4 = pl + (size_t)D_P4 * a.n_pad;
+    const int ptile = tile / a.S;
+    double* sw = s_w[wid];
+    for (int s = lane; s < nseg; s += 32) sw[s] = ly.wk[a.seg[s].mol - 1];
+    if (a.pcoef && lane < kFarK) s_pcoef[wid][lane] = a.pcoef[((size_t)ptile * Ltot + L) * kFarK + lane];
+    __syncwarp();
+    const double cen = 0.5 * (th.wlo + th.whi), hh = 0.5 * (th.whi - th.wlo);
+    const double m2h = -2. * hh, mhh = -hh * hh;
+    int npm = 0;                        // number of leading non-mixing pieces
+    while (npm < np && !((s_pc[npm].info >> 17) & 1)) npm++;
+
+    double A[kFarK];
+#pragma unroll
+    for (int i = 0; i < kFarK; i++) A[i] = 0.;
+    {
+        const int vend = th.nunits;
+        auto fetch = [&](int v, int& pi, double& D1, double& g1, double& w1, double& p1, double& D2, double& g2, double& w2, double& p2) {
+            D1 = 1.; g1 = 1.; w1 = 0.; p1 = 0.; D2 = 1.; g2 = 1.; w2 = 0.; p2 = 0.;
+            if (v >= vend) return;
+            while (pi + 1 < npm && v >= s_pc[pi + 1].off) pi++;
+            const FarPiece fp = s_pc[pi];
+            const int kk = v - fp.off;
+            const double ws = sw[fp.info & 0xffff];
+            if ((fp.info >> 16) & 1) {                    // both resonances of one line: cen - xnu and cen + xnu
+                const int q = fp.lo + kk;
+                const double xnu = __ldg(pXNU + q);
+                g1 = g2 = __ldg(pH2 + q);
+                w1 = w2 = ws * __ldg(pCN + q);
+                p1 = p2 = ws * __ldg(pP3 + q);
+                D1 = cen - xnu;
+                D2 = cen + xnu;
+            } else {                                      // two adjacent single-resonance lines
+                const int q = fp.lo + 2 * kk;
+                D1 = cen - __ldg(pXNU + q);
+                g1 = __ldg(pH2 + q);
+                w1 = ws * __ldg(pCN + q);
+                p1 = ws * __ldg(pP3 + q);
+                if (2 * kk + 1 < fp.n) {
+                    D2 = cen - __ldg(pXNU + q + 1);
+                    g2 = __ldg(pH2 + q + 1);
+                    w2 = ws * __ldg(pCN + q + 1);
+                    p2 = ws * __ldg(pP3 + q + 1);
+                }
+            }
+        };
+        int pi = 0;
+        int v = lane;
+        double D1, g1, w1, p1, D2, g2, w2, p2;
+        if (npm > 0) {
+            fetch(v, pi, D1, g1, w1, p1, D2, g2, w2, p2);
+            while (v < vend) {
+                const int vn = v + 32;
+                double D1n, g1n, w1n, p1n, D2n, g2n, w2n, p2n;
+                fetch(vn, pi, D1n, g1n, w1n, p1n, D2n, g2n, w2n, p2n);
+                far_accum2(D1, g1, w1, p1, D2, g2, w2, p2, m2h, mhh, A);
+                D1 = D1n; g1 = g1n; w1 = w1n; p1 = p1n;
+                D2 = D2n; g2 = g2n; w2 = w2n; p2 = p2n;
+                v = vn;
+            }
+        }
+        // first-order mixing pieces: few lines, one line (both resonances) per lane and step
+        for (int pj = npm; pj < np; pj++) {
+            const FarPiece fp = s_pc[pj];
+            const double ws = sw[fp.info & 0xffff];
+            for (int q = fp.lo + lane; q < fp.lo + fp.n; q += 32) {
+                const double xnu = __ldg(pXNU + q), h2 = __ldg(pH2 + q), cg = ws * __ldg(pP3 + q), cq = ws * __ldg(pP4 + q);
+                far_accum_mix(cen - xnu, h2, cg, cq, hh, m2h, mhh, A);
+                far_accum_mix(cen + xnu, h2, cg, -cq, hh, m2h, mhh, A);
+            }
+        }
+    }
+    // warp sums; lane i keeps coefficient i
+    double mine = 0.;
+#pragma unroll
+    for (int i = 0; i < kFarK; i++) {
+        double v = A[i];
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+        if (lane == i) mine = v;
+    }
+    if (lane < kFarK) {
+        if (a.pcoef) {
+            // coefficient `lane` of the parent's polynomial p(alpha + beta*s) re-expanded in s:
+            // beta^lane * sum_{j>=lane} c_j C(j,lane) alpha^(j-lane)
+            const TileHdr ph = a.phdr[ptile];
+            const double pc = 0.5 * (ph.wlo + ph.whi), phh = 0.5 * (ph.whi - ph.wlo);
+            double alpha = 0., beta = 0.;
+            if (phh > 0.) { alpha = (cen - pc) / phh; beta = hh / phh; }
+            const double* pcf = s_pcoef[wid];
+            double acc = 0.;
+            for (int j = kFarK - 1; j >= lane; j--) acc = fma(acc, alpha, pcf[j] * c_binom.c[j][lane]);
+            double bk = 1.;
+            for (int i = 0; i < lane; i++) bk *= beta;
+            mine += acc * bk;
+        }
+        a.coef[((size_t)tile * Ltot + L) * kFarK + lane] = mine;
+    }
+    if (a.counters && lane == 0) {
+        long long n_far = th.nterms;
+        for (int pj = npm; pj < np; pj++) n_far += 2ll * s_pc[pj].n;
+        atomicAdd(a.counters + 0, (unsigned long long)n_far);
+    }
+}
+
+// =============================================================================================
 // near_kernel: the per-(line,layer,frequency) evaluations that remain after the far field is taken
 // out.  CTA = (NT*F frequencies, one layer, one profile); each thread owns F (frequency, layer)
 // accumulators.  The tile's plan (plan_kernel) is copied from HBM: no searches here.
@@ -1813,7 +1962,7 @@ __global__ void __launch_bounds__(NT, MRTM_NEAR2_MINB) near2_kernel(LinesArgs a)
     }
     const double cen = 0.5 * (wA + wB), hh = 0.5 * (wB - wA);
     const double hinv = hh > 0. ? 1. / hh : 0.;
-    const double Rn = a.ff_ratio * hh, R2 = Rn * Rn;
+    const double Rn = a.ffw_ratio * hh, R2 = Rn * Rn;
     const double m2h = -2. * hh, mhh = -hh * hh;
     const double rp = ly.rp, rp2 = ly.rp2;
     const int vmode_mask = a.layer_voigt[L] ? 0xff : (0xff & ~M_VOIGT);
