@@ -177,8 +177,10 @@ class Session:
     # ---- fused batched path ---------------------------------------------------------------------
     def profiles(self, wn, dvset, prof, scor, irt, tmpsfc, emiss, reflc, cntnm=CNTNM_ALL_ONE, iout=1, idu=1,
                  sclcpl=1.0, sclhw=1.0, y0res=0.0, ibrd=0, want_o=False, want_otot_by_mol=False,
-                 selection=False, global_range=None, line_mode=0):
-        """prof: dict from synth.synthetic_profiles / profio (arrays with trailing profile dim)."""
+                 selection=False, global_range=None, line_mode=0, out=None):
+        """prof: dict from synth.synthetic_profiles / profio (arrays with trailing profile dim).
+        out: optional dict of caller-owned float64 Fortran-ordered (nwn, nprof) arrays rad, tb, tmr, trtot, rup, rdn
+        that receive the spectra (e.g. views of pinned host memory, reused from call to call)."""
         wn = _f(wn)
         nwn, nlay, nprof, nmol = wn.shape[0], int(prof["nlay"]), int(prof["nprof"]), int(prof["nmol"])
         p, t, clw, wbrodl = (_f(prof[k], (nlay, nprof)) for k in ("p", "t", "clw", "wbrodl"))
@@ -187,7 +189,15 @@ class Session:
         scor = None if scor is None else _f(scor, (42, 9, nlay, nprof))
         ts = _f(np.broadcast_to(np.asarray(tmpsfc, dtype=np.float64), (nprof,)).copy())
         emiss, reflc = _f(emiss, (nwn,)), _f(reflc, (nwn,))
-        outs = {k: np.zeros((nwn, nprof), order="F") for k in ("rad", "tb", "tmr", "trtot", "rup", "rdn")}
+        if out is not None:
+            outs = {}
+            for k in ("rad", "tb", "tmr", "trtot", "rup", "rdn"):
+                v = out[k]
+                if v.dtype != np.float64 or v.size != nwn * nprof or not (v.flags.f_contiguous or v.flags.c_contiguous and min(v.shape) == 1):
+                    raise ValueError("out[%r] must be a contiguous float64 array of nwn*nprof elements" % k)
+                outs[k] = v
+        else:
+            outs = {k: np.zeros((nwn, nprof), order="F") for k in ("rad", "tb", "tmr", "trtot", "rup", "rdn")}
         o = np.zeros((nwn, nlay, nprof), order="F") if want_o else None
         otot = np.zeros((MXMOL, nwn, nprof), order="F") if want_otot_by_mol else None
         sel = None
