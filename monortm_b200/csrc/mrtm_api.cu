@@ -53,6 +53,9 @@ struct mrtm_ctx {
     DevBuf b_plan[kMaxLevels], b_hdr[kMaxLevels], b_coef[kMaxLevels], b_pieces[kMaxLevels], b_npieces;
     int64_t farw_min = 4096;                      // (tile, layer) pairs of a level from which far_warp_kernel takes it (MRTM_FARW_MIN)
     int ff_levels = 3, ff_S = 6;                  // far-field hierarchy (MRTM_FF_LEVELS 1..3, MRTM_FF_S)
+    cudaStream_t side = nullptr;                  // high-priority stream: plans and far-field levels overlap derive / near field
+    cudaEvent_t evf[4] = {nullptr, nullptr, nullptr, nullptr};
+    int use_side = 1;                             // MRTM_SIDE_STREAM=0: everything on one stream
     int use_near2 = 1;                            // per-warp re-planning near-field kernel (MRTM_NEAR2=0 disables)
     DevBuf b_layer, b_scorc, b_absrb, b_planes, b_o, b_obm, b_oc, b_in[16], b_out[16], b_sel[2], b_tmps, b_fbeta;
     mrtm_stats st;
@@ -149,6 +152,13 @@ extern "C" int mrtm_init(int device, mrtm_ctx** out)
     if (cudaSetDevice(device) != cudaSuccess) { delete ctx; return set_err(nullptr, MRTM_ECUDA, "cudaSetDevice failed"); }
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return set_err(nullptr, MRTM_ECUDA, "cudaStreamCreate failed"); }
     for (auto& ev : ctx->ev) cudaEventCreate(&ev);
+    {
+        int lo = 0, hi = 0;
+        cudaDeviceGetStreamPriorityRange(&lo, &hi);
+        if (cudaStreamCreateWithPriority(&ctx->side, cudaStreamNonBlocking, hi) != cudaSuccess) ctx->side = nullptr;
+        for (auto& ev : ctx->evf) cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+    }
+    if (const char* s = std::getenv("MRTM_SIDE_STREAM")) ctx->use_side = std::atoi(s) != 0;
     if (const char* s = std::getenv("MRTM_PLANES_GB")) ctx->planes_budget = (size_t)(std::atof(s) * (double)(1ull << 30));
     if (const char* s = std::getenv("MRTM_FF_LEVELS")) ctx->ff_levels = std::min(std::max(std::atoi(s), 1), kMaxLevels);
     if (const char* s = std::getenv("MRTM_NEAR2")) ctx->use_near2 = std::atoi(s) != 0;
@@ -204,6 +214,8 @@ extern "C" int mrtm_free(mrtm_ctx* ctx)
     if (ctx->errflag_dev) cudaFree(ctx->errflag_dev);
     if (ctx->counters_dev) cudaFree(ctx->counters_dev);
     for (auto& ev : ctx->ev) cudaEventDestroy(ev);
+    for (auto& ev : ctx->evf) if (ev) cudaEventDestroy(ev);
+    if (ctx->side) cudaStreamDestroy(ctx->side);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
     return MRTM_OK;
@@ -324,7 +336,7 @@ struct RunDesc {
 };
 
 template <int F, int NT>
-static void launch_lines(const LinesArgs& la, dim3 grid, bool sel, cudaStream_t s)
+static void launch_lines(const LinesArgs& la, dim3 grid, bool sel, cudaStream_t s, cudaEvent_t far_done)
 {
     // near field (direct), Voigt branch, then polynomial + continuum + totals
     const size_t dyn = sizeof(double) * kStages * 4 * kTile + (size_t)std::max(la.nseg, 1) * sizeof(SegWork);
@@ -347,6 +359,7 @@ static void launch_lines(const LinesArgs& la, dim3 grid, bool sel, cudaStream_t 
         near_kernel<F, false, NT><<<grid, NT, dyn, s>>>(la);
     }
     voigt_kernel<F, NT><<<grid, NT, 0, s>>>(la);
+    if (far_done) cudaStreamWaitEvent(s, far_done, 0);     // the far-field coefficients come from the side stream
     final_kernel<F, NT><<<grid, NT, 0, s>>>(la);
 }
 
@@ -439,9 +452,20 @@ static int run_device(mrtm_ctx* ctx, const RunDesc& r, cudaStream_t s)
             pa.scorc = (double*)ctx->b_scorc.p;
             pa.errflag = ctx->errflag_dev;
             pa.sm_max_bits = (unsigned long long*)ctx->b_vtmax.p;
+            pa.vtmax = (unsigned long long*)ctx->b_vtmax.p + 1;
+            pa.seg = ctx->seg_dev;
+            pa.nseg = (int32_t)h.segments.size();
             CU(cudaMemsetAsync(ctx->b_vtmax.p, 0, (1 + std::max<size_t>(1, h.segments.size())) * 8, s));
             layer_prep_kernel<<<(unsigned)((Lb + 127) / 128), 128, 0, s>>>(pa);
             st.kernel_launches++;
+            // plans (they need only the layer tables) and the far-field levels run on a second, high-priority stream:
+            // side: [layer_prep] plan ... | [derive] far ...      main: continuum, derive | [plan] near, voigt | [far] final
+            const bool side_on = ctx->use_side && ctx->side != nullptr;
+            cudaStream_t sp = side_on ? ctx->side : s;
+            if (side_on) {
+                CU(cudaEventRecord(ctx->evf[0], s));
+                CU(cudaStreamWaitEvent(sp, ctx->evf[0], 0));
+            }
 
             ca.nlayers = Lb;
             ca.lay = (const LayerDev*)ctx->b_layer.p;
@@ -461,7 +485,6 @@ static int run_device(mrtm_ctx* ctx, const RunDesc& r, cudaStream_t s)
             da.y0res = r.y0res;
             da.ibrd = (int32_t)r.ibrd;
             da.planes = (double*)ctx->b_planes.p;
-            da.vtmax = (unsigned long long*)ctx->b_vtmax.p + 1;
             da.nseg = (int32_t)h.segments.size();
             if ((rc = ensure(ctx, ctx->b_lvoigt, (size_t)Lb * sizeof(int)))) return rc;
             CU(cudaMemsetAsync(ctx->b_lvoigt.p, 0, (size_t)Lb * sizeof(int), s));
@@ -469,6 +492,7 @@ static int run_device(mrtm_ctx* ctx, const RunDesc& r, cudaStream_t s)
             CU(cudaEventRecord(ctx->ev[0], s));
             derive_kernel<<<dim3((unsigned)((n_pad + 255) / 256), (unsigned)Lb), 256, 0, s>>>(da);
             CU(cudaEventRecord(ctx->ev[1], s));
+            if (side_on) CU(cudaEventRecord(ctx->evf[1], s));
             st.kernel_launches++;
 
             LinesArgs la;
@@ -563,13 +587,18 @@ static int run_device(mrtm_ctx* ctx, const RunDesc& r, cudaStream_t s)
                     pl.near_pieces = (NearPiece*)ctx->b_npieces.p;
                     la.near_pieces = pl.near_pieces;
                 }
-                plan_kernel<<<(unsigned)ntiles[lv], 128, (size_t)std::max(nseg_i, 1) * (sizeof(SegWork) + kPiecePerSeg * sizeof(FarPiece)), s>>>(pl);
+                plan_kernel<<<(unsigned)ntiles[lv], 128, (size_t)std::max(nseg_i, 1) * (sizeof(SegWork) + kPiecePerSeg * sizeof(FarPiece)), sp>>>(pl);
                 st.kernel_launches++;
                 la.plan[lv] = (const SegWork*)ctx->b_plan[lv].p;
                 la.hdr[lv] = (const TileHdr*)ctx->b_hdr[lv].p;
                 la.coef[lv] = (la.ff_ratio > 0.) ? (const double*)ctx->b_coef[lv].p : nullptr;
             }
             la.slot_mol = ctx->ld.slot_mol;
+            if (side_on) {
+                CU(cudaEventRecord(ctx->evf[3], sp));            // plans done: the near field may start
+                CU(cudaStreamWaitEvent(s, ctx->evf[3], 0));
+                CU(cudaStreamWaitEvent(sp, ctx->evf[1], 0));     // derived planes ready: the far field may start
+            }
             if (la.ff_ratio > 0.)
                 for (int lv = nlev - 1; lv >= 0; lv--) {      // top level first: each level folds its parent's polynomial in
                     FarArgs fa;
@@ -594,15 +623,20 @@ static int run_device(mrtm_ctx* ctx, const RunDesc& r, cudaStream_t s)
                     // many small tiles (level 0 above all): one warp per (tile, layer); few large tiles: one CTA
                     const size_t far_dyn = (size_t)std::max(nseg_i, 1) * kPiecePerSeg * sizeof(FarPiece);
                     if (combined && ntiles[lv] * nlay * nb >= ctx->farw_min)
-                        far_warp_kernel<<<dim3((unsigned)ntiles[lv], (unsigned)((nlay + kFarWarps - 1) / kFarWarps), (unsigned)nb), 32 * kFarWarps, far_dyn, s>>>(fa);
+                        far_warp_kernel<<<dim3((unsigned)ntiles[lv], (unsigned)((nlay + kFarWarps - 1) / kFarWarps), (unsigned)nb), 32 * kFarWarps, far_dyn, sp>>>(fa);
                     else
-                        far_kernel<<<dim3((unsigned)ntiles[lv], (unsigned)nlay, (unsigned)nb), 128, far_dyn, s>>>(fa);
+                        far_kernel<<<dim3((unsigned)ntiles[lv], (unsigned)nlay, (unsigned)nb), 128, far_dyn, sp>>>(fa);
                     st.kernel_launches++;
                 }
             st.kernel_launches += 2;       // voigt_kernel, final_kernel (near_kernel is counted below)
-            if (F == 4) launch_lines<4, 128>(la, grid, sel, s);
-            else if (F == 2) launch_lines<2, 128>(la, grid, sel, s);
-            else launch_lines<1, 128>(la, grid, sel, s);
+            cudaEvent_t far_done = nullptr;
+            if (side_on) {
+                CU(cudaEventRecord(ctx->evf[2], sp));
+                far_done = ctx->evf[2];
+            }
+            if (F == 4) launch_lines<4, 128>(la, grid, sel, s, far_done);
+            else if (F == 2) launch_lines<2, 128>(la, grid, sel, s, far_done);
+            else launch_lines<1, 128>(la, grid, sel, s, far_done);
             CU(cudaEventRecord(ctx->ev[3], s));
             st.kernel_launches++;
             CU(cudaGetLastError());

@@ -38,6 +38,7 @@ struct Segment {          // contiguous run of staged lines of one (molecule, cl
     int32_t slot;         // compact index of the molecule among the molecules that own lines
     uint64_t hash_all;    // sum of line keys (for O2 every line passes modm.f90:384)
     double vfac;          // 100*HWHM_D upper bound factor: vthr <= vfac*sqrt(T)
+    double vrate;         // the same bound per unit |Xnu|: 100*HWHM_D/|Xnu| <= vrate*sqrt(T)
 };
 
 constexpr int kMaxSegments = 96;

@@ -61,6 +61,11 @@ struct LayerPrepArgs {
     double* scorc;             // [L][nsi]
     int* errflag;              // bit0: TIPS range/partition-sum failure
     unsigned long long* sm_max_bits;   // max over the batch of shift_margin (bits of a non-negative double)
+    // upper bound of 100*HWHM_D/|Xnu| per segment over the layers of the batch (bits of a non-negative double): the
+    // plans need it before derive_kernel has run (the plan kernels overlap it on a second stream)
+    unsigned long long* vtmax;         // [nseg]
+    const Segment* seg;
+    int32_t nseg, pad3;
 };
 
 // AtoB, tips_2003.f90:4610-4700 (4-point Lagrange, 3-point at the table ends)
@@ -163,6 +168,11 @@ __global__ void layer_prep_kernel(LayerPrepArgs a)
     }
     o.shift_margin = sm;
     if (a.sm_max_bits) atomicMax(a.sm_max_bits, (unsigned long long)__double_as_longlong(sm));   // sm >= 0
+    if (a.vtmax)
+        for (int s = 0; s < a.nseg; s++) {
+            const unsigned long long bits = (unsigned long long)__double_as_longlong(a.seg[s].vrate * o.sqrt_t);
+            if (bits > *(volatile unsigned long long*)(a.vtmax + s)) atomicMax(a.vtmax + s, bits);
+        }
     // CONTNM scalars (P0=1013, T0=296 there: contnm.f90:86)
     {
         const double cp0 = 1013., ct0 = 296., xlosmt = 2.68675E+19;
@@ -341,7 +351,6 @@ struct DeriveArgs {
     double sclcpl, sclhw, y0res;
     int32_t ibrd, pad;
     double* planes;           // [L][D_NPLANES][n_pad]
-    unsigned long long* vtmax; // [nseg]: max over the segment and the batch's layers of VT/|Xnu| (bits of a non-negative double), 0 = no Voigt-capable line
     int* layer_voigt;          // [L] set to 1 when some line of the layer can take the Voigt branch (zeta <= 0.99)
     int32_t nseg, pad2;
 };
@@ -456,13 +465,6 @@ __global__ void __launch_bounds__(256) derive_kernel(DeriveArgs a)
     const double vt = (zeta > 0.99) ? -1.0 : 100. * hwhm_d;
     pl[(size_t)D_VT * np + q] = vt;
     if (vt >= 0.) {
-        // 100*HWHM_D is proportional to |Xnu| (modm.f90:453): keep the largest ratio per segment; most threads
-        // find the running maximum already at or above their value
-        if (fabs(xnu) > 1e-9) {
-            unsigned long long* addr = a.vtmax + a.ln.segidx[q];
-            const unsigned long long bits = (unsigned long long)__double_as_longlong(vt / fabs(xnu));
-            if (bits > *(volatile unsigned long long*)addr) atomicMax(addr, bits);
-        }
         if (*(volatile int*)(a.layer_voigt + L) == 0) a.layer_voigt[L] = 1;
     }
     pl[(size_t)D_STILD * np + q] = stild;

@@ -209,6 +209,7 @@ int stage_lines_host(const int64_t nblm[MRTM_MXMOL], int64_t iim, const int64_t*
         }
         // HALFWHM_D (modm.f90:453) upper bound: 100*AD <= vfac*sqrt(T)
         s.vfac = 100. * ((xmax + 1.0) / kCLIGHT) * std::sqrt(2. * std::log(2.) * (kBOLTZ / (mmin / kAVOGAD))) * (1. + 1e-6);
+        s.vrate = 100. * (1.0 / kCLIGHT) * std::sqrt(2. * std::log(2.) * (kBOLTZ / (mmin / kAVOGAD))) * (1. + 1e-6);
         if ((int)out.segments.size() >= kMaxSegments) {
             out.error = "too many (molecule,class) segments";
             return MRTM_EARG;
