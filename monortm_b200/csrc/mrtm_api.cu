@@ -55,6 +55,8 @@ struct mrtm_ctx {
     int ff_levels = 3, ff_S = 6;                  // far-field hierarchy (MRTM_FF_LEVELS 1..3, MRTM_FF_S)
     cudaStream_t side = nullptr;                  // high-priority stream: plans and far-field levels overlap derive / near field
     cudaEvent_t evf[4] = {nullptr, nullptr, nullptr, nullptr};
+    int voigt_side = 0;                           // MRTM_VOIGT_SIDE=1: Voigt branch on the side stream into a scratch plane (measured: no gain, off by default)
+    DevBuf b_ov;
     int use_side = 1;                             // MRTM_SIDE_STREAM=0: everything on one stream
     int use_near2 = 1;                            // per-warp re-planning near-field kernel (MRTM_NEAR2=0 disables)
     DevBuf b_layer, b_scorc, b_absrb, b_planes, b_o, b_obm, b_oc, b_in[16], b_out[16], b_sel[2], b_tmps, b_fbeta;
@@ -159,6 +161,7 @@ extern "C" int mrtm_init(int device, mrtm_ctx** out)
         for (auto& ev : ctx->evf) cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
     }
     if (const char* s = std::getenv("MRTM_SIDE_STREAM")) ctx->use_side = std::atoi(s) != 0;
+    if (const char* s = std::getenv("MRTM_VOIGT_SIDE")) ctx->voigt_side = std::atoi(s) != 0;
     if (const char* s = std::getenv("MRTM_PLANES_GB")) ctx->planes_budget = (size_t)(std::atof(s) * (double)(1ull << 30));
     if (const char* s = std::getenv("MRTM_FF_LEVELS")) ctx->ff_levels = std::min(std::max(std::atoi(s), 1), kMaxLevels);
     if (const char* s = std::getenv("MRTM_NEAR2")) ctx->use_near2 = std::atoi(s) != 0;
@@ -201,7 +204,7 @@ extern "C" int mrtm_free(mrtm_ctx* ctx)
     cudaStreamSynchronize(ctx->stream);
     free_lines(ctx);
     for (void* p : ctx->table_allocs) cudaFree(p);
-    DevBuf* bufs[] = {&ctx->b_lvoigt, &ctx->b_vtmax, &ctx->b_layer, &ctx->b_scorc, &ctx->b_absrb, &ctx->b_planes, &ctx->b_o, &ctx->b_obm, &ctx->b_oc, &ctx->b_sel[0], &ctx->b_sel[1], &ctx->b_tmps, &ctx->b_fbeta, &ctx->b_npieces};
+    DevBuf* bufs[] = {&ctx->b_ov, &ctx->b_lvoigt, &ctx->b_vtmax, &ctx->b_layer, &ctx->b_scorc, &ctx->b_absrb, &ctx->b_planes, &ctx->b_o, &ctx->b_obm, &ctx->b_oc, &ctx->b_sel[0], &ctx->b_sel[1], &ctx->b_tmps, &ctx->b_fbeta, &ctx->b_npieces};
     for (DevBuf* b : bufs) if (b->p) cudaFree(b->p);
     for (int i = 0; i < kMaxLevels; i++) {
         if (ctx->b_plan[i].p) cudaFree(ctx->b_plan[i].p);
@@ -336,7 +339,7 @@ struct RunDesc {
 };
 
 template <int F, int NT>
-static void launch_lines(const LinesArgs& la, dim3 grid, bool sel, cudaStream_t s, cudaEvent_t far_done)
+static void launch_lines(const LinesArgs& la, dim3 grid, bool sel, cudaStream_t s, cudaEvent_t far_done, cudaStream_t sv)
 {
     // near field (direct), Voigt branch, then polynomial + continuum + totals
     const size_t dyn = sizeof(double) * kStages * 4 * kTile + (size_t)std::max(la.nseg, 1) * sizeof(SegWork);
@@ -358,7 +361,13 @@ static void launch_lines(const LinesArgs& la, dim3 grid, bool sel, cudaStream_t 
         cudaFuncSetAttribute(near_kernel<F, false, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
         near_kernel<F, false, NT><<<grid, NT, dyn, s>>>(la);
     }
-    voigt_kernel<F, NT><<<grid, NT, 0, s>>>(la);
+    // with a scratch plane for its sums the Voigt branch runs on the side stream (after the far field, beside the near field)
+    if (la.o_v && sv) {
+        voigt_kernel<F, NT><<<grid, NT, 0, sv>>>(la);
+        cudaEventRecord(far_done, sv);
+    } else {
+        voigt_kernel<F, NT><<<grid, NT, 0, s>>>(la);
+    }
     if (far_done) cudaStreamWaitEvent(s, far_done, 0);     // the far-field coefficients come from the side stream
     final_kernel<F, NT><<<grid, NT, 0, s>>>(la);
 }
@@ -634,9 +643,17 @@ static int run_device(mrtm_ctx* ctx, const RunDesc& r, cudaStream_t s)
                 CU(cudaEventRecord(ctx->evf[2], sp));
                 far_done = ctx->evf[2];
             }
-            if (F == 4) launch_lines<4, 128>(la, grid, sel, s, far_done);
-            else if (F == 2) launch_lines<2, 128>(la, grid, sel, s, far_done);
-            else launch_lines<1, 128>(la, grid, sel, s, far_done);
+            cudaStream_t sv = nullptr;
+            if (side_on && ctx->voigt_side && !r.o_by_mol) {
+                const size_t ob = (size_t)nwn * nlay * nb * 8;
+                if ((rc = ensure(ctx, ctx->b_ov, ob))) return rc;
+                CU(cudaMemsetAsync(ctx->b_ov.p, 0, ob, sp));
+                la.o_v = (double*)ctx->b_ov.p;
+                sv = sp;
+            }
+            if (F == 4) launch_lines<4, 128>(la, grid, sel, s, far_done, sv);
+            else if (F == 2) launch_lines<2, 128>(la, grid, sel, s, far_done, sv);
+            else launch_lines<1, 128>(la, grid, sel, s, far_done, sv);
             CU(cudaEventRecord(ctx->ev[3], s));
             st.kernel_launches++;
             CU(cudaGetLastError());

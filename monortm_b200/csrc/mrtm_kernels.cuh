@@ -515,6 +515,7 @@ struct LinesArgs {
     double v1abs, v2abs, v1, dvset;
     // outputs (any may be null).  Strides in elements.
     double* o;        int64_t o_lds;  int64_t o_prof;     // o[iw + k*o_lds + prof*o_prof]
+    double* o_v;                  // zeroed scratch with o's strides: voigt_kernel adds there (it then runs beside the near field), or null
     double* o_by_mol; int64_t obm_ldm; int64_t obm_ldk;   // [iw + (mol-1)*ldm + k*ldk] (+prof*ldk*nlay)
     double* oc;                                           // same strides as o_by_mol
     double* o_clw;                                        // same strides as o
@@ -2462,7 +2463,7 @@ __global__ void __launch_bounds__(NT, MRTM_VOIGT_MINB) voigt_kernel(LinesArgs a)
                 }
             }
             if (by_mol) flush_mol(); else vsum = msum;
-            if (valid && vsum != 0.) a.o[(size_t)iw + (size_t)k * a.o_lds + (size_t)prof * a.o_prof] += vsum;
+            if (valid && vsum != 0.) (a.o_v ? a.o_v : a.o)[(size_t)iw + (size_t)k * a.o_lds + (size_t)prof * a.o_prof] += vsum;
             __syncwarp();                          // the list is rebuilt by the next sub-block
         }
     }
@@ -2511,6 +2512,7 @@ __global__ void __launch_bounds__(NT) final_kernel(LinesArgs a)
             const int iw = base + f * NT + tid;
             const size_t fl = (size_t)iw + (size_t)k * a.o_lds + (size_t)prof * a.o_prof;
             double v = valid[f] ? a.o[fl] : 0.;
+            if (a.o_v && valid[f]) v += a.o_v[fl];
             if (have_far) {
                 double p = s_coef[kFarK - 1];
 #pragma unroll
