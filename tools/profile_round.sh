@@ -19,6 +19,10 @@ ls -la $out | tail -20
 # reports are ~9 MB each and gpurun brings back at most 64 MiB: summarise on the box, keep only the summaries
 python tools/ncu_summary.py $out/${tag}_*.ncu-rep > $out/${tag}_ncu_summary.md 2>&1
 for k in near2_kernel far_warp_kernel voigt_kernel final_kernel derive_kernel rt_kernel; do
-  python tools/ncu_lines.py $out/${tag}_$k.ncu-rep monortm_b200/lib/libmonortm_b200.so $k 40 > $out/${tag}_lines_$k.txt 2>&1
+  m=$k      # mangled-name substring of the instantiation that was captured (templates have several)
+  [ $k = near2_kernel ] && m=near2_kernelILi4ELb0E
+  [ $k = voigt_kernel ] && m=voigt_kernelILi4E
+  [ $k = final_kernel ] && m=final_kernelILi4E
+  python tools/ncu_lines.py $out/${tag}_$k.ncu-rep monortm_b200/lib/libmonortm_b200.so $m 40 > $out/${tag}_lines_$k.txt 2>&1
 done
 rm -f $out/${tag}_*.ncu-rep
