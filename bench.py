@@ -201,6 +201,17 @@ def workload_config(args):
             "l2": "L2 flushed (256 MiB write) between timed steps"}
 
 
+def ncu_traffic(args):
+    """DRAM bytes the line-path kernels move per step, from the committed ncu capture of the default workload."""
+    try:
+        if args.nwn_per_gpu != 125000 or args.n_filler != N_FILLER:
+            return None
+        with open(os.path.join(ROOT, "profiles", "r01_v13_traffic.json")) as f:
+            return float(json.load(f)["lines_group_bytes_per_step"])
+    except Exception:
+        return None
+
+
 def main():
     args = parse()
     if args.impl == "reference":
@@ -379,8 +390,11 @@ def main():
             "gpu_launches": int(launches),
             "wall_ms_per_step_incl_flush": 1e3 * t_wall / args.steps,
             "clocks": sampler.summary(),
-            "roofline": {"bound": "fp64", "kernel": "lines_kernel", "achieved": achieved, "peak": fp64_peak,
-                         "unit": "TFLOP/s", "frac": achieved / fp64_peak if fp64_peak else None, "traffic": None,
+            "roofline": {"bound": "fp64", "achieved": achieved, "peak": fp64_peak,
+                         "unit": "TFLOP/s", "frac": achieved / fp64_peak if fp64_peak else None, "traffic": ncu_traffic(args),
+                         "traffic_source": "profiles/r01_v13_traffic.json: dram bytes read+written by the line-path kernels of one step "
+                                           "(ncu --set full, default workload only; null otherwise)",
+                         "kernel": "plan+far+near2+voigt+final (the line path of one step)",
                          "peak_source": "measured live: mrtm_fp64_peak DFMA probe (MEASURED_PEAKS.json has no FP64 figure)",
                          "flop_per_direct_eval": FLOP_PER_INWINDOW_EVAL, "flop_per_far_expansion": FLOP_PER_FAR_EXPANSION,
                          "far_expansions_per_launch": far_n, "direct_evals_per_launch": dir_n,

@@ -123,3 +123,32 @@ def test_dense_grid_far_field_expansion():
         ref, gpu = check_case(case)
         assert gpu["stats"]["far_expansions"] > 0
         assert gpu["stats"]["direct_evals"] < 0.2 * ref["sel_count"].sum()
+
+
+@pytest.mark.parametrize("env", [
+    {"MRTM_FARW_MIN": "1", "MRTM_FF_S": "2", "MRTM_FF_LEVELS": "4"},      # far_warp_kernel on every level, 4 levels
+    {"MRTM_FARW_MIN": "1000000000"},                                      # far_kernel (one CTA per tile and layer) only
+    {"MRTM_SIDE_STREAM": "0"},                                            # everything on one stream
+    {"MRTM_VOIGT_SIDE": "1"},                                             # Voigt branch on the side stream (scratch plane)
+    {"MRTM_NEAR2": "0"},                                                  # near_kernel for every tile
+])
+def test_kernel_variants_on_the_dense_grid(env, monkeypatch):
+    """The library reads its tuning switches when a context is created: run the dense-grid case (13 layers, not a
+    multiple of far_warp_kernel's four layers per CTA) under each variant against the oracle and the direct mode."""
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    monkeypatch.setattr(harness, "_session", None)
+    wn = 5.5e-5 * np.arange(13400, 13400 + 2304)
+    case = harness.make_case(n_filler=1536, nlay=13, wn=wn, irt=1, line_kw=dict(n_co2=4, n_generic_lc=4))
+    ref = harness.run_oracle(case)
+    direct = harness.run_gpu(case, line_mode=1)
+    for by_mol in (True, False):
+        gpu = harness.run_gpu(case, by_mol=by_mol, selection=by_mol)
+        assert harness.rel_diff(gpu["o"], ref["o"]) < OD_RTOL
+        assert harness.rel_diff(gpu["o"], direct["o"]) < 1e-11
+        assert np.max(np.abs(gpu["tb"] - ref["tb"])) < TB_ATOL
+        assert gpu["stats"]["far_expansions"] > 0
+        if by_mol:
+            assert np.array_equal(gpu["sel_count"], ref["sel_count"])
+            assert np.array_equal(gpu["sel_hash"], ref["sel_hash"])
+    monkeypatch.setattr(harness, "_session", None)     # the next test creates its context with the default switches
