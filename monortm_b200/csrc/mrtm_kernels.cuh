@@ -2330,7 +2330,10 @@ __global__ void __launch_bounds__(NT, MRTM_VOIGT_MINB) voigt_kernel(LinesArgs a)
     __shared__ double s_vt[kVCap], s_x[kVCap], s_inv[kVCap], s_y[kVCap], s_c[kVCap], s_pd[kVCap], s_g[kVCap], s_b[kVCap];
     __shared__ int s_q[kVCap];
     __shared__ unsigned char s_kind[kVCap], s_mol[kVCap];
-    __shared__ unsigned char s_list[NW][kVCap];
+    // fast path (generic uncoupled line, single resonance, Humlicek region I): Re w = y*(a+q)/(q*(q+b)+a*a), q = x*x,
+    // a = .5+y*y, b = 2*y*y-1 -- the reference's t*.5641896/(.5+t*t) (modm.f90:1105) multiplied out
+    __shared__ double s_fa[kVCap], s_fb[kVCap], s_fa2[kVCap], s_fcy[kVCap], s_fcpd[kVCap];
+    __shared__ unsigned short s_list[NW][kVCap];
     __shared__ int s_zlo[kMaxSegments], s_zoff[kMaxSegments + 1];
     const int base = blockIdx.x * (NT * F) + wid * (32 * F);
     const double rp = ly.rp, rp2 = ly.rp2;
@@ -2338,15 +2341,21 @@ __global__ void __launch_bounds__(NT, MRTM_VOIGT_MINB) voigt_kernel(LinesArgs a)
     const bool by_mol = a.o_by_mol != nullptr;
     const unsigned lt_mask = (1u << lane) - 1u;
     // zone directory: entry e of the CTA's zone list lies in segment s with s_zoff[s] <= e < s_zoff[s+1]
+    // (one thread per segment fetches its zone from the plan, then one thread sums the counts in shared memory)
+    for (int s = tid; s < a.nseg; s += NT) {
+        const Segment sg = a.seg[s];
+        const bool use = (sg.cls != CLS_GENERAL) && (ly.wk[sg.mol - 1] != 0.);
+        const int v0 = plan[s].v0, v1 = plan[s].v1;
+        s_zlo[s] = v0;
+        s_zoff[s + 1] = (use && v1 > v0) ? (v1 - v0) : 0;
+    }
+    __syncthreads();
     if (tid == 0) {
         int tot = 0;
         for (int s = 0; s < a.nseg; s++) {
-            const int cls = a.seg[s].cls;
-            const bool use = (cls != CLS_GENERAL) && (ly.wk[a.seg[s].mol - 1] != 0.);
-            const int v0 = plan[s].v0, v1 = plan[s].v1;
-            s_zlo[s] = v0;
+            const int c = s_zoff[s + 1];
             s_zoff[s] = tot;
-            tot += (use && v1 > v0) ? (v1 - v0) : 0;
+            tot += c;
         }
         s_zoff[a.nseg] = tot;
     }
@@ -2354,7 +2363,8 @@ __global__ void __launch_bounds__(NT, MRTM_VOIGT_MINB) voigt_kernel(LinesArgs a)
     const int total = s_zoff[a.nseg];
     if (total == 0) return;
     int err = 0;
-    unsigned char* lst = s_list[wid];
+    unsigned short* lst = s_list[wid];
+    double* const odst = (a.o_v ? a.o_v : a.o) + (size_t)k * a.o_lds + (size_t)prof * a.o_prof;
     for (int e0 = 0; e0 < total; e0 += kVCap) {
         const int n = min(kVCap, total - e0);
         if (e0 > 0) __syncthreads();
@@ -2387,11 +2397,20 @@ __global__ void __launch_bounds__(NT, MRTM_VOIGT_MINB) voigt_kernel(LinesArgs a)
                     s_pd[i] = (kind == 0) ? w4_re_fast(sl2 * (kDELTNUC * inv), y) : 0.;
                     s_g[i] = (kind == 3) ? (__ldg(pAIP + q) * (1 / hw) * rp) : 0.;
                     s_b[i] = (kind == 3) ? (__ldg(pBIP + q) * rp2) : 0.;
+                    if (kind == 0 && vt <= kDELTNUC) {      // inside the zone the window test cannot fail
+                        const double y2 = y * y, aa = .5 + y2;
+                        s_fa[i] = aa;
+                        s_fb[i] = 2. * y2 - 1.;
+                        s_fa2[i] = aa * aa;
+                        s_fcy[i] = s_c[i] * (.5641896 * y);
+                        s_fcpd[i] = s_c[i] * s_pd[i];
+                        s_kind[i] = (unsigned char)(kind | 0x80);
+                    }
                 }
             }
         }
         __syncthreads();
-        for (int f = 0; f < F; f++) {
+        for (int f = 0; f < F; f++) {              // not unrolled: four copies of the loop body run slower
             const int iw = base + f * 32 + lane;
             const bool valid = iw < a.nwn;
             const double wn = a.wn[valid ? iw : (a.nwn - 1)];
@@ -2407,18 +2426,25 @@ __global__ void __launch_bounds__(NT, MRTM_VOIGT_MINB) voigt_kernel(LinesArgs a)
             for (int ib = 0; ib < n; ib += 32) {
                 const int i = ib + lane;
                 bool hit = false;
+                int ent = i;
                 if (i < n) {
                     const double vt = s_vt[i];
                     if (vt >= 0.) {
                         const double x = s_x[i];
                         hit = !((wB - x) < -vt) && !((wA - x) > vt);
+                        // fast entry: plain line and no frequency of the sub-block has the second resonance
+                        // (WN+Xnu-25 <= 0, modm.f90:746; the rounded sum is monotone in WN)
+                        if ((s_kind[i] & 0x80) && ((wA + x) - kDELTNUC) > 0.) ent |= 0x100;
                     }
                 }
                 const unsigned m = __ballot_sync(0xffffffffu, hit);
-                if (hit) lst[nl + __popc(m & lt_mask)] = (unsigned char)i;
+                if (hit) lst[nl + __popc(m & lt_mask)] = (unsigned short)ent;
                 nl += __popc(m);
             }
             __syncwarp();
+            if (nl == 0) continue;                 // warp-uniform: no zone reaches this sub-block
+            // the optical depth this sub-block adds to: loaded now, needed after the evaluation loop
+            const double oprev = valid ? odst[iw] : 0.;
             double vsum = 0., msum = 0.;
             int cur_mol = -1;
             bool many = false;
@@ -2433,14 +2459,30 @@ __global__ void __launch_bounds__(NT, MRTM_VOIGT_MINB) voigt_kernel(LinesArgs a)
                 many = false;
             };
             for (int g = 0; g < nl; g++) {
-                const int i = lst[g];
-                const int kind = s_kind[i];
+                const int ent = lst[g];
+                const int i = ent & 0xff;
                 if (by_mol && (int)s_mol[i] != cur_mol) {
                     flush_mol();
                     cur_mol = s_mol[i];
                 }
                 const double xnu = s_x[i];
                 const double dm = wn - xnu;
+                if (ent & 0x100) {
+                    if (fabs(dm) <= s_vt[i]) {
+                        const double y = s_y[i];
+                        const double x = sl2 * (dm * s_inv[i]);
+                        if (!(fabs(x) + y < 15.)) {
+                            const double q = x * x;
+                            const double den = fma(q, q + s_fb[i], s_fa2[i]);
+                            msum += fma(s_fcy[i] * (s_fa[i] + q), rcp3(den), -s_fcpd[i]);
+                        } else {
+                            msum = fma(s_c[i], w4_re_near(x, y), msum) - s_fcpd[i];
+                        }
+                        many = true;
+                    }
+                    continue;
+                }
+                const int kind = s_kind[i] & 0x7f;
                 const bool inwin = (kind <= 1) ? !(fabs(dm) > kDELTNUC) : true;
                 if (inwin && fabs(dm) <= s_vt[i]) {
                     const double inv = s_inv[i];
@@ -2463,7 +2505,7 @@ __global__ void __launch_bounds__(NT, MRTM_VOIGT_MINB) voigt_kernel(LinesArgs a)
                 }
             }
             if (by_mol) flush_mol(); else vsum = msum;
-            if (valid && vsum != 0.) (a.o_v ? a.o_v : a.o)[(size_t)iw + (size_t)k * a.o_lds + (size_t)prof * a.o_prof] += vsum;
+            if (valid && vsum != 0.) odst[iw] = oprev + vsum;
             __syncwarp();                          // the list is rebuilt by the next sub-block
         }
     }
