@@ -180,9 +180,6 @@ __device__ __forceinline__ double cdiv_re(cplx a, cplx b)
 }
 __device__ __noinline__ double w4_re_near(double x, double y)
 {
-#ifdef MRTM_EXPERIMENT_NO_NEAR
-    return 0.;     // timing experiment only
-#endif
     const cplx t = cmk(y, -x);
     const double s = fabs(x) + y;
     if (!(s < 5.5)) {                    // region II

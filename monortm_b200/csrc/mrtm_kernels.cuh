@@ -473,12 +473,11 @@ __global__ void __launch_bounds__(256) derive_kernel(DeriveArgs a)
 }
 
 // =============================================================================================
-// lines_kernel: CTA = (frequency tile, layer, profile); each thread owns F (frequency, layer)
-// accumulators.  Per (molecule, class) segment the CTA binary-searches the sorted static centres
-// for the lines that can fall inside the 25 cm-1 window of any of its frequencies, then walks
-// them; the cutoff test itself is the reference's exact |WN-Xnu| > 25 on the bit-exact shifted
-// centre (modm.f90:384).  Epilogue fuses RFT (:257), the continuum interpolation + RADFN
-// (:218-230), cloud liquid water (:264) and the total (:265-269).
+// The line path (modm.f90:277-440).  plan_kernel classifies every (frequency tile, segment) once per call,
+// far_kernel / far_warp_kernel expand the far lines level by level, near2_kernel (near_kernel for oversize
+// tiles) evaluates the remaining (line, layer, frequency) triples with the reference's exact tests,
+// voigt_kernel adds the Voigt-branch pairs and final_kernel closes the sums (RFT :257, continuum
+// interpolation + RADFN :218-230, cloud liquid water :264, total :265-269).  LinesArgs is shared by them.
 // =============================================================================================
 struct SegWork;
 struct TileHdr;
