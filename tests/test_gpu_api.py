@@ -149,3 +149,23 @@ def test_ragged_and_single_element_inputs():
     gpu = harness.run_gpu(case)
     assert np.all(ref["sel_count"] == 0) and np.array_equal(gpu["sel_count"], ref["sel_count"])
     assert harness.rel_diff(gpu["o"], ref["o"]) < 1e-9
+
+
+def test_caller_owned_output_buffers_and_tile_size_by_spectral_width():
+    """profiles(out=...) writes the spectra into the caller's arrays (pinned host memory in bench.py); a coarse grid
+    (wide tiles would defeat the far field) and a dense grid of the same length give oracle-exact results whichever
+    tile size the library picks."""
+    for wn in (np.linspace(0.3, 50.0, 2600), 5.5e-5 * np.arange(20000, 22600)):
+        case = harness.make_case(n_filler=512, nlay=8, wn=wn, irt=1, nprof=2)
+        ref = _fused(case)
+        nwn = len(wn)
+        out = {k: np.full((nwn, 2), np.nan, order="F") for k in ("rad", "tb", "tmr", "trtot", "rup", "rdn")}
+        got = _fused(case, out=out)
+        for k in out:
+            assert got[k] is out[k]
+            assert np.array_equal(out[k], ref[k]), k
+        for ip in range(2):
+            orc = harness.run_oracle(case, ip=ip)
+            assert np.max(np.abs(out["tb"][:, ip] - orc["tb"])) < 1e-5
+    with pytest.raises(ValueError):
+        _fused(case, out={k: np.zeros((3, 2), order="F") for k in ("rad", "tb", "tmr", "trtot", "rup", "rdn")})
