@@ -355,7 +355,10 @@ struct DeriveArgs {
     int32_t nseg, pad2;
 };
 
-__global__ void __launch_bounds__(256) derive_kernel(DeriveArgs a)
+#ifndef MRTM_DERIVE_MINB
+#define MRTM_DERIVE_MINB 6
+#endif
+__global__ void __launch_bounds__(256, MRTM_DERIVE_MINB) derive_kernel(DeriveArgs a)
 {
     const int q = blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t L = blockIdx.y;
@@ -2515,8 +2518,11 @@ __global__ void __launch_bounds__(NT, MRTM_VOIGT_MINB) voigt_kernel(LinesArgs a)
 // final_kernel: per (frequency, layer): the far-field polynomial of the level-0 tile, RFT (modm.f90:257),
 // the continuum interpolation + RADFN (:218-230), cloud liquid water (:264) and the total (:265-269).
 // =============================================================================================
+#ifndef MRTM_FINAL_MINB
+#define MRTM_FINAL_MINB 8
+#endif
 template <int F, int NT>
-__global__ void __launch_bounds__(NT) final_kernel(LinesArgs a)
+__global__ void __launch_bounds__(NT, MRTM_FINAL_MINB) final_kernel(LinesArgs a)
 {
     const int tid = threadIdx.x;
     const int k = blockIdx.y, prof = blockIdx.z;
