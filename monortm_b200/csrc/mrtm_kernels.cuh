@@ -2688,7 +2688,7 @@ __global__ void rt_prep_kernel(int n_t, const double* t, double* fb, int n_tz, c
 // there; the upwelling sum (:192-204) needs, for layer l, the optical depth above it, which the same pass carries
 // as a running sum from the top (the reference subtracts from the total going up: same value up to rounding).
 // Per (frequency, layer): Planck at the layer temperature and at one new level (the lower boundary becomes the
-// next layer's upper boundary), exp(-tau), and the two path transmittances: 5 exp instead of 8.
+// next layer's upper boundary) and exp(-tau); the two path transmittances follow by recurrence: 3 exp instead of 8.
 __global__ void __launch_bounds__(128) rt_kernel(RtArgs a)
 {
     const int iw = blockIdx.x * blockDim.x + threadIdx.x;
@@ -2707,23 +2707,27 @@ __global__ void __launch_bounds__(128) rt_kernel(RtArgs a)
     const double c1v3 = kRADCN1 * (vv * vv * vv);
     double rup = 0., rdn = 0.;
     double odt = odtot;          // optical depth below the current layer after the subtraction (down loops)
-    double oda = 0.;             // optical depth above the current layer (up loop)
     double bb_top = c1v3 / (exp(vv * __ldg(fbz + a.nlay)) - 1.);
+    // Path transmittances by recurrence instead of one exponential each per layer: above the layer
+    // tra = prod(tri of the layers above) (underflow to 0 is the right limit); below it trt(l) = trt(l+1)/tri(l),
+    // re-anchored with exp(-odt) while either factor is too small to divide by (opaque columns).  The relative
+    // error grows by ~1.5 ulp per layer (<= 1e-13 over 300 layers; bar: 1e-5 K).  3 exp per layer instead of 5.
+    double trt = exp(-odt);
+    double tra = 1.;
     for (int l = a.nlay; l >= 1; l--) {
         const double odvi = o[(size_t)(l - 1) * a.o_lds];
-        const double bb = c1v3 / (exp(vv * __ldg(fb + l - 1)) - 1.);
-        const double bb_bot = c1v3 / (exp(vv * __ldg(fbz + l - 1)) - 1.);
+        const double bb = c1v3 * rcp3(exp(vv * __ldg(fb + l - 1)) - 1.);
+        const double bb_bot = c1v3 * rcp3(exp(vv * __ldg(fbz + l - 1)) - 1.);
         odt = odt - odvi;
         const double tri = exp(-odvi);
-        const double trt = exp(-odt);
+        trt = (trt > 1e-250 && tri > 1e-50) ? trt * rcp3(tri) : exp(-odt);
         const double pade = 0.193 * odvi + 0.013 * (odvi * odvi);
-        const double rden = 1. / (1. + pade);
+        const double rden = rcp3(1. + pade);
         const double emis = 1. - tri;
         rdn = rdn + trt * emis * ((bb + pade * bb_bot) * rden);
         if (up) {
-            const double tra = exp(-oda);
             rup = rup + tra * emis * ((bb + pade * bb_top) * rden);
-            oda = oda + odvi;
+            tra = tra * tri;
         }
         bb_top = bb_bot;
     }
