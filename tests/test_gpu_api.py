@@ -169,3 +169,31 @@ def test_caller_owned_output_buffers_and_tile_size_by_spectral_width():
             assert np.max(np.abs(out["tb"][:, ip] - orc["tb"])) < 1e-5
     with pytest.raises(ValueError):
         _fused(case, out={k: np.zeros((3, 2), order="F") for k in ("rad", "tb", "tmr", "trtot", "rup", "rdn")})
+
+
+def test_rtm_and_calctmr_on_opaque_and_transparent_columns():
+    """RTM / CALCTMR on hand-made optical depths: transparent, ordinary and opaque layers (exp(-tau) underflows, the
+    column total exceeds 745) -- rt_kernel forms the path transmittances by recurrence and must re-anchor them where a
+    factor underflows (RTMmono.f90:157-221)."""
+    rng = np.random.default_rng(7)
+    nwn, nlay = 257, 31
+    wn = np.sort(rng.uniform(0.05, 55.0, nwn))
+    t = np.linspace(288.0, 210.0, nlay)
+    tz = np.linspace(290.0, 209.0, nlay + 1)
+    o = 10.0 ** rng.uniform(-9, 0.5, (nwn, nlay))
+    o[::7, 3] = 900.0                    # one opaque layer low in the column
+    o[1::7, nlay - 2] = 2000.0           # one near the top
+    o[2::7, :] = 60.0                    # opaque everywhere: total 1860
+    o[3::7, :] = 1e-12                   # transparent
+    o = np.asfortranarray(o)
+    em, rf = np.full(nwn, 0.85), np.full(nwn, 0.15)
+    s = harness.session()
+    for irt in (1, 3):
+        ref = harness.oracle_rtm(1, irt, wn, t, tz, o, 285.0, rf, em)
+        got = s.rtm(1, irt, wn, t, tz, o, 285.0, rf, em)
+        for k in ("rad", "rup", "rdn", "trtot"):
+            assert harness.rel_diff(got[k], ref[k], floor=1e-300) < 1e-10, (k, irt)
+        assert np.max(np.abs(got["tb"] - ref["tb"])) < 1e-7
+    tmr_ref = harness.oracle_calctmr(wn, t, tz, o)
+    tmr = s.calctmr(wn, t, tz, o)
+    assert np.max(np.abs(tmr - tmr_ref)) < 1e-7
