@@ -499,9 +499,9 @@ static int run_device(mrtm_ctx* ctx, const RunDesc& r, cudaStream_t s)
             da.ibrd = (int32_t)r.ibrd;
             da.planes = (double*)ctx->b_planes.p;
             da.nseg = (int32_t)h.segments.size();
-            if ((rc = ensure(ctx, ctx->b_lvoigt, (size_t)Lb * sizeof(int)))) return rc;
-            CU(cudaMemsetAsync(ctx->b_lvoigt.p, 0, (size_t)Lb * sizeof(int), s));
-            da.layer_voigt = (int*)ctx->b_lvoigt.p;
+            if ((rc = ensure(ctx, ctx->b_lvoigt, (size_t)Lb * sizeof(unsigned long long)))) return rc;
+            CU(cudaMemsetAsync(ctx->b_lvoigt.p, 0xff, (size_t)Lb * sizeof(unsigned long long), s));
+            da.layer_voigt = (unsigned long long*)ctx->b_lvoigt.p;
             CU(cudaEventRecord(ctx->ev[0], s));
             derive_kernel<<<dim3((unsigned)((n_pad + 255) / 256), (unsigned)Lb), 256, 0, s>>>(da);
             CU(cudaEventRecord(ctx->ev[1], s));
@@ -526,7 +526,7 @@ static int run_device(mrtm_ctx* ctx, const RunDesc& r, cudaStream_t s)
             la.ff_ratio = (r.line_mode == 1) ? 0. : ctx->ff_ratio;
             la.ffw_ratio = ctx->ffw_ratio;
             la.counters = ctx->counters_dev;
-            la.layer_voigt = (const int*)ctx->b_lvoigt.p;
+            la.layer_voigt = (const unsigned long long*)ctx->b_lvoigt.p;
             la.planes = (const double*)ctx->b_planes.p;
             la.lay = (const LayerDev*)ctx->b_layer.p;
             la.absrb = (const double*)ctx->b_absrb.p;

@@ -351,18 +351,19 @@ struct DeriveArgs {
     double sclcpl, sclhw, y0res;
     int32_t ibrd, pad;
     double* planes;           // [L][D_NPLANES][n_pad]
-    int* layer_voigt;          // [L] set to 1 when some line of the layer can take the Voigt branch (zeta <= 0.99)
+    unsigned long long* layer_voigt;   // [L] bits of the smallest |Xnu| among the lines of the layer that can take the Voigt branch
+                                       // (zeta <= 0.99; 100*HWHM_D grows with |Xnu|), all ones = none
     int32_t nseg, pad2;
 };
 
 #ifndef MRTM_DERIVE_MINB
 #define MRTM_DERIVE_MINB 6
 #endif
-__global__ void __launch_bounds__(256, MRTM_DERIVE_MINB) derive_kernel(DeriveArgs a)
+// one (line, layer): returns the bits of |Xnu| when the line can take the Voigt branch in this layer, else all ones
+__device__ __forceinline__ unsigned long long derive_one(const DeriveArgs& a, int q, int64_t L)
 {
-    const int q = blockIdx.x * blockDim.x + threadIdx.x;
-    const int64_t L = blockIdx.y;
-    if (q >= a.ln.n_pad) return;
+    const unsigned long long kNone = ~0ull;
+    if (q >= a.ln.n_pad) return kNone;
     double* pl = a.planes + (size_t)L * D_NPLANES * a.ln.n_pad;
     if (q >= a.ln.n) {   // padding: far away, zero strength
         pl[(size_t)D_XNU * a.ln.n_pad + q] = 1.0e30;
@@ -376,7 +377,7 @@ __global__ void __launch_bounds__(256, MRTM_DERIVE_MINB) derive_kernel(DeriveArg
         pl[(size_t)D_STILD * a.ln.n_pad + q] = 0.;
         pl[(size_t)D_AIP * a.ln.n_pad + q] = 0.;
         pl[(size_t)D_BIP * a.ln.n_pad + q] = 0.;
-        return;
+        return kNone;
     }
     const LayerDev& ly = a.lay[L];
     const int mol = a.ln.mol[q], xf = a.ln.xf[q], cls = a.ln.cls[q];
@@ -467,12 +468,30 @@ __global__ void __launch_bounds__(256, MRTM_DERIVE_MINB) derive_kernel(DeriveArg
     pl[(size_t)D_AD * np + q] = hwhm_d;
     const double vt = (zeta > 0.99) ? -1.0 : 100. * hwhm_d;
     pl[(size_t)D_VT * np + q] = vt;
-    if (vt >= 0.) {
-        if (*(volatile int*)(a.layer_voigt + L) == 0) a.layer_voigt[L] = 1;
-    }
     pl[(size_t)D_STILD * np + q] = stild;
     pl[(size_t)D_AIP * np + q] = aip;
     pl[(size_t)D_BIP * np + q] = bip;
+    return (vt >= 0.) ? (unsigned long long)__double_as_longlong(fabs(xnu)) : kNone;
+}
+
+__global__ void __launch_bounds__(256, MRTM_DERIVE_MINB) derive_kernel(DeriveArgs a)
+{
+    const int64_t L = blockIdx.y;
+    unsigned long long xb = derive_one(a, blockIdx.x * blockDim.x + threadIdx.x, L);
+    // smallest |Xnu| of the layer's Voigt-capable lines: warp minimum, block minimum, one global atomic per block at most
+    __shared__ unsigned long long s_min[8];
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        const unsigned long long o = __shfl_xor_sync(0xffffffffu, xb, off);
+        xb = o < xb ? o : xb;
+    }
+    if ((threadIdx.x & 31) == 0) s_min[threadIdx.x >> 5] = xb;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long m = s_min[0];
+        for (int w = 1; w < 8; w++) m = s_min[w] < m ? s_min[w] : m;
+        if (m < *(volatile unsigned long long*)(a.layer_voigt + L)) atomicMin(a.layer_voigt + L, m);
+    }
 }
 
 // =============================================================================================
@@ -509,7 +528,7 @@ struct LinesArgs {
     const double* coef[kMaxLevels];     // lv >= 1: [tile][L][slot][kFarK] from far_kernel
     int32_t nslot, pad0;
     const NearPiece* near_pieces;       // [ntiles][kMaxNearPieces] (plan_kernel, level 0); null: near2_kernel not in use
-    const int* layer_voigt;             // [L] 0: every line of the layer is Lorentz-only (zeta > 0.99)
+    const unsigned long long* layer_voigt;   // [L] bits of the smallest |Xnu| of the layer's Voigt-capable lines (derive_kernel), all ones = none
     const int32_t* slot_mol;            // [nslot]
     // continuum
     const double* absrb;          // [L][3][nptabs_pad]
@@ -541,6 +560,15 @@ __device__ __forceinline__ int upper_bound_d(const double* a, int lo, int hi, do
         if (__ldg(a + mid) <= v) lo = mid + 1; else hi = mid;
     }
     return lo;
+}
+
+// Can a (line, frequency) pair of this layer take the Voigt branch for a frequency <= whi?  A pair needs
+// |WN-Xnu| <= 100*HWHM_D <= 2e-3*|Xnu| (T < 3000 K, molecular mass >= 1), so Xnu <= 1.0021*whi; the layer's
+// Voigt-capable lines all have |Xnu| >= the recorded minimum.
+__device__ __forceinline__ bool voigt_possible(const unsigned long long* layer_voigt, int64_t L, double whi)
+{
+    const unsigned long long bound = (unsigned long long)__double_as_longlong(fabs(whi) * 1.01 + 1e-3);
+    return bound >= layer_voigt[L];
 }
 
 // RADFN, lblrtm_sub.f90:36-97
@@ -1571,7 +1599,7 @@ __global__ void __launch_bounds__(NT, (MRTM_LINES_MINB * 128) / NT) near_kernel(
         nvalid = rem < NT * F ? rem : NT * F;
     }
     // a layer without Voigt-capable lines runs its Voigt zones as plain near-field ranges
-    const int vmode_mask = a.layer_voigt[L] ? 0xff : (0xff & ~M_VOIGT);
+    const int vmode_mask = voigt_possible(a.layer_voigt, L, a.hdr[0][blockIdx.x].whi) ? 0xff : (0xff & ~M_VOIGT);
     int cur_mol = 0;
     auto finish_mol = [&](int mol) {
         if (mol <= 0) return;
@@ -1970,7 +1998,7 @@ __global__ void __launch_bounds__(NT, MRTM_NEAR2_MINB) near2_kernel(LinesArgs a)
     const double Rn = a.ffw_ratio * hh, R2 = Rn * Rn;
     const double m2h = -2. * hh, mhh = -hh * hh;
     const double rp = ly.rp, rp2 = ly.rp2;
-    const int vmode_mask = a.layer_voigt[L] ? 0xff : (0xff & ~M_VOIGT);
+    const int vmode_mask = voigt_possible(a.layer_voigt, L, th.whi) ? 0xff : (0xff & ~M_VOIGT);
     // a line is in at most one list: D1 and T1 grow from the front of their array, D2 and T2 from the back
     unsigned short* lD1 = s_list + (size_t)(wid * 2 + 0) * kListLen;
     unsigned short* lD2 = lD1 + (kListLen - 1);
@@ -2313,7 +2341,7 @@ __global__ void __launch_bounds__(NT, MRTM_VOIGT_MINB) voigt_kernel(LinesArgs a)
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int k = blockIdx.y, prof = blockIdx.z;
     const int64_t L = (int64_t)prof * a.nlay + k;
-    if (!a.layer_voigt[L]) return;
+    if (!voigt_possible(a.layer_voigt, L, a.hdr[0][blockIdx.x].whi)) return;
     const LayerDev& ly = a.lay[L];
     const double* pl = a.planes + (size_t)L * D_NPLANES * a.n_pad;
     const double* __restrict__ pXNU = pl + (size_t)D_XNU * a.n_pad;
