@@ -51,8 +51,8 @@ struct mrtm_ctx {
     DevBuf b_vtmax;                               // [0] sm_max bits, [1..nseg] vtmax per segment
     DevBuf b_lvoigt;                              // [L] per-layer "has Voigt-capable lines" flag
     DevBuf b_plan[kMaxLevels], b_hdr[kMaxLevels], b_coef[kMaxLevels], b_pieces[kMaxLevels], b_npieces;
-    int64_t farw_min = 4096;                      // (tile, layer) pairs of a level from which far_warp_kernel takes it (MRTM_FARW_MIN)
-    int ff_levels = 3, ff_S = 6;                  // far-field hierarchy (MRTM_FF_LEVELS 1..3, MRTM_FF_S)
+    int64_t farw_min = 1400;                      // (tile, layer) pairs of a level from which far_warp_kernel takes it (MRTM_FARW_MIN)
+    int ff_levels = 4, ff_S = 4;                  // far-field hierarchy (MRTM_FF_LEVELS 1..4, MRTM_FF_S)
     cudaStream_t side = nullptr;                  // high-priority stream: plans and far-field levels overlap derive / near field
     cudaEvent_t evf[4] = {nullptr, nullptr, nullptr, nullptr};
     double tile_width = 0.1;                      // cm-1, MRTM_TILE_WIDTH (see the tile-size choice in run_device)
