@@ -152,3 +152,15 @@ def test_kernel_variants_on_the_dense_grid(env, monkeypatch):
             assert np.array_equal(gpu["sel_count"], ref["sel_count"])
             assert np.array_equal(gpu["sel_hash"], ref["sel_hash"])
     monkeypatch.setattr(harness, "_session", None)     # the next test creates its context with the default switches
+
+
+def test_unsorted_frequency_list():
+    """List mode (MONORTM.IN record 1.3.1, monortm_sub.F90:264-276) takes the frequencies in any order: a shuffled
+    dense list (far field, Voigt zones and window edges inside every tile) must give the oracle's numbers."""
+    rng = np.random.default_rng(11)
+    wn = np.concatenate([5.5e-5 * np.arange(13400, 13400 + 700), np.linspace(0.3, 54.0, 300), 2.0 + np.linspace(-0.02, 0.02, 100)])
+    rng.shuffle(wn)
+    case = harness.make_case(n_filler=1024, nlay=14, wn=wn, irt=1)
+    ref = harness.run_oracle(case)
+    gpu = harness.run_gpu(case)
+    _check_against(ref, gpu, OD_RTOL)
