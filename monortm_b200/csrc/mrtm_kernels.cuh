@@ -2488,8 +2488,7 @@ __global__ void __launch_bounds__(NT, MRTM_VOIGT_MINB) voigt_kernel(LinesArgs a)
                 }
                 many = false;
             };
-            for (int g = 0; g < nl; g++) {
-                const int ent = lst[g];
+            auto one = [&](const int ent) {
                 const int i = ent & 0xff;
                 if (by_mol && (int)s_mol[i] != cur_mol) {
                     flush_mol();
@@ -2510,7 +2509,7 @@ __global__ void __launch_bounds__(NT, MRTM_VOIGT_MINB) voigt_kernel(LinesArgs a)
                         }
                         many = true;
                     }
-                    continue;
+                    return;
                 }
                 const int kind = s_kind[i] & 0x7f;
                 const bool inwin = (kind <= 1) ? !(fabs(dm) > kDELTNUC) : true;
@@ -2533,7 +2532,30 @@ __global__ void __launch_bounds__(NT, MRTM_VOIGT_MINB) voigt_kernel(LinesArgs a)
                     }
                     many = true;
                 }
+            };
+            // two fast entries per step when possible: the region-I arithmetic of both is independent (it is done for
+            // every lane and selected afterwards), which hides the shared-memory and FP64 latencies of the serial walk
+            int g = 0;
+            if (!by_mol) {
+                for (; g + 1 < nl; g += 2) {
+                    const int e0 = lst[g], e1 = lst[g + 1];
+                    if (!(e0 & e1 & 0x100)) { one(e0); one(e1); continue; }
+                    const int i0 = e0 & 0xff, i1 = e1 & 0xff;
+                    const double dm0 = wn - s_x[i0], dm1 = wn - s_x[i1];
+                    const bool in0 = fabs(dm0) <= s_vt[i0], in1 = fabs(dm1) <= s_vt[i1];
+                    const double y0 = s_y[i0], y1 = s_y[i1];
+                    const double x0 = sl2 * (dm0 * s_inv[i0]), x1 = sl2 * (dm1 * s_inv[i1]);
+                    const bool r0 = !(fabs(x0) + y0 < 15.), r1 = !(fabs(x1) + y1 < 15.);
+                    const double q0 = x0 * x0, q1 = x1 * x1;
+                    const double den0 = fma(q0, q0 + s_fb[i0], s_fa2[i0]), den1 = fma(q1, q1 + s_fb[i1], s_fa2[i1]);
+                    const double v0 = fma(s_fcy[i0] * (s_fa[i0] + q0), rcp3(den0), -s_fcpd[i0]);
+                    const double v1 = fma(s_fcy[i1] * (s_fa[i1] + q1), rcp3(den1), -s_fcpd[i1]);
+                    if (in0) msum = r0 ? (msum + v0) : (fma(s_c[i0], w4_re_near(x0, y0), msum) - s_fcpd[i0]);
+                    if (in1) msum = r1 ? (msum + v1) : (fma(s_c[i1], w4_re_near(x1, y1), msum) - s_fcpd[i1]);
+                    many = many || in0 || in1;
+                }
             }
+            for (; g < nl; g++) one(lst[g]);
             if (by_mol) flush_mol(); else vsum = msum;
             if (valid && vsum != 0.) odst[iw] = oprev + vsum;
             __syncwarp();                          // the list is rebuilt by the next sub-block
