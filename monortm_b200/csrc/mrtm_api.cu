@@ -701,7 +701,7 @@ static int run_device(mrtm_ctx* ctx, const RunDesc& r, cudaStream_t s)
                 ra.fbz = fb + n_t;
                 st.kernel_launches++;
             }
-            rt_kernel<<<dim3((unsigned)((nwn + kRtFreqs - 1) / kRtFreqs), (unsigned)nb), 2 * kRtFreqs, 0, s>>>(ra);
+            rt_kernel<<<dim3((unsigned)((nwn + kRtFreqs - 1) / kRtFreqs), (unsigned)nb), kRtParts * kRtFreqs, 0, s>>>(ra);
             CU(cudaEventRecord(ctx->ev[5], s));
             st.kernel_launches++;
             CU(cudaGetLastError());

@@ -2739,14 +2739,18 @@ __global__ void rt_prep_kernel(int n_t, const double* t, double* fb, int n_tz, c
 // as a running sum from the top (the reference subtracts from the total going up: same value up to rounding).
 // Per (frequency, layer): Planck at the layer temperature and at one new level (the lower boundary becomes the
 // next layer's upper boundary) and exp(-tau); the two path transmittances follow by recurrence: 3 exp instead of 8.
-// Two threads share a frequency: one walks the upper half of the layers, the other the lower half (its starting
-// transmittances come from the upper half's optical depth); the partial sums meet in shared memory.  Twice the
-// warps for the same arithmetic -- the layer loop is a latency-bound chain.
-constexpr int kRtFreqs = 64;        // frequencies per CTA (128 threads)
-__global__ void __launch_bounds__(2 * kRtFreqs) rt_kernel(RtArgs a)
+// kRtParts threads share a frequency: each walks a contiguous block of layers (part 0 the uppermost; a part's
+// starting transmittances come from the optical depth of the parts above it) and the partial sums meet in shared
+// memory.  kRtParts times the warps for the same arithmetic -- the layer loop is a latency-bound chain.
+#ifndef MRTM_RT_PARTS
+#define MRTM_RT_PARTS 4
+#endif
+constexpr int kRtParts = MRTM_RT_PARTS;
+constexpr int kRtFreqs = 128 / kRtParts;     // frequencies per CTA (128 threads)
+__global__ void __launch_bounds__(kRtParts * kRtFreqs) rt_kernel(RtArgs a)
 {
-    __shared__ double s_sum[2][kRtFreqs], s_rdn[kRtFreqs], s_rup[kRtFreqs];
-    const int fi = threadIdx.x & (kRtFreqs - 1), half = threadIdx.x / kRtFreqs;      // half 0: upper layers
+    __shared__ double s_sum[kRtParts][kRtFreqs], s_rdn[kRtParts][kRtFreqs], s_rup[kRtParts][kRtFreqs];
+    const int fi = threadIdx.x % kRtFreqs, part = threadIdx.x / kRtFreqs;
     const int iw_raw = blockIdx.x * kRtFreqs + fi;
     const bool live = iw_raw < a.nwn;
     const int iw = live ? iw_raw : (a.nwn - 1);
@@ -2756,28 +2760,32 @@ __global__ void __launch_bounds__(2 * kRtFreqs) rt_kernel(RtArgs a)
     const double* __restrict__ fb = a.fb + (size_t)prof * a.nlay;
     const double* __restrict__ fbz = a.fbz + (size_t)prof * (a.nlay + 1);
     const size_t out = (size_t)iw + (size_t)prof * a.nwn;
-    const int mid = a.nlay / 2;                       // lower half: layers 1..mid, upper half: mid+1..nlay
-    const int l_hi = half == 0 ? a.nlay : mid, l_lo = half == 0 ? mid + 1 : 1;
+    // part p owns layers (lo_p, hi_p], cut points at multiples of nlay/kRtParts counted from the top
+    const int l_hi = a.nlay - (int)(((long long)a.nlay * part) / kRtParts);
+    const int l_lo = a.nlay - (int)(((long long)a.nlay * (part + 1)) / kRtParts) + 1;
 
-    double part = 0.;
-    for (int l = l_lo; l <= l_hi; l++) part = part + o[(size_t)(l - 1) * a.o_lds];
-    s_sum[half][fi] = part;
+    double psum = 0.;
+    for (int l = l_lo; l <= l_hi; l++) psum = psum + o[(size_t)(l - 1) * a.o_lds];
+    s_sum[part][fi] = psum;
     __syncthreads();
-    const double od_upper = s_sum[0][fi];
-    const double odtot = s_sum[1][fi] + od_upper;     // layers in index order within each half (RTMmono.f90:177-181)
+    double od_above = 0., odtot = 0.;
+#pragma unroll
+    for (int p = kRtParts - 1; p >= 0; p--) odtot = odtot + s_sum[p][fi];       // lowest layers first (RTMmono.f90:177-181)
+#pragma unroll
+    for (int p = 0; p < kRtParts; p++) od_above += (p < part) ? s_sum[p][fi] : 0.;
 
     const bool up = a.do_rtm && a.irt != 3;
     const double c1v3 = kRADCN1 * (vv * vv * vv);
     double rup = 0., rdn = 0.;
-    // optical depth below the current layer after the subtraction (down loops); the lower half starts below the upper one
-    double odt = half == 0 ? odtot : (odtot - od_upper);
+    // optical depth below the current layer after the subtraction (down loops); a lower part starts below the parts above it
+    double odt = odtot - od_above;
     double bb_top = c1v3 / (exp(vv * __ldg(fbz + l_hi)) - 1.);
     // Path transmittances by recurrence instead of one exponential each per layer: above the layer
     // tra = prod(tri of the layers above) (underflow to 0 is the right limit); below it trt(l) = trt(l+1)/tri(l),
     // re-anchored with exp(-odt) while either factor is too small to divide by (opaque columns).  The relative
     // error grows by ~1.5 ulp per layer (<= 1e-13 over 300 layers; bar: 1e-5 K).  3 exp per layer instead of 5.
     double trt = exp(-odt);
-    double tra = half == 0 ? 1. : exp(-od_upper);
+    double tra = part == 0 ? 1. : exp(-od_above);
     for (int l = l_hi; l >= l_lo; l--) {
         const double odvi = o[(size_t)(l - 1) * a.o_lds];
         const double bb = c1v3 * rcp3(exp(vv * __ldg(fb + l - 1)) - 1.);
@@ -2795,11 +2803,15 @@ __global__ void __launch_bounds__(2 * kRtFreqs) rt_kernel(RtArgs a)
         }
         bb_top = bb_bot;
     }
-    if (half == 1) { s_rdn[fi] = rdn; s_rup[fi] = rup; }
+    s_rdn[part][fi] = rdn;
+    s_rup[part][fi] = rup;
     __syncthreads();
-    if (half == 1 || !live) return;
-    rdn = rdn + s_rdn[fi];                            // upper layers first, as the reference's top-down loops add them
-    rup = rup + s_rup[fi];
+    if (part != 0 || !live) return;
+#pragma unroll
+    for (int p = 1; p < kRtParts; p++) {                // upper layers first, as the reference's top-down loops add them
+        rdn = rdn + s_rdn[p][fi];
+        rup = rup + s_rup[p][fi];
+    }
     const double trtot = exp(-odtot);
     if (a.do_tmr && a.tmr) {
         double radtmr = rdn / (1. - exp(-1 * odtot));
