@@ -55,6 +55,7 @@ struct mrtm_ctx {
     int ff_levels = 4, ff_S = 4;                  // far-field hierarchy (MRTM_FF_LEVELS 1..4, MRTM_FF_S)
     cudaStream_t side = nullptr;                  // high-priority stream: plans and far-field levels overlap derive / near field
     cudaEvent_t evf[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev_in = nullptr;                  // emiss / reflc arrived (host-buffer path)
     double tile_width = 0.1;                      // cm-1, MRTM_TILE_WIDTH (see the tile-size choice in run_device)
     const void* span_ptr = nullptr; int64_t span_nwn = 0; double span_val = -1.;   // cached span of a device-resident wn
     int voigt_side = 0;                           // MRTM_VOIGT_SIDE=1: Voigt branch on the side stream into a scratch plane (measured: no gain, off by default)
@@ -161,6 +162,7 @@ extern "C" int mrtm_init(int device, mrtm_ctx** out)
         cudaDeviceGetStreamPriorityRange(&lo, &hi);
         if (cudaStreamCreateWithPriority(&ctx->side, cudaStreamNonBlocking, hi) != cudaSuccess) ctx->side = nullptr;
         for (auto& ev : ctx->evf) cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&ctx->ev_in, cudaEventDisableTiming);
     }
     if (const char* s = std::getenv("MRTM_SIDE_STREAM")) ctx->use_side = std::atoi(s) != 0;
     if (const char* s = std::getenv("MRTM_TILE_WIDTH")) ctx->tile_width = std::atof(s);
@@ -221,6 +223,7 @@ extern "C" int mrtm_free(mrtm_ctx* ctx)
     if (ctx->counters_dev) cudaFree(ctx->counters_dev);
     for (auto& ev : ctx->ev) cudaEventDestroy(ev);
     for (auto& ev : ctx->evf) if (ev) cudaEventDestroy(ev);
+    if (ctx->ev_in) cudaEventDestroy(ctx->ev_in);
     if (ctx->side) cudaStreamDestroy(ctx->side);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -340,6 +343,8 @@ struct RunDesc {
     int64_t iw0;
     int line_mode;                  // mrtm_opts.line_mode
     double wn_span;                 // |wn[nwn-1] - wn[0]| of this call's frequencies, < 0: unknown (tile-size heuristic only)
+    double* h_spec[6];              // host destinations of rad, tb, tmr, trtot, rup, rdn (or null): copied per batch right behind rt_kernel
+    cudaEvent_t rt_ready;           // recorded when emiss / reflc have arrived on another stream (or null)
 };
 
 template <int F, int NT>
@@ -691,6 +696,7 @@ static int run_device(mrtm_ctx* ctx, const RunDesc& r, cudaStream_t s)
             auto off = [&](double* q) { return q ? q + (size_t)b0 * nwn : nullptr; };
             ra.rad = off(r.rad); ra.tb = off(r.tb); ra.tmr = off(r.tmr);
             ra.trtot = off(r.trtot); ra.rup = off(r.rup); ra.rdn = off(r.rdn);
+            if (r.rt_ready) CU(cudaStreamWaitEvent(s, r.rt_ready, 0));
             CU(cudaEventRecord(ctx->ev[4], s));
             {   // RADCN2/T per layer and level, once per batch
                 const int n_t = (int)(nb * nlay), n_tz = (int)(nb * (nlay + 1));
@@ -705,6 +711,11 @@ static int run_device(mrtm_ctx* ctx, const RunDesc& r, cudaStream_t s)
             CU(cudaEventRecord(ctx->ev[5], s));
             st.kernel_launches++;
             CU(cudaGetLastError());
+            // the spectra of this batch go home at once (the host is still waiting on the events below)
+            double* dev_spec[6] = {r.rad, r.tb, r.tmr, r.trtot, r.rup, r.rdn};
+            for (int i = 0; i < 6; i++)
+                if (r.h_spec[i] && dev_spec[i])
+                    CU(cudaMemcpyAsync(r.h_spec[i] + (size_t)b0 * nwn, dev_spec[i] + (size_t)b0 * nwn, (size_t)nb * nwn * 8, cudaMemcpyDeviceToHost, s));
         }
         // per-batch kernel times (needs the batch to finish; cheap next to the kernels themselves)
         if (r.nprof > B || true) {
@@ -944,8 +955,12 @@ extern "C" int mrtm_profiles(mrtm_ctx* ctx, int64_t nprof, int64_t nwn, const do
     if ((rc = h2d(ctx, ctx->b_in[5], wbrodl, L * 8, s, &r.wbrodl))) return rc;
     if (scor) { if ((rc = h2d(ctx, ctx->b_in[6], scor, L * MRTM_NSCOR1 * MRTM_NSCOR2 * 8, s, &r.scor))) return rc; }
     if ((rc = h2d(ctx, ctx->b_in[8], tz, (size_t)nprof * (nlay + 1) * 8, s, &r.tz))) return rc;
-    if ((rc = h2d(ctx, ctx->b_in[9], emiss, nwn * 8, s, &r.emiss))) return rc;
-    if ((rc = h2d(ctx, ctx->b_in[10], reflc, nwn * 8, s, &r.reflc))) return rc;
+    {   // emissivity / reflectivity are only read by rt_kernel: their copies ride the second stream beside the kernels
+        cudaStream_t sc = (ctx->use_side && ctx->side && ctx->ev_in) ? ctx->side : s;
+        if ((rc = h2d(ctx, ctx->b_in[9], emiss, nwn * 8, sc, &r.emiss))) return rc;
+        if ((rc = h2d(ctx, ctx->b_in[10], reflc, nwn * 8, sc, &r.reflc))) return rc;
+        if (sc != s) { CU(cudaEventRecord(ctx->ev_in, sc)); r.rt_ready = ctx->ev_in; }
+    }
     if (irt == 3 || irt == 2) for (int64_t i = 0; i < nprof; i++) tmpsfc[i] = 2.75;   // RTMmono.f90:113-123
     { const double* q; if ((rc = h2d(ctx, ctx->b_tmps, tmpsfc, nprof * 8, s, &q))) return rc; r.tmpsfc = (double*)q; }
     double** outs[6] = {&r.rad, &r.tb, &r.tmr, &r.trtot, &r.rup, &r.rdn};
@@ -961,7 +976,9 @@ extern "C" int mrtm_profiles(mrtm_ctx* ctx, int64_t nprof, int64_t nwn, const do
     if (opts && opts->sel_hash) { if ((rc = ensure(ctx, ctx->b_sel[1], fl))) return rc; r.sel_hash = (unsigned long long*)ctx->b_sel[1].p; }
 
     if (!otot_by_mol) {
+        for (int i = 0; i < 6; i++) r.h_spec[i] = hosts[i];
         if ((rc = run_device(ctx, r, s))) return rc;
+        for (int i = 0; i < 6; i++) hosts[i] = nullptr;          // already on their way
     } else {
         // per-molecule column sums need the (nwn,39,nlay) planes: one profile at a time
         const size_t fml = (size_t)nwn * MRTM_MXMOL * nlay * 8;
