@@ -219,11 +219,17 @@ def main():
 
     import torch
     import torch.distributed as dist
-    from monortm_b200 import api
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    # the library normally travels with the tree (built by __graft_entry__.build()); build it here only if it is
+    # missing (one rank, before anybody loads it) -- there is no other code path: without it the bench fails loudly
+    lib_path = os.environ.get("MRTM_LIB", os.path.join(ROOT, "monortm_b200", "lib", "libmonortm_b200.so"))
+    if not os.path.exists(lib_path) and world == 1:
+        import __graft_entry__
+        __graft_entry__.build()
+    from monortm_b200 import api
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
