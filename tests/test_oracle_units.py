@@ -226,3 +226,55 @@ def test_oracle_o0_and_o2_builds_agree():
     assert np.array_equal(a["sel_hash"], b["sel_hash"])
     assert harness.rel_diff(a["o"], b["o"]) < 1e-13
     assert np.max(np.abs(a["tb"] - b["tb"])) < 1e-9
+
+
+def test_isolated_line_matches_textbook_formula():
+    """One isolated N2O-like line, one layer: the oracle's line optical depth against the textbook expression written
+    from scratch in numpy -- HITRAN intensity scaling S(T) = S0 Q0/Q(T) exp(-c2 E (1/T - 1/T0)) (1-e^{-c2 v0/T})/(1-e^{-c2 v0/T0}),
+    the radiation-field form k(v) = W S(T) [v tanh(c2 v/2T)] / [v0 tanh(c2 v0/2T)] (L(v-v0) + L(v+v0)) with Lorentzians cut at
+    25 cm-1 and their value there subtracted (the negative-frequency partner only while v+v0 <= 25), the half width
+    mixed from air and self broadening with the number-density ratio, the centre shifted by delta times that ratio.
+    Independent of the oracle's code path: anchors units, strength conversion, radiation term, shape and cutoff."""
+    import os
+    import tempfile
+    from monortm_b200 import api, linefile, synth
+
+    c2 = 6.62606876E-27 * 2.99792458E+10 / 1.3806503E-16
+    t0, p0 = 296.0, 1013.25
+    v0, s0, g_air, g_self, epp, xexp, delta = 12.3456, 3.0e-23, 0.08, 0.11, 350.0, 0.7, -2.0e-3
+    rec = synth._line(v0, s0, g_air, g_self, epp, xexp, delta, 4, 1)
+    recs = np.zeros(1, synth.REC_DTYPE)
+    recs[0] = rec
+    with tempfile.NamedTemporaryFile(suffix=".tape3", delete=False) as f:
+        path = f.name
+    try:
+        linefile.write_tape3(path, recs)
+        ls = linefile.read_tape3(path, 0.0, 55.0)
+    finally:
+        os.unlink(path)
+    # the file keeps float32 parameters: take them back from the store so both sides see the same numbers
+    g_air, g_self = float(ls.alpf[3, 0]), float(ls.alps[3, 0])
+    epp, xexp, delta = float(ls.e[3, 0]), float(ls.x[3, 0]), float(ls.deltnu[3, 0])
+    s0 = float(ls.s0[3, 0]) * (v0 * (1.0 - np.exp(-c2 * v0 / t0)))          # back from the LBLRTM form on the file
+    wn = np.array([0.5, 5.0, 12.0, 12.3, 12.3456, 12.4, 20.0, 30.0, 37.3, 37.4, 40.0])
+    for t, p in ((296.0, 500.0), (250.0, 800.0), (296.0, 1013.25)):
+        w_n2o, w_n2 = 3.0e17, 1.0e23
+        wkl = np.zeros((39, 1), order="F")
+        wkl[3, 0] = w_n2o
+        scor = api.scor_for_layers(7, np.array([[t]]))[:, :, :, 0]
+        m = harness.oracle_modm(ls, wn, 0.0, np.array([p]), np.array([t]), np.array([0.0]), 7, wkl, np.array([w_n2]), scor)
+        got = m["o_by_mol"][:, 3, 0]
+        qratio = scor[3, 0, 0]                                                 # Q(296)/Q(T) of N2O isotopologue 1 (TIPS)
+        rho = (p / t) / (p0 / t0)                                              # number-density ratio
+        x_self = w_n2o / (w_n2o + w_n2)
+        vc = v0 + delta * rho
+        gam = (g_air * (1.0 - x_self) + g_self * x_self) * rho * (t / t0) ** xexp
+        s_t = s0 * qratio * np.exp(-c2 * epp * (1.0 / t - 1.0 / t0)) * (1 - np.exp(-c2 * vc / t)) / (1 - np.exp(-c2 * vc / t0))
+
+        def lor(d):
+            return gam / (np.pi * (d * d + gam * gam))
+        shape = np.where(np.abs(wn - vc) <= 25.0, lor(wn - vc) - lor(25.0) + np.where(wn + vc <= 25.0, lor(wn + vc) - lor(25.0), 0.0), 0.0)
+        want = w_n2o * s_t * (wn * np.tanh(c2 * wn / (2 * t))) / (vc * np.tanh(c2 * vc / (2 * t))) * shape
+        assert np.all((want == 0) == (got == 0))
+        nz = want != 0
+        assert np.max(np.abs(got[nz] / want[nz] - 1.0)) < 2e-9, (t, p)     # 13-digit pi in the reference: 1e-13; float32 S: exact here
