@@ -278,3 +278,92 @@ def test_isolated_line_matches_textbook_formula():
         assert np.all((want == 0) == (got == 0))
         nz = want != 0
         assert np.max(np.abs(got[nz] / want[nz] - 1.0)) < 2e-9, (t, p)     # 13-digit pi in the reference: 1e-13; float32 S: exact here
+
+
+def test_isolated_line_voigt_branch_matches_scipy_voigt_profile():
+    """The same isolated line at 0.3 hPa (Doppler width ~ Lorentz width): inside 100 Doppler half-widths the reference takes
+    the Voigt branch (modm.f90:427-431).  Against scipy's Voigt profile with the textbook Doppler half-width
+    v0/c sqrt(2 ln2 kT/m), within the 1e-4 the Humlicek routine claims (modm.f90:1094).  Pins the Doppler width, the
+    isotopologue mass table and the normalisation of the Voigt branch independently of the oracle's code."""
+    import os
+    import tempfile
+    from scipy.special import voigt_profile
+    from monortm_b200 import api, linefile, synth
+
+    c2 = 6.62606876E-27 * 2.99792458E+10 / 1.3806503E-16
+    kb, clight, amu = 1.3806503E-16, 2.99792458E+10, 1.0 / 6.02214199E+23
+    t0, p0 = 296.0, 1013.25
+    v0 = 25.4321
+    recs = np.zeros(1, synth.REC_DTYPE)
+    recs[0] = synth._line(v0, 2.0e-22, 0.07, 0.10, 120.0, 0.7, 0.0, 4, 1)            # N2O 446, 44.0 amu
+    with tempfile.NamedTemporaryFile(suffix=".tape3", delete=False) as f:
+        path = f.name
+    try:
+        linefile.write_tape3(path, recs)
+        ls = linefile.read_tape3(path, 0.0, 55.0)
+    finally:
+        os.unlink(path)
+    g_air, g_self, epp, xexp = float(ls.alpf[3, 0]), float(ls.alps[3, 0]), float(ls.e[3, 0]), float(ls.x[3, 0])
+    s0 = float(ls.s0[3, 0]) * (v0 * (1.0 - np.exp(-c2 * v0 / t0)))
+    t, p = 250.0, 0.3
+    mass = 44.0128                                                                  # 14N2 16O, g/mol
+    a_d = v0 / clight * np.sqrt(2 * np.log(2.0) * kb * t / (mass * amu))
+    wn = v0 + a_d * np.array([-60.0, -20.0, -5.0, -1.5, -0.4, 0.0, 0.3, 1.0, 3.0, 12.0, 45.0, 90.0])
+    w_n2o, w_n2 = 3.0e15, 1.0e21
+    wkl = np.zeros((39, 1), order="F")
+    wkl[3, 0] = w_n2o
+    scor = api.scor_for_layers(7, np.array([[t]]))[:, :, :, 0]
+    m = harness.oracle_modm(ls, wn, 0.0, np.array([p]), np.array([t]), np.array([0.0]), 7, wkl, np.array([w_n2]), scor)
+    assert m["n_voigt"] == len(wn)                                                   # every pair took the Voigt branch
+    got = m["o_by_mol"][:, 3, 0]
+    rho = (p / t) / (p0 / t0)
+    x_self = w_n2o / (w_n2o + w_n2)
+    gam = (g_air * (1.0 - x_self) + g_self * x_self) * rho * (t / t0) ** xexp
+    assert 0.05 < gam / a_d < 20.0                                                   # a genuine Voigt regime
+    s_t = s0 * scor[3, 0, 0] * np.exp(-c2 * epp * (1.0 / t - 1.0 / t0)) * (1 - np.exp(-c2 * v0 / t)) / (1 - np.exp(-c2 * v0 / t0))
+    sigma = a_d / np.sqrt(2 * np.log(2.0))
+    shape = voigt_profile(wn - v0, sigma, gam) - voigt_profile(25.0, sigma, gam)
+    want = w_n2o * s_t * (wn * np.tanh(c2 * wn / (2 * t))) / (v0 * np.tanh(c2 * v0 / (2 * t))) * shape
+    assert np.max(np.abs(got / want - 1.0)) < 2e-4
+
+
+def test_rtm_matches_exact_linear_in_tau_layers():
+    """RAD_UP_DN / RTM (RTMmono.f90:13-221) against an independent numpy integration of the same atmosphere in which
+    the Planck function varies linearly with optical depth inside each layer (layer mean = B(T), value at the boundary
+    facing the observer = B(TZ)) and every layer is integrated exactly.  The reference's Pade weight 0.193 tau + 0.013 tau^2
+    approximates exactly that model, so radiances agree to a few 1e-4 relative (0.05 K): a structural pin of the
+    direction of the loops, the boundary terms, the surface reflection and the cosmic background."""
+    rng = np.random.default_rng(3)
+    nwn, nlay = 40, 24
+    wn = np.linspace(0.7, 30.0, nwn)
+    tz = np.linspace(291.0, 215.0, nlay + 1)
+    t = 0.5 * (tz[:-1] + tz[1:]) + rng.normal(0, 0.3, nlay)
+    o = np.asfortranarray(10.0 ** rng.uniform(-3.5, 0.3, (nwn, nlay)))
+    em, rf, tsfc = np.full(nwn, 0.8), np.full(nwn, 0.2), 293.0
+
+    def planck(v, temp):
+        return RADCN1 * v ** 3 / np.expm1(RADCN2 * v / temp)
+
+    def layer_emission(tau, b_mean, b_near):
+        # integral of B(tau') exp(-tau') dtau' over the layer, B linear in tau' from b_near at the observer's side with mean b_mean
+        return b_near * (-np.expm1(-tau)) + (b_mean - b_near) * (2.0 / tau) * (1.0 - (1.0 + tau) * np.exp(-tau))
+
+    rup, rdn = np.zeros(nwn), np.zeros(nwn)
+    for iw in range(nwn):
+        tau = o[iw]
+        above = np.concatenate([np.cumsum(tau[::-1])[::-1][1:], [0.0]])      # optical depth between layer l and space
+        below = np.concatenate([[0.0], np.cumsum(tau)[:-1]])                 # ... between layer l and the surface
+        for l in range(nlay):
+            rup[iw] += np.exp(-above[l]) * layer_emission(tau[l], planck(wn[iw], t[l]), planck(wn[iw], tz[l + 1]))
+            rdn[iw] += np.exp(-below[l]) * layer_emission(tau[l], planck(wn[iw], t[l]), planck(wn[iw], tz[l]))
+    trtot = np.exp(-o.sum(axis=1))
+    cosmic = planck(wn, 2.75)
+    up = rup + trtot * (em * planck(wn, tsfc) + rf * (rdn + trtot * cosmic))
+    dn = rdn + trtot * cosmic
+    r1 = harness.oracle_rtm(1, 1, wn, t, tz, o, tsfc, rf, em)
+    r3 = harness.oracle_rtm(1, 3, wn, t, tz, o, tsfc, rf, em)
+    assert np.max(np.abs(r1["rup"] / rup - 1)) < 1e-3 and np.max(np.abs(r1["rdn"] / rdn - 1)) < 1e-3
+    assert np.max(np.abs(r1["rad"] / up - 1)) < 1e-3 and np.max(np.abs(r3["rad"] / dn - 1)) < 1e-3
+    assert np.allclose(r1["trtot"], trtot, rtol=1e-12)
+    tb_up = RADCN2 * wn / np.log(RADCN1 * wn ** 3 / up + 1.0)
+    assert np.max(np.abs(r1["tb"] - tb_up)) < 0.1
