@@ -367,3 +367,50 @@ def test_rtm_matches_exact_linear_in_tau_layers():
     assert np.allclose(r1["trtot"], trtot, rtol=1e-12)
     tb_up = RADCN2 * wn / np.log(RADCN1 * wn ** 3 / up + 1.0)
     assert np.max(np.abs(r1["tb"] - tb_up)) < 0.1
+
+
+def test_o2_line_with_first_order_mixing_matches_textbook_formula():
+    """One O2 line with an IFLG=1 coefficient record (Y and G equal at the four tabulated temperatures, so the temperature
+    interpolation is trivial): against the first-order line-mixing expression written from scratch,
+    k(v) = W S~ v tanh(c2 v/2T) (1/pi) { [g(1+G p^2) + Y p (v-v0)]/((v-v0)^2+g^2) + [g(1+G p^2) - Y p (v+v0)]/((v+v0)^2+g^2) },
+    p = P/P0, no cutoff and no pedestal for O2 (modm.f90:384, :757-786).  Pins the sign convention of the mixing term on the
+    negative-frequency resonance, the pressure scalings and the record layout of the coefficients."""
+    import os
+    import tempfile
+    from monortm_b200 import api, linefile, synth
+
+    c2 = 6.62606876E-27 * 2.99792458E+10 / 1.3806503E-16
+    t0, p0 = 296.0, 1013.25
+    v0, yv, gv = 2.0843, 0.35, -0.02
+    recs = np.zeros(2, synth.REC_DTYPE)
+    recs[0] = synth._line(v0, 1.0e-25, 0.045, 0.047, 2.08, 0.8, 0.0, 7, 1, iflg=1)
+    recs[1] = linefile.coupling_record([yv] * 4, [gv] * 4, 1)
+    with tempfile.NamedTemporaryFile(suffix=".tape3", delete=False) as f:
+        path = f.name
+    try:
+        linefile.write_tape3(path, recs)
+        ls = linefile.read_tape3(path, 0.0, 55.0)
+    finally:
+        os.unlink(path)
+    g_air, g_self, epp, xexp = float(ls.alpf[6, 0]), float(ls.alps[6, 0]), float(ls.e[6, 0]), float(ls.x[6, 0])
+    yv, gv = float(np.float32(yv)), float(np.float32(gv))
+    s0 = float(ls.s0[6, 0]) * (v0 * (1.0 - np.exp(-c2 * v0 / t0)))
+    wn = np.array([0.2, 1.5, 2.0, 2.0843, 2.2, 3.9, 10.0, 30.0, 54.0])         # the last ones lie beyond 25 cm-1: O2 is never cut
+    for t, p in ((296.0, 1013.25), (296.0, 300.0), (270.0, 700.0)):
+        w_o2, w_n2 = 4.0e23, 1.5e24
+        wkl = np.zeros((39, 1), order="F")
+        wkl[6, 0] = w_o2
+        scor = api.scor_for_layers(7, np.array([[t]]))[:, :, :, 0]
+        m = harness.oracle_modm(ls, wn, 0.0, np.array([p]), np.array([t]), np.array([0.0]), 7, wkl, np.array([w_n2]), scor)
+        got = m["o_by_mol"][:, 6, 0]
+        rho, pr = (p / t) / (p0 / t0), p / p0
+        x_self = w_o2 / (w_o2 + w_n2)
+        # lnfl_mod.f90:98-113: the O2 air width on the file is corrected to a foreign width with the 0.21 mixing ratio
+        g_for = (float(np.float32(0.045)) - 0.21 * g_self) / (1.0 - 0.21)
+        assert abs(g_for - g_air) < 1e-7
+        gam = (g_air * (1.0 - x_self) + g_self * x_self) * rho * (t / t0) ** xexp
+        s_t = s0 * scor[6, 0, 0] * np.exp(-c2 * epp * (1.0 / t - 1.0 / t0)) * (1 - np.exp(-c2 * v0 / t)) / (1 - np.exp(-c2 * v0 / t0))
+        dm, dp = wn - v0, wn + v0
+        shape = ((gam * (1 + gv * pr ** 2) + yv * pr * dm) / (dm ** 2 + gam ** 2) + (gam * (1 + gv * pr ** 2) - yv * pr * dp) / (dp ** 2 + gam ** 2)) / np.pi
+        want = w_o2 * s_t * (wn * np.tanh(c2 * wn / (2 * t))) / (v0 * np.tanh(c2 * v0 / (2 * t))) * shape
+        assert np.max(np.abs(got / want - 1.0)) < 5e-9, (t, p, got / want)
