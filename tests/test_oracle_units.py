@@ -414,3 +414,51 @@ def test_o2_line_with_first_order_mixing_matches_textbook_formula():
         shape = ((gam * (1 + gv * pr ** 2) + yv * pr * dm) / (dm ** 2 + gam ** 2) + (gam * (1 + gv * pr ** 2) - yv * pr * dp) / (dp ** 2 + gam ** 2)) / np.pi
         want = w_o2 * s_t * (wn * np.tanh(c2 * wn / (2 * t))) / (v0 * np.tanh(c2 * v0 / (2 * t))) * shape
         assert np.max(np.abs(got / want - 1.0)) < 5e-9, (t, p, got / want)
+
+
+def _table(name):
+    import os
+    import re
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "monortm_b200", "csrc", "tables", "mtckd_tables.inc")
+    txt = open(path).read()
+    m = re.search(r"%s\[\d+\]\s*=\s*\{(.*?)\};" % name, txt, re.S)
+    body = re.sub(r"/\*.*?\*/", "", m.group(1), flags=re.S)
+    return np.array([float(x) for x in body.replace("\n", " ").split(",") if x.strip()])
+
+
+def test_h2o_self_continuum_at_table_nodes_matches_the_mt_ckd_expression():
+    """MT_CKD water-vapour self continuum (contnm.f90:300-371) at frequencies that are nodes of the 10 cm-1 coefficient
+    grid, where both interpolation stages return the tabulated value exactly: optical depth =
+    W_h2o * C_s(296) (C_s(260)/C_s(296))^((T-296)/(260-296)) * x_h2o (P/1013)(296/T) 1e-20 * v tanh(c2 v/2T), written
+    from the tables in numpy.  Pins the units, the density factor, the temperature exponent, the grid alignment and
+    the radiation term of the continuum path."""
+    from monortm_b200 import api, linefile, synth
+    import os
+    import tempfile
+
+    s296, s260 = _table("MTCKD_SH2O_296"), _table("MTCKD_SH2O_260")
+    assert len(s296) == 2003 and len(s260) == 2003
+    recs = np.zeros(1, synth.REC_DTYPE)
+    recs[0] = synth._line(70.0, 1.0e-30, 0.05, 0.05, 100.0, 0.7, 0.0, 4, 1)        # a line far from the frequencies used
+    with tempfile.NamedTemporaryFile(suffix=".tape3", delete=False) as f:
+        path = f.name
+    try:
+        linefile.write_tape3(path, recs)
+        ls = linefile.read_tape3(path, 0.0, 80.0)
+    finally:
+        os.unlink(path)
+    wn = np.array([10.0, 20.0, 30.0])
+    for t, p in ((270.0, 800.0), (296.0, 1013.0), (245.0, 400.0)):
+        w_h2o, w_o2, w_n2 = 2.0e22, 4.0e23, 1.5e24
+        wkl = np.zeros((39, 1), order="F")
+        wkl[0, 0], wkl[6, 0] = w_h2o, w_o2
+        scor = api.scor_for_layers(7, np.array([[t]]))[:, :, :, 0]
+        m = harness.oracle_modm(ls, wn, 0.0, np.array([p]), np.array([t]), np.array([0.0]), 7, wkl, np.array([w_n2]), scor,
+                                cntnm=(1., 0., 0., 0., 0., 0., 0.))                 # self continuum only
+        got = m["oc"][:, 0, 0]
+        idx = ((wn + 20.0) / 10.0).astype(int)                                      # table starts at -20 cm-1, step 10
+        cs = s296[idx] * (s260[idx] / s296[idx]) ** ((t - 296.0) / (260.0 - 296.0))
+        x_h2o = w_h2o / (w_h2o + w_o2 + w_n2)
+        radfn = wn * np.tanh(RADCN2 * wn / (2.0 * t))
+        want = w_h2o * cs * x_h2o * (p / 1013.0) * (296.0 / t) * 1.0e-20 * radfn
+        assert np.max(np.abs(got / want - 1.0)) < 1e-12, (t, p, got / want)
