@@ -10,7 +10,10 @@
  *
  * Build: gcc -O0 -ffp-contract=off -fcx-fortran-rules (oracle/Makefile).
  *
- * PARITY UNPINNED by reference-owned goldens (none exist).
+ * PARITY UNPINNED by reference-owned goldens (none exist).  What anchors this file instead:
+ * tests/test_oracle_units.py -- from-scratch numpy evaluations of the textbook expressions (isolated Lorentz line,
+ * O2 line with first-order mixing, Voigt branch against scipy, layer-exact radiative transfer, the self continuum at
+ * its table nodes), analytic identities and scipy.special.wofz for W4.
  *
  * Defined behaviour chosen where the reference has undefined behaviour:
  *  - modm.f90:845 indexes rho_molec(mol) for mol > 7 although the array has 7
