@@ -164,3 +164,55 @@ def test_unsorted_frequency_list():
     ref = harness.run_oracle(case)
     gpu = harness.run_gpu(case)
     _check_against(ref, gpu, OD_RTOL)
+
+
+def test_gpu_isolated_line_against_the_textbook_expression():
+    """The CUDA path itself (not only the oracle) against the from-scratch numpy expression for one isolated N2O-like
+    line: Lorentz regime at three (T, p) points to 2e-9 (HITRAN intensity scaling, radiation-field term, 25 cm-1 cutoff
+    with pedestal, negative-frequency partner, width mixing, density-scaled shift) -- see
+    tests/test_oracle_units.py::test_isolated_line_matches_textbook_formula for the derivation."""
+    import os
+    import tempfile
+    from monortm_b200 import api, linefile
+
+    c2 = 6.62606876E-27 * 2.99792458E+10 / 1.3806503E-16
+    t0, p0 = 296.0, 1013.25
+    v0 = 12.3456
+    recs = np.zeros(1, synth.REC_DTYPE)
+    recs[0] = synth._line(v0, 3.0e-23, 0.08, 0.11, 350.0, 0.7, -2.0e-3, 4, 1)
+    with tempfile.NamedTemporaryFile(suffix=".tape3", delete=False) as f:
+        path = f.name
+    try:
+        linefile.write_tape3(path, recs)
+        ls = linefile.read_tape3(path, 0.0, 55.0)
+    finally:
+        os.unlink(path)
+    g_air, g_self = float(ls.alpf[3, 0]), float(ls.alps[3, 0])
+    epp, xexp, delta = float(ls.e[3, 0]), float(ls.x[3, 0]), float(ls.deltnu[3, 0])
+    s0 = float(ls.s0[3, 0]) * (v0 * (1.0 - np.exp(-c2 * v0 / t0)))
+    wn = np.array([0.5, 5.0, 12.0, 12.3, 12.3456, 12.4, 20.0, 30.0, 37.3, 37.4, 40.0])
+    s = harness.session()
+    s.stage_lines(ls)
+    for t, p in ((296.0, 500.0), (250.0, 800.0), (296.0, 1013.25)):
+        w_n2o, w_n2 = 3.0e17, 1.0e23
+        wkl = np.zeros((39, 1), order="F")
+        wkl[3, 0] = w_n2o
+        scor = api.scor_for_layers(7, np.array([[t]]))[:, :, :, 0]
+        for mode in (0, 1):
+            m = s.modm(wn, 0.0, np.array([p]), np.array([t]), np.array([0.0]), 7, wkl, np.array([w_n2]), scor,
+                       want_by_mol=True, selection=False, line_mode=mode)
+            got = m["o_by_mol"][:, 3, 0]
+            rho = (p / t) / (p0 / t0)
+            x_self = w_n2o / (w_n2o + w_n2)
+            vc = v0 + delta * rho
+            gam = (g_air * (1.0 - x_self) + g_self * x_self) * rho * (t / t0) ** xexp
+            s_t = s0 * scor[3, 0, 0] * np.exp(-c2 * epp * (1.0 / t - 1.0 / t0)) * (1 - np.exp(-c2 * vc / t)) / (1 - np.exp(-c2 * vc / t0))
+
+            def lor(d):
+                return gam / (np.pi * (d * d + gam * gam))
+            shape = np.where(np.abs(wn - vc) <= 25.0,
+                             lor(wn - vc) - lor(25.0) + np.where(wn + vc <= 25.0, lor(wn + vc) - lor(25.0), 0.0), 0.0)
+            want = w_n2o * s_t * (wn * np.tanh(c2 * wn / (2 * t))) / (vc * np.tanh(c2 * vc / (2 * t))) * shape
+            assert np.all((want == 0) == (got == 0))
+            nz = want != 0
+            assert np.max(np.abs(got[nz] / want[nz] - 1.0)) < 2e-9, (t, p, mode)
