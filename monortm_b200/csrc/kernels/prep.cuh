@@ -1,0 +1,456 @@
+// prep.cuh -- layer_prep_kernel, continuum_kernel, derive_kernel: per-(profile,layer) and per-(line,layer) preparation.
+// Part of mrtm_kernels.cuh (included from there, inside namespace mrtm).
+// =============================================================================================
+// layer_prep_kernel: one thread per (profile,layer).  INITI (modm.f90:868-883), the layer part
+// of LINES (:302-313) and the scalar part of CONTNM (contnm.f90:222-240,300-302,334,487,919).
+// Only + - * / appear, evaluated with non-contracted IEEE operations so that the shift ratio
+// Xn/XN0 -- which decides the selected line set -- is bit-identical to the reference's.
+// =============================================================================================
+struct LayerPrepArgs {
+    int64_t nlayers;          // nprof*nlay
+    int64_t nlay;
+    int32_t nmol, ibrd;
+    const double *p, *t, *clw, *wkl, *wbrodl;   // (nlay,nprof), wkl (39,nlay,nprof)
+    double cntnm[7];
+    double max_abs_deltnu, max_abs_brd_dshift;
+    LayerDev* out;
+    // scor: either gathered from a full (42,9,L) device array or computed from TIPS tables
+    const double* scor_full;   // may be null
+    TipsDev tips;
+    int32_t nsi;
+    const int32_t* scor_index;
+    double* scorc;             // [L][nsi]
+    int* errflag;              // bit0: TIPS range/partition-sum failure
+    unsigned long long* sm_max_bits;   // max over the batch of shift_margin (bits of a non-negative double)
+    // upper bound of 100*HWHM_D/|Xnu| per segment over the layers of the batch (bits of a non-negative double): the
+    // plans need it before derive_kernel has run (the plan kernels overlap it on a second stream)
+    unsigned long long* vtmax;         // [nseg]
+    const Segment* seg;
+    int32_t nseg, pad3;
+};
+
+// AtoB, tips_2003.f90:4610-4700 (4-point Lagrange, 3-point at the table ends)
+__device__ inline double tips_atob(double aa, const double* A, const double* B, int npt)
+{
+    double bb = 0.;
+    for (int I = 2; I <= npt; I++) {
+        if (A[I - 1] >= aa) {
+            if (I < 3 || I == npt) {
+                int J = I;
+                if (I < 3) J = 3;
+                if (I == npt) J = npt;
+                double a0d1 = xsub(A[J - 3], A[J - 2]); if (a0d1 == 0.) a0d1 = 0.0001;
+                double a0d2 = xsub(A[J - 3], A[J - 1]); if (a0d2 == 0.) a0d2 = 0.0001;
+                double a1d1 = xsub(A[J - 2], A[J - 3]); if (a1d1 == 0.) a1d1 = 0.0001;
+                double a1d2 = xsub(A[J - 2], A[J - 1]); if (a1d2 == 0.) a1d2 = 0.0001;
+                double a2d1 = xsub(A[J - 1], A[J - 3]); if (a2d1 == 0.) a2d1 = 0.0001;
+                double a2d2 = xsub(A[J - 1], A[J - 2]); if (a2d2 == 0.) a2d2 = 0.0001;
+                double a0 = xdiv(xmul(xsub(aa, A[J - 2]), xsub(aa, A[J - 1])), xmul(a0d1, a0d2));
+                double a1 = xdiv(xmul(xsub(aa, A[J - 3]), xsub(aa, A[J - 1])), xmul(a1d1, a1d2));
+                double a2 = xdiv(xmul(xsub(aa, A[J - 3]), xsub(aa, A[J - 2])), xmul(a2d1, a2d2));
+                bb = xadd(xadd(xmul(a0, B[J - 3]), xmul(a1, B[J - 2])), xmul(a2, B[J - 1]));
+            } else {
+                int J = I;
+                double a0d1 = xsub(A[J - 3], A[J - 2]); if (a0d1 == 0.) a0d1 = 0.0001;
+                double a0d2 = xsub(A[J - 3], A[J - 1]); if (a0d2 == 0.) a0d2 = 0.0001;
+                double a0d3 = xsub(A[J - 3], A[J]);     if (a0d3 == 0.) a0d3 = 0.0001;
+                double a1d1 = xsub(A[J - 2], A[J - 3]); if (a1d1 == 0.) a1d1 = 0.0001;
+                double a1d2 = xsub(A[J - 2], A[J - 1]); if (a1d2 == 0.) a1d2 = 0.0001;
+                double a1d3 = xsub(A[J - 2], A[J]);     if (a1d3 == 0.) a1d3 = 0.0001;
+                double a2d1 = xsub(A[J - 1], A[J - 3]); if (a2d1 == 0.) a2d1 = 0.0001;
+                double a2d2 = xsub(A[J - 1], A[J - 2]); if (a2d2 == 0.) a2d2 = 0.0001;
+                double a2d3 = xsub(A[J - 1], A[J]);     if (a2d3 == 0.) a2d3 = 0.0001;
+                double a3d1 = xsub(A[J], A[J - 3]);     if (a3d1 == 0.) a3d1 = 0.0001;
+                double a3d2 = xsub(A[J], A[J - 2]);     if (a3d2 == 0.) a3d2 = 0.0001;
+                double a3d3 = xsub(A[J], A[J - 1]);     if (a3d3 == 0.) a3d3 = 0.0001;
+                double a0 = xmul(xmul(xsub(aa, A[J - 2]), xsub(aa, A[J - 1])), xsub(aa, A[J]));
+                a0 = xdiv(a0, xmul(xmul(a0d1, a0d2), a0d3));
+                double a1 = xmul(xmul(xsub(aa, A[J - 3]), xsub(aa, A[J - 1])), xsub(aa, A[J]));
+                a1 = xdiv(a1, xmul(xmul(a1d1, a1d2), a1d3));
+                double a2 = xmul(xmul(xsub(aa, A[J - 3]), xsub(aa, A[J - 2])), xsub(aa, A[J]));
+                a2 = xdiv(a2, xmul(xmul(a2d1, a2d2), a2d3));
+                double a3 = xmul(xmul(xsub(aa, A[J - 3]), xsub(aa, A[J - 2])), xsub(aa, A[J - 1]));
+                a3 = xdiv(a3, xmul(xmul(a3d1, a3d2), a3d3));
+                bb = xadd(xadd(xadd(xmul(a0, B[J - 3]), xmul(a1, B[J - 2])), xmul(a2, B[J - 1])), xmul(a3, B[J]));
+            }
+            break;
+        }
+    }
+    return bb;
+}
+
+__global__ void layer_prep_kernel(LayerPrepArgs a)
+{
+    int64_t L = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (L >= a.nlayers) return;
+    const double* wk = a.wkl + (size_t)L * MRTM_MXMOL;
+    const double pp = a.p[L], tt = a.t[L], wbrod = a.wbrodl[L];
+    LayerDev o;
+    // INITI
+    o.radct = xdiv(xmul(kPLANCK, kCLIGHT), kBOLTZ);
+    double xn0 = xmul(xdiv(kP0, xmul(kBOLTZ, kT0)), 1.E+3);
+    double xn = xmul(xdiv(pp, xmul(kBOLTZ, tt)), 1.E+3);
+    // LINES prologue
+    double wtot = 0.;
+    for (int m = 0; m < a.nmol; m++) wtot = xadd(wtot, wk[m]);
+    wtot = xadd(wtot, wbrod);
+    o.wtot = wtot;
+    o.t = tt;
+    o.p = pp;
+    o.rp = xdiv(pp, kP0);
+    o.rp2 = xmul(o.rp, o.rp);
+    const double templc[4] = {200.0, 250.0, 296.0, 340.0};
+    int ilc = 1;
+    for (int il = 1; il <= 3; il++) {
+        ilc = il;
+        if (tt < templc[ilc]) break;
+    }
+    o.ilc = ilc;
+    o.rectlc = xdiv(1.0, xsub(templc[ilc], templc[ilc - 1]));
+    o.tmpdif = xsub(tt, templc[ilc - 1]);
+    o.rt = xdiv(tt, kT0);
+    o.lnrt = log(o.rt);
+    o.dinvt = 1. / kT0 - 1. / tt;
+    o.rhorat = xdiv(xn, xn0);
+    for (int k = 0; k < 7; k++) o.rho_molec[k] = xdiv(xmul(o.rhorat, wk[k]), wtot);
+    for (int m = 0; m < MRTM_MXMOL; m++) {
+        o.wk[m] = (m < a.nmol) ? wk[m] : 0.;
+        // rho_molec(mol) for mol>7 is out of bounds in the reference (modm.f90:845); natural extension
+        o.rho_self[m] = (m < 7) ? o.rho_molec[m] : ((m < a.nmol) ? xdiv(xmul(o.rhorat, wk[m]), wtot) : 0.);
+    }
+    o.xkt = xdiv(tt, kRADCN2);
+    o.clw = a.clw[L];
+    o.sqrt_t = sqrt(tt);
+    double sm = a.max_abs_deltnu * fabs(o.rhorat) * (1. + 1e-9) + 1e-12;
+    if (a.ibrd != 0) {
+        double sr = 0.;
+        for (int k = 0; k < 7; k++) sr += fabs(o.rho_molec[k]);
+        sm += sr * a.max_abs_brd_dshift * (1. + 1e-9);
+    }
+    o.shift_margin = sm;
+    if (a.sm_max_bits) atomicMax(a.sm_max_bits, (unsigned long long)__double_as_longlong(sm));   // sm >= 0
+    if (a.vtmax)
+        for (int s = 0; s < a.nseg; s++) {
+            const unsigned long long bits = (unsigned long long)__double_as_longlong(a.seg[s].vrate * o.sqrt_t);
+            if (bits > *(volatile unsigned long long*)(a.vtmax + s)) atomicMax(a.vtmax + s, bits);
+        }
+    // CONTNM scalars (P0=1013, T0=296 there: contnm.f90:86)
+    {
+        const double cp0 = 1013., ct0 = 296., xlosmt = 2.68675E+19;
+        double rhoave = xmul(xdiv(pp, cp0), xdiv(ct0, tt));
+        double amagat = xmul(xdiv(pp, cp0), xdiv(273., tt));
+        double cw = wbrod;
+        for (int m = 0; m < a.nmol; m++) cw = xadd(cw, wk[m]);
+        double wk1 = wk[0];
+        double wk2 = (a.nmol >= 2) ? wk[1] : 0.;
+        double wk7 = (a.nmol >= 7) ? wk[6] : 0.;
+        double xh2o = xdiv(wk1, cw), xo2 = xdiv(wk7, cw);
+        double xn2 = xsub(xsub(1., xh2o), xo2);
+        double wn2 = xmul(xn2, cw);
+        double h2o_fac = xdiv(wk1, cw);
+        o.c_wk1 = wk1;
+        o.c_rself = xmul(xmul(xmul(h2o_fac, rhoave), 1.e-20), a.cntnm[0]);
+        o.c_rfrgn = xmul(xmul(xmul(xsub(1., h2o_fac), rhoave), 1.e-20), a.cntnm[1]);
+        o.c_tfac_h2o = xdiv(xsub(tt, ct0), xsub(260., ct0));
+        o.c_wco2 = xmul(xmul(xmul(wk2, rhoave), 1.0E-20), a.cntnm[2]);
+        o.c_trat = xdiv(tt, 246.);
+        o.c_taufac = xmul(xmul(a.cntnm[5], xdiv(wn2, xlosmt)), amagat);
+        o.c_tfac_n2 = xdiv(xsub(tt, 296.), xsub(220., 296.));
+        o.c_xn2 = xn2;
+        o.c_xo2 = xo2;
+        o.c_xh2o = xh2o;
+    }
+    o.pad = 0;
+    a.out[L] = o;
+
+    // scor for the compact (molecule,isotopologue) list
+    for (int s = 0; s < a.nsi; s++) {
+        double v;
+        if (a.scor_full) {
+            v = a.scor_full[(size_t)L * (MRTM_NSCOR1 * MRTM_NSCOR2) + a.scor_index[s]];
+        } else {
+            int row = a.tips.row[s];
+            if (row < 0 || tt < 70. || tt > 3000.) {
+                atomicOr(a.errflag, 1);
+                v = 1.;
+            } else {
+                double q296 = tips_atob(296., a.tips.tdat, a.tips.qoft + (size_t)row * 119, 119);
+                double qt = tips_atob(tt, a.tips.tdat, a.tips.qoft + (size_t)row * 119, 119);
+                if (!(qt > 0.) || !(q296 > 0.)) atomicOr(a.errflag, 1);
+                v = xdiv(q296, qt);
+            }
+        }
+        a.scorc[(size_t)L * a.nsi + s] = v;
+    }
+}
+
+// =============================================================================================
+// continuum_kernel: one CTA per (profile,layer).  MT_CKD_3.5 branches that fire for V2 < 820:
+// H2O self (contnm.f90:325-371), H2O foreign (:380-457), CO2 (:484-528), N2 roto-translational
+// CIA (:906-943), each 4-point interpolated (XINT, lblrtm_sub.f90:1-34) onto the 1 cm-1 grid.
+// Output planes: absrb[L][3][nptabs_pad] for species selectors im = 1 (H2O), 2 (CO2), 22 (N2).
+// =============================================================================================
+struct ContArgs {
+    int64_t nlayers;
+    ContGrid g[4];            // 0 self, 1 foreign, 2 co2, 3 n2
+    double v1abs;
+    int32_t nptabs, nptabs_pad;
+    ContTablesDev tb;
+    const LayerDev* lay;
+    double* absrb;
+};
+
+__device__ __forceinline__ double xint_point(const double* a, double v1a, double dva, double vi)
+{
+    // body of the XINT loop (lblrtm_sub.f90:20-31); a is 0-based with a[j-1] = A(J)
+    const double onepl = 1.001;
+    double recdva = 1. / dva;
+    int j = (int)((vi - v1a) * recdva + onepl);
+    double vj = v1a + dva * (double)(j - 1);
+    double p = recdva * (vi - vj);
+    double c = (3. - 2. * p) * p * p;
+    double b = 0.5 * p * (1. - p);
+    double b1 = b * (1. - p);
+    double b2 = b * p;
+    return -a[j - 2] * b1 + a[j - 1] * (1. - c + b2) + a[j] * (c + b1) - a[j + 1] * b2;
+}
+
+__global__ void __launch_bounds__(128) continuum_kernel(ContArgs a)
+{
+    extern __shared__ double sm[];
+    const int64_t L = blockIdx.x;
+    const LayerDev& ly = a.lay[L];
+    double* s_self = sm;
+    double* s_frgn = s_self + a.g[0].nptc;
+    double* s_co2 = s_frgn + a.g[1].nptc;
+    double* s_n2 = s_co2 + a.g[2].nptc;
+    const int tid = threadIdx.x;
+
+    if (a.g[0].active) {
+        for (int j = tid; j < a.g[0].nptc; j += blockDim.x) {
+            int i = a.g[0].i1 + j;
+            double s0 = 0., s1 = 0., sh2o = 0.;
+            if (i >= 1 && i <= 2003) { s0 = a.tb.sh2o_296[i - 1]; s1 = a.tb.sh2o_260[i - 1]; }
+            if (s0 > 0.) sh2o = s0 * pow(s1 / s0, ly.c_tfac_h2o);
+            s_self[j] = ly.c_wk1 * (sh2o * ly.c_rself);
+        }
+    }
+    if (a.g[1].active) {
+        const double f0 = 0.06, v0f1 = 255.67, hwsq1 = 240. * 240., beta1 = 57.83, c_1 = -0.42, c_2 = 0.3, beta2 = 630.;
+        for (int j = tid; j < a.g[1].nptc; j += blockDim.x) {
+            int i = a.g[1].i1 + j;
+            double f = (i >= 1 && i <= 2003) ? a.tb.fh2o[i - 1] : 0.;
+            double vj = a.g[1].v1c + a.g[1].dvc * (double)j;
+            double fscal;
+            if (vj <= 600.) {
+                int jfac = (int)((vj + 10.) / 10. + 0.00001);
+                fscal = a.tb.xfac_rhu[jfac + 1];
+            } else {
+                double t1 = (vj - v0f1) / beta1, t2 = (vj + v0f1) / beta1, t3 = vj / beta2;
+                double vf1 = t1 * t1; vf1 *= vf1; vf1 *= vf1;
+                double vmf1 = t2 * t2; vmf1 *= vmf1; vmf1 *= vmf1;
+                double vf2 = t3 * t3; vf2 *= vf2; vf2 *= vf2;
+                fscal = 1. + (f0 + c_1 * ((hwsq1 / ((vj - v0f1) * (vj - v0f1) + hwsq1 + vf1)) +
+                                          (hwsq1 / ((vj + v0f1) * (vj + v0f1) + hwsq1 + vmf1)))) /
+                                 (1. + c_2 * vf2);
+            }
+            f = f * fscal;
+            s_frgn[j] = (ly.c_wk1 * f) * ly.c_rfrgn;
+        }
+    }
+    if (a.g[2].active) {
+        for (int j = tid; j < a.g[2].nptc; j += blockDim.x) {
+            int i = a.g[2].i1 + j;
+            double f = 0.;
+            if (i >= 1 && i <= 5003) {
+                double tcor = 1.;
+                if (i >= 1196 && i <= 1220) tcor = pow(ly.c_trat, a.tb.co2_tdep[i - 1196]);
+                f = tcor * a.tb.fco2[i - 1];
+            }
+            s_co2[j] = f * ly.c_wco2;
+        }
+    }
+    if (a.g[3].active) {
+        for (int j = tid; j < a.g[3].nptc; j += blockDim.x) {
+            int i = a.g[3].i1 + j;
+            double c0 = 0., c1 = 0.;
+            if (i >= 1 && i <= 73) {
+                c0 = a.tb.n2_296[i - 1] * pow(a.tb.n2_220[i - 1] / a.tb.n2_296[i - 1], ly.c_tfac_n2);
+                double sf_t = a.tb.n2_296_sf[i - 1] * pow(a.tb.n2_220_sf[i - 1] / a.tb.n2_296_sf[i - 1], ly.c_tfac_n2);
+                c1 = (sf_t - 1.) * 0.79 / 0.21;
+            }
+            s_n2[j] = ly.c_taufac * c0 * (ly.c_xn2 + c1 * ly.c_xo2 + 1. * ly.c_xh2o);
+        }
+    }
+    __syncthreads();
+    double* out = a.absrb + (size_t)L * 3 * a.nptabs_pad;
+    for (int i = 1 + tid; i <= a.nptabs_pad; i += blockDim.x) {
+        double vi = a.v1abs + 1.0 * (double)(i - 1);
+        double h = 0., c = 0., n = 0.;
+        if (i <= a.nptabs) {
+            if (a.g[0].active && i >= a.g[0].ilo && i <= a.g[0].ihi) h = h + xint_point(s_self, a.g[0].v1c, a.g[0].dvc, vi);
+            if (a.g[1].active && i >= a.g[1].ilo && i <= a.g[1].ihi) h = h + xint_point(s_frgn, a.g[1].v1c, a.g[1].dvc, vi);
+            if (a.g[2].active && i >= a.g[2].ilo && i <= a.g[2].ihi) c = xint_point(s_co2, a.g[2].v1c, a.g[2].dvc, vi);
+            if (a.g[3].active && i >= a.g[3].ilo && i <= a.g[3].ihi) n = xint_point(s_n2, a.g[3].v1c, a.g[3].dvc, vi);
+        }
+        out[i - 1] = h;
+        out[a.nptabs_pad + i - 1] = c;
+        out[2 * a.nptabs_pad + i - 1] = n;
+    }
+}
+
+// =============================================================================================
+// derive_kernel: one thread per (line, layer).  Everything in LINES that does not depend on the
+// frequency: coupling coefficients (modm.f90:328-368), shifted centre (:375-380,
+// bit exact), INTENS (:860-865), HALFWHM_C (:833-857), HALFWHM_D (:442-454), zeta (:419).
+// =============================================================================================
+struct DeriveArgs {
+    int64_t nlayers;
+    LinesDev ln;
+    const LayerDev* lay;
+    const double* scorc;      // [L][nsi]
+    double sclcpl, sclhw, y0res;
+    int32_t ibrd, pad;
+    double* planes;           // [L][D_NPLANES][n_pad]
+    unsigned long long* layer_voigt;   // [L] bits of the smallest |Xnu| among the lines of the layer that can take the Voigt branch
+                                       // (zeta <= 0.99; 100*HWHM_D grows with |Xnu|), all ones = none
+    int32_t nseg, pad2;
+};
+
+#ifndef MRTM_DERIVE_MINB
+#define MRTM_DERIVE_MINB 6
+#endif
+// one (line, layer): returns the bits of |Xnu| when the line can take the Voigt branch in this layer, else all ones
+__device__ __forceinline__ unsigned long long derive_one(const DeriveArgs& a, int q, int64_t L)
+{
+    const unsigned long long kNone = ~0ull;
+    if (q >= a.ln.n_pad) return kNone;
+    double* pl = a.planes + (size_t)L * D_NPLANES * a.ln.n_pad;
+    if (q >= a.ln.n) {   // padding: far away, zero strength
+        pl[(size_t)D_XNU * a.ln.n_pad + q] = 1.0e30;
+        pl[(size_t)D_H2 * a.ln.n_pad + q] = 1.0;
+        pl[(size_t)D_CN * a.ln.n_pad + q] = 0.;
+        pl[(size_t)D_P3 * a.ln.n_pad + q] = 0.;
+        pl[(size_t)D_P4 * a.ln.n_pad + q] = 0.;
+        pl[(size_t)D_H * a.ln.n_pad + q] = 1.0;
+        pl[(size_t)D_AD * a.ln.n_pad + q] = 1.0;
+        pl[(size_t)D_VT * a.ln.n_pad + q] = -1.0;
+        pl[(size_t)D_STILD * a.ln.n_pad + q] = 0.;
+        pl[(size_t)D_AIP * a.ln.n_pad + q] = 0.;
+        pl[(size_t)D_BIP * a.ln.n_pad + q] = 0.;
+        return kNone;
+    }
+    const LayerDev& ly = a.lay[L];
+    const int mol = a.ln.mol[q], xf = a.ln.xf[q], cls = a.ln.cls[q];
+    const double rhorat = ly.rhorat, rho_self = ly.rho_self[mol - 1];
+    const double radct = ly.radct, t = ly.t;
+
+    double aip = 0., bip = 0.;
+    const int lci = a.ln.lcidx[q];
+    if (lci >= 0) {
+        const double* c = a.ln.lc + (size_t)lci * 16;
+        double A[4] = {c[0], c[1], c[2], c[3]}, B[4] = {c[4], c[5], c[6], c[7]};
+        if (a.ln.lc_self[lci]) {
+            double rho_for = (rhorat - rho_self) / rhorat;
+            double rho_sel = rho_self / rhorat;
+            for (int k = 0; k < 4; k++) {
+                A[k] = xadd(xmul(rho_for, A[k]), xmul(rho_sel, c[8 + k]));
+                B[k] = xadd(xmul(rho_for, B[k]), xmul(rho_sel, c[12 + k]));
+            }
+        }
+        const int ilc = ly.ilc;
+        aip = A[ilc - 1] + ((A[ilc] - A[ilc - 1]) * ly.rectlc) * ly.tmpdif;
+        bip = B[ilc - 1] + ((B[ilc] - B[ilc - 1]) * ly.rectlc) * ly.tmpdif;
+    }
+    if (xf == -1) {
+        aip = aip * a.sclcpl + a.y0res;
+        bip = bip * a.sclcpl + a.y0res;
+    }
+    if (xf == -3) {
+        aip = aip * a.sclhw;
+        bip = bip * a.sclhw;
+    }
+
+    // shifted line centre: exactly Xnu0 + deltnu*(Xn/XN0) [+ sum(rho*flg*(shft-deltnu))], no FMA
+    const double xnu0 = a.ln.xnu0[q], deltnu = a.ln.deltnu[q];
+    double xnu = xadd(xnu0, xmul(deltnu, rhorat));
+    const int bi = a.ln.brdidx[q];
+    const bool use_brd = (mol <= MRTM_MXBRDMOL) && (a.ibrd != 0);
+    const double* brd = (bi >= 0) ? a.ln.brd + (size_t)bi * 28 : nullptr;
+    if (use_brd) {
+        double s = 0.;
+        if (brd)
+            for (int k = 0; k < 7; k++) s = xadd(s, xmul(xmul(ly.rho_molec[k], brd[k]), xsub(brd[21 + k], deltnu)));
+        xnu = xadd(xnu, s);
+    }
+
+    // INTENS
+    const double xipsf = a.scorc[(size_t)L * a.ln.nsi + a.ln.sidx[q]];
+    const double es = a.ln.e[q];
+    // exp(-c2 E/T)/exp(-c2 E/T0) as one exponential (modm.f90 INTENS)
+    double s = a.ln.s0adj[q] * exp(radct * es * ly.dinvt) * xipsf;
+    double stild = s * ((1 + exp(-(radct * xnu / t))) / (xnu * (1 - exp(-(radct * xnu / kT0)))));
+
+    // HALFWHM_C
+    const double af = a.ln.alpf[q], as = a.ln.alps[q];
+    const double rtx = exp(a.ln.x[q] * ly.lnrt);         // (T/T0)^x with the layer's log(T/T0)
+    const double alfa0i = af * rtx, hwhmsi = as * rtx;
+    double hwhm_c = alfa0i * (rhorat - rho_self) + hwhmsi * rho_self;
+    if (use_brd && brd) {
+        double alfsum = 0., sflgrho = 0.;
+        for (int k = 0; k < 7; k++) {
+            double tmpcor = pow(ly.rt, brd[14 + k]);
+            alfsum = alfsum + ly.rho_molec[k] * brd[k] * (brd[7 + k] * tmpcor);
+            sflgrho = sflgrho + ly.rho_molec[k] * brd[k];
+        }
+        hwhm_c = (rhorat - sflgrho) * alfa0i + alfsum;
+        if (brd[mol - 1] == 0.) hwhm_c = hwhm_c + rho_self * (hwhmsi - alfa0i);
+    }
+    // HALFWHM_D
+    const double hwhm_d = (xnu / kCLIGHT) * sqrt(2. * log(2.) * ((kBOLTZ * t) / (a.ln.mass[q] / kAVOGAD)));
+    if (xf == -3) hwhm_c = hwhm_c * (1 - (aip * ly.rp) - (bip * ly.rp2));
+    const double zeta = hwhm_c / (hwhm_c + hwhm_d);
+
+    const double h2 = hwhm_c * hwhm_c;
+    const double cn = stild * hwhm_c / kPI;
+    double p3 = 0., p4 = 0.;
+    if (cls == CLS_PED) p3 = cn / (kDELTNUC * kDELTNUC + h2);
+    if (cls == CLS_O2_LC1) {
+        p3 = cn * (1. + bip * ly.rp2);
+        p4 = cn * (aip * (1 / hwhm_c) * ly.rp);
+    }
+    const size_t np = a.ln.n_pad;
+    pl[(size_t)D_XNU * np + q] = xnu;
+    pl[(size_t)D_H2 * np + q] = h2;
+    pl[(size_t)D_CN * np + q] = cn;
+    pl[(size_t)D_P3 * np + q] = p3;
+    pl[(size_t)D_P4 * np + q] = p4;
+    pl[(size_t)D_H * np + q] = hwhm_c;
+    pl[(size_t)D_AD * np + q] = hwhm_d;
+    const double vt = (zeta > 0.99) ? -1.0 : 100. * hwhm_d;
+    pl[(size_t)D_VT * np + q] = vt;
+    pl[(size_t)D_STILD * np + q] = stild;
+    pl[(size_t)D_AIP * np + q] = aip;
+    pl[(size_t)D_BIP * np + q] = bip;
+    return (vt >= 0.) ? (unsigned long long)__double_as_longlong(fabs(xnu)) : kNone;
+}
+
+__global__ void __launch_bounds__(256, MRTM_DERIVE_MINB) derive_kernel(DeriveArgs a)
+{
+    const int64_t L = blockIdx.y;
+    unsigned long long xb = derive_one(a, blockIdx.x * blockDim.x + threadIdx.x, L);
+    // smallest |Xnu| of the layer's Voigt-capable lines: warp minimum, block minimum, one global atomic per block at most
+    __shared__ unsigned long long s_min[8];
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        const unsigned long long o = __shfl_xor_sync(0xffffffffu, xb, off);
+        xb = o < xb ? o : xb;
+    }
+    if ((threadIdx.x & 31) == 0) s_min[threadIdx.x >> 5] = xb;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long m = s_min[0];
+        for (int w = 1; w < 8; w++) m = s_min[w] < m ? s_min[w] : m;
+        if (m < *(volatile unsigned long long*)(a.layer_voigt + L)) atomicMin(a.layer_voigt + L, m);
+    }
+}
