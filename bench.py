@@ -117,7 +117,7 @@ class ClockSampler(threading.Thread):
                 "samples": len(self.rows), "power_w_max": max(r[1] for r in self.rows)}
 
 
-def cpu_sample(inp, nwn_sample, opt="O0"):
+def cpu_sample(inp, nwn_sample, opt="O0", keep=None):
     """Time the CPU oracle on `nwn_sample` evenly spaced frequencies of this shard (all layers, all lines)."""
     import harness
     idx = np.linspace(0, len(inp["wn"]) - 1, nwn_sample).astype(int)
@@ -126,11 +126,38 @@ def cpu_sample(inp, nwn_sample, opt="O0"):
     t0 = time.time()
     m = harness.oracle_modm(inp["ls"], wn, 0.0, pr["p"][:, 0], pr["t"][:, 0], pr["clw"][:, 0], 22, pr["wkl"][:, :, 0],
                             pr["wbrodl"][:, 0], inp["scor"][:, :, :, 0], opt=opt)
-    harness.oracle_calctmr(wn, pr["t"][:, 0], pr["tz"][:, 0], m["o"])
-    harness.oracle_rtm(1, inp["irt"], wn, pr["t"][:, 0], pr["tz"][:, 0], m["o"], inp["tmpsfc"], inp["reflc"][idx], inp["emiss"][idx])
+    tmr = harness.oracle_calctmr(wn, pr["t"][:, 0], pr["tz"][:, 0], m["o"])
+    r = harness.oracle_rtm(1, inp["irt"], wn, pr["t"][:, 0], pr["tz"][:, 0], m["o"], inp["tmpsfc"], inp["reflc"][idx], inp["emiss"][idx])
     dt = time.time() - t0
     nlines = logical_lines(inp["ls"])
+    if keep is not None:
+        keep.update(idx=idx, o=m["o"], sel_count=m["sel_count"], sel_hash=m["sel_hash"], tmr=tmr, tb=r["tb"], rad=r["rad"])
     return dt, float(nlines) * NLAY * nwn_sample, float(m["sel_count"].sum())
+
+
+def parity_check(sess, inp, hprof, hscor, oracle):
+    """The bench workload itself against the oracle (outside the timed region): the full shard runs once more through
+    the public host-buffer call with layer optical depths and the selection instrumentation switched on, in the default
+    mode (far-field expansion) and in the direct mode, and is compared with the oracle at the cpu_baseline sample
+    frequencies.  Bars (BASELINE.json north_star): selected-line set bit-exact, OD 1e-9 relative, TB (and TMR) 1e-5 K."""
+    idx = oracle["idx"]
+    out = {"n_freq": int(len(idx)), "nlay": NLAY, "line_modes": [0, 1], "od_rtol_bar": 1e-9, "tb_atol_K_bar": 1e-5,
+           "max_rel_od": 0.0, "max_dtb_K": 0.0, "max_dtmr_K": 0.0, "max_rel_rad": 0.0, "sel_exact": True,
+           "what": "GPU (mrtm_profiles, whole shard, both line modes) vs oracle at the cpu_baseline sample frequencies x all layers"}
+    for mode in (0, 1):
+        g = sess.profiles(inp["wn"], 0.0, hprof, hscor, inp["irt"], inp["tmpsfc"], inp["emiss"], inp["reflc"],
+                          global_range=(inp["v1"], inp["v2"], inp["iw0"]), want_o=True, selection=True, line_mode=mode)
+        o = g["o"][idx, :, 0]
+        out["max_rel_od"] = max(out["max_rel_od"], float(np.max(np.abs(o - oracle["o"]) / np.abs(oracle["o"]))))
+        out["max_dtb_K"] = max(out["max_dtb_K"], float(np.max(np.abs(g["tb"][idx, 0] - oracle["tb"]))))
+        out["max_dtmr_K"] = max(out["max_dtmr_K"], float(np.max(np.abs(g["tmr"][idx, 0] - oracle["tmr"]))))
+        out["max_rel_rad"] = max(out["max_rel_rad"], float(np.max(np.abs(g["rad"][idx, 0] / oracle["rad"] - 1.0))))
+        out["sel_exact"] = bool(out["sel_exact"] and np.array_equal(g["sel_count"][idx, :, 0], oracle["sel_count"])
+                                and np.array_equal(g["sel_hash"][idx, :, 0], oracle["sel_hash"]))
+        del g
+    out["selected_pairs_compared"] = int(oracle["sel_count"].sum()) * 2
+    out["pass"] = bool(out["sel_exact"] and out["max_rel_od"] < 1e-9 and out["max_dtb_K"] < 1e-5 and out["max_dtmr_K"] < 1e-5)
+    return out
 
 
 def logical_lines(ls):
@@ -361,6 +388,7 @@ def main():
     sampler.stop_flag = True
     sampler.join(timeout=2)
 
+    parity_failed = False
     if rank == 0:
         # in-window fraction: exact counts (selection-instrumented kernel) on a 1/64 frequency subsample
         sub = np.arange(0, nwn, 64)
@@ -425,15 +453,21 @@ def main():
                                                 "frac": d_ach / fp64_peak if fp64_peak else None,
                                                 "flop_per_inwindow_eval": FLOP_PER_INWINDOW_EVAL}}
         if not args.no_cpu_baseline:
-            dt, nominal, inwin = cpu_sample(inp, args.cpu_sample_nwn)
+            orc = {}
+            dt, nominal, inwin = cpu_sample(inp, args.cpu_sample_nwn, keep=orc)
+            line["parity_check"] = parity_check(sess, inp, hprof, hscor, orc)
             line["cpu_baseline"] = {"value": nominal / dt, "unit": "evals/s", "cores": 1, "kind": "port",
                                     "sample": "%d evenly spaced frequencies of the shard x %d layers x all %d lines, oracle -O0 "
                                               "(C restatement; the Fortran reference cannot be compiled here), %.1f s" %
                                               (args.cpu_sample_nwn, NLAY, nlines, dt)}
         print(json.dumps(line))
+        if "parity_check" in line and not line["parity_check"]["pass"]:
+            parity_failed = True
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+    if parity_failed:
+        raise SystemExit("bench.py: parity_check failed (see the JSON line): the throughput above is not valid")
 
 
 if __name__ == "__main__":

@@ -54,7 +54,7 @@ def scor_for_layers(nmol, t):
     for idx in np.ndindex(t.shape):
         key = float(t[idx])
         if key not in cache:
-            cache[key] = tips_2003(min(int(nmol), 33), key)
+            cache[key] = tips_2003(int(nmol), key)
         out[(slice(None), slice(None)) + idx] = cache[key]
     return out
 

@@ -754,7 +754,7 @@ extern "C" int mrtm_host_run_monortm(const char* workdir, int device, int64_t nw
             std::vector<double> scor((size_t)MRTM_NSCOR1 * MRTM_NSCOR2 * (size_t)pr.nlay, 0.);
             for (int64_t k = 0; k < pr.nlay; k++) {
                 rc = mrtm_host_tips_2003(pr.nmol, pr.t[(size_t)k], scor.data() + (size_t)MRTM_NSCOR1 * MRTM_NSCOR2 * (size_t)k);
-                if (rc) throw Stop(rc, "TIPS_2003: temperature outside 70..3000 K, molecule beyond 33 or partition sum <= 0 (tips_2003.f90:271-277)");
+                if (rc) throw Stop(rc, "TIPS_2003: temperature outside 70..3000 K or partition sum <= 0 (tips_2003.f90:271-277)");
             }
             std::vector<double> o((size_t)nwn * (size_t)pr.nlay);
             // MODM + CALCTMR + RTM (monortm.f90:557-574) on the GPU

@@ -170,7 +170,9 @@ __global__ void layer_prep_kernel(LayerPrepArgs a)
             v = a.scor_full[(size_t)L * (MRTM_NSCOR1 * MRTM_NSCOR2) + a.scor_index[s]];
         } else {
             int row = a.tips.row[s];
-            if (row < 0 || tt < 70. || tt > 3000.) {
+            if (row == -2 && !(tt < 70. || tt > 3000.)) {
+                v = 1.;                 // molecules 34 and 39: scor == 1 (tips_2003.f90:233-238, 260-292)
+            } else if (row < 0 || tt < 70. || tt > 3000.) {
                 atomicOr(a.errflag, 1);
                 v = 1.;
             } else {

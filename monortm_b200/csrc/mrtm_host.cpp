@@ -96,10 +96,13 @@ namespace mrtm {
 const double* tips_qoft() { return TIPS_QOFT; }
 const double* tips_tdat() { return TIPS_TDAT; }
 int tips_rows() { return TIPS_QROWS; }
-// row of (mol, iso) in TIPS_QOFT or -1
+// row of (mol, iso) in TIPS_QOFT; -2: the reference's dispatch yields scor == 1 (molecule 34, atomic oxygen: gi=1, QT=1,
+// tips_2003.f90:233-238; molecule 39, CH3OH: both qt_296 and qt_temp end up as the stale QT of the previous call,
+// :260-268, 288-292); -1: no such (molecule, isotopologue)
 int tips_row(int mol, int iso)
 {
-    if (mol < 1 || mol > 38) return -1;
+    if (mol < 1 || mol > 39) return -1;
+    if (mol == 34 || mol == 39) return iso == 1 ? -2 : -1;
     int nuse = TIPS_ISONM[mol - 1] < 9 ? TIPS_ISONM[mol - 1] : 9;   // min(9,isonm(mol)), tips_2003.f90:60
     if (iso < 1 || iso > nuse || iso > TIPS_QNISO[mol - 1]) return -1;
     return TIPS_QOFFSET[mol - 1] + (iso - 1);
@@ -108,11 +111,13 @@ int tips_row(int mol, int iso)
 
 extern "C" int mrtm_host_tips_2003(int64_t mol_max, double temp, double* scor)
 {
-    // mol 34 (O) has Q == 0 -> "partition sum less than 0." STOP (tips_2003.f90:271-277);
-    // mol 39 is a special case never reached because of that STOP.
-    if (mol_max < 1 || mol_max > 33) return MRTM_ETIPS;
+    if (mol_max < 1 || mol_max > 39) return MRTM_ETIPS;
     if (temp < 70. || temp > 3000.) return MRTM_ETIPS;     // Qt=-1 -> STOP
     for (int64_t mol = 1; mol <= mol_max; mol++) {
+        if (mol == 34 || mol == 39) {                      // QT := 1 (O, tips_2003.f90:233-238); CH3OH: stale QT / stale QT (:260-292)
+            scor[(mol - 1)] = 1.0;
+            continue;
+        }
         int nuse = TIPS_ISONM[mol - 1] < 9 ? TIPS_ISONM[mol - 1] : 9;
         for (int iso = 1; iso <= nuse; iso++) {
             const double* q = TIPS_QOFT + (size_t)(TIPS_QOFFSET[mol - 1] + iso - 1) * 119;

@@ -62,8 +62,10 @@ int stage_lines_host(const int64_t nblm[MRTM_MXMOL], int64_t iim, const int64_t*
             RawLine r;
             std::memset(&r, 0, sizeof r);
             double xgj = xg[ix(i, j)];
-            if (!(xgj == 0 || is_lc(xgj))) {
-                out.error = "LC flag not recognized: must be 0, -1, -3 or -5 (lnfl_mod.f90:61-63)";
+            // GET_LNFL stores XG = -IFLG for IFLG in 0..100 (lnfl_mod.f90:44-45, 73-77); LINES and the LSF routines compare XG
+            // with -1, -3, -5 only, so every other flag value is an uncoupled line.  Anything else cannot come out of GET_LNFL.
+            if (!(xgj <= 0. && xgj >= -100. && xgj == std::floor(xgj))) {
+                out.error = "XG outside -(0..100): not a value GET_LNFL stores (lnfl_mod.f90:44-63, 73-77)";
                 return MRTM_ELINEFILE;
             }
             if (is_lc(xgj)) {                            // :328-351
@@ -116,8 +118,8 @@ int stage_lines_host(const int64_t nblm[MRTM_MXMOL], int64_t iim, const int64_t*
                 r.has_brd = any;
             }
             if (i == 7) {
-                r.cls = (r.xf == 0) ? CLS_O2 : (r.xf == -1 ? CLS_O2_LC1 : CLS_O2_LC35);
-            } else if (i == 2 || r.xf != 0) {
+                r.cls = !is_lc(xgj) ? CLS_O2 : (r.xf == -1 ? CLS_O2_LC1 : CLS_O2_LC35);
+            } else if (i == 2 || is_lc(xgj)) {
                 r.cls = CLS_GENERAL;
             } else {
                 r.cls = CLS_PED;

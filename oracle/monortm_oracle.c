@@ -630,6 +630,12 @@ void orc_sd_humlicek(double x1, double y1, double x2, double y2, double *re, dou
 
 static __thread int g_sdv_stop;   /* set when modm.f90:1062 would STOP */
 static __thread int64_t g_nvoigt;
+/* test instrumentation: which Voigt-branch cases a run reached.  [0] Voigt-branch evaluations (= g_nvoigt), [1] SDVOIGT calls
+ * that took the speed-dependent branch (:1022-1066), [2] CO2 lines, [3] CO2 lines with XF=-1, [4] coupled lines of molecules
+ * other than CO2/O2 (:588-615), [5] coupled O2 lines, [6] lines with an XG outside {0,-1,-3,-5}, [7] negative-frequency resonance
+ * evaluated on the Voigt branch (DIFF <= 0) */
+static __thread int64_t g_branch[8];
+void orc_branch_counts(int64_t out[8]) { for (int i = 0; i < 8; i++) out[i] = g_branch[i]; }
 
 /* SDVOIGT, modm.f90:965-1087 (the AVC interpolation :1004-1009 feeds nothing) */
 static double sdvoigt(double deltnu, double alphal, double alphad, double sdep)
@@ -645,6 +651,7 @@ static double sdvoigt(double deltnu, double alphal, double alphad, double sdep)
     if (zeta == 1.00 && fabs(sdep) < tiny)
         return (alphal / (pi * (alphal * alphal + (deltnu) * (deltnu))));
     if (fabs(sdep) > tiny) {
+        g_branch[1]++;
         double gamma2 = alphal * sdep;
         double alfa = (alphal / gamma2) - 1.5;
         double beta = (deltnu / gamma2);
@@ -1019,6 +1026,13 @@ static int lines(double xn, double wn, double t, int64_t nmol, const double *wk,
             } else {
                 sls = lsf_sdvoigt(xgj, rp, rp2, aip, bip, hwhm_c, wn, xnu, hwhm_d, i, ln->sdep[IX(i, j)]);
                 g_nvoigt++;
+                g_branch[0]++;
+                if (i == 2) g_branch[2]++;
+                if (i == 2 && xgj == -1) g_branch[3]++;
+                if (i != 2 && i != 7 && IS_LC(xgj)) g_branch[4]++;
+                if (i == 7 && IS_LC(xgj)) g_branch[5]++;
+                if (!IS_LC(xgj) && xgj != 0) g_branch[6]++;
+                if ((wn + xnu) - 25. <= 0.) g_branch[7]++;
             }
             sf = sf + (stild * sls);
             j = jj;
@@ -1051,6 +1065,7 @@ int orc_modm(int64_t nwn, const double *wn, double dvset, int64_t nlay,
     memset(wkc, 0, sizeof wkc);
     g_sdv_stop = 0;
     g_nvoigt = 0;
+    for (int ib_ = 0; ib_ < 8; ib_++) g_branch[ib_] = 0;
     if (nwn < 1 || nlay < 1 || nmol < 1 || nmol > ORC_MXMOL) return fail(40, "bad dimensions");
 
     double radcn2 = RADCN2ref;

@@ -86,6 +86,10 @@ double orc_bb_fn(double v, double fbeta);                                /* RTMm
 int orc_contnm_one(int64_t im, const double cntnm[7], double pave, double tave,
                    const double *wk, double wbroad, int64_t nmol, double v1, double v2,
                    double v1abs, double v2abs, int64_t nptabs, double *absrb);
+/* test instrumentation of the last orc_modm call on this thread: [0] Voigt-branch evaluations, [1] speed-dependent SDVOIGT
+ * calls, [2] CO2 lines on the Voigt branch, [3] of those XF=-1, [4] coupled non-CO2/O2 lines, [5] coupled O2 lines,
+ * [6] lines with XG outside {0,-1,-3,-5}, [7] Voigt-branch evaluations with the negative-frequency resonance */
+void orc_branch_counts(int64_t out[8]);
 uint64_t orc_line_key(int64_t mol, int64_t rec);  /* splitmix64 of (mol<<32 | rec), 1-based */
 const char *orc_last_error(void);
 

@@ -50,6 +50,7 @@ def oracle_lib(opt="O0"):
     lib.orc_line_key.restype = C.c_uint64
     lib.orc_line_key.argtypes = [I, I]
     lib.orc_last_error.restype = C.c_char_p
+    lib.orc_branch_counts.argtypes = [P]
     _orc[opt] = lib
     return lib
 
@@ -124,7 +125,10 @@ def oracle_modm(ls, wn, dvset, p, t, clw, nmol, wkl, wbrodl, scor, cntnm=(1.,) *
                       int(ibrd), _p(arrs[5]), C.byref(s), _p(selc), _p(selh), C.byref(nv))
     if rc:
         raise RuntimeError("orc_modm rc=%d: %s" % (rc, lib.orc_last_error().decode()))
-    return dict(o=o, o_by_mol=obm, oc=oc, o_clw=oclw, odxsec=odx, sel_count=selc, sel_hash=selh, n_voigt=nv.value)
+    br = np.zeros(8, np.int64)
+    lib.orc_branch_counts(_p(br))
+    return dict(o=o, o_by_mol=obm, oc=oc, o_clw=oclw, odxsec=odx, sel_count=selc, sel_hash=selh, n_voigt=nv.value,
+                branches=dict(zip(("voigt", "sdep", "co2", "co2_lc1", "generic_lc", "o2_lc", "other_flag", "neg_res"), br.tolist())))
 
 
 def oracle_calctmr(wn, t, tz, o):

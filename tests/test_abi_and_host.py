@@ -65,8 +65,15 @@ def test_tips_scor():
     assert s[0, 0] > 1.0 and api.tips_2003(22, 320.0)[0, 0] < 1.0      # Q grows with T
     with pytest.raises(api.MonortmError):
         api.tips_2003(22, 60.0)                                          # outside 70-3000 K -> STOP
+    # molecules 34..39: the reference does not stop at atomic oxygen -- it sets gi=1, QT=1
+    # (tips_2003.f90:233-238) so scor(34,1)=1; 35-38 come from their tables; for CH3OH (39) both qt_296 and qt_temp end
+    # up as the stale QT of the previous call (:260-268, 288-292), i.e. scor(39,1)=1 as well
+    s39 = api.tips_2003(39, 250.0)
+    assert s39[33, 0] == 1.0 and s39[38, 0] == 1.0
+    assert np.all(s39[34:38, 0] > 1.0) and s39[34, 1] > 1.0 and s39[36, 1] > 1.0 and s39[37, 1] > 1.0
+    assert np.array_equal(s39[:33], api.tips_2003(33, 250.0)[:33])
     with pytest.raises(api.MonortmError):
-        api.tips_2003(34, 250.0)                                         # molecule 34 (O): Q=0 -> STOP
+        api.tips_2003(40, 250.0)
 
 
 def test_tables_spot_values():

@@ -125,9 +125,10 @@ def test_error_behaviour_mirrors_reference_stops():
     with pytest.raises(api.MonortmError) as e:
         s.modm(wn, 0.0, pr["p"][:, 0], bad, pr["clw"][:, 0], 22, pr["wkl"][:, :, 0], pr["wbrodl"][:, 0], None)
     assert e.value.code == 11
-    # a malformed line store (LC flag not 1/3/5) is refused at staging
+    # a malformed line store (an XG that GET_LNFL cannot produce: it stores -IFLG for IFLG in 0..100 and the negative
+    # flags -1, -3, -5 themselves, lnfl_mod.f90:44-63, 73-77) is refused at staging
     ls = harness.copy_store(case["ls"])
-    ls.xg[0, 0] = -2.0
+    ls.xg[0, 0] = 2.0
     with pytest.raises(api.MonortmError) as e:
         s.stage_lines(ls)
     assert e.value.code == 5
