@@ -1275,3 +1275,26 @@ int orc_calctmr(int64_t nlayrs, int64_t nwn, const double *wn, const double *t,
     free(bbavec);
     return 0;
 }
+
+/* ---- building blocks exported for the reference-text pins (tests/test_ref_goldens.py) ---------------------- */
+double orc_lsf_lortz(double xf, double rp, double rp2, double aip, double bip, double hwhm, double wn, double xnu, int64_t mol)
+{
+    return lsf_lortz(xf, rp, rp2, aip, bip, hwhm, wn, xnu, mol);
+}
+double orc_lsf_sdvoigt(double xf, double rp, double rp2, double aip, double bip, double hwhm, double wn, double xnu,
+                       double ad, int64_t mol, double sdep)
+{
+    return lsf_sdvoigt(xf, rp, rp2, aip, bip, hwhm, wn, xnu, ad, mol, sdep);
+}
+double orc_halfwhm_d(int64_t mol, int64_t iso, double xnu, double t) { return halfwhm_d(mol, iso, xnu, t); }
+double orc_intens(double t, double s0s, double es, double radct, double t0, double xnus, double xipsf)
+{
+    return intens(t, s0s, es, radct, t0, xnus, xipsf);
+}
+double orc_xlorentz(double z) { return xlorentz(z); }
+/* XINT with 1-based arrays a[0..na-1] = A(1..na), r3[0..] = R3(1..) as the reference passes them */
+void orc_xint(double v1a, double v2a, double dva, const double *a, double afact, double vft, double dvr3, double *r3,
+              int64_t n1r3, int64_t n2r3)
+{
+    xint(v1a, v2a, dva, a, afact, vft, dvr3, r3, n1r3, n2r3);
+}

@@ -7,11 +7,17 @@
  * __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs
  * may load this library; the product (monortm_b200/) never does.
  *
- * PARITY UNPINNED: the reference ships no golden outputs, no TAPE3 line file
- * and cannot be compiled here (no Fortran compiler).
- * The restatement is pinned only by (i) analytic identities, (ii) an
- * independent scipy.special.wofz check of the Humlicek routine and (iii) the
- * reference's own input fixtures (run/in), see tests/test_oracle_*.py.
+ * PARITY PIN: the reference ships no golden outputs and no TAPE3 line file, and it cannot be COMPILED here (100 %
+ * Fortran, no Fortran compiler in the image), so there is no oracle/_ref binary.  Instead the
+ * reference's own source TEXT is executed: tools/f90fn.py translates /root/reference/src/{modm,contnm,RTMmono,
+ * lblrtm_sub,CloudOptProp,CntnmFactors,tips_2003,PhysConstants,PlanetEarth,lblparams}.f90 + isotope.incl mechanically,
+ * statement by statement, into Python (tools/ref_exec.py), and tools/gen_ref_goldens.py writes its outputs to
+ * tests/golden/ref_*.npz (scalar routines and whole MODM + CALCTMR + RTM cases, TIPS_2003 and CONTNM inside).
+ * tests/test_ref_goldens.py holds this restatement to those vectors: scalar routines to a few ulp, layer optical
+ * depths to 1e-13 (measured: 0 .. 4e-15), TB to 1e-9 K.  What that pin does not cover: libgfortran's own intrinsics
+ * (exp, log, pow, tanh here come from glibc / CPython) and the binary128 promotion of d0 literals in
+ * CloudOptProp.f90 under -fdefault-real-8 (modelled here with __float128; ~1e-14 relative on the cloud term).
+ * Further independent pins: from-scratch numpy physics checks and scipy.special.wofz (tests/test_oracle_units.py).
  *
  * All arrays are Fortran column-major, exactly as the reference holds them.
  */

@@ -3,7 +3,7 @@
 ! (modm.f90:282-283) finds its arrays.  GET_LNFL itself (binary TAPE3 I/O) is not translated: the golden generator fills
 ! these arrays from a LineStore.  IIM is the allocated second dimension (250000 in the reference; smaller here).
 MODULE LNFL_MOD
-   PARAMETER (MXMOL=39,IIM=4096,MXBRDMOL=7)
+   PARAMETER (MXMOL=39,IIM=8192,MXBRDMOL=7)
    INTEGER :: NBLM(mxmol),ISO(mxmol,IIM)
    REAL*8 :: XNU0(mxmol,IIM)
    REAL, dimension(mxmol,iim) ::  DELTNU,E,ALPS,ALPF,X,XG,S0,RMOL,SDEP

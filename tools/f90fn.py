@@ -1344,7 +1344,7 @@ class Emitter:
     def call(self, u, callee, args, pre):
         """-> (python call expression, [write-back statements using @R for the result tuple])"""
         parts, wb = [], []
-        mod_list = [a for a in callee.args if a in callee.modified]
+        mod_list = [a for a in callee.args if a in callee.modified and callee.vars[a].dims is None]
         for pos, a in enumerate(args):
             if a[0] == "kw":
                 dn, ae = a[1], a[2]
@@ -1561,7 +1561,7 @@ class Emitter:
     def ret(self, u):
         vals = [self.ref(u, u.result) if u.result else "None"]
         for a in u.args:
-            if a in u.modified:
+            if a in u.modified and u.vars[a].dims is None:       # arrays are associated by reference
                 vals.append(self.ref(u, a))
         return "(" + ", ".join(vals) + ("," if len(vals) == 1 else "") + ")"
 
