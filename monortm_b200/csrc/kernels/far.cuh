@@ -118,6 +118,9 @@ struct FarArgs {
     int32_t S;                // tiles of this level per parent tile
     int32_t combined;         // 1: one coefficient set, lines weighted by their molecule's column amount (nslot == 1)
     const double* planes;
+    const double* lcplanes;   // [L][LCP_NPLANES][nlc_pad]
+    const int32_t* lcidx;     // static per line
+    int32_t nlc_pad, pad1;
     const LayerDev* lay;
     double* coef;             // [tile][L][slot][kFarK]
     unsigned long long* counters;
@@ -143,7 +146,7 @@ __global__ void __launch_bounds__(128, MRTM_FAR_MINB) far_kernel(FarArgs a)
     const double* __restrict__ pH2 = pl + (size_t)D_H2 * a.n_pad;
     const double* __restrict__ pCN = pl + (size_t)D_CN * a.n_pad;
     const double* __restrict__ pP3 = pl + (size_t)D_P3 * a.n_pad;
-    const double* __restrict__ pP4 = pl + (size_t)D_P4 * a.n_pad;
+    const double* __restrict__ lcp = a.lcplanes + (size_t)L * LCP_NPLANES * a.nlc_pad;
     const int nseg = a.nseg;
     const int ptile = tile / a.S;
     const TileHdr th = a.hdr[tile];
@@ -235,7 +238,8 @@ __global__ void __launch_bounds__(128, MRTM_FAR_MINB) far_kernel(FarArgs a)
             const FarPiece fp = s_pc[pi];
             const double ws = weighted ? s_w[fp.info & 0xffff] : 1.;
             for (int q = fp.lo + tid; q < fp.lo + fp.n; q += NT) {
-                const double xnu = __ldg(pXNU + q), h2 = __ldg(pH2 + q), cg = ws * __ldg(pP3 + q), cq = ws * __ldg(pP4 + q);
+                const double xnu = __ldg(pXNU + q), h2 = __ldg(pH2 + q), cg = ws * __ldg(pP3 + q);
+                const double cq = ws * lc1_slope(__ldg(pCN + q), h2, lcp[(size_t)LCP_AIP * a.nlc_pad + a.lcidx[q]], ly.rp);
                 far_accum_mix(cen - xnu, h2, cg, cq, hh, m2h, mhh, A);
                 far_accum_mix(cen + xnu, h2, cg, -cq, hh, m2h, mhh, A);
             }
@@ -342,7 +346,7 @@ __global__ void __launch_bounds__(32 * kFarWarps, MRTM_FARW_MINB) far_warp_kerne
     const double* __restrict__ pH2 = pl + (size_t)D_H2 * a.n_pad;
     const double* __restrict__ pCN = pl + (size_t)D_CN * a.n_pad;
     const double* __restrict__ pP3 = pl + (size_t)D_P3 * a.n_pad;
-    const double* __restrict__ pP4 = pl + (size_t)D_P4 * a.n_pad;
+    const double* __restrict__ lcp = a.lcplanes + (size_t)L * LCP_NPLANES * a.nlc_pad;
     const int ptile = tile / a.S;
     double* sw = s_w[wid];
     for (int s = lane; s < nseg; s += 32) sw[s] = ly.wk[a.seg[s].mol - 1];
@@ -407,7 +411,8 @@ __global__ void __launch_bounds__(32 * kFarWarps, MRTM_FARW_MINB) far_warp_kerne
             const FarPiece fp = s_pc[pj];
             const double ws = sw[fp.info & 0xffff];
             for (int q = fp.lo + lane; q < fp.lo + fp.n; q += 32) {
-                const double xnu = __ldg(pXNU + q), h2 = __ldg(pH2 + q), cg = ws * __ldg(pP3 + q), cq = ws * __ldg(pP4 + q);
+                const double xnu = __ldg(pXNU + q), h2 = __ldg(pH2 + q), cg = ws * __ldg(pP3 + q);
+                const double cq = ws * lc1_slope(__ldg(pCN + q), h2, lcp[(size_t)LCP_AIP * a.nlc_pad + a.lcidx[q]], ly.rp);
                 far_accum_mix(cen - xnu, h2, cg, cq, hh, m2h, mhh, A);
                 far_accum_mix(cen + xnu, h2, cg, -cq, hh, m2h, mhh, A);
             }

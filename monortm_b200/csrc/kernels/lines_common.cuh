@@ -10,7 +10,7 @@
 struct SegWork;
 struct TileHdr;
 struct NearPiece;
-constexpr int kMaxLevels = 4;   // far-field hierarchy: level 0 = the line kernel's own tiles
+constexpr int kMaxLevels = 8;   // far-field hierarchy: level 0 = the line kernel's own tiles
 struct LinesArgs {
     int32_t nwn, nlay;            // frequencies in this call/chunk, layers per profile
     int32_t nseg, n_pad;
@@ -26,6 +26,9 @@ struct LinesArgs {
     double ffw_ratio;             // the same ratio for near2_kernel's in-warp expansion about the warp's own block
     unsigned long long* counters; // [2] far-field expansions, direct (line,frequency) evaluations (may be null)
     const double* planes;         // [L][D_NPLANES][n_pad]
+    const double* lcplanes;       // [L][LCP_NPLANES][nlc_pad] coupling coefficients of the coupled lines (compact)
+    const int32_t* lcidx_s;       // static per line: index into the compact coupling planes or -1
+    int32_t nlc_pad, pad1;
     const LayerDev* lay;          // [L]
     // far-field hierarchy: level 0 = this kernel's tiles, level lv tiles are S^lv times wider
     int32_t nlev, S;
@@ -50,6 +53,24 @@ struct LinesArgs {
     long long* sel_count; unsigned long long* sel_hash;   // same strides as o
     int* errflag;                                         // bit1: SDVOIGT negative real part
 };
+
+// the per-(line,layer) quantities that are not stored (see DPlane)
+struct ColdLine { double hw, ad, stild, aip, bip; };
+__device__ __forceinline__ ColdLine cold_line(const double* __restrict__ pl, int n_pad, int q, const int32_t* __restrict__ lcidx,
+                                              const double* __restrict__ lcp, int nlc_pad)
+{
+    ColdLine c;
+    c.hw = sqrt(pl[(size_t)D_H2 * n_pad + q]);
+    const double vt = pl[(size_t)D_VT * n_pad + q];
+    c.ad = vt >= 0. ? vt * 0.01 : 1.0;
+    c.stild = (pl[(size_t)D_CN * n_pad + q] * kPI) / c.hw;
+    const int lci = lcidx[q];
+    c.aip = lci >= 0 ? lcp[(size_t)LCP_AIP * nlc_pad + lci] : 0.;
+    c.bip = lci >= 0 ? lcp[(size_t)LCP_BIP * nlc_pad + lci] : 0.;
+    return c;
+}
+// first-order mixing slope of a CLS_O2_LC1 line: CN*AIP*(1/HWHM_C)*RP (modm.f90:781-782 regrouped), as derive_kernel would form it
+__device__ __forceinline__ double lc1_slope(double cn, double h2, double aip, double rp) { return cn * (aip * (1 / sqrt(h2)) * rp); }
 
 __device__ __forceinline__ int lower_bound_d(const double* a, int lo, int hi, double v)
 {   // first index in [lo,hi) with a[i] >= v

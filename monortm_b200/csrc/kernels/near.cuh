@@ -30,7 +30,7 @@ __global__ void __launch_bounds__(NT, (MRTM_LINES_MINB * 128) / NT) near_kernel(
     const double* __restrict__ pH2 = pl + (size_t)D_H2 * a.n_pad;
     const double* __restrict__ pCN = pl + (size_t)D_CN * a.n_pad;
     const double* __restrict__ pP3 = pl + (size_t)D_P3 * a.n_pad;
-    const double* __restrict__ pP4 = pl + (size_t)D_P4 * a.n_pad;
+    const double* __restrict__ lcp = a.lcplanes + (size_t)L * LCP_NPLANES * a.nlc_pad;
     const double* __restrict__ pVT = pl + (size_t)D_VT * a.n_pad;
 
     __shared__ __align__(8) uint64_t s_bar[kStages];
@@ -162,8 +162,9 @@ __global__ void __launch_bounds__(NT, (MRTM_LINES_MINB * 128) / NT) near_kernel(
         const int rem = a.nwn - base;
         nvalid = rem < NT * F ? rem : NT * F;
     }
-    // a layer without Voigt-capable lines runs its Voigt zones as plain near-field ranges
-    const int vmode_mask = voigt_possible(a.layer_voigt, L, a.hdr[0][blockIdx.x].whi) ? 0xff : (0xff & ~M_VOIGT);
+    // every pair is evaluated with the Lorentz form here; voigt_kernel replaces it by the Voigt form where the reference
+    // takes that branch (modm.f90:427), so the plan's Voigt zones run as plain near-field ranges
+    const int vmode_mask = 0xff & ~M_VOIGT;
     int cur_mol = 0;
     auto finish_mol = [&](int mol) {
         if (mol <= 0) return;
@@ -363,14 +364,15 @@ MRTM_UNROLL(MRTM_UNROLL_BOTH)
             for (int r = 0; r < wk.nrun; r++) {
                 if (a.counters) n_direct += (long long)(wk.run_hi[r] - wk.run_lo[r]) * nvalid;
                 for (int q = wk.run_lo[r]; q < wk.run_hi[r]; q++) {
-                    const double xnu = pXNU[q], h2 = pH2[q], cg = pP3[q], cq = pP4[q], vt = pVT[q];
+                    const double xnu = pXNU[q], h2 = pH2[q], cg = pP3[q];
+                    const double cq = lc1_slope(pCN[q], h2, lcp[(size_t)LCP_AIP * a.nlc_pad + a.lcidx_s[q]], rp);
 #pragma unroll
                     for (int f = 0; f < F; f++) {
                         const double dm = wn[f] - xnu, sp = wn[f] + xnu;
                         const double r1 = rcp3(fma(dm, dm, h2));
                         const double r2 = rcp3(fma(sp, sp, h2));
                         const double val = fma(cq, dm, cg) * r1 + fma(-cq, sp, cg) * r2;
-                        sf[f] += (fabs(dm) <= vt) ? 0. : val;           // Voigt-branch pairs: voigt_kernel
+                        sf[f] += val;                                   // Voigt-branch pairs: corrected by voigt_kernel
                     }
                 }
             }
@@ -378,9 +380,8 @@ MRTM_UNROLL(MRTM_UNROLL_BOTH)
             if (a.counters) n_direct += (long long)(wk.q1 - wk.q0) * nvalid;
             for (int q = wk.q0; q < wk.q1; q++) {
                 const double xnu = pXNU[q], vt = pVT[q];
-                const double hw = pl[(size_t)D_H * a.n_pad + q], ad = pl[(size_t)D_AD * a.n_pad + q];
-                const double st = pl[(size_t)D_STILD * a.n_pad + q];
-                const double aip = pl[(size_t)D_AIP * a.n_pad + q], bip = pl[(size_t)D_BIP * a.n_pad + q];
+                const ColdLine cl = cold_line(pl, a.n_pad, q, a.lcidx_s, lcp, a.nlc_pad);
+                const double hw = cl.hw, ad = cl.ad, st = cl.stild, aip = cl.aip, bip = cl.bip;
                 const int xf = a.xf_s[q];
 #pragma unroll
                 for (int f = 0; f < F; f++) {
@@ -448,7 +449,7 @@ __global__ void __launch_bounds__(NT, MRTM_NEAR2_MINB) near2_kernel(LinesArgs a)
     const double* __restrict__ pH2 = pl + (size_t)D_H2 * a.n_pad;
     const double* __restrict__ pCN = pl + (size_t)D_CN * a.n_pad;
     const double* __restrict__ pP3 = pl + (size_t)D_P3 * a.n_pad;
-    const double* __restrict__ pP4 = pl + (size_t)D_P4 * a.n_pad;
+    const double* __restrict__ lcp = a.lcplanes + (size_t)L * LCP_NPLANES * a.nlc_pad;
     const double* __restrict__ pVT = pl + (size_t)D_VT * a.n_pad;
 
     __shared__ __align__(8) uint64_t s_all_bar;
@@ -562,7 +563,7 @@ __global__ void __launch_bounds__(NT, MRTM_NEAR2_MINB) near2_kernel(LinesArgs a)
     const double Rn = a.ffw_ratio * hh, R2 = Rn * Rn;
     const double m2h = -2. * hh, mhh = -hh * hh;
     const double rp = ly.rp, rp2 = ly.rp2;
-    const int vmode_mask = voigt_possible(a.layer_voigt, L, th.whi) ? 0xff : (0xff & ~M_VOIGT);
+    const int vmode_mask = 0xff & ~M_VOIGT;       // Voigt-branch pairs: Lorentz here, corrected by voigt_kernel
     // a line is in at most one list: D1 and T1 grow from the front of their array, D2 and T2 from the back
     unsigned short* lD1 = s_list + (size_t)(wid * 2 + 0) * kListLen;
     unsigned short* lD2 = lD1 + (kListLen - 1);
@@ -814,14 +815,15 @@ MRTM_UNROLL(MRTM_UNROLL_BOTH)
                 for (int r = 0; r < wk.nrun; r++) {
                     if (a.counters) n_direct += (long long)(wk.run_hi[r] - wk.run_lo[r]) * nvalid_w;
                     for (int q = wk.run_lo[r]; q < wk.run_hi[r]; q++) {
-                        const double xnu = pXNU[q], h2 = pH2[q], cg = pP3[q], cq = pP4[q], vt = pVT[q];
+                        const double xnu = pXNU[q], h2 = pH2[q], cg = pP3[q];
+                    const double cq = lc1_slope(pCN[q], h2, lcp[(size_t)LCP_AIP * a.nlc_pad + a.lcidx_s[q]], rp);
 #pragma unroll
                         for (int f = 0; f < F; f++) {
                             const double dm = wn[f] - xnu, sp = wn[f] + xnu;
                             const double r1 = rcp3(fma(dm, dm, h2));
                             const double r2 = rcp3(fma(sp, sp, h2));
                             const double val = fma(cq, dm, cg) * r1 + fma(-cq, sp, cg) * r2;
-                            ss[f] += (fabs(dm) <= vt) ? 0. : val;           // Voigt-branch pairs: voigt_kernel
+                            ss[f] += val;                                   // Voigt-branch pairs: corrected by voigt_kernel
                         }
                     }
                 }
@@ -829,9 +831,8 @@ MRTM_UNROLL(MRTM_UNROLL_BOTH)
                 if (a.counters) n_direct += (long long)(wk.q1 - wk.q0) * nvalid_w;
                 for (int q = wk.q0; q < wk.q1; q++) {
                     const double xnu = pXNU[q], vt = pVT[q];
-                    const double hw = pl[(size_t)D_H * a.n_pad + q], ad = pl[(size_t)D_AD * a.n_pad + q];
-                    const double st = pl[(size_t)D_STILD * a.n_pad + q];
-                    const double aip = pl[(size_t)D_AIP * a.n_pad + q], bip = pl[(size_t)D_BIP * a.n_pad + q];
+                    const ColdLine cl = cold_line(pl, a.n_pad, q, a.lcidx_s, lcp, a.nlc_pad);
+                    const double hw = cl.hw, ad = cl.ad, st = cl.stild, aip = cl.aip, bip = cl.bip;
                     const int xf = a.xf_s[q];
 #pragma unroll
                     for (int f = 0; f < F; f++) {

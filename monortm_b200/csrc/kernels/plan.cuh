@@ -19,7 +19,57 @@ struct PlanArgs {
     int32_t S, pad2;                          // tiles of this level per parent tile
     FarPiece* pieces;                         // [ntiles][nseg*kPiecePerSeg]
     NearPiece* near_pieces;                   // [ntiles][kMaxNearPieces] (level 0 only, may be null)
+    const int* replan;                        // plan cache: 0 = the plans of the previous call are still valid, leave them
 };
+
+// ---- plan cache ------------------------------------------------------------------------------------------------
+// The plans depend on the frequencies, the staged centres and two kinds of margins (largest line shift, largest Voigt-zone
+// rate per segment, both maxima over the layers of the call).  A repeated call on the same frequency list (the steps of a
+// sweep, the batches of an ensemble) reuses them: wn_hash_kernel hashes the list, plan_check_kernel compares the hash and
+// checks that the margins the cached plans were built with still cover this call's; the plan kernels return at once when
+// they do.  Everything stays on the device: no host synchronisation.
+__global__ void wn_hash_kernel(const double* __restrict__ wn, int n, unsigned long long* acc)
+{
+    unsigned long long h = 0ull;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        unsigned long long z = (unsigned long long)__double_as_longlong(wn[i]) + 0x9E3779B97F4A7C15ull * (unsigned long long)(i + 1);
+        z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+        z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+        h += z ^ (z >> 31);
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) h += __shfl_xor_sync(0xffffffffu, h, off);
+    if ((threadIdx.x & 31) == 0) atomicAdd(acc, h);
+}
+struct PlanCheckArgs {
+    const unsigned long long* need;           // [1 + nseg] this call's margins (bits of non-negative doubles): shift, Voigt rates
+    unsigned long long* have;                 // [1 + nseg] the margins the cached plans were built with (the plan kernels read these)
+    unsigned long long* hash;                 // [2] this call's frequency hash (cleared here for the next call), the cached one
+    int nseg, force;
+    int* replan;
+};
+__global__ void plan_check_kernel(PlanCheckArgs a)
+{
+    __shared__ int s_re;
+    if (threadIdx.x == 0) s_re = (a.force || a.hash[0] != a.hash[1]) ? 1 : 0;
+    __syncthreads();
+    for (int i = threadIdx.x; i <= a.nseg; i += blockDim.x)
+        if (a.need[i] > a.have[i]) s_re = 1;              // non-negative doubles order like their bit patterns
+    __syncthreads();
+    if (s_re) {
+        // rebuild with some head room so that the neighbouring profiles of an ensemble still fit
+        for (int i = threadIdx.x; i <= a.nseg; i += blockDim.x) {
+            const double v = __longlong_as_double((long long)a.need[i]);
+            a.have[i] = (unsigned long long)__double_as_longlong(v * (i == 0 ? 1.25 : 1.08));
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        *a.replan = s_re;
+        a.hash[1] = a.hash[0];
+        a.hash[0] = 0ull;
+    }
+}
 
 __global__ void __launch_bounds__(128) plan_kernel(PlanArgs a)
 {
@@ -27,6 +77,7 @@ __global__ void __launch_bounds__(128) plan_kernel(PlanArgs a)
     extern __shared__ __align__(128) unsigned char s_dyn[];
     SegWork* s_work = reinterpret_cast<SegWork*>(s_dyn);
     __shared__ double s_lo[4], s_hi[4];
+    if (a.replan && *a.replan == 0) return;           // cached plans are valid
     const int tid = threadIdx.x;
     const int tile = blockIdx.x;
     const int i0 = tile * a.tile_freqs;

@@ -314,6 +314,8 @@ struct DeriveArgs {
     double sclcpl, sclhw, y0res;
     int32_t ibrd, pad;
     double* planes;           // [L][D_NPLANES][n_pad]
+    double* lcplanes;         // [L][LCP_NPLANES][nlc_pad]
+    int32_t nlc_pad, pad3;
     unsigned long long* layer_voigt;   // [L] bits of the smallest |Xnu| among the lines of the layer that can take the Voigt branch
                                        // (zeta <= 0.99; 100*HWHM_D grows with |Xnu|), all ones = none
     int32_t nseg, pad2;
@@ -333,13 +335,7 @@ __device__ __forceinline__ unsigned long long derive_one(const DeriveArgs& a, in
         pl[(size_t)D_H2 * a.ln.n_pad + q] = 1.0;
         pl[(size_t)D_CN * a.ln.n_pad + q] = 0.;
         pl[(size_t)D_P3 * a.ln.n_pad + q] = 0.;
-        pl[(size_t)D_P4 * a.ln.n_pad + q] = 0.;
-        pl[(size_t)D_H * a.ln.n_pad + q] = 1.0;
-        pl[(size_t)D_AD * a.ln.n_pad + q] = 1.0;
         pl[(size_t)D_VT * a.ln.n_pad + q] = -1.0;
-        pl[(size_t)D_STILD * a.ln.n_pad + q] = 0.;
-        pl[(size_t)D_AIP * a.ln.n_pad + q] = 0.;
-        pl[(size_t)D_BIP * a.ln.n_pad + q] = 0.;
         return kNone;
     }
     const LayerDev& ly = a.lay[L];
@@ -415,25 +411,21 @@ __device__ __forceinline__ unsigned long long derive_one(const DeriveArgs& a, in
 
     const double h2 = hwhm_c * hwhm_c;
     const double cn = stild * hwhm_c / kPI;
-    double p3 = 0., p4 = 0.;
+    double p3 = 0.;
     if (cls == CLS_PED) p3 = cn / (kDELTNUC * kDELTNUC + h2);
-    if (cls == CLS_O2_LC1) {
-        p3 = cn * (1. + bip * ly.rp2);
-        p4 = cn * (aip * (1 / hwhm_c) * ly.rp);
-    }
+    if (cls == CLS_O2_LC1) p3 = cn * (1. + bip * ly.rp2);
     const size_t np = a.ln.n_pad;
     pl[(size_t)D_XNU * np + q] = xnu;
     pl[(size_t)D_H2 * np + q] = h2;
     pl[(size_t)D_CN * np + q] = cn;
     pl[(size_t)D_P3 * np + q] = p3;
-    pl[(size_t)D_P4 * np + q] = p4;
-    pl[(size_t)D_H * np + q] = hwhm_c;
-    pl[(size_t)D_AD * np + q] = hwhm_d;
     const double vt = (zeta > 0.99) ? -1.0 : 100. * hwhm_d;
     pl[(size_t)D_VT * np + q] = vt;
-    pl[(size_t)D_STILD * np + q] = stild;
-    pl[(size_t)D_AIP * np + q] = aip;
-    pl[(size_t)D_BIP * np + q] = bip;
+    if (lci >= 0) {
+        double* lcp = a.lcplanes + (size_t)L * LCP_NPLANES * a.nlc_pad;
+        lcp[(size_t)LCP_AIP * a.nlc_pad + lci] = aip;
+        lcp[(size_t)LCP_BIP * a.nlc_pad + lci] = bip;
+    }
     return (vt >= 0.) ? (unsigned long long)__double_as_longlong(fabs(xnu)) : kNone;
 }
 

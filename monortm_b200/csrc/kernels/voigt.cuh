@@ -3,8 +3,10 @@
 // =============================================================================================
 // voigt_kernel: the Voigt branch (modm.f90:427-431).  CTA = (frequency tile, layer, profile); it leaves
 // at once when the layer has no Voigt-capable line.  For the lines of the plan's Voigt zones it applies
-// the reference's test |WN-Xnu| <= 100*HWHM_D per (line, frequency) and adds W*STILD*SLS of the pairs that
-// pass (the near kernels skipped exactly those) to O [and O_BY_MOL].
+// the reference's test |WN-Xnu| <= 100*HWHM_D per (line, frequency) and, for the pairs that pass, adds
+// W*STILD*(SLS_Voigt - SLS_Lorentz) to O [and O_BY_MOL]: the near- and far-field kernels evaluate every pair with the
+// Lorentz form (they never look at the Doppler width), this kernel replaces it where the reference takes the Voigt
+// branch.  Same result as evaluating those pairs once with the Voigt form, to rounding.
 // Each warp owns a contiguous block of 32*F frequencies and walks it in F sub-blocks of 32.  Per sub-block
 // the lanes first cull the staged zone lines against the sub-block's frequency extent (one line per lane,
 // exact: the rounded difference WN-Xnu is monotone in WN) into a compact list, so the per-(line,frequency)
@@ -25,11 +27,10 @@ __global__ void __launch_bounds__(NT, MRTM_VOIGT_MINB) voigt_kernel(LinesArgs a)
     const double* pl = a.planes + (size_t)L * D_NPLANES * a.n_pad;
     const double* __restrict__ pXNU = pl + (size_t)D_XNU * a.n_pad;
     const double* __restrict__ pVT = pl + (size_t)D_VT * a.n_pad;
-    const double* __restrict__ pH = pl + (size_t)D_H * a.n_pad;
-    const double* __restrict__ pAD = pl + (size_t)D_AD * a.n_pad;
-    const double* __restrict__ pST = pl + (size_t)D_STILD * a.n_pad;
-    const double* __restrict__ pAIP = pl + (size_t)D_AIP * a.n_pad;
-    const double* __restrict__ pBIP = pl + (size_t)D_BIP * a.n_pad;
+    const double* __restrict__ pH2 = pl + (size_t)D_H2 * a.n_pad;
+    const double* __restrict__ pCN = pl + (size_t)D_CN * a.n_pad;
+    const double* __restrict__ pP3 = pl + (size_t)D_P3 * a.n_pad;
+    const double* __restrict__ lcp = a.lcplanes + (size_t)L * LCP_NPLANES * a.nlc_pad;
     const SegWork* plan = a.plan[0] + (size_t)blockIdx.x * a.nseg;
     // The zone lines of all segments are staged together (one barrier pair per CTA in the usual case), and per zone
     // line, once per CTA (amortised over the NT*F frequencies), everything of LSF_SDVOIGT/SDVOIGT that does not depend
@@ -42,6 +43,8 @@ __global__ void __launch_bounds__(NT, MRTM_VOIGT_MINB) voigt_kernel(LinesArgs a)
     // fast path (generic uncoupled line, single resonance, Humlicek region I): Re w = y*(a+q)/(q*(q+b)+a*a), q = x*x,
     // a = .5+y*y, b = 2*y*y-1 -- the reference's t*.5641896/(.5+t*t) (modm.f90:1105) multiplied out
     __shared__ double s_fa[kVCap], s_fb[kVCap], s_fa2[kVCap], s_fcy[kVCap], s_fcpd[kVCap];
+    // the Lorentz form the other kernels added for the same pair: H2, W*CN, W*P3 (pedestal or mixing numerator), W*P4
+    __shared__ double s_h2[kVCap], s_cn[kVCap], s_p3[kVCap], s_p4[kVCap];
     __shared__ unsigned short s_list[NW][kVCap];
     __shared__ int s_zlo[kMaxSegments], s_zoff[kMaxSegments + 1];
     const int base = blockIdx.x * (NT * F) + wid * (32 * F);
@@ -91,8 +94,16 @@ __global__ void __launch_bounds__(NT, MRTM_VOIGT_MINB) voigt_kernel(LinesArgs a)
             s_kind[i] = (unsigned char)kind;
             s_mol[i] = (unsigned char)mol;
             if (vt >= 0.) {
-                const double hw = __ldg(pH + q), ad = __ldg(pAD + q);
+                const ColdLine cl = cold_line(pl, a.n_pad, q, a.lcidx_s, lcp, a.nlc_pad);
+                const double hw = cl.hw, ad = cl.ad;
                 const double zeta = hw / (hw + ad);
+                {
+                    const double wl = by_mol ? 1. : ly.wk[mol - 1];
+                    s_h2[i] = __ldg(pH2 + q);
+                    s_cn[i] = wl * __ldg(pCN + q);
+                    s_p3[i] = wl * __ldg(pP3 + q);
+                    s_p4[i] = (kind == 3) ? wl * lc1_slope(__ldg(pCN + q), s_h2[i], cl.aip, rp) : 0.;
+                }
                 if (fabs(__ldg(a.sdep_s + q)) > 1.0e-4 || !(zeta < 1.0)) {
                     s_inv[i] = -1.;        // speed dependence / degenerate Doppler width: the general routine per pair
                     s_c[i] = by_mol ? 1. : ly.wk[mol - 1];
@@ -102,10 +113,10 @@ __global__ void __launch_bounds__(NT, MRTM_VOIGT_MINB) voigt_kernel(LinesArgs a)
                     const double wgt = by_mol ? 1. : ly.wk[mol - 1];           // one sum over all molecules: weight folded in
                     s_inv[i] = inv;
                     s_y[i] = y;
-                    s_c[i] = wgt * (__ldg(pST + q) * (0.46971863934982516 * inv));   // sqrt(log(2)/PI), 13-digit PI
+                    s_c[i] = wgt * (cl.stild * (0.46971863934982516 * inv));   // sqrt(log(2)/PI), 13-digit PI
                     s_pd[i] = (kind == 0) ? w4_re_fast(sl2 * (kDELTNUC * inv), y) : 0.;
-                    s_g[i] = (kind == 3) ? (__ldg(pAIP + q) * (1 / hw) * rp) : 0.;
-                    s_b[i] = (kind == 3) ? (__ldg(pBIP + q) * rp2) : 0.;
+                    s_g[i] = (kind == 3) ? (cl.aip * (1 / hw) * rp) : 0.;
+                    s_b[i] = (kind == 3) ? (cl.bip * rp2) : 0.;
                     if (kind == 0 && vt <= kDELTNUC) {      // inside the zone the window test cannot fail
                         const double y2 = y * y, aa = .5 + y2;
                         s_fa[i] = aa;
@@ -167,6 +178,16 @@ __global__ void __launch_bounds__(NT, MRTM_VOIGT_MINB) voigt_kernel(LinesArgs a)
                 }
                 many = false;
             };
+            // what the near / far kernels added for this pair (their regrouped Lorentz forms, modm.f90:742-791)
+            auto lorentz_of = [&](const int i, const int kind, const double dm, const double sp, const bool second) -> double {
+                const double h2 = s_h2[i], cn = s_cn[i];
+                const double r1 = rcp3(fma(dm, dm, h2));
+                if (kind == 3) return fma(s_p4[i], dm, s_p3[i]) * r1 + fma(-s_p4[i], sp, s_p3[i]) * rcp3(fma(sp, sp, h2));
+                double v = cn * r1;
+                if (second) v = fma(cn, rcp3(fma(sp, sp, h2)), v);
+                if (kind == 0) v -= (second ? 2. : 1.) * s_p3[i];
+                return v;
+            };
             auto one = [&](const int ent) {
                 const int i = ent & 0xff;
                 if (by_mol && (int)s_mol[i] != cur_mol) {
@@ -179,12 +200,13 @@ __global__ void __launch_bounds__(NT, MRTM_VOIGT_MINB) voigt_kernel(LinesArgs a)
                     if (fabs(dm) <= s_vt[i]) {
                         const double y = s_y[i];
                         const double x = sl2 * (dm * s_inv[i]);
+                        const double lor = fma(s_cn[i], rcp3(fma(dm, dm, s_h2[i])), -s_p3[i]);
                         if (!(fabs(x) + y < 15.)) {
                             const double q = x * x;
                             const double den = fma(q, q + s_fb[i], s_fa2[i]);
-                            msum += fma(s_fcy[i] * (s_fa[i] + q), rcp3(den), -s_fcpd[i]);
+                            msum += fma(s_fcy[i] * (s_fa[i] + q), rcp3(den), -s_fcpd[i]) - lor;
                         } else {
-                            msum = fma(s_c[i], w4_re_near(x, y), msum) - s_fcpd[i];
+                            msum = (fma(s_c[i], w4_re_near(x, y), msum) - s_fcpd[i]) - lor;
                         }
                         many = true;
                     }
@@ -194,8 +216,12 @@ __global__ void __launch_bounds__(NT, MRTM_VOIGT_MINB) voigt_kernel(LinesArgs a)
                 const bool inwin = (kind <= 1) ? !(fabs(dm) > kDELTNUC) : true;
                 if (inwin && fabs(dm) <= s_vt[i]) {
                     const double inv = s_inv[i];
+                    {
+                        const double spl = wn + xnu;
+                        msum -= lorentz_of(i, kind, dm, spl, (kind >= 2) || ((spl - kDELTNUC) <= 0.));
+                    }
                     if (inv < 0.) {
-                        msum = fma(s_c[i], voigt_lines_term(kind, wn, xnu, pl, a.n_pad, s_q[i], a.sdep_s[s_q[i]], rp, rp2, &err), msum);
+                        msum = fma(s_c[i], voigt_lines_term(kind, wn, xnu, cold_line(pl, a.n_pad, s_q[i], a.lcidx_s, lcp, a.nlc_pad), a.sdep_s[s_q[i]], rp, rp2, &err), msum);
                     } else {
                         const double y = s_y[i], sp = wn + xnu;
                         const bool second = (kind >= 2) || ((sp - kDELTNUC) <= 0.);
@@ -229,8 +255,10 @@ __global__ void __launch_bounds__(NT, MRTM_VOIGT_MINB) voigt_kernel(LinesArgs a)
                     const double den0 = fma(q0, q0 + s_fb[i0], s_fa2[i0]), den1 = fma(q1, q1 + s_fb[i1], s_fa2[i1]);
                     const double v0 = fma(s_fcy[i0] * (s_fa[i0] + q0), rcp3(den0), -s_fcpd[i0]);
                     const double v1 = fma(s_fcy[i1] * (s_fa[i1] + q1), rcp3(den1), -s_fcpd[i1]);
-                    if (in0) msum = r0 ? (msum + v0) : (fma(s_c[i0], w4_re_near(x0, y0), msum) - s_fcpd[i0]);
-                    if (in1) msum = r1 ? (msum + v1) : (fma(s_c[i1], w4_re_near(x1, y1), msum) - s_fcpd[i1]);
+                    const double l0 = fma(s_cn[i0], rcp3(fma(dm0, dm0, s_h2[i0])), -s_p3[i0]);
+                    const double l1 = fma(s_cn[i1], rcp3(fma(dm1, dm1, s_h2[i1])), -s_p3[i1]);
+                    if (in0) msum = (r0 ? (msum + v0) : (fma(s_c[i0], w4_re_near(x0, y0), msum) - s_fcpd[i0])) - l0;
+                    if (in1) msum = (r1 ? (msum + v1) : (fma(s_c[i1], w4_re_near(x1, y1), msum) - s_fcpd[i1])) - l1;
                     many = many || in0 || in1;
                 }
             }

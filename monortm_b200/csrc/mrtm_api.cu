@@ -62,7 +62,18 @@ struct mrtm_ctx {
     DevBuf b_ov;
     int use_side = 1;                             // MRTM_SIDE_STREAM=0: everything on one stream
     int use_near2 = 1;                            // per-warp re-planning near-field kernel (MRTM_NEAR2=0 disables)
-    DevBuf b_layer, b_scorc, b_absrb, b_planes, b_o, b_obm, b_oc, b_in[16], b_out[16], b_sel[2], b_tmps, b_fbeta;
+    int use_near3 = 1;                            // plan-driven near-field kernel of the production path (MRTM_NEAR3=0: near2_kernel)
+    int force_f = 0;                              // MRTM_LINES_F: frequencies per thread of the line kernels (1, 2, 4; 0 = chosen per call)
+    int near3_lb = 0;                             // layers per CTA of near3_kernel (MRTM_NEAR3_LB; 0 = chosen per call)
+    DevBuf b_t3, b_pool3, b_segof3;
+    // plan cache (see kernels/plan.cuh): margins the cached plans were built with, frequency hashes, replan flag
+    DevBuf b_pcache;
+    int use_plan_cache = 1;                       // MRTM_PLAN_CACHE=0: rebuild the plans on every call
+    int64_t stage_gen = 0;                        // bumped by mrtm_stage_lines
+    struct PlanKey { int64_t nwn, stage_gen, batch_layers; int F, nlev, S, nseg, near2, near3; double ff_ratio, ffw_ratio; const void* bufs[4 * kMaxLevels + 4]; };
+    PlanKey plan_key;
+    bool plan_key_valid = false;
+    DevBuf b_layer, b_scorc, b_absrb, b_planes, b_lcplanes, b_o, b_obm, b_oc, b_in[16], b_out[16], b_sel[2], b_tmps, b_fbeta;
     mrtm_stats st;
     size_t planes_budget = (size_t)8 << 30;
 };
@@ -170,6 +181,10 @@ extern "C" int mrtm_init(int device, mrtm_ctx** out)
     if (const char* s = std::getenv("MRTM_PLANES_GB")) ctx->planes_budget = (size_t)(std::atof(s) * (double)(1ull << 30));
     if (const char* s = std::getenv("MRTM_FF_LEVELS")) ctx->ff_levels = std::min(std::max(std::atoi(s), 1), kMaxLevels);
     if (const char* s = std::getenv("MRTM_NEAR2")) ctx->use_near2 = std::atoi(s) != 0;
+    if (const char* s = std::getenv("MRTM_PLAN_CACHE")) ctx->use_plan_cache = std::atoi(s) != 0;
+    if (const char* s = std::getenv("MRTM_NEAR3")) ctx->use_near3 = std::atoi(s) != 0;
+    if (const char* s = std::getenv("MRTM_LINES_F")) ctx->force_f = std::atoi(s);
+    if (const char* s = std::getenv("MRTM_NEAR3_LB")) ctx->near3_lb = std::max(std::atoi(s), 0);
     if (const char* s = std::getenv("MRTM_FFW_RATIO")) ctx->ffw_ratio = std::max(std::atof(s), 4.0);
     if (const char* s = std::getenv("MRTM_FARW_MIN")) ctx->farw_min = std::atoll(s);
     if (const char* s = std::getenv("MRTM_FF_S")) ctx->ff_S = std::min(std::max(std::atoi(s), 2), 64);
@@ -209,7 +224,7 @@ extern "C" int mrtm_free(mrtm_ctx* ctx)
     cudaStreamSynchronize(ctx->stream);
     free_lines(ctx);
     for (void* p : ctx->table_allocs) cudaFree(p);
-    DevBuf* bufs[] = {&ctx->b_ov, &ctx->b_lvoigt, &ctx->b_vtmax, &ctx->b_layer, &ctx->b_scorc, &ctx->b_absrb, &ctx->b_planes, &ctx->b_o, &ctx->b_obm, &ctx->b_oc, &ctx->b_sel[0], &ctx->b_sel[1], &ctx->b_tmps, &ctx->b_fbeta, &ctx->b_npieces};
+    DevBuf* bufs[] = {&ctx->b_pcache, &ctx->b_t3, &ctx->b_pool3, &ctx->b_segof3, &ctx->b_ov, &ctx->b_lvoigt, &ctx->b_vtmax, &ctx->b_layer, &ctx->b_scorc, &ctx->b_absrb, &ctx->b_planes, &ctx->b_lcplanes, &ctx->b_o, &ctx->b_obm, &ctx->b_oc, &ctx->b_sel[0], &ctx->b_sel[1], &ctx->b_tmps, &ctx->b_fbeta, &ctx->b_npieces};
     for (DevBuf* b : bufs) if (b->p) cudaFree(b->p);
     for (int i = 0; i < kMaxLevels; i++) {
         if (ctx->b_plan[i].p) cudaFree(ctx->b_plan[i].p);
@@ -281,6 +296,8 @@ extern "C" int mrtm_stage_lines(mrtm_ctx* ctx, const int64_t nblm[MRTM_MXMOL], i
         ctx->tips.row = rd;
     }
     ctx->have_lines = true;
+    ctx->stage_gen++;
+    ctx->plan_key_valid = false;
     ctx->st.lines_staged = h.n;
     return MRTM_OK;
 }
@@ -348,11 +365,15 @@ struct RunDesc {
 };
 
 template <int F, int NT>
-static void launch_lines(const LinesArgs& la, dim3 grid, bool sel, cudaStream_t s, cudaEvent_t far_done, cudaStream_t sv)
+static void launch_lines(const LinesArgs& la, dim3 grid, bool sel, cudaStream_t s, cudaEvent_t far_done, cudaStream_t sv,
+                         const Near3Args* n3)
 {
     // near field (direct), Voigt branch, then polynomial + continuum + totals
     const size_t dyn = sizeof(double) * kStages * 4 * kTile + (size_t)std::max(la.nseg, 1) * sizeof(SegWork);
-    if (la.near_pieces) {       // tiles whose direct lines fit the staging area: per-warp re-planning kernel
+    if (la.near_pieces && n3 && F == 4) {      // production path: plan-driven lists, a group of layers per CTA
+        cudaFuncSetAttribute(near3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kN3Smem);
+        near3_kernel<<<dim3(grid.x, (grid.y + n3->lb - 1) / n3->lb, grid.z), 256, kN3Smem, s>>>(la, *n3);
+    } else if (la.near_pieces) {       // tiles whose direct lines fit the staging area: per-warp re-planning kernel
         const size_t dyn2 = sizeof(double) * 4 * (kNearCap + 8) + sizeof(unsigned short) * (NT / 32) * 2 * (kNearCap + 8) + kNearCap +
                             sizeof(NearPiece) * kMaxNearPieces + (size_t)std::max(la.nseg, 1) * sizeof(SegWork);
         if (sel) {
@@ -407,6 +428,7 @@ static int run_device(mrtm_ctx* ctx, const RunDesc& r, cudaStream_t s)
 
     const HostLines& h = ctx->hl;
     const int n_pad = r.do_lines ? (int)h.n_pad : 0;
+    const int nlc_pad = r.do_lines ? (int)(((h.lc.size() / 16) + 8) & ~(size_t)7) : 8;
     // profiles per batch
     int64_t B = r.nprof;
     if (r.do_lines) {
@@ -436,6 +458,7 @@ static int run_device(mrtm_ctx* ctx, const RunDesc& r, cudaStream_t s)
         if ((rc = ensure(ctx, ctx->b_scorc, (size_t)B * nlay * std::max(1, (int)ctx->ld.nsi) * 8))) return rc;
         if ((rc = ensure(ctx, ctx->b_absrb, (size_t)B * nlay * 3 * nptabs_pad * 8))) return rc;
         if ((rc = ensure(ctx, ctx->b_planes, (size_t)B * nlay * D_NPLANES * (size_t)n_pad * 8))) return rc;
+        if ((rc = ensure(ctx, ctx->b_lcplanes, (size_t)B * nlay * LCP_NPLANES * (size_t)nlc_pad * 8))) return rc;
         if ((rc = ensure(ctx, ctx->b_vtmax, (1 + std::max<size_t>(1, h.segments.size())) * 8))) return rc;
         CU(cudaMemsetAsync(ctx->errflag_dev, 0, sizeof(int), s));
         CU(cudaMemsetAsync(ctx->counters_dev, 0, 2 * sizeof(unsigned long long), s));
@@ -503,6 +526,8 @@ static int run_device(mrtm_ctx* ctx, const RunDesc& r, cudaStream_t s)
             da.y0res = r.y0res;
             da.ibrd = (int32_t)r.ibrd;
             da.planes = (double*)ctx->b_planes.p;
+            da.lcplanes = (double*)ctx->b_lcplanes.p;
+            da.nlc_pad = nlc_pad;
             da.nseg = (int32_t)h.segments.size();
             if ((rc = ensure(ctx, ctx->b_lvoigt, (size_t)Lb * sizeof(unsigned long long)))) return rc;
             CU(cudaMemsetAsync(ctx->b_lvoigt.p, 0xff, (size_t)Lb * sizeof(unsigned long long), s));
@@ -533,6 +558,9 @@ static int run_device(mrtm_ctx* ctx, const RunDesc& r, cudaStream_t s)
             la.counters = ctx->counters_dev;
             la.layer_voigt = (const unsigned long long*)ctx->b_lvoigt.p;
             la.planes = (const double*)ctx->b_planes.p;
+            la.lcplanes = (const double*)ctx->b_lcplanes.p;
+            la.lcidx_s = ctx->ld.lcidx;
+            la.nlc_pad = nlc_pad;
             la.lay = (const LayerDev*)ctx->b_layer.p;
             la.absrb = (const double*)ctx->b_absrb.p;
             la.nptabs = nptabs;
@@ -556,7 +584,7 @@ static int run_device(mrtm_ctx* ctx, const RunDesc& r, cudaStream_t s)
             const bool sel = (r.sel_count != nullptr) || (r.sel_hash != nullptr);
             // frequencies per CTA: 128 threads x F (512 on dense grids, smaller tiles for short channel lists)
             const int NTsel = 128;                         // 256-thread CTAs measured 4% slower on the dense sweep
-            static const int force_f = std::getenv("MRTM_LINES_F") ? std::atoi(std::getenv("MRTM_LINES_F")) : 0;
+            const int force_f = ctx->force_f;
             // The far field pays when a tile is narrow next to the line spacing: take the largest tile that the
             // frequencies fill and whose mean spectral width stays under tile_width (measured: 0.028 cm-1 tiles are
             // best on the 5.5e-5 cm-1 sweep; on the 5.5e-3 cm-1 grid of the 300-layer case 128-frequency tiles are 2.2x
@@ -586,6 +614,47 @@ static int run_device(mrtm_ctx* ctx, const RunDesc& r, cudaStream_t s)
             la.nlev = nlev;
             la.S = ctx->ff_S;
             la.nslot = nslot;
+            const bool use3 = ctx->use_near3 && ctx->use_near2 && la.ff_ratio > 0. && !sel && combined && F == 4;
+            // ---- plan cache: buffers first (a reallocation invalidates the cached plans), then the device-side check
+            const size_t npc_words = 1 + std::max<size_t>(1, h.segments.size());
+            if ((rc = ensure(ctx, ctx->b_pcache, (npc_words + 4) * 8))) return rc;
+            for (int lv = 0; lv < nlev; lv++) {
+                if ((rc = ensure(ctx, ctx->b_pieces[lv], (size_t)ntiles[lv] * std::max(nseg_i, 1) * kPiecePerSeg * sizeof(FarPiece)))) return rc;
+                if ((rc = ensure(ctx, ctx->b_plan[lv], (size_t)ntiles[lv] * std::max(nseg_i, 1) * sizeof(SegWork)))) return rc;
+                if ((rc = ensure(ctx, ctx->b_hdr[lv], (size_t)ntiles[lv] * sizeof(TileHdr)))) return rc;
+            }
+            if (la.ff_ratio > 0. && ctx->use_near2 && (rc = ensure(ctx, ctx->b_npieces, (size_t)ntiles[0] * kMaxNearPieces * sizeof(NearPiece)))) return rc;
+            if (use3) {
+                if ((rc = ensure(ctx, ctx->b_t3, (size_t)ntiles[0] * sizeof(Tile3)))) return rc;
+                if ((rc = ensure(ctx, ctx->b_pool3, (size_t)ntiles[0] * kN3Pool * sizeof(unsigned short)))) return rc;
+                if ((rc = ensure(ctx, ctx->b_segof3, (size_t)ntiles[0] * kNearCap))) return rc;
+            }
+            unsigned long long* pc_have = (unsigned long long*)ctx->b_pcache.p;          // [npc_words] cached margins
+            unsigned long long* pc_hash = pc_have + npc_words;                            // [2]
+            int* pc_replan = (int*)(pc_hash + 2);
+            {
+                mrtm_ctx::PlanKey key;
+                std::memset(&key, 0, sizeof key);
+                key.nwn = nwn; key.stage_gen = ctx->stage_gen; key.F = F; key.nlev = nlev; key.S = ctx->ff_S; key.nseg = nseg_i;
+                key.near2 = ctx->use_near2; key.near3 = use3 ? 1 : 0; key.ff_ratio = la.ff_ratio; key.ffw_ratio = ctx->ffw_ratio;
+                int nb_ = 0;
+                for (int lv = 0; lv < nlev; lv++) { key.bufs[nb_++] = ctx->b_pieces[lv].p; key.bufs[nb_++] = ctx->b_plan[lv].p; key.bufs[nb_++] = ctx->b_hdr[lv].p; }
+                key.bufs[nb_++] = ctx->b_npieces.p; key.bufs[nb_++] = ctx->b_t3.p; key.bufs[nb_++] = ctx->b_pool3.p; key.bufs[nb_++] = ctx->b_pcache.p;
+                const bool same = ctx->use_plan_cache && ctx->plan_key_valid && std::memcmp(&key, &ctx->plan_key, sizeof key) == 0;
+                if (!same) CU(cudaMemsetAsync(ctx->b_pcache.p, 0, (npc_words + 4) * 8, sp));
+                ctx->plan_key = key;
+                ctx->plan_key_valid = true;
+                wn_hash_kernel<<<(unsigned)std::min<int64_t>(64, (nwn + 255) / 256), 256, 0, sp>>>(r.wn, (int)nwn, pc_hash);
+                PlanCheckArgs pk;
+                pk.need = (const unsigned long long*)ctx->b_vtmax.p;
+                pk.have = pc_have;
+                pk.hash = pc_hash;
+                pk.nseg = (int)std::max<size_t>(1, h.segments.size());
+                pk.force = same ? 0 : 1;
+                pk.replan = pc_replan;
+                plan_check_kernel<<<1, 128, 0, sp>>>(pk);
+                st.kernel_launches += 2;
+            }
             for (int lv = nlev - 1; lv >= 0; lv--) {       // top level first: a level's far work list excludes its parent's
                 if ((rc = ensure(ctx, ctx->b_pieces[lv], (size_t)ntiles[lv] * std::max(nseg_i, 1) * kPiecePerSeg * sizeof(FarPiece)))) return rc;
                 if ((rc = ensure(ctx, ctx->b_plan[lv], (size_t)ntiles[lv] * std::max(nseg_i, 1) * sizeof(SegWork)))) return rc;
@@ -599,8 +668,9 @@ static int run_device(mrtm_ctx* ctx, const RunDesc& r, cudaStream_t s)
                 pl.wn = r.wn;
                 pl.seg = ctx->seg_dev;
                 pl.xnu0 = ctx->ld.xnu0;
-                pl.sm_max_bits = (const unsigned long long*)ctx->b_vtmax.p;
-                pl.vtmax_seg = (const unsigned long long*)ctx->b_vtmax.p + 1;
+                pl.sm_max_bits = pc_have;                 // the (cached) margins, see the plan cache
+                pl.vtmax_seg = pc_have + 1;
+                pl.replan = pc_replan;
                 pl.ff_ratio = la.ff_ratio;
                 pl.out = (SegWork*)ctx->b_plan[lv].p;
                 pl.hdr = (TileHdr*)ctx->b_hdr[lv].p;
@@ -619,6 +689,38 @@ static int run_device(mrtm_ctx* ctx, const RunDesc& r, cudaStream_t s)
                 la.coef[lv] = (la.ff_ratio > 0.) ? (const double*)ctx->b_coef[lv].p : nullptr;
             }
             la.slot_mol = ctx->ld.slot_mol;
+            // production path (one sum over all molecules, no selection instrumentation, 512-frequency tiles): plan-driven lists
+            Near3Args n3;
+            std::memset(&n3, 0, sizeof n3);
+            if (use3) {
+                Plan3Args p3;
+                std::memset(&p3, 0, sizeof p3);
+                p3.nwn = (int32_t)nwn;
+                p3.nseg = nseg_i;
+                p3.wn = r.wn;
+                p3.seg = ctx->seg_dev;
+                p3.xnu0 = ctx->ld.xnu0;
+                p3.deltnu = ctx->ld.deltnu;
+                p3.brdidx = ctx->ld.brdidx;
+                p3.max_abs_deltnu = h.max_abs_deltnu;
+                p3.sm_max_bits = pc_have;
+                p3.vtmax_seg = pc_have + 1;
+                p3.replan = pc_replan;
+                p3.hdr = (TileHdr*)ctx->b_hdr[0].p;
+                p3.near_pieces = la.near_pieces;
+                p3.plan = (const SegWork*)ctx->b_plan[0].p;
+                p3.ffw_ratio = ctx->ffw_ratio;
+                p3.out = (Tile3*)ctx->b_t3.p;
+                p3.pool = (unsigned short*)ctx->b_pool3.p;
+                p3.segof = (unsigned char*)ctx->b_segof3.p;
+                plan3_kernel<<<(unsigned)ntiles[0], 128, 0, sp>>>(p3);
+                st.kernel_launches++;
+                n3.t3 = p3.out;
+                n3.pool = p3.pool;
+                n3.segof = p3.segof;
+                const int64_t pairs = ntiles[0] * nlay * nb;
+                n3.lb = ctx->near3_lb > 0 ? ctx->near3_lb : (int)std::min<int64_t>(16, std::max<int64_t>(1, pairs / 4440));
+            }
             if (side_on) {
                 CU(cudaEventRecord(ctx->evf[3], sp));            // plans done: the near field may start
                 CU(cudaStreamWaitEvent(s, ctx->evf[3], 0));
@@ -642,6 +744,9 @@ static int run_device(mrtm_ctx* ctx, const RunDesc& r, cudaStream_t s)
                     fa.S = ctx->ff_S;
                     fa.combined = combined ? 1 : 0;
                     fa.planes = la.planes;
+                    fa.lcplanes = la.lcplanes;
+                    fa.lcidx = la.lcidx_s;
+                    fa.nlc_pad = la.nlc_pad;
                     fa.lay = la.lay;
                     fa.coef = (double*)ctx->b_coef[lv].p;
                     fa.counters = ctx->counters_dev;
@@ -667,9 +772,9 @@ static int run_device(mrtm_ctx* ctx, const RunDesc& r, cudaStream_t s)
                 la.o_v = (double*)ctx->b_ov.p;
                 sv = sp;
             }
-            if (F == 4) launch_lines<4, 128>(la, grid, sel, s, far_done, sv);
-            else if (F == 2) launch_lines<2, 128>(la, grid, sel, s, far_done, sv);
-            else launch_lines<1, 128>(la, grid, sel, s, far_done, sv);
+            if (F == 4) launch_lines<4, 128>(la, grid, sel, s, far_done, sv, use3 ? &n3 : nullptr);
+            else if (F == 2) launch_lines<2, 128>(la, grid, sel, s, far_done, sv, nullptr);
+            else launch_lines<1, 128>(la, grid, sel, s, far_done, sv, nullptr);
             CU(cudaEventRecord(ctx->ev[3], s));
             st.kernel_launches++;
             CU(cudaGetLastError());

@@ -208,15 +208,16 @@ __device__ __forceinline__ double w4_re_fast(double x, double y)
 // coupling (:618-626), 2 O2 XF=-3/-5 (:650-653), 3 O2 XF=-1 first-order mixing (:642-649).
 // Returns STILD*SLS.  Same Humlicek regions and constants as SDVOIGT/W4; the three profile values share
 // one reciprocal of the Doppler width, and the far ones (s >= 15) take region I inline.
-__device__ __noinline__ double voigt_lines_term(int kind, double wn, double xnu, const double* __restrict__ pl, int n_pad, int q,
-                                                double sdep, double rp, double rp2, int* err)
+struct ColdLine;
+template <class CL>
+__device__ __noinline__ double voigt_lines_term(int kind, double wn, double xnu, const CL cl, double sdep, double rp, double rp2, int* err)
 {
-    const double hw = pl[(size_t)D_H * n_pad + q], ad = pl[(size_t)D_AD * n_pad + q], stild = pl[(size_t)D_STILD * n_pad + q];
+    const double hw = cl.hw, ad = cl.ad, stild = cl.stild;
     const double dm = wn - xnu, sp = wn + xnu;
     const bool second = (kind >= 2) || ((sp - kDELTNUC) <= 0.);
     double y1 = 1., y2 = 1.;
     if (kind == 3) {
-        const double aip = pl[(size_t)D_AIP * n_pad + q], bip = pl[(size_t)D_BIP * n_pad + q];
+        const double aip = cl.aip, bip = cl.bip;
         y1 = (1. + (aip * (1 / hw) * rp * dm) + (bip * rp2));
         y2 = (1. - (aip * (1 / hw) * rp * sp) + (bip * rp2));
     }

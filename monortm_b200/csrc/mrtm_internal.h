@@ -45,20 +45,19 @@ constexpr int kMaxSegments = 96;
 constexpr int kMaxSlots = MRTM_MXMOL;   // molecules that own lines, compacted
 
 // derived per-(layer,line) parameter planes written by derive_kernel
+// Five dense planes, 40 B per (line, layer).  Everything else a kernel may need follows from them and from two compact
+// planes that exist only for coupled lines (LCP_AIP, LCP_BIP, indexed by lcidx): HWHM_C = sqrt(H2) (exact: H2 is the
+// rounded square of HWHM_C), HWHM_D = VT/100 where the line can take the Voigt branch (VT >= 0; it is not used otherwise),
+// STILD = CN*PI/HWHM_C (2 ulp), the first-order mixing slope CN*AIP*(1/HWHM_C)*RP.
 enum DPlane : int {
     D_XNU = 0,    // shifted centre, bit-exact modm.f90:375-380
     D_H2,         // HWHM_C**2
     D_CN,         // STILD*HWHM_C/PI
     D_P3,         // pedestal CN/(625+H2) (CLS_PED) | CN*(1+BIP*RP2) (CLS_O2_LC1) | 0
-    D_P4,         // CN*AIP*(1/H)*RP (CLS_O2_LC1) | 0
-    D_H,          // HWHM_C
-    D_AD,         // HWHM_D
     D_VT,         // 100*HWHM_D, or -1 when zeta>0.99 (always Lorentz, modm.f90:427)
-    D_STILD,
-    D_AIP,
-    D_BIP,
     D_NPLANES
 };
+enum LcPlane : int { LCP_AIP = 0, LCP_BIP, LCP_NPLANES };
 
 // per (profile,layer) scalars prepared on the host with reference evaluation order
 struct LayerDev {

@@ -44,6 +44,7 @@ struct TipsDev {
 #include "kernels/plan.cuh"
 #include "kernels/far.cuh"
 #include "kernels/near.cuh"
+#include "kernels/near3.cuh"
 #include "kernels/voigt.cuh"
 #include "kernels/final.cuh"
 #include "kernels/rt.cuh"

@@ -1298,3 +1298,84 @@ void orc_xint(double v1a, double v2a, double dva, const double *a, double afact,
 {
     xint(v1a, v2a, dva, a, afact, vft, dvr3, r3, n1r3, n2r3);
 }
+
+/* ======================================================================= */
+/*  tips_2003.f90 (harness side of the boundary: scor = Q(296)/Q(T))        */
+/* ======================================================================= */
+#include "../monortm_b200/csrc/tables/tips_tables.inc"
+
+/* AtoB, tips_2003.f90:4610-4700: 4-point Lagrange (3-point at the ends of the table); a[], b[] are used 1-based */
+static double tips_atob(double aa, const double *a0, const double *b0, int npt)
+{
+    double bb = 0.;
+#define a(i) a0[(i) - 1]
+#define b(i) b0[(i) - 1]
+#define NZ(d) ((d) == 0. ? 0.0001 : (d))
+    for (int i = 2; i <= npt; i++) {
+        if (a(i) >= aa) {
+            if (i < 3 || i == npt) {
+                int j = i;
+                if (i < 3) j = 3;
+                if (i == npt) j = npt;
+                double d01 = NZ(a(j - 2) - a(j - 1)), d02 = NZ(a(j - 2) - a(j));
+                double d11 = NZ(a(j - 1) - a(j - 2)), d12 = NZ(a(j - 1) - a(j));
+                double d21 = NZ(a(j) - a(j - 2)), d22 = NZ(a(j) - a(j - 1));
+                double c0 = (aa - a(j - 1)) * (aa - a(j)) / (d01 * d02);
+                double c1 = (aa - a(j - 2)) * (aa - a(j)) / (d11 * d12);
+                double c2 = (aa - a(j - 2)) * (aa - a(j - 1)) / (d21 * d22);
+                bb = c0 * b(j - 2) + c1 * b(j - 1) + c2 * b(j);
+            } else {
+                int j = i;
+                double d01 = NZ(a(j - 2) - a(j - 1)), d02 = NZ(a(j - 2) - a(j)), d03 = NZ(a(j - 2) - a(j + 1));
+                double d11 = NZ(a(j - 1) - a(j - 2)), d12 = NZ(a(j - 1) - a(j)), d13 = NZ(a(j - 1) - a(j + 1));
+                double d21 = NZ(a(j) - a(j - 2)), d22 = NZ(a(j) - a(j - 1)), d23 = NZ(a(j) - a(j + 1));
+                double d31 = NZ(a(j + 1) - a(j - 2)), d32 = NZ(a(j + 1) - a(j - 1)), d33 = NZ(a(j + 1) - a(j));
+                double c0 = (aa - a(j - 1)) * (aa - a(j)) * (aa - a(j + 1));
+                c0 = c0 / (d01 * d02 * d03);
+                double c1 = (aa - a(j - 2)) * (aa - a(j)) * (aa - a(j + 1));
+                c1 = c1 / (d11 * d12 * d13);
+                double c2 = (aa - a(j - 2)) * (aa - a(j - 1)) * (aa - a(j + 1));
+                c2 = c2 / (d21 * d22 * d23);
+                double c3 = (aa - a(j - 2)) * (aa - a(j - 1)) * (aa - a(j));
+                c3 = c3 / (d31 * d32 * d33);
+                bb = c0 * b(j - 2) + c1 * b(j - 1) + c2 * b(j) + c3 * b(j + 1);
+            }
+            break;                                               /* GO TO 100 */
+        }
+    }
+#undef NZ
+#undef a
+#undef b
+    return bb;
+}
+
+/* TIPS_2003, tips_2003.f90:2-298.  scor is (42,9).  Returns 0, or 11 where the reference STOPs
+ * ("partition sum less than 0.": T outside 70..3000 K gives Qt = -1 in every QT_* routine). */
+int orc_tips_2003(int64_t mol_max, double temp_lbl, double *scor)
+{
+    if (mol_max < 1 || mol_max > 39) return fail(11, "tips_2003: mol_max out of range");
+    double qt = 0., qt_296 = 0., qt_temp = 0.;
+    for (int64_t mol = 1; mol <= mol_max; mol++) {
+        int niso = TIPS_ISONM[mol - 1] < 9 ? TIPS_ISONM[mol - 1] : 9;         /* min(9,isonm(mol)), :60 */
+        for (int iso = 1; iso <= niso; iso++) {
+            for (int itemp = 1; itemp <= 2; itemp++) {
+                double temp = (itemp == 1) ? 296. : temp_lbl;
+                if (mol == 34) {
+                    qt = 1.;                                                  /* not applicable to O; set to 1, :233-238 */
+                } else if (mol == 39) {
+                    /* :260-268: sets qt_296 / qt_temp, which :288-289 then overwrite with the stale QT */
+                    if (itemp == 1) qt_296 = 296.;
+                    if (itemp == 2) qt_temp = pow(temp / 296., 1.5);
+                } else {
+                    if (temp < 70. || temp > 3000.) qt = -1.;                 /* every QT_* routine */
+                    else qt = tips_atob(temp, TIPS_TDAT, TIPS_QOFT + (size_t)(TIPS_QOFFSET[mol - 1] + iso - 1) * 119, 119);
+                }
+                if (qt <= 0.) return fail(11, "tips_2003: partition sum less than 0.");
+                if (itemp == 1) qt_296 = qt;
+                if (itemp == 2) qt_temp = qt;
+            }
+            scor[(mol - 1) + (size_t)(iso - 1) * 42] = qt_296 / qt_temp;
+        }
+    }
+    return 0;
+}

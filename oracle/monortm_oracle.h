@@ -92,6 +92,9 @@ double orc_bb_fn(double v, double fbeta);                                /* RTMm
 int orc_contnm_one(int64_t im, const double cntnm[7], double pave, double tave,
                    const double *wk, double wbroad, int64_t nmol, double v1, double v2,
                    double v1abs, double v2abs, int64_t nptabs, double *absrb);
+/* TIPS_2003 (src/tips_2003.f90:2-298): scor(42,9) = Q(296)/Q(T) for molecules 1..mol_max (the Fortran host calls it per
+ * layer, modm.f90:250).  Lets the CPU legs of bench.py run without the product library. */
+int orc_tips_2003(int64_t mol_max, double temp_lbl, double *scor);
 /* test instrumentation of the last orc_modm call on this thread: [0] Voigt-branch evaluations, [1] speed-dependent SDVOIGT
  * calls, [2] CO2 lines on the Voigt branch, [3] of those XF=-1, [4] coupled non-CO2/O2 lines, [5] coupled O2 lines,
  * [6] lines with XG outside {0,-1,-3,-5}, [7] Voigt-branch evaluations with the negative-frequency resonance */

@@ -51,6 +51,8 @@ def oracle_lib(opt="O0"):
     lib.orc_line_key.argtypes = [I, I]
     lib.orc_last_error.restype = C.c_char_p
     lib.orc_branch_counts.argtypes = [P]
+    lib.orc_tips_2003.restype = C.c_int
+    lib.orc_tips_2003.argtypes = [I, D, P]
     _orc[opt] = lib
     return lib
 
@@ -129,6 +131,28 @@ def oracle_modm(ls, wn, dvset, p, t, clw, nmol, wkl, wbrodl, scor, cntnm=(1.,) *
     lib.orc_branch_counts(_p(br))
     return dict(o=o, o_by_mol=obm, oc=oc, o_clw=oclw, odxsec=odx, sel_count=selc, sel_hash=selh, n_voigt=nv.value,
                 branches=dict(zip(("voigt", "sdep", "co2", "co2_lc1", "generic_lc", "o2_lc", "other_flag", "neg_res"), br.tolist())))
+
+
+def oracle_tips_2003(mol_max, temp, opt="O0"):
+    lib = oracle_lib(opt)
+    scor = np.zeros((42, 9), order="F")
+    rc = lib.orc_tips_2003(int(mol_max), float(temp), _p(scor))
+    if rc:
+        raise RuntimeError("orc_tips_2003 rc=%d: %s" % (rc, lib.orc_last_error().decode()))
+    return scor
+
+
+def oracle_scor_for_layers(nmol, t):
+    """scor(42,9,nlay[,nprof]) from the oracle's own TIPS_2003 (no product code involved)"""
+    t = np.asarray(t, dtype=np.float64)
+    out = np.zeros((42, 9) + t.shape, order="F")
+    cache = {}
+    for idx in np.ndindex(t.shape):
+        key = float(t[idx])
+        if key not in cache:
+            cache[key] = oracle_tips_2003(nmol, key)
+        out[(slice(None), slice(None)) + idx] = cache[key]
+    return out
 
 
 def oracle_calctmr(wn, t, tz, o):

@@ -172,3 +172,52 @@ def test_radiance_recurrence_at_600_layers_with_negative_optical_depths():
     ok = np.isfinite(tmr_ref)
     assert np.array_equal(ok, np.isfinite(tmr_gpu))
     assert np.max(np.abs(tmr_gpu[ok] - tmr_ref[ok])) < TB_ATOL
+
+
+@pytest.mark.parametrize("i0,nlay,lb", [(1, 7, 0), (13100, 9, 4), (400000, 5, 2), (453000, 6, 1), (909000, 3, 16)])
+def test_production_near_field_kernel_on_dense_grids(i0, nlay, lb, monkeypatch):
+    """near3_kernel (plan-driven lists, a group of layers per CTA) is what runs when neither per-molecule outputs nor the
+    selection instrumentation are requested: dense 5.5e-5 cm-1 grids next to zero frequency (both resonances everywhere),
+    across the 22 GHz line and the window edges of the strong lines, with layer groups that do not divide the layer
+    count, a ragged last tile, CO2 / coupled lines in the list.  Against the oracle and the direct mode."""
+    if lb:
+        monkeypatch.setenv("MRTM_NEAR3_LB", str(lb))
+    monkeypatch.setattr(harness, "_session", None)
+    n = 4096 + 300
+    wn = 5.5e-5 * np.arange(i0, i0 + n)
+    case = harness.make_case(n_filler=4096, nlay=nlay, wn=wn, irt=1, line_kw=dict(n_co2=4, n_generic_lc=4, n_sdep=4))
+    idx = np.unique(np.concatenate([np.arange(0, n, 16), [n - 1]]))
+    sub = dict(case, wn=wn[idx], emiss=case["emiss"][idx], reflc=case["reflc"][idx])
+    ref = harness.run_oracle(sub)
+    direct = harness.run_gpu(case, by_mol=False, selection=False, line_mode=1)
+    fast = harness.run_gpu(case, by_mol=False, selection=False)
+    assert fast["stats"]["far_expansions"] > 0
+    assert harness.rel_diff(fast["o"][idx], ref["o"]) < OD_RTOL
+    assert harness.rel_diff(fast["o"], direct["o"]) < 1e-11
+    assert np.max(np.abs(fast["tb"][idx] - ref["tb"])) < TB_ATOL
+    assert np.max(np.abs(fast["tb"] - direct["tb"])) < 1e-7
+    # the instrumented path (near2_kernel) gives the same numbers and the oracle's selection
+    inst = harness.run_gpu(case, by_mol=False, selection=True)
+    assert harness.rel_diff(inst["o"], fast["o"]) < 1e-11
+    assert np.array_equal(inst["sel_hash"][idx], ref["sel_hash"])
+    monkeypatch.setattr(harness, "_session", None)
+
+
+def test_production_near_field_kernel_unsorted_and_voigt_zone():
+    rng = np.random.default_rng(3)
+    sd, co2, glc, o2lc = _special_centres(384, KW)
+    wn = np.concatenate([zone_frequencies(sd + co2 + glc + o2lc), 5.5e-5 * np.arange(13400, 13400 + 2200), np.linspace(0.3, 54.0, 400)])
+    wn = wn[(wn > 0.05) & (wn < 55.0)]
+    rng.shuffle(wn)
+    case = harness.make_case(n_filler=384, nlay=11, wn=wn, irt=1, line_kw=KW)
+    ref = harness.run_oracle(case)
+    import os
+    os.environ["MRTM_LINES_F"] = "4"
+    try:
+        harness._session = None
+        fast = harness.run_gpu(case, by_mol=False, selection=False)
+    finally:
+        del os.environ["MRTM_LINES_F"]
+        harness._session = None
+    assert harness.rel_diff(fast["o"], ref["o"]) < OD_RTOL
+    assert np.max(np.abs(fast["tb"] - ref["tb"])) < TB_ATOL

@@ -125,6 +125,10 @@ def test_host_tips_2003_matches_the_reference_text_for_all_39_molecules():
     for t, want in zip(FN["tips_t"], FN["tips_scor"]):
         got = api.tips_2003(39, float(t))
         assert np.max(np.abs(got - want) / np.maximum(np.abs(want), 1e-300)) < 2e-15, t
+        orc = harness.oracle_tips_2003(39, float(t))          # the oracle's own TIPS (CPU legs of bench.py)
+        assert np.max(np.abs(orc - want) / np.maximum(np.abs(want), 1e-300)) < 2e-15, t
+    with pytest.raises(RuntimeError):
+        harness.oracle_tips_2003(22, 60.0)
     assert FN["tips_scor"][2, 33, 0] == 1.0 and FN["tips_scor"][2, 38, 0] == 1.0      # O and CH3OH: scor = 1
 
 

@@ -41,6 +41,8 @@ def main():
     ia, isamp, iinst = hdr.index("Address"), hdr.index("# Samples"), hdr.index("Instructions Executed")
     stall_cols = [i for i, h in enumerate(hdr) if h.startswith("stall_") and "Not Issued" not in h]
     base = None
+    isrc = hdr.index("Source") if "Source" in hdr else None
+    ops = defaultdict(int)
     per = defaultdict(lambda: [0, 0, defaultdict(int)])
     started = False
     for r in rows:
@@ -53,6 +55,10 @@ def main():
         e = per[ln]
         e[0] += int(r[isamp] or 0)
         e[1] += int(r[iinst] or 0)
+        if isrc is not None:
+            m = re.match(r"\s*(?:@!?U?P\d+\s+)?([A-Z0-9_]+)", r[isrc])
+            if m:
+                ops[m.group(1)] += int(r[iinst] or 0)
         for i in stall_cols:
             v = int(r[i] or 0)
             if v:
@@ -64,6 +70,15 @@ def main():
         st = sorted(e[2].items(), key=lambda kv: -kv[1])[:3]
         print("%5.1f%%  inst %5.1f%%  %-28s %s" % (100.0 * e[0] / max(tot, 1), 100.0 * e[1] / max(toti, 1), ln,
                                                  " ".join("%s=%d" % (k.replace("stall_", ""), v) for k, v in st)))
+
+
+    if ops:
+        print("\nexecuted warp instructions by opcode (top 30):")
+        for k, v in sorted(ops.items(), key=lambda kv: -kv[1])[:30]:
+            print("  %-12s %6.2f%%  %d" % (k, 100.0 * v / max(toti, 1), v))
+    print("\ntop source lines by executed instructions:")
+    for ln, e in sorted(per.items(), key=lambda kv: -kv[1][1])[:25]:
+        print("  inst %5.1f%%  samples %5.1f%%  %s" % (100.0 * e[1] / max(toti, 1), 100.0 * e[0] / max(tot, 1), ln))
 
 
 if __name__ == "__main__":
