@@ -46,6 +46,11 @@ def parse():
     ap.add_argument("--cpu-sample-nwn", type=int, default=32)
     ap.add_argument("--direct-steps", type=int, default=3, help="extra steps timed with line_mode=1 (direct evaluation)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--config", default="c3", choices=["c3", "c4"],
+                    help="c3 (default, the headline): dense sweep sharded by frequency; c4: retrieval ensemble "
+                         "(1000 channels x 100 layers x --nprof-per-gpu profiles) sharded by profile")
+    ap.add_argument("--nprof-per-gpu", type=int, default=1024, help="profiles per GPU of --config c4")
+    ap.add_argument("--nchan", type=int, default=1000, help="channels of --config c4 (log-spaced 0.1-30 cm-1)")
     return ap.parse_args()
 
 
@@ -295,8 +300,271 @@ def ncu_traffic(args):
         return None
 
 
+# =====================================================================================================================
+# --config c4: the retrieval ensemble of BASELINE config 4 (profile axis; monortm.f90:357 profile loop)
+# =====================================================================================================================
+C4_V1, C4_V2 = 0.1, 30.0
+
+
+def c4_config(args):
+    return {"workload": "C4 retrieval ensemble: %d log-spaced channels 0.1-30 cm-1 x %d layers x %d profiles/GPU (profile-sharded, "
+                        "profiles-synth seeds 1000+global index) x TAPE3-synth %s line list (%d filler + physical seed lines), IRT=1, "
+                        "MODM+CALCTMR+RTM per step, partition sums on the device (scor=NULL)"
+                        % (args.nchan, NLAY, args.nprof_per_gpu, "full-like" if args.n_filler >= 65536 else "fast-like", args.n_filler),
+            "n_filler": args.n_filler, "nwn": args.nchan, "nlay": NLAY, "nprof_per_gpu": args.nprof_per_gpu,
+            "sharding": "profile", "parallelism": "profile-shard x%d" % args.gpus,
+            "l2": "inputs + derived planes of one step (> 1 GB) exceed L2; no flush needed"}
+
+
+def c4_inputs(args, rank, oracle_only=False, nprof=None):
+    import harness
+    from monortm_b200 import synth
+    wn = synth.freq_c4_channels(args.nchan)
+    nprof = args.nprof_per_gpu if nprof is None else nprof
+    prof = synth.synthetic_profiles(nprof, NLAY, seed0=1000 + rank * args.nprof_per_gpu, clw_layers=False, nmol=22)
+    if oracle_only:
+        ls = oracle_only_store(args.n_filler, float(wn[0]), float(wn[-1]))
+    else:
+        ls = harness.synthetic_store(args.n_filler, v1=float(wn[0]), v2=float(wn[-1]))
+    return dict(wn=wn, ls=ls, prof=prof, emiss=np.full(len(wn), 0.9), reflc=np.full(len(wn), 0.1), tmpsfc=288.2, irt=1)
+
+
+def c4_oracle_sample(inp, ips, idx, opt="O0", keep=None):
+    """The oracle on profiles `ips` x channels `idx` x all layers x all lines; scor from the oracle's own TIPS_2003."""
+    import harness
+    pr = inp["prof"]
+    wn = inp["wn"][idx]
+    t0 = time.time()
+    res = []
+    for ip in ips:
+        scor = harness.oracle_scor_for_layers(22, pr["t"][:, ip])
+        m = harness.oracle_modm(inp["ls"], wn, 0.0, pr["p"][:, ip], pr["t"][:, ip], pr["clw"][:, ip], 22, pr["wkl"][:, :, ip],
+                                pr["wbrodl"][:, ip], scor, opt=opt)
+        tmr = harness.oracle_calctmr(wn, pr["t"][:, ip], pr["tz"][:, ip], m["o"])
+        r = harness.oracle_rtm(1, inp["irt"], wn, pr["t"][:, ip], pr["tz"][:, ip], m["o"], inp["tmpsfc"], inp["reflc"][idx], inp["emiss"][idx])
+        res.append(dict(o=m["o"], sel_count=m["sel_count"], sel_hash=m["sel_hash"], tmr=tmr, tb=r["tb"], rad=r["rad"]))
+    dt = time.time() - t0
+    if keep is not None:
+        keep["res"] = res
+    return dt, float(logical_lines(inp["ls"])) * NLAY * len(idx) * len(ips)
+
+
+def _c4_farm_worker(a):
+    ip, lo, hi, opt = a
+    dt, nominal = c4_oracle_sample(_FARM["inp"], [ip], np.arange(lo, hi), opt=opt)
+    return dt, nominal
+
+
+def run_c4_reference(args):
+    """Reference arm of --config c4: the oracle farmed over the host cores, one profile x a few channels per worker."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    import multiprocessing as mp
+    import harness
+    cores = os.cpu_count() or 1
+    per = 8
+    _FARM["inp"] = c4_inputs(args, 0, oracle_only=True, nprof=min(cores, args.nprof_per_gpu))
+    harness.oracle_lib("O0"), harness.oracle_lib("O2")
+    npf = _FARM["inp"]["prof"]["nprof"]
+    jobs = [(c % npf, (c * 37) % (args.nchan - per), (c * 37) % (args.nchan - per) + per, "O0") for c in range(cores)]
+    times, nominal = [], 0.0
+    with mp.get_context("fork").Pool(cores) as pool:
+        for it in range(args.warmup + args.steps):
+            t0 = time.time()
+            res = pool.map(_c4_farm_worker, jobs)
+            dt = time.time() - t0
+            if it >= args.warmup:
+                times.append(dt)
+                nominal = sum(r[1] for r in res)
+        t0 = time.time()
+        res2 = pool.map(_c4_farm_worker, [j[:3] + ("O2",) for j in jobs])
+        o2_farm = sum(r[1] for r in res2) / (time.time() - t0)
+    ms = 1e3 * float(np.mean(times))
+    val = nominal / (ms * 1e-3)
+    per_spec = float(logical_lines(_FARM["inp"]["ls"])) * NLAY * args.nchan
+    line = {"metric": "line x layer x frequency evaluations/s", "value": val, "unit": "evals/s", "impl": "reference",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": c4_config(args),
+            "spectra_per_s": val / per_spec,
+            "cpu_baseline": {"value": val, "unit": "evals/s", "cores": cores, "kind": "port", "farm_O2": o2_farm,
+                             "sample": "%d processes x (1 profile x %d channels x %d layers x all lines) per step (oracle -O0, "
+                                       "process farm; inputs prepared once in the parent; no product library loaded: %s)"
+                                       % (cores, per, NLAY, not any("libmonortm_b200" in l for l in open("/proc/self/maps")))},
+            "e2e": {"value": val, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def run_c4(args):
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    lib_path = os.environ.get("MRTM_LIB", os.path.join(ROOT, "monortm_b200", "lib", "libmonortm_b200.so"))
+    if not os.path.exists(lib_path) and world == 1:
+        import __graft_entry__
+        __graft_entry__.build()
+    from monortm_b200 import api
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product has no CPU path")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    inp = c4_inputs(args, rank)
+    wn, pr = inp["wn"], inp["prof"]
+    nwn, nprof = len(wn), pr["nprof"]
+    sess = api.Session(local)
+    nlines = sess.stage_lines(inp["ls"])
+
+    def dv(a):
+        return torch.from_numpy(np.ascontiguousarray(np.asarray(a).reshape(-1, order="F"))).to(dev)
+    d = {k: dv(pr[k]) for k in ("p", "t", "tz", "clw", "wkl", "wbrodl")}
+    d["wn"], d["emiss"], d["reflc"] = dv(wn), dv(inp["emiss"]), dv(inp["reflc"])
+    d["tmpsfc"] = torch.full((nprof,), inp["tmpsfc"], dtype=torch.float64, device=dev)
+    outs = torch.zeros(6, nprof, nwn, dtype=torch.float64, device=dev)       # each spectrum block is (nwn, nprof) column-major
+    gathered = torch.zeros(world, 6, nprof, nwn, dtype=torch.float64, device=dev) if world > 1 else None
+    ptrs = {k: v.data_ptr() for k, v in d.items()}
+    for i, k in enumerate(("rad", "tb", "tmr", "trtot", "rup", "rdn")):
+        ptrs[k] = outs[i].data_ptr()
+    stream = torch.cuda.current_stream()
+
+    def step_dev():
+        sess.profiles_dev(nprof, nwn, NLAY, 22, 0.0, ptrs, float(wn[0]), float(wn[-1]), 0, inp["irt"], stream=stream.cuda_stream)
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, outs)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step_dev()
+    barrier()
+    sess.reset_stats()
+    sampler = ClockSampler(local)
+    sampler.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    lines_ms, rt_ms, derive_ms, far_exp, direct_ev = [], [], [], [], []
+    barrier()
+    for i in range(args.steps):
+        ev[i][0].record(stream)
+        step_dev()
+        ev[i][1].record(stream)
+        st = sess.stats()
+        lines_ms.append(st["last_lines_kernel_ms"]); rt_ms.append(st["last_rt_kernel_ms"]); derive_ms.append(st["last_derive_kernel_ms"])
+        far_exp.append(st["far_expansions"]); direct_ev.append(st["direct_evals"])
+    barrier()
+    dev_ms = sum(a.elapsed_time(b) for a, b in ev)
+    launches = sess.stats()["kernel_launches"]
+    tmax = torch.tensor([dev_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    ms_per_step = float(tmax.item()) / args.steps
+    nominal_per_step = float(nlines) * NLAY * nwn * nprof * world
+    value = nominal_per_step / (ms_per_step * 1e-3)
+
+    # ---- e2e: pinned host buffers through mrtm_profiles; the spectra land in pinned host memory
+    def pin(a):
+        return torch.from_numpy(np.ascontiguousarray(np.asarray(a).reshape(-1, order="F"))).pin_memory()
+    hp = {k: pin(pr[k]) for k in ("p", "t", "tz", "clw", "wkl", "wbrodl")}
+    hp["wn"], hp["emiss"], hp["reflc"] = pin(wn), pin(inp["emiss"]), pin(inp["reflc"])
+    hprof = dict(nlay=NLAY, nprof=nprof, nmol=22,
+                 p=hp["p"].numpy().reshape(NLAY, nprof, order="F"), t=hp["t"].numpy().reshape(NLAY, nprof, order="F"),
+                 tz=hp["tz"].numpy().reshape(NLAY + 1, nprof, order="F"), clw=hp["clw"].numpy().reshape(NLAY, nprof, order="F"),
+                 wbrodl=hp["wbrodl"].numpy().reshape(NLAY, nprof, order="F"), wkl=hp["wkl"].numpy().reshape(39, NLAY, nprof, order="F"))
+    h2d_bytes = sum(hp[k].numel() * 8 for k in hp)
+    d2h_bytes = 6 * nwn * nprof * 8
+    hout_t = torch.zeros(6, nprof, nwn, dtype=torch.float64).pin_memory()
+    hout = {k: hout_t[i].numpy().reshape(-1).reshape(nwn, nprof, order="F") for i, k in enumerate(("rad", "tb", "tmr", "trtot", "rup", "rdn"))}
+
+    def step_e2e():
+        return sess.profiles(hp["wn"].numpy(), 0.0, hprof, None, inp["irt"], inp["tmpsfc"], hp["emiss"].numpy(), hp["reflc"].numpy(), out=hout)
+    step_e2e()
+    barrier()
+    e2e_steps = max(1, min(args.steps, 5))
+    t0 = time.time()
+    for _ in range(e2e_steps):
+        step_e2e()
+    barrier()
+    e2e_ms = 1e3 * (time.time() - t0) / e2e_steps
+    te = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = nominal_per_step / (float(te.item()) * 1e-3)
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+
+    failed = False
+    if rank == 0:
+        fp64_peak = sess.fp64_peak_tflops()
+        lk_ms = float(np.mean(lines_ms))
+        far_n, dir_n = float(np.mean(far_exp)), float(np.mean(direct_ev))
+        achieved = (far_n * FLOP_PER_FAR_EXPANSION + dir_n * FLOP_PER_INWINDOW_EVAL) / (lk_ms * 1e-3) / 1e12
+        line = {"metric": "line x layer x frequency evaluations/s", "value": value, "unit": "evals/s", "n_gpus": world,
+                "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": c4_config(args),
+                "spectra_per_s": nprof * world / (ms_per_step * 1e-3), "logical_lines": nlines,
+                "e2e": {"value": e2e_value, "unit": "evals/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
+                        "ms_per_step": float(te.item()), "spectra_per_s": nprof * world / (float(te.item()) * 1e-3), "steps": e2e_steps},
+                "gpu_launches": int(launches), "clocks": sampler.summary(),
+                "roofline": {"bound": "fp64", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
+                             "frac": achieved / fp64_peak if fp64_peak else None, "traffic": None,
+                             "kernel": "plan+far+near+voigt+final (the line path of one step; near_kernel's streamed direct loops dominate "
+                                       "on sparse channels: a 128-channel tile spans several cm-1, so nearly every in-window line is near)",
+                             "peak_source": "measured live: mrtm_fp64_peak DFMA probe (MEASURED_PEAKS.json has no FP64 figure)",
+                             "flop_per_direct_eval": FLOP_PER_INWINDOW_EVAL, "flop_per_far_expansion": FLOP_PER_FAR_EXPANSION,
+                             "far_expansions_per_launch": far_n, "direct_evals_per_launch": dir_n,
+                             "kernel_ms": lk_ms, "share_of_step": lk_ms / ms_per_step},
+                "derive_kernel_ms": float(np.mean(derive_ms)), "rt_kernel_ms": float(np.mean(rt_ms))}
+        if not args.no_cpu_baseline:
+            # parity on a profile x channel subsample, then the CPU baseline figures
+            ips = sorted({0, nprof // 2, nprof - 1})[:3]
+            idx = np.linspace(0, nwn - 1, 12).astype(int)
+            keep = {}
+            dt, nominal = c4_oracle_sample(inp, ips, idx, keep=keep)
+            sub = dict(pr)
+            for k in ("p", "t", "tz", "clw", "wbrodl"):
+                sub[k] = np.asfortranarray(pr[k][:, ips])
+            sub["wkl"] = np.asfortranarray(pr["wkl"][:, :, ips])
+            sub["nprof"] = len(ips)
+            pc = {"profiles": [int(i) for i in ips], "n_channels": int(len(idx)), "nlay": NLAY, "od_rtol_bar": 1e-9, "tb_atol_K_bar": 1e-5,
+                  "max_rel_od": 0.0, "max_dtb_K": 0.0, "max_dtmr_K": 0.0, "sel_exact": True, "line_modes": [0, 1],
+                  "what": "GPU (mrtm_profiles on the full channel list, device TIPS, both line modes) vs oracle (own TIPS_2003) on a "
+                          "profile x channel subsample x all layers"}
+            for mode in (0, 1):
+                g = sess.profiles(wn, 0.0, sub, None, inp["irt"], inp["tmpsfc"], inp["emiss"], inp["reflc"], want_o=True, selection=True,
+                                  line_mode=mode)
+                for j, r in enumerate(keep["res"]):
+                    o = g["o"][idx, :, j]
+                    pc["max_rel_od"] = max(pc["max_rel_od"], float(np.max(np.abs(o - r["o"]) / np.abs(r["o"]))))
+                    pc["max_dtb_K"] = max(pc["max_dtb_K"], float(np.max(np.abs(g["tb"][idx, j] - r["tb"]))))
+                    pc["max_dtmr_K"] = max(pc["max_dtmr_K"], float(np.max(np.abs(g["tmr"][idx, j] - r["tmr"]))))
+                    pc["sel_exact"] = bool(pc["sel_exact"] and np.array_equal(g["sel_count"][idx, :, j], r["sel_count"])
+                                           and np.array_equal(g["sel_hash"][idx, :, j], r["sel_hash"]))
+                del g
+            # the batched device-resident result of the timed steps against the per-profile call
+            pc["pass"] = bool(pc["sel_exact"] and pc["max_rel_od"] < 1e-9 and pc["max_dtb_K"] < 1e-5 and pc["max_dtmr_K"] < 1e-5)
+            line["parity_check"] = pc
+            dt2, nominal2 = c4_oracle_sample(inp, ips[:1], idx, opt="O2")
+            line["cpu_baseline"] = {"value": nominal / dt, "unit": "evals/s", "cores": 1, "kind": "port", "value_O2": nominal2 / dt2,
+                                    "sample": "%d profiles x %d channels x %d layers x all %d lines, oracle -O0 (C restatement; the Fortran "
+                                              "reference cannot be compiled here), %.1f s" % (len(ips), len(idx), NLAY, nlines, dt)}
+            failed = not pc["pass"]
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if failed:
+        raise SystemExit("bench.py: parity_check failed (see the JSON line): the throughput above is not valid")
+
+
 def main():
     args = parse()
+    if args.config == "c4":
+        return run_c4_reference(args) if args.impl == "reference" else run_c4(args)
     if args.impl == "reference":
         return run_reference(args)
 
