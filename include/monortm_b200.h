@@ -41,7 +41,7 @@ enum {
     MRTM_EARG = 3,         /* bad argument / dimension */
     MRTM_ENOLINES = 4,     /* mrtm_stage_lines has not been called */
     MRTM_ELINEFILE = 5,    /* malformed line store (LC flag not 1/3/5: lnfl_mod.f90:61-63; bad isotope) */
-    MRTM_ERANGE = 6,       /* spectral range needs continuum branches not built (V2 >= 820 cm-1) */
+    MRTM_ERANGE = 6,       /* reserved (round 1: V2 >= 820 cm-1 was refused; every MT_CKD branch is built now) */
     MRTM_ESDVOIGT = 7,     /* REAL(v) < 0 in SDVOIGT: modm.f90:1062 STOP */
     MRTM_EIDU = 8,         /* IDU != 1: RTMmono.f90:173 STOP */
     MRTM_ENOMEM = 9,

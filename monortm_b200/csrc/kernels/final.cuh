@@ -81,8 +81,8 @@ __global__ void __launch_bounds__(NT, MRTM_FINAL_MINB) final_kernel(LinesArgs a)
     }
 
     // ---- epilogue: continuum, cloud, totals ---------------------------------------------------
-    const double* ab = a.absrb + (size_t)L * 3 * a.nptabs_pad;
-    const int cont_mol[3] = {1, 2, 22};
+    const double* ab = a.absrb + (size_t)L * CP_COUNT * a.nptabs_pad;
+    const int cont_mol[5] = {1, 2, 3, 7, 22};                          // index_cont, modm.f90:165-166 (planes in CP_* order)
 #pragma unroll
     for (int f = 0; f < F; f++) {
         if (!valid[f]) continue;
@@ -105,16 +105,22 @@ __global__ void __launch_bounds__(NT, MRTM_FINAL_MINB) final_kernel(LinesArgs a)
         }
         const double rf = radfn(wn[f], ly.xkt);
 #pragma unroll
-        for (int c = 0; c < 3; c++) {
+        for (int c = 0; c < 5; c++) {
+            if (!((a.cont_mask >> c) & 1)) continue;                   // no component of this species fires: its oc stays 0
             double v = 0.;
             if (in_rng) v = 0. + xint_point(ab + (size_t)c * a.nptabs_pad, a.v1abs, 1.0, vi) * 1.0;
             v = v * rf;
             soc = soc + v;                                             // sum(oc(m,1:22,k)) in index order
             if (a.oc) a.oc[(size_t)iw + (size_t)(cont_mol[c] - 1) * a.obm_ldm + (size_t)L * a.obm_ldk] = v;
         }
+        double oray = 0.;                                              // modm.f90:231-244 (zero below 820 cm-1)
+        if ((a.cont_mask >> CP_RAYL) & 1) {
+            if (in_rng) oray = 0. + xint_point(ab + (size_t)CP_RAYL * a.nptabs_pad, a.v1abs, 1.0, vi) * 1.0;
+            oray = oray * wn[f] / 1.0e4;
+        }
         double oclw = (ly.clw == 0.) ? 0. : odclw_tkc(wn[f], ly.t, ly.clw);   // modm.f90:264
         double odx = a.odxsec ? a.odxsec[fl] : 0.;
-        double tot = osum[f] + odx + 0. + soc + oclw;                  // :268-269 (oc_rayl = 0 for V2 < 820)
+        double tot = osum[f] + odx + oray + soc + oclw;                // :268-269
         a.o[fl] = tot;
         if (a.o_clw) a.o_clw[fl] = oclw;
     }

@@ -40,8 +40,9 @@ struct LinesArgs {
     const unsigned long long* layer_voigt;   // [L] bits of the smallest |Xnu| of the layer's Voigt-capable lines (derive_kernel), all ones = none
     const int32_t* slot_mol;            // [nslot]
     // continuum
-    const double* absrb;          // [L][3][nptabs_pad]
+    const double* absrb;          // [L][CP_COUNT][nptabs_pad]
     int32_t nptabs, nptabs_pad;
+    int32_t cont_mask, pad_cm;    // bit c: plane c of absrb has an active component (bits of ContPlane)
     double v1abs, v2abs, v1, dvset;
     // outputs (any may be null).  Strides in elements.
     double* o;        int64_t o_lds;  int64_t o_prof;     // o[iw + k*o_lds + prof*o_prof]

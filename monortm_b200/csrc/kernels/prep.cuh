@@ -159,6 +159,11 @@ __global__ void layer_prep_kernel(LayerPrepArgs a)
         o.c_xn2 = xn2;
         o.c_xo2 = xo2;
         o.c_xh2o = xh2o;
+        o.c_amagat = amagat;
+        o.c_rhoave = rhoave;
+        o.c_wk3 = (a.nmol >= 3) ? wk[2] : 0.;
+        o.c_wk7 = wk7;
+        o.c_cw = cw;
     }
     o.pad = 0;
     a.out[L] = o;
@@ -187,16 +192,20 @@ __global__ void layer_prep_kernel(LayerPrepArgs a)
 }
 
 // =============================================================================================
-// continuum_kernel: one CTA per (profile,layer).  MT_CKD_3.5 branches that fire for V2 < 820:
-// H2O self (contnm.f90:325-371), H2O foreign (:380-457), CO2 (:484-528), N2 roto-translational
-// CIA (:906-943), each 4-point interpolated (XINT, lblrtm_sub.f90:1-34) onto the 1 cm-1 grid.
-// Output planes: absrb[L][3][nptabs_pad] for species selectors im = 1 (H2O), 2 (CO2), 22 (N2).
+// continuum_kernel: one CTA per (profile,layer).  Every MT_CKD_3.5 component of CONTNM (contnm.f90:325-1131): H2O self and
+// foreign, CO2, O3 (Chappuis / Hartley-Huggins / UV), O2 (fundamental, 1.27 um, 9100-11000, A band, visible, Herzberg, far
+// UV), N2 (roto-translational, fundamental, first overtone) and Rayleigh.  A component is evaluated on its own coefficient
+// grid and 4-point interpolated (XINT, lblrtm_sub.f90:1-34) onto the 1 cm-1 grid of its species' plane:
+// absrb[L][CP_COUNT][nptabs_pad], planes H2O, CO2, O3, O2, N2 (species selectors im = 1, 2, 3, 7, 22 of modm.f90:165) and
+// Rayleigh.  Which components fire, their table offsets and XINT bounds are layer independent (host, make_grid).
 // =============================================================================================
 struct ContArgs {
     int64_t nlayers;
-    ContGrid g[4];            // 0 self, 1 foreign, 2 co2, 3 n2
+    ContGrid g[CB_COUNT];
     double v1abs;
     int32_t nptabs, nptabs_pad;
+    int32_t rayl_active, pad;
+    double cntnm[7];
     ContTablesDev tb;
     const LayerDev* lay;
     double* absrb;
@@ -217,87 +226,197 @@ __device__ __forceinline__ double xint_point(const double* a, double v1a, double
     return -a[j - 2] * b1 + a[j - 1] * (1. - c + b2) + a[j] * (c + b1) - a[j + 1] * b2;
 }
 
+__device__ __forceinline__ int cont_plane(int b)
+{
+    switch (b) {
+    case CB_H2O_SELF: case CB_H2O_FRGN: return CP_H2O;
+    case CB_CO2: return CP_CO2;
+    case CB_N2_ROT: case CB_N2_FUND: case CB_N2_OVER: return CP_N2;
+    case CB_O3_CHAP: case CB_O3_HH: case CB_O3_UV: return CP_O3;
+    default: return CP_O2;
+    }
+}
+
+// RADFN, lblrtm_sub.f90:36-97 (the Rayleigh term divides it out again, contnm.f90:1124)
+__device__ __forceinline__ double cont_radfn(double vi, double xkt)
+{
+    if (xkt > 0.0) {
+        const double x = vi / xkt;
+        if (x <= 0.01) return 0.5 * x * vi;
+        if (x <= 10.0) { const double e = exp(-x); return vi * (1. - e) / (1. + e); }
+        return vi;
+    }
+    return vi;
+}
+
+// value of component b at point j (0-based) of its coefficient grid: the accessor routine (table look-up, radiation term
+// removed) times the layer factor of the calling block in CONTNM
+__device__ double cont_value(int b, const ContGrid& g, int j, const LayerDev& ly, const ContArgs& a)
+{
+    const int i = g.i1 + j;                                   // 1-based table index
+    const double vj = g.v1c + g.dvc * (double)j;
+    const double xlosmt = 2.68675E+19;
+    switch (b) {
+    case CB_H2O_SELF: {                                       // contnm.f90:325-363, SL296/SL260
+        double s0 = 0., s1 = 0., sh2o = 0.;
+        if (i >= 1 && i <= 2003) { s0 = a.tb.sh2o_296[i - 1]; s1 = a.tb.sh2o_260[i - 1]; }
+        if (s0 > 0.) sh2o = s0 * pow(s1 / s0, ly.c_tfac_h2o);
+        return ly.c_wk1 * (sh2o * ly.c_rself);
+    }
+    case CB_H2O_FRGN: {                                       // :380-457, FRN296
+        const double f0 = 0.06, v0f1 = 255.67, hwsq1 = 240. * 240., beta1 = 57.83, c_1 = -0.42, c_2 = 0.3, beta2 = 630.;
+        double f = (i >= 1 && i <= 2003) ? a.tb.fh2o[i - 1] : 0.;
+        double fscal;
+        if (vj <= 600.) {
+            int jfac = (int)((vj + 10.) / 10. + 0.00001);
+            fscal = a.tb.xfac_rhu[jfac + 1];
+        } else {
+            double t1 = (vj - v0f1) / beta1, t2 = (vj + v0f1) / beta1, t3 = vj / beta2;
+            double vf1 = t1 * t1; vf1 *= vf1; vf1 *= vf1;
+            double vmf1 = t2 * t2; vmf1 *= vmf1; vmf1 *= vmf1;
+            double vf2 = t3 * t3; vf2 *= vf2; vf2 *= vf2;
+            fscal = 1. + (f0 + c_1 * ((hwsq1 / ((vj - v0f1) * (vj - v0f1) + hwsq1 + vf1)) +
+                                      (hwsq1 / ((vj + v0f1) * (vj + v0f1) + hwsq1 + vmf1)))) /
+                             (1. + c_2 * vf2);
+        }
+        f = f * fscal;
+        return (ly.c_wk1 * f) * ly.c_rfrgn;
+    }
+    case CB_CO2: {                                            // :484-528, FRNCO2
+        double f = 0.;
+        if (i >= 1 && i <= 5003) {
+            double tcor = 1.;
+            if (i >= 1196 && i <= 1220) tcor = pow(ly.c_trat, a.tb.co2_tdep[i - 1196]);
+            f = tcor * a.tb.fco2[i - 1];
+        }
+        if (vj >= 2000. && vj <= 2998.) {                     // :510-513
+            const int jfac = (int)((vj - 1998.) / 2. + 0.00001);
+            f = a.tb.xfacco2[jfac - 1] * f;
+        }
+        return f * ly.c_wco2;
+    }
+    case CB_N2_ROT: {                                         // :906-943, xn2_r
+        double c0 = 0., c1 = 0.;
+        if (i >= 1 && i <= 73) {
+            c0 = a.tb.n2_296[i - 1] * pow(a.tb.n2_220[i - 1] / a.tb.n2_296[i - 1], ly.c_tfac_n2);
+            double sf_t = a.tb.n2_296_sf[i - 1] * pow(a.tb.n2_220_sf[i - 1] / a.tb.n2_296_sf[i - 1], ly.c_tfac_n2);
+            c1 = (sf_t - 1.) * 0.79 / 0.21;
+        }
+        return ly.c_taufac * c0 * (ly.c_xn2 + c1 * ly.c_xo2 + 1. * ly.c_xh2o);
+    }
+    case CB_N2_FUND: {                                        // :963-1013, n2_ver_1 :4331-4417
+        if (i < 1 || i > 228) return 0.;
+        const double t_272 = 272., t_228 = 228.;
+        const double xtfac = ((1. / ly.t) - (1. / t_272)) / ((1. / t_228) - (1. / t_272));
+        const double xt_lin = (ly.t - t_272) / (t_228 - t_272);
+        const double a_o2 = 1.294 - 0.4545 * ly.t / 296.;
+        const double x2 = a.tb.n2f_272[i - 1], x8 = a.tb.n2f_228[i - 1];
+        double c = ((x2 > 0.) && (x8 > 0.)) ? x2 * pow(x8 / x2, xtfac) : x2 + (x8 - x2) * xt_lin;
+        c = c / vj;
+        const double c1 = a_o2 * c, c2 = (9. / 7.) * a.tb.n2f_ah2o[i - 1] * c;
+        return ly.c_taufac * (ly.c_xn2 * c + ly.c_xo2 * c1 + ly.c_xh2o * c2);
+    }
+    case CB_N2_OVER: {                                        // :1025-1068, n2_overtone1
+        if (i < 1 || i > 191) return 0.;
+        return (ly.c_taufac * (ly.c_xn2 + 1. * ly.c_xo2 + 1. * ly.c_xh2o)) * (a.tb.n2f1[i - 1] / vj);
+    }
+    case CB_O3_CHAP: {                                        // :536-553, XO3CHP
+        if (i < 1 || i > 3150) return 0.;
+        const double wo3 = ly.c_wk3 * 1.0E-20 * a.cntnm[3], dt = ly.t - 273.15;
+        const double c0 = a.tb.o3ch_x[i - 1] / vj, c1 = a.tb.o3ch_y[i - 1] / vj, c2 = a.tb.o3ch_z[i - 1] / vj;
+        return (c0 + (c1 + c2 * dt) * dt) * wo3;
+    }
+    case CB_O3_HH: {                                          // :555-599, O3HHT0/1/2
+        if (i < 1 || i > 2687) return 0.;
+        const double wo3 = ly.c_wk3 * 1.E-20 * a.cntnm[3], tc = ly.t - 273.15;
+        double c = (a.tb.o3hh0[i - 1] / vj) * wo3;
+        return c * (1. + a.tb.o3hh1[i - 1] * tc + a.tb.o3hh2[i - 1] * tc * tc);
+    }
+    case CB_O3_UV: {                                          // :603-642, O3HHUV
+        if (i < 1 || i > 133) return 0.;
+        return (a.tb.o3huv[i - 1] / vj) * (ly.c_wk3 * a.cntnm[3]);
+    }
+    case CB_O2_FUND: {                                        // :657-693, o2_ver_1
+        if (i < 1 || i > 103) return 0.;
+        const double tau_fac = a.cntnm[4] * ly.c_wk7 * 1.e-20 * ly.c_amagat;
+        const double xktfac = (1. / 296.) - (1. / ly.t);
+        return tau_fac * ((1.e+20 / 2.68675e+19) * a.tb.o2f[i - 1] * exp(a.tb.o2f_t[i - 1] * xktfac) / vj);
+    }
+    case CB_O2_INF1: {                                        // :709-734, O2INF1
+        if (i < 1 || i > 483) return 0.;
+        const double tau_fac = a.cntnm[4] * (ly.c_wk7 / xlosmt) * ly.c_amagat *
+                               ((1. / 0.446) * ly.c_xo2 + (0.3 / 0.446) * ly.c_xn2 + 1. * ly.c_xh2o);
+        return tau_fac * (a.tb.o2inf1[i - 1] / vj);
+    }
+    case CB_O2_INF2: {                                        // :745-766, O2INF2 (analytic, its own grid set-up)
+        if (!((vj > 9100.) && (vj < 11000.))) return 0.;
+        const double v1_osc = 9375., hw1 = 58.96, v2_osc = 9439., hw2 = 45.04, s1 = 1.166E-04, s2 = 3.086E-05;
+        const double dv1 = vj - v1_osc, dv2 = vj - v2_osc;
+        const double damp1 = (dv1 < 0.0) ? exp(dv1 / 176.1) : 1.0, damp2 = (dv2 < 0.0) ? exp(dv2 / 176.1) : 1.0;
+        const double q1 = dv1 / hw1, q2 = dv2 / hw2;
+        const double o2inf = 0.31831 * (((s1 * damp1 / hw1) / (1. + q1 * q1)) + ((s2 * damp2 / hw2) / (1. + q2 * q2))) * 1.054;
+        const double wo2 = a.cntnm[4] * (ly.c_wk7 * 1.e-20) * ly.c_rhoave;
+        return (o2inf / vj) * ((ly.c_wk7 / ly.c_cw) * (1. / 0.209) * wo2);
+    }
+    case CB_O2_INF3: {                                        // :773-792, O2INF3
+        if (i < 1 || i > 261) return 0.;
+        return (a.cntnm[4] * (ly.c_wk7 / xlosmt) * ly.c_amagat) * (a.tb.o2inf3[i - 1] / vj);
+    }
+    case CB_O2_VIS: {                                         // :807-830, O2_vis
+        if (i < 1 || i > 1474) return 0.;
+        const double wo2 = ly.c_wk7 * 1.e-20 * ((ly.p / 1013.) * (273. / ly.t)) * a.cntnm[4];
+        const double q = 55. * 273. / 296.;
+        const double factor = 1. / ((xlosmt * 1.e-20 * (q * q)) * 89.5);
+        return (factor * a.tb.o2vis[i - 1] / vj) * ((ly.c_wk7 / ly.c_cw) * wo2);
+    }
+    case CB_O2_HERZ: {                                        // :834-850, O2HERZ, HERTDA, HERPRS
+        if (i < 1) return 0.;
+        double herz = 0.0;
+        if (!(vj <= 36000.00)) {
+            double corr = 0.;
+            if (vj <= 40000.) corr = ((40000. - vj) / 4000.) * 7.917E-07;
+            const double yratio = vj / 48811.0, lg = log(yratio);
+            herz = 6.884E-04 * (yratio) * exp(-69.738 * (lg * lg)) - corr;
+        }
+        herz = herz * (1. + .83 * (ly.p / 1013.) * (273.16 / ly.t));
+        return (herz / vj) * (ly.c_wk7 * 1.e-20 * a.cntnm[4]);
+    }
+    case CB_O2_FUV: {                                         // :857-875, O2FUV
+        if (i < 1 || i > 1512) return 0.;
+        return (a.tb.o2fuv[i - 1] / vj) * (ly.c_wk7 * 1.e-20 * a.cntnm[4]);
+    }
+    default: return 0.;
+    }
+}
+
 __global__ void __launch_bounds__(128) continuum_kernel(ContArgs a)
 {
-    extern __shared__ double sm[];
+    extern __shared__ double s_c[];
     const int64_t L = blockIdx.x;
     const LayerDev& ly = a.lay[L];
-    double* s_self = sm;
-    double* s_frgn = s_self + a.g[0].nptc;
-    double* s_co2 = s_frgn + a.g[1].nptc;
-    double* s_n2 = s_co2 + a.g[2].nptc;
     const int tid = threadIdx.x;
-
-    if (a.g[0].active) {
-        for (int j = tid; j < a.g[0].nptc; j += blockDim.x) {
-            int i = a.g[0].i1 + j;
-            double s0 = 0., s1 = 0., sh2o = 0.;
-            if (i >= 1 && i <= 2003) { s0 = a.tb.sh2o_296[i - 1]; s1 = a.tb.sh2o_260[i - 1]; }
-            if (s0 > 0.) sh2o = s0 * pow(s1 / s0, ly.c_tfac_h2o);
-            s_self[j] = ly.c_wk1 * (sh2o * ly.c_rself);
-        }
-    }
-    if (a.g[1].active) {
-        const double f0 = 0.06, v0f1 = 255.67, hwsq1 = 240. * 240., beta1 = 57.83, c_1 = -0.42, c_2 = 0.3, beta2 = 630.;
-        for (int j = tid; j < a.g[1].nptc; j += blockDim.x) {
-            int i = a.g[1].i1 + j;
-            double f = (i >= 1 && i <= 2003) ? a.tb.fh2o[i - 1] : 0.;
-            double vj = a.g[1].v1c + a.g[1].dvc * (double)j;
-            double fscal;
-            if (vj <= 600.) {
-                int jfac = (int)((vj + 10.) / 10. + 0.00001);
-                fscal = a.tb.xfac_rhu[jfac + 1];
-            } else {
-                double t1 = (vj - v0f1) / beta1, t2 = (vj + v0f1) / beta1, t3 = vj / beta2;
-                double vf1 = t1 * t1; vf1 *= vf1; vf1 *= vf1;
-                double vmf1 = t2 * t2; vmf1 *= vmf1; vmf1 *= vmf1;
-                double vf2 = t3 * t3; vf2 *= vf2; vf2 *= vf2;
-                fscal = 1. + (f0 + c_1 * ((hwsq1 / ((vj - v0f1) * (vj - v0f1) + hwsq1 + vf1)) +
-                                          (hwsq1 / ((vj + v0f1) * (vj + v0f1) + hwsq1 + vmf1)))) /
-                                 (1. + c_2 * vf2);
-            }
-            f = f * fscal;
-            s_frgn[j] = (ly.c_wk1 * f) * ly.c_rfrgn;
-        }
-    }
-    if (a.g[2].active) {
-        for (int j = tid; j < a.g[2].nptc; j += blockDim.x) {
-            int i = a.g[2].i1 + j;
-            double f = 0.;
-            if (i >= 1 && i <= 5003) {
-                double tcor = 1.;
-                if (i >= 1196 && i <= 1220) tcor = pow(ly.c_trat, a.tb.co2_tdep[i - 1196]);
-                f = tcor * a.tb.fco2[i - 1];
-            }
-            s_co2[j] = f * ly.c_wco2;
-        }
-    }
-    if (a.g[3].active) {
-        for (int j = tid; j < a.g[3].nptc; j += blockDim.x) {
-            int i = a.g[3].i1 + j;
-            double c0 = 0., c1 = 0.;
-            if (i >= 1 && i <= 73) {
-                c0 = a.tb.n2_296[i - 1] * pow(a.tb.n2_220[i - 1] / a.tb.n2_296[i - 1], ly.c_tfac_n2);
-                double sf_t = a.tb.n2_296_sf[i - 1] * pow(a.tb.n2_220_sf[i - 1] / a.tb.n2_296_sf[i - 1], ly.c_tfac_n2);
-                c1 = (sf_t - 1.) * 0.79 / 0.21;
-            }
-            s_n2[j] = ly.c_taufac * c0 * (ly.c_xn2 + c1 * ly.c_xo2 + 1. * ly.c_xh2o);
+    double* out = a.absrb + (size_t)L * CP_COUNT * a.nptabs_pad;
+    for (int i = tid; i < CP_COUNT * a.nptabs_pad; i += blockDim.x) out[i] = 0.;
+    if (a.rayl_active) {                                      // contnm.f90:1107-1131 with JRAD = 0, IAERSL = 0
+        const double conv_cm2mol = a.cntnm[6] * 1.E-20 / (2.68675e-1 * 1.e5);
+        double* pr = out + (size_t)CP_RAYL * a.nptabs_pad;
+        for (int i = 1 + tid; i <= a.nptabs; i += blockDim.x) {
+            const double vr = a.v1abs + (double)(i - 1) * 1.0;
+            const double x = vr / 1.e4;
+            double ray = ((x * x * x) / (9.38076E2 - 10.8426 * (x * x))) * (ly.c_cw * conv_cm2mol);
+            pr[i - 1] = ray * x / cont_radfn(vr, ly.xkt);
         }
     }
     __syncthreads();
-    double* out = a.absrb + (size_t)L * 3 * a.nptabs_pad;
-    for (int i = 1 + tid; i <= a.nptabs_pad; i += blockDim.x) {
-        double vi = a.v1abs + 1.0 * (double)(i - 1);
-        double h = 0., c = 0., n = 0.;
-        if (i <= a.nptabs) {
-            if (a.g[0].active && i >= a.g[0].ilo && i <= a.g[0].ihi) h = h + xint_point(s_self, a.g[0].v1c, a.g[0].dvc, vi);
-            if (a.g[1].active && i >= a.g[1].ilo && i <= a.g[1].ihi) h = h + xint_point(s_frgn, a.g[1].v1c, a.g[1].dvc, vi);
-            if (a.g[2].active && i >= a.g[2].ilo && i <= a.g[2].ihi) c = xint_point(s_co2, a.g[2].v1c, a.g[2].dvc, vi);
-            if (a.g[3].active && i >= a.g[3].ilo && i <= a.g[3].ihi) n = xint_point(s_n2, a.g[3].v1c, a.g[3].dvc, vi);
-        }
-        out[i - 1] = h;
-        out[a.nptabs_pad + i - 1] = c;
-        out[2 * a.nptabs_pad + i - 1] = n;
+    for (int b = 0; b < CB_COUNT; b++) {
+        const ContGrid g = a.g[b];
+        if (!g.active) continue;
+        for (int j = tid; j < g.nptc; j += blockDim.x) s_c[j] = cont_value(b, g, j, ly, a);
+        __syncthreads();
+        double* pl = out + (size_t)cont_plane(b) * a.nptabs_pad;
+        for (int i = g.ilo + tid; i <= g.ihi; i += blockDim.x)
+            pl[i - 1] = pl[i - 1] + xint_point(s_c, g.v1c, g.dvc, a.v1abs + 1.0 * (double)(i - 1));
+        __syncthreads();
     }
 }
 

@@ -14,6 +14,7 @@
 #include "mrtm_kernels.cuh"
 #include "mrtm_stage.h"
 #include "tables/mtckd_tables.inc"
+#include "tables/mtckd_ir_tables.inc"
 
 namespace mrtm {
 const double* tips_qoft();
@@ -136,7 +137,7 @@ extern "C" const char* mrtm_strerror(int code)
     case MRTM_EARG: return "bad argument";
     case MRTM_ENOLINES: return "line list not staged (call mrtm_stage_lines first)";
     case MRTM_ELINEFILE: return "malformed line store";
-    case MRTM_ERANGE: return "spectral range needs continuum branches that are not built (V2 >= 820 cm-1)";
+    case MRTM_ERANGE: return "spectral range out of bounds";
     case MRTM_ESDVOIGT: return "SDVOIGT: REAL(v) < 0 (reference STOPs, modm.f90:1062)";
     case MRTM_EIDU: return "ERROR IN IDU. OPTION NOT SUPPORTED YET";
     case MRTM_ENOMEM: return "out of (device) memory";
@@ -192,12 +193,16 @@ extern "C" int mrtm_init(int device, mrtm_ctx** out)
         double v = std::atof(s);
         ctx->ff_ratio = (v <= 0.) ? 0. : std::max(v, 4.0);
     }
-    // continuum + TIPS tables -> HBM (about 190 KB)
+    // continuum + TIPS tables -> HBM (about 350 KB)
     int rc;
 #define UP(NAME, FIELD) if ((rc = upload_arr(ctx, NAME, sizeof(NAME) / sizeof(double), ctx->table_allocs, &ctx->tb.FIELD))) { *out = ctx; return rc; }
     UP(MTCKD_SH2O_296, sh2o_296) UP(MTCKD_SH2O_260, sh2o_260) UP(MTCKD_FH2O, fh2o) UP(MTCKD_FCO2, fco2)
     UP(MTCKD_N2RT_296, n2_296) UP(MTCKD_N2RT_296_SF, n2_296_sf) UP(MTCKD_N2RT_220, n2_220) UP(MTCKD_N2RT_220_SF, n2_220_sf)
     UP(MTCKD_XFAC_RHU, xfac_rhu) UP(MTCKD_CO2_TDEP_BANDHEAD, co2_tdep)
+    UP(MTCKD_XFACCO2, xfacco2) UP(MTCKD_N2F_272, n2f_272) UP(MTCKD_N2F_228, n2f_228) UP(MTCKD_N2F_AH2O, n2f_ah2o) UP(MTCKD_N2F1, n2f1)
+    UP(MTCKD_O3CH_X, o3ch_x) UP(MTCKD_O3CH_Y, o3ch_y) UP(MTCKD_O3CH_Z, o3ch_z) UP(MTCKD_O3HH0, o3hh0) UP(MTCKD_O3HH1, o3hh1)
+    UP(MTCKD_O3HH2, o3hh2) UP(MTCKD_O3HUV, o3huv) UP(MTCKD_O2F, o2f) UP(MTCKD_O2F_T, o2f_t) UP(MTCKD_O2INF1, o2inf1)
+    UP(MTCKD_O2INF3, o2inf3) UP(MTCKD_O2VIS, o2vis) UP(MTCKD_O2FUV, o2fuv)
 #undef UP
     if ((rc = upload_arr(ctx, tips_qoft(), (size_t)tips_rows() * 119, ctx->table_allocs, &ctx->tips.qoft))) { *out = ctx; return rc; }
     if ((rc = upload_arr(ctx, tips_tdat(), 119, ctx->table_allocs, &ctx->tips.tdat))) { *out = ctx; return rc; }
@@ -306,7 +311,8 @@ extern "C" int mrtm_stage_lines(mrtm_ctx* ctx, const int64_t nblm[MRTM_MXMOL], i
 // continuum index set-up (layer independent): table accessors (contnm.f90:1441-1456 and twins),
 // pre_xint (:1146-1164) and the XINT loop bounds (lblrtm_sub.f90:13-17), evaluated on the host.
 // ---------------------------------------------------------------------------------------------
-static ContGrid make_grid(double v1abs, double v2abs, int nptabs, double v1s, double v2s, double dvs, int npts, bool active)
+static ContGrid make_grid(double v1abs, double v2abs, int nptabs, double v1s, double v2s, double dvs, int npts, bool active,
+                          double eps = 0.01, bool cap = true)
 {
     ContGrid g;
     std::memset(&g, 0, sizeof g);
@@ -315,11 +321,11 @@ static ContGrid make_grid(double v1abs, double v2abs, int nptabs, double v1s, do
     double v1c = v1abs - dvc, v2c = v2abs + dvc;
     long long i1;
     if (v1c < v1s) i1 = -1;
-    else i1 = (long long)((v1c - v1s) / dvs + 0.01);
+    else i1 = (long long)((v1c - v1s) / dvs + eps);
     v1c = v1s + dvs * (double)(i1 - 1);
-    long long i2 = (long long)((v2c - v1s) / dvs + 0.01);
+    long long i2 = (long long)((v2c - v1s) / dvs + eps);
     long long nptc = i2 - i1 + 3;
-    if (nptc > npts) nptc = npts + 4;
+    if (cap && nptc > npts) nptc = npts + 4;
     v2c = v1c + dvs * (double)(nptc - 1);
     long long nb1 = (long long)(2 + (v1s - v1abs) / dvabs + 1.e-5);
     long long ist = std::max<long long>(1, nb1);
@@ -335,8 +341,76 @@ static ContGrid make_grid(double v1abs, double v2abs, int nptabs, double v1s, do
     g.i1 = (int32_t)i1;
     g.ilo = (int32_t)ilo;
     g.ihi = (int32_t)ihi;
-    g.active = active ? 1 : 0;
+    g.active = (active && nptc > 0) ? 1 : 0;
     return g;
+}
+
+// O2INF2 (contnm.f90:9227-9279) sets up its own grid: no table, the coefficient range clamps V1C, V2C
+static ContGrid make_grid_o2inf2(double v1abs, double v2abs, int nptabs, bool active)
+{
+    ContGrid g;
+    std::memset(&g, 0, sizeof g);
+    const double v1s = 9100., v2s = 11000., dvs = 2., dvabs = 1.0, onemi = 0.999;
+    double dvc = dvs, v1c = v1abs - dvc, v2c = v2abs + dvc;
+    if (v1c < v1s) v1c = v1s - 2. * dvs;
+    if (v2c > v2s) v2c = v2s + 2. * dvs;
+    long long nptc = (long long)((v2c - v1c) / dvc + 3.01);
+    v2c = v1c + dvc * (double)(nptc - 1);
+    long long ist = std::max<long long>(1, (long long)(2 + (v1s - v1abs) / dvabs + 1.e-5));
+    long long last = std::min<long long>(nptabs, (long long)(1 + (v2s - v1abs) / dvabs + 1.e-5));
+    long long ilo = std::max((long long)((v1c + dvc - v1abs) / dvabs + 1. + onemi), ist);
+    long long ihi = std::min((long long)((v2c - dvc - v1abs) / dvabs + onemi), last);
+    g.v1c = v1c;
+    g.dvc = dvc;
+    g.nptc = (int32_t)nptc;
+    g.i1 = 0;
+    g.ilo = (int32_t)ilo;
+    g.ihi = (int32_t)ihi;
+    g.active = (active && nptc > 0) ? 1 : 0;
+    return g;
+}
+
+// every component of CONTNM with its gate (contnm.f90:325, 387, 484, 536, 555, 603, 657, 709, 745, 773, 807, 834, 857, 906,
+// 963, 1025, 1107); returns the ContPlane mask of the species that have an active component
+static int make_cont_grids(ContGrid* g, double v1, double v2, double v1abs, double v2abs, int nptabs, const double cn[7], int* rayl)
+{
+    const double xself = cn[0], xfrgn = cn[1], xco2c = cn[2], xo3cn = cn[3], xo2cn = cn[4], xn2cn = cn[5], xrayl = cn[6];
+    const bool gate_h2o = (v2 > -20.0) && (v1 < 20000.);
+    g[CB_H2O_SELF] = make_grid(v1abs, v2abs, nptabs, -20.0, 20000.0, 10.0, 2003, gate_h2o && xself > 0.);
+    g[CB_H2O_FRGN] = make_grid(v1abs, v2abs, nptabs, -20.0, 20000.0, 10.0, 2003, gate_h2o && xfrgn > 0.);
+    g[CB_CO2] = make_grid(v1abs, v2abs, nptabs, -4.0, 10000.0, 2.0, 5003, (v2 > -20.0) && (v1 < 10000.) && xco2c > 0);
+    g[CB_N2_ROT] = make_grid(v1abs, v2abs, nptabs, -10., 350., 5.0, 73, (v2 > -10.0) && (v1 < 350.) && xn2cn > 0.);
+    g[CB_N2_FUND] = make_grid(v1abs, v2abs, nptabs, 1997.784896, 2901.576661, 3.981461525, 228, (v2 > 2001.77) && (v1 < 2897.59) && xn2cn > 0.);
+    g[CB_N2_OVER] = make_grid(v1abs, v2abs, nptabs, 4340.0, 4910.0, 3.0, 191, (v2 > 4340.0) && (v1 < 4910.) && xn2cn > 0.);
+    g[CB_O3_CHAP] = make_grid(v1abs, v2abs, nptabs, 8920.0, 24665.0, 5.0, 3150, v2 > 8920.0 && v1 <= 24665.0 && xo3cn > 0.);
+    g[CB_O3_HH] = make_grid(v1abs, v2abs, nptabs, 27370., 40800., 5.0, 2687, v2 > 27370. && v1 < 40800. && xo3cn > 0.);
+    g[CB_O3_UV] = make_grid(v1abs, v2abs, nptabs, 40800., 54000., 100., 133, v2 > 40800. && v1 < 54000. && xo3cn > 0.);
+    {
+        // Hartley-Huggins / UV hand-over at 40800 cm-1: each branch restores the other's side of the 1 cm-1 grid after its
+        // interpolation (ABSBSV, contnm.f90:573-599 and :619-640), i.e. it contributes only on its own side of I_FIX
+        const long long i_fix = (long long)((40800. - v1abs) / 1.0 + 1.001);
+        ContGrid& hh = g[CB_O3_HH];
+        const double vj_last = hh.v1c + hh.dvc * (double)(hh.nptc - 1);
+        if (hh.active && (vj_last > 40815.) && (v2 > 40800)) hh.ihi = (int32_t)std::min<long long>(hh.ihi, i_fix - 1);
+        ContGrid& uv = g[CB_O3_UV];
+        if (uv.active && (v1 < 40800)) uv.ilo = (int32_t)std::max<long long>(uv.ilo, i_fix);
+    }
+    g[CB_O2_FUND] = make_grid(v1abs, v2abs, nptabs, 1340.0, 1850.0, 5.0, 103, (v2 > 1340.0) && (v1 < 1850.) && xo2cn > 0.);
+    g[CB_O2_INF1] = make_grid(v1abs, v2abs, nptabs, 7536.0, 8500.0, 2.0, 483, (v2 > 7536.0) && (v1 < 8500.) && xo2cn > 0.);
+    g[CB_O2_INF2] = make_grid_o2inf2(v1abs, v2abs, nptabs, (v2 > 9100.0) && (v1 < 11000.) && xo2cn > 0.);
+    g[CB_O2_INF3] = make_grid(v1abs, v2abs, nptabs, 12961.5, 13221.5, 1.0, 261, (v2 > 12961.5) && (v1 < 13221.5) && xo2cn > 0.);
+    g[CB_O2_VIS] = make_grid(v1abs, v2abs, nptabs, 15140.0, 29870.0, 10.0, 1474, (v2 > 15000.0) && (v1 < 29870.) && xo2cn > 0.);
+    g[CB_O2_HERZ] = make_grid(v1abs, v2abs, nptabs, 36000., 99999., 10., 0, v2 > 36000.0 && xo2cn > 0., 0.01, false);
+    g[CB_O2_FUV] = make_grid(v1abs, v2abs, nptabs, 56740.0, 86960.0, 20.0, 1512, v2 > 56740.0 && xo2cn > 0., 1.e-5, true);
+    *rayl = (v2 >= 820. && xrayl > 0.) ? 1 : 0;
+    int mask = 0;
+    if (g[CB_H2O_SELF].active || g[CB_H2O_FRGN].active) mask |= 1 << CP_H2O;
+    if (g[CB_CO2].active) mask |= 1 << CP_CO2;
+    if (g[CB_O3_CHAP].active || g[CB_O3_HH].active || g[CB_O3_UV].active) mask |= 1 << CP_O3;
+    for (int b = CB_O2_FUND; b <= CB_O2_FUV; b++) if (g[b].active) mask |= 1 << CP_O2;
+    if (g[CB_N2_ROT].active || g[CB_N2_FUND].active || g[CB_N2_OVER].active) mask |= 1 << CP_N2;
+    if (*rayl) mask |= 1 << CP_RAYL;
+    return mask;
 }
 
 // everything below works on device pointers
@@ -414,7 +488,6 @@ static int run_device(mrtm_ctx* ctx, const RunDesc& r, cudaStream_t s)
     if (r.do_lines) {
         if (!ctx->have_lines) return set_err(ctx, MRTM_ENOLINES, mrtm_strerror(MRTM_ENOLINES));
         if (r.nmol < 1 || r.nmol > MRTM_MXMOL) return set_err(ctx, MRTM_EARG, "nmol out of 1..39");
-        if (!(r.v2 < 820.0)) return set_err(ctx, MRTM_ERANGE, mrtm_strerror(MRTM_ERANGE));
         if ((r.o_by_mol || r.oc || r.o_clw) && r.nprof != 1) return set_err(ctx, MRTM_EARG, "per-molecule outputs need nprof == 1");
     }
     if ((r.do_rtm || r.do_tmr) && r.do_rtm && r.idu != 1) return set_err(ctx, MRTM_EIDU, mrtm_strerror(MRTM_EIDU));
@@ -443,20 +516,18 @@ static int run_device(mrtm_ctx* ctx, const RunDesc& r, cudaStream_t s)
     if (own_o && (rc = ensure(ctx, bo, (size_t)nwn * nlay * B * 8))) return rc;
 
     ContArgs ca;
+    int cont_mask = 0;
     if (r.do_lines) {
         std::memset(&ca, 0, sizeof ca);
-        const bool gate_h2o = (v2 > -20.0) && (v1 < 20000.);
-        ca.g[0] = make_grid(v1abs, v2abs, nptabs, -20.0, 20000.0, 10.0, 2003, gate_h2o && r.cntnm[0] > 0.);
-        ca.g[1] = make_grid(v1abs, v2abs, nptabs, -20.0, 20000.0, 10.0, 2003, gate_h2o && r.cntnm[1] > 0.);
-        ca.g[2] = make_grid(v1abs, v2abs, nptabs, -4.0, 10000.0, 2.0, 5003, (v2 > -20.0) && (v1 < 10000.) && r.cntnm[2] > 0);
-        ca.g[3] = make_grid(v1abs, v2abs, nptabs, -10., 350., 5.0, 73, (v2 > -10.0) && (v1 < 350.) && r.cntnm[5] > 0.);
+        cont_mask = make_cont_grids(ca.g, v1, v2, v1abs, v2abs, nptabs, r.cntnm, &ca.rayl_active);
+        for (int i = 0; i < 7; i++) ca.cntnm[i] = r.cntnm[i];
         ca.v1abs = v1abs;
         ca.nptabs = nptabs;
         ca.nptabs_pad = nptabs_pad;
         ca.tb = ctx->tb;
         if ((rc = ensure(ctx, ctx->b_layer, (size_t)B * nlay * sizeof(LayerDev)))) return rc;
         if ((rc = ensure(ctx, ctx->b_scorc, (size_t)B * nlay * std::max(1, (int)ctx->ld.nsi) * 8))) return rc;
-        if ((rc = ensure(ctx, ctx->b_absrb, (size_t)B * nlay * 3 * nptabs_pad * 8))) return rc;
+        if ((rc = ensure(ctx, ctx->b_absrb, (size_t)B * nlay * CP_COUNT * nptabs_pad * 8))) return rc;
         if ((rc = ensure(ctx, ctx->b_planes, (size_t)B * nlay * D_NPLANES * (size_t)n_pad * 8))) return rc;
         if ((rc = ensure(ctx, ctx->b_lcplanes, (size_t)B * nlay * LCP_NPLANES * (size_t)nlc_pad * 8))) return rc;
         if ((rc = ensure(ctx, ctx->b_vtmax, (1 + std::max<size_t>(1, h.segments.size())) * 8))) return rc;
@@ -511,7 +582,11 @@ static int run_device(mrtm_ctx* ctx, const RunDesc& r, cudaStream_t s)
             ca.nlayers = Lb;
             ca.lay = (const LayerDev*)ctx->b_layer.p;
             ca.absrb = (double*)ctx->b_absrb.p;
-            size_t smem = (size_t)(ca.g[0].nptc + ca.g[1].nptc + ca.g[2].nptc + ca.g[3].nptc + 8) * 8;
+            int nptc_max = 0;
+            for (int b = 0; b < CB_COUNT; b++) if (ca.g[b].active) nptc_max = std::max(nptc_max, (int)ca.g[b].nptc);
+            const size_t smem = (size_t)(nptc_max + 8) * 8;
+            if (smem > 200 * 1024) return set_err(ctx, MRTM_EARG, "spectral range too wide for one call (continuum coefficient grid)");
+            if (smem > 48 * 1024) CU(cudaFuncSetAttribute(continuum_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             continuum_kernel<<<(unsigned)Lb, 128, smem, s>>>(ca);
             st.kernel_launches++;
 
@@ -565,6 +640,7 @@ static int run_device(mrtm_ctx* ctx, const RunDesc& r, cudaStream_t s)
             la.absrb = (const double*)ctx->b_absrb.p;
             la.nptabs = nptabs;
             la.nptabs_pad = nptabs_pad;
+            la.cont_mask = cont_mask;
             la.v1abs = v1abs;
             la.v2abs = v2abs;
             la.v1 = v1;

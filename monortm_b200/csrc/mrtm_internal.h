@@ -79,9 +79,19 @@ struct LayerDev {
     // continuum per-layer scalars (contnm.f90:222-240,300-302,487,919)
     double c_wk1, c_rself, c_rfrgn, c_tfac_h2o, c_wco2, c_trat, c_taufac, c_tfac_n2;
     double c_xn2, c_xo2, c_xh2o;
+    // ... and of the branches above the microwave (contnm.f90:229, 541, 665, 718, 756, 820, 838)
+    double c_amagat, c_rhoave, c_wk3, c_wk7, c_cw;
     int32_t ilc;       // 1..3
     int32_t pad;
 };
+
+// continuum components of CONTNM (contnm.f90:325-1131) and the per-species planes they accumulate into (MODM calls CONTNM
+// once per species with the other scale factors zeroed, modm.f90:210-214)
+enum ContBranch : int {
+    CB_H2O_SELF = 0, CB_H2O_FRGN, CB_CO2, CB_N2_ROT, CB_N2_FUND, CB_N2_OVER, CB_O3_CHAP, CB_O3_HH, CB_O3_UV,
+    CB_O2_FUND, CB_O2_INF1, CB_O2_INF2, CB_O2_INF3, CB_O2_VIS, CB_O2_HERZ, CB_O2_FUV, CB_COUNT
+};
+enum ContPlane : int { CP_H2O = 0, CP_CO2, CP_O3, CP_O2, CP_N2, CP_RAYL, CP_COUNT };
 
 struct ContGrid {     // accessor/XINT index set-up for one continuum component (layer independent)
     double v1c, dvc;

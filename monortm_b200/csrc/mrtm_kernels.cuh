@@ -31,6 +31,9 @@ struct LinesDev {
 struct ContTablesDev {
     const double *sh2o_296, *sh2o_260, *fh2o, *fco2, *n2_296, *n2_296_sf, *n2_220, *n2_220_sf;
     const double *xfac_rhu, *co2_tdep;
+    // branches above the microwave (tables/mtckd_ir_tables.inc)
+    const double *xfacco2, *n2f_272, *n2f_228, *n2f_ah2o, *n2f1, *o3ch_x, *o3ch_y, *o3ch_z, *o3hh0, *o3hh1, *o3hh2, *o3huv;
+    const double *o2f, *o2f_t, *o2inf1, *o2inf3, *o2vis, *o2fuv;
 };
 
 struct TipsDev {

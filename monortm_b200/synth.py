@@ -75,7 +75,7 @@ def physical_seed_lines():
 
 
 def synthetic_records(n_filler=4096, seed=20260101, vmax=80.0, with_physical=True, n_co2=0,
-                      n_sdep=0, n_generic_lc=0, brd_fraction=0.0):
+                      n_sdep=0, n_generic_lc=0, brd_fraction=0.0, vmin=0.02):
     """Build a TAPE3-synth record array in file order.
 
     filler: molecule in {1,3,4,5,7} with weights {.15,.6,.1,.05,.1}; S log-uniform 1e-30..1e-22;
@@ -88,7 +88,7 @@ def synthetic_records(n_filler=4096, seed=20260101, vmax=80.0, with_physical=Tru
     mols = np.array([1, 3, 4, 5, 7])
     pm = np.array([.15, .6, .1, .05, .1])
     mol = rng.choice(mols, size=n_filler, p=pm)
-    vnu = rng.uniform(0.02, vmax, n_filler)
+    vnu = rng.uniform(vmin, vmax, n_filler)      # vmin > 0.02: a list above the microwave (continuum branches of SURVEY 8f-2)
     s = 10.0 ** rng.uniform(-30, -22, n_filler)
     alfa = rng.uniform(0.03, 0.11, n_filler)
     hwhm = rng.uniform(0.05, 0.5, n_filler)
@@ -100,7 +100,7 @@ def synthetic_records(n_filler=4096, seed=20260101, vmax=80.0, with_physical=Tru
         groups.append([_line(vnu[i], s[i], alfa[i], hwhm[i], epp[i], tmpalf[i], pshift[i], int(mol[i]), int(iso[i]))])
     # a few H2O lines with zero self width exercise the 5x fix-up (modm.f90:841)
     for i in range(min(8, n_filler // 64)):
-        v = rng.uniform(1.0, vmax)
+        v = rng.uniform(max(1.0, vmin), vmax)
         groups.append([_line(v, 10.0 ** rng.uniform(-26, -23), 0.08, 0.0, 200.0, 0.7, 1e-3, 1)])
     for i in range(n_sdep):
         v = rng.uniform(0.5, min(vmax, 40.0))

@@ -29,6 +29,7 @@
 #include <string.h>
 
 #include "../monortm_b200/csrc/tables/mtckd_tables.inc"
+#include "../monortm_b200/csrc/tables/mtckd_ir_tables.inc"
 #include "../monortm_b200/csrc/tables/smass_table.inc"
 
 typedef double _Complex cplx;
@@ -337,6 +338,41 @@ static void accessor_grid(double v1abs, double v2abs, double v1s, double dvs, in
     *i1out = i1;
 }
 
+/* the same set-up with the two details some accessors change: the offset added before truncation (O2FUV uses 1.e-5,
+ * contnm.f90:9968-9973) and the NPTS cap (absent in O2HERZ, :9833-9836) */
+static void accessor_grid2(double v1abs, double v2abs, double v1s, double dvs, int64_t npts, double eps, int cap,
+                           double *v1c, double *v2c, double *dvc, int64_t *nptc, int64_t *i1out)
+{
+    int64_t i1, i2;
+    *dvc = dvs;
+    *v1c = v1abs - *dvc;
+    *v2c = v2abs + *dvc;
+    if (*v1c < v1s) i1 = -1;
+    else i1 = (int64_t)((*v1c - v1s) / dvs + eps);
+    *v1c = v1s + dvs * (double)(i1 - 1);
+    i2 = (int64_t)((*v2c - v1s) / dvs + eps);
+    *nptc = i2 - i1 + 3;
+    if (cap && *nptc > npts) *nptc = npts + 4;
+    *v2c = *v1c + dvs * (double)(*nptc - 1);
+    *i1out = i1;
+}
+
+/* HERTDA + HERPRS, contnm.f90:9856-9948 */
+static double herzberg(double v, double t, double p)
+{
+    double herz = 0.0;
+    if (!(v <= 36000.00)) {
+        double corr = 0.;
+        if (v <= 40000.) corr = ((40000. - v) / 4000.) * 7.917E-07;
+        double yratio = v / 48811.0;
+        double lg = log(yratio);
+        herz = 6.884E-04 * (yratio) * exp(-69.738 * (lg * lg)) - corr;
+    }
+    const double po = 1013., to = 273.16;
+    herz = herz * (1. + .83 * (p / po) * (to / t));
+    return herz;
+}
+
 /* XFAC_RHU(-1:61), contnm.f90:186-202 */
 static double xfac_rhu(int64_t i) { return MTCKD_XFAC_RHU[i + 1]; }
 
@@ -356,8 +392,6 @@ int orc_contnm_one(int64_t im, const double cntnm[7], double pave, double tave,
     case 99: xrayl = cntnm[6]; break;
     default: break;
     }
-    (void)xo3cn; (void)xo2cn; (void)xrayl;
-    if (!(v2 < 820.0)) return fail(20, "continuum branches for V2 >= 820 cm-1 are not built (SURVEY 8f-2)");
     if (nptabs > N_ABSRB - 2) return fail(21, "NPTABS too large");
 
     const double dvabs = 1.0;
@@ -460,7 +494,10 @@ int orc_contnm_one(int64_t im, const double cntnm[7], double pave, double tave,
         for (int64_t j = 1; j <= nptc; j++) {
             double vj = v1c + dvc * (double)(j - 1);
             double cfac = 1.;
-            if (vj >= 2000. && vj <= 2998.) return fail(22, "XFACCO2 range not built");
+            if (vj >= 2000. && vj <= 2998.) {                        /* :510-513 */
+                int64_t jfac = (int64_t)((vj - 1998.) / 2. + 0.00001);
+                cfac = MTCKD_XFACCO2[jfac - 1];
+            }
             fco2[j - 1] = cfac * fco2[j - 1];
             c[j - 1] = fco2[j - 1] * wco2;
         }
@@ -490,8 +527,285 @@ int orc_contnm_one(int64_t im, const double cntnm[7], double pave, double tave,
         pre_xint(-10., 350., v1abs, dvabs, nptabs, &ist, &last);
         xint(v1c, v2c, dvc, c, 1.0, v1abs, dvabs, absrb, ist, last);
     }
-    /* O3 (V2>8920), O2 (V2>1340), N2 fundamental (V2>2001.77), Rayleigh (V2>=820):
-     * gated off for V2 < 820, contnm.f90:536,657,963,1107. */
+
+    /* ---- N2 collision-induced fundamental, contnm.f90:963-1013, n2_ver_1 :4331-4417 ---- */
+    if ((v2 > 2001.77) && (v1 < 2897.59) && xn2cn > 0.) {
+        double *cn0 = c0, *cn1 = c1, *cn2 = c2;
+        memset(c0, 0, sizeof c0);
+        memset(c1, 0, sizeof c1);
+        memset(c2, 0, sizeof c2);
+        double tau_fac = xn2cn * (wn2 / XLOSMT) * amagat;
+        const double t_272 = 272., t_228 = 228.;
+        double xtfac = ((1. / tave) - (1. / t_272)) / ((1. / t_228) - (1. / t_272));
+        double xt_lin = (tave - t_272) / (t_228 - t_272);
+        double a_o2 = 1.294 - 0.4545 * tave / 296.;
+        accessor_grid(v1abs, v2abs, 1997.784896, 3.981461525, 228, &v1c, &v2c, &dvc, &nptc, &i1);
+        for (int64_t j = 1; j <= nptc; j++) {
+            int64_t i = i1 + (j - 1);
+            cn0[j - 1] = 0.;
+            if (i < 1 || i > 228) continue;
+            double vj = v1c + dvc * (double)(j - 1);
+            double a = MTCKD_N2F_272[i - 1], b = MTCKD_N2F_228[i - 1];
+            if ((a > 0.) && (b > 0.)) cn0[j - 1] = a * pow(b / a, xtfac);
+            else cn0[j - 1] = a + (b - a) * xt_lin;
+            cn0[j - 1] = cn0[j - 1] / vj;
+            cn1[j - 1] = a_o2 * cn0[j - 1];
+            cn2[j - 1] = (9. / 7.) * MTCKD_N2F_AH2O[i - 1] * cn0[j - 1];
+        }
+        for (int64_t j = 1; j <= nptc; j++)
+            c[j - 1] = tau_fac * (x_vmr_n2 * cn0[j - 1] + x_vmr_o2 * cn1[j - 1] + x_vmr_h2o * cn2[j - 1]);
+        pre_xint(1997.784896, 2901.576661, v1abs, dvabs, nptabs, &ist, &last);
+        xint(v1c, v2c, dvc, c, 1.0, v1abs, dvabs, absrb, ist, last);
+    }
+
+    /* ---- N2 collision-induced first overtone, contnm.f90:1025-1068, n2_overtone1 :4579-4631 ---- */
+    if ((v2 > 4340.0) && (v1 < 4910.) && xn2cn > 0.) {
+        memset(c0, 0, sizeof c0);
+        double a_o2 = 1., a_h2o = 1.;
+        double tau_fac = xn2cn * (wn2 / XLOSMT) * amagat * (x_vmr_n2 + a_o2 * x_vmr_o2 + a_h2o * x_vmr_h2o);
+        accessor_grid(v1abs, v2abs, 4340.0, 3.0, 191, &v1c, &v2c, &dvc, &nptc, &i1);
+        for (int64_t j = 1; j <= nptc; j++) {
+            int64_t i = i1 + (j - 1);
+            c0[j - 1] = 0.;
+            if (i < 1 || i > 191) continue;
+            double vj = v1c + dvc * (double)(j - 1);
+            c0[j - 1] = MTCKD_N2F1[i - 1] / vj;
+        }
+        for (int64_t j = 1; j <= nptc; j++) c[j - 1] = tau_fac * c0[j - 1];
+        pre_xint(4340.0, 4910.0, v1abs, dvabs, nptabs, &ist, &last);
+        xint(v1c, v2c, dvc, c, 1.0, v1abs, dvabs, absrb, ist, last);
+    }
+
+    /* ---- O3 Chappuis / Wulf, contnm.f90:536-553, XO3CHP :4685-4732 ---- */
+    if (v2 > 8920.0 && v1 <= 24665.0 && xo3cn > 0.) {
+        double wo3 = wk[2] * 1.0E-20 * xo3cn;
+        double dt = tave - 273.15;
+        accessor_grid(v1abs, v2abs, 8920.0, 5.0, 3150, &v1c, &v2c, &dvc, &nptc, &i1);
+        for (int64_t j = 1; j <= nptc; j++) {
+            int64_t i = i1 + (j - 1);
+            double cch0 = 0., cch1 = 0., cch2 = 0.;
+            if (!(i < 1 || i > 3150)) {
+                double vj = v1c + dvc * (double)(j - 1);
+                cch0 = MTCKD_O3CH_X[i - 1] / vj;
+                cch1 = MTCKD_O3CH_Y[i - 1] / vj;
+                cch2 = MTCKD_O3CH_Z[i - 1] / vj;
+            }
+            c[j - 1] = (cch0 + (cch1 + cch2 * dt) * dt) * wo3;
+        }
+        pre_xint(8920.0, 24665.0, v1abs, dvabs, nptabs, &ist, &last);
+        xint(v1c, v2c, dvc, c, 1.0, v1abs, dvabs, absrb, ist, last);
+    }
+
+    /* ---- O3 Hartley-Huggins, contnm.f90:555-599, O3HHT0/1/2 :6850-8216 (the three tables share one grid) ---- */
+    if (v2 > 27370. && v1 < 40800. && xo3cn > 0.) {
+        static double absbsv[N_ABSRB];
+        double wo3 = wk[2] * 1.E-20 * xo3cn;
+        double tc = tave - 273.15;
+        accessor_grid(v1abs, v2abs, 27370., 5.0, 2687, &v1c, &v2c, &dvc, &nptc, &i1);
+        double vj = 0.;
+        for (int64_t j = 1; j <= nptc; j++) {
+            int64_t i = i1 + (j - 1);
+            double s0v = 0., ct1 = 0., ct2 = 0.;
+            vj = v1c + dvc * (double)(j - 1);
+            if (!(i < 1 || i > 2687)) {
+                s0v = MTCKD_O3HH0[i - 1] / vj;
+                ct1 = MTCKD_O3HH1[i - 1];
+                ct2 = MTCKD_O3HH2[i - 1];
+            }
+            c[j - 1] = s0v * wo3;
+            c[j - 1] = c[j - 1] * (1. + ct1 * tc + ct2 * tc * tc);
+        }
+        int64_t i_fix = 0;
+        int fix = (vj > 40815.) && (v2 > 40800);                  /* :573-578: VJ is the last grid point of the loop */
+        if (fix) {
+            i_fix = (int64_t)((40800. - v1abs) / dvabs + 1.001);
+            for (int64_t i = i_fix; i <= nptabs; i++) absbsv[i - 1] = absrb[i - 1];
+        }
+        pre_xint(27370., 40800., v1abs, dvabs, nptabs, &ist, &last);
+        xint(v1c, v2c, dvc, c, 1.0, v1abs, dvabs, absrb, ist, last);
+        if (fix)
+            for (int64_t i = i_fix; i <= nptabs; i++) absrb[i - 1] = absbsv[i - 1];
+    }
+
+    /* ---- O3 UV Hartley-Huggins, contnm.f90:603-642, O3HHUV :8826-8866 ---- */
+    if (v2 > 40800. && v1 < 54000. && xo3cn > 0.) {
+        static double absbsv[N_ABSRB];
+        double wo3 = wk[2] * xo3cn;
+        accessor_grid(v1abs, v2abs, 40800., 100., 133, &v1c, &v2c, &dvc, &nptc, &i1);
+        for (int64_t j = 1; j <= nptc; j++) {
+            int64_t i = i1 + (j - 1);
+            double c0v = 0.;
+            if (!(i < 1 || i > 133)) {
+                double vj = v1c + dvc * (double)(j - 1);
+                c0v = MTCKD_O3HUV[i - 1] / vj;
+            }
+            c[j - 1] = c0v * wo3;
+        }
+        int64_t i_fix = 0;
+        if (v1 < 40800) {
+            i_fix = (int64_t)((40800. - v1abs) / dvabs + 1.001);
+            for (int64_t i = 1; i <= i_fix - 1; i++) absbsv[i - 1] = absrb[i - 1];
+        }
+        pre_xint(40800., 54000., v1abs, dvabs, nptabs, &ist, &last);
+        xint(v1c, v2c, dvc, c, 1.0, v1abs, dvabs, absrb, ist, last);
+        if (v1 < 40800)
+            for (int64_t i = 1; i <= i_fix - 1; i++) absrb[i - 1] = absbsv[i - 1];
+    }
+
+    /* ---- O2 collision-induced fundamental, contnm.f90:657-693, o2_ver_1 :8917-8981 ---- */
+    if ((v2 > 1340.0) && (v1 < 1850.) && xo2cn > 0.) {
+        double tau_fac = xo2cn * wk[6] * 1.e-20 * amagat;
+        double xktfac = (1. / 296.) - (1. / tave);
+        double factor = (1.e+20 / 2.68675e+19);
+        accessor_grid(v1abs, v2abs, 1340.0, 5.0, 103, &v1c, &v2c, &dvc, &nptc, &i1);
+        for (int64_t j = 1; j <= nptc; j++) {
+            int64_t i = i1 + (j - 1);
+            double c0v = 0.;
+            if (!(i < 1 || i > 103)) {
+                double vj = v1c + dvc * (double)(j - 1);
+                c0v = factor * MTCKD_O2F[i - 1] * exp(MTCKD_O2F_T[i - 1] * xktfac) / vj;
+            }
+            c[j - 1] = tau_fac * c0v;
+        }
+        pre_xint(1340.0, 1850.0, v1abs, dvabs, nptabs, &ist, &last);
+        xint(v1c, v2c, dvc, c, 1.0, v1abs, dvabs, absrb, ist, last);
+    }
+
+    /* ---- O2 1.27 um (Mate et al.), contnm.f90:709-734, O2INF1 :9047-9100 ---- */
+    if ((v2 > 7536.0) && (v1 < 8500.) && xo2cn > 0.) {
+        double a_o2 = 1. / 0.446, a_n2 = 0.3 / 0.446, a_h2o = 1.;
+        double tau_fac = xo2cn * (wk[6] / XLOSMT) * amagat * (a_o2 * x_vmr_o2 + a_n2 * x_vmr_n2 + a_h2o * x_vmr_h2o);
+        accessor_grid(v1abs, v2abs, 7536.0, 2.0, 483, &v1c, &v2c, &dvc, &nptc, &i1);
+        for (int64_t j = 1; j <= nptc; j++) {
+            int64_t i = i1 + (j - 1);
+            double c0v = 0.;
+            if (!(i < 1 || i > 483)) {
+                double vj = v1c + dvc * (double)(j - 1);
+                c0v = MTCKD_O2INF1[i - 1] / vj;
+            }
+            c[j - 1] = tau_fac * c0v;
+        }
+        pre_xint(7536.0, 8500.0, v1abs, dvabs, nptabs, &ist, &last);
+        xint(v1c, v2c, dvc, c, 1.0, v1abs, dvabs, absrb, ist, last);
+    }
+
+    /* ---- O2 9100-11000 cm-1 (Mlawer et al.), contnm.f90:745-766, O2INF2 :9227-9279 ---- */
+    if ((v2 > 9100.0) && (v1 < 11000.) && xo2cn > 0.) {
+        const double v1_osc = 9375., hw1 = 58.96, v2_osc = 9439., hw2 = 45.04, s1 = 1.166E-04, s2 = 3.086E-05;
+        const double v1s = 9100., v2s = 11000., dvs = 2.;
+        double wo2 = xo2cn * (wk[6] * 1.e-20) * rhoave;
+        double adjwo2 = (wk[6] / wtot) * (1. / 0.209) * wo2;
+        dvc = dvs;
+        v1c = v1abs - dvc;
+        v2c = v2abs + dvc;
+        if (v1c < v1s) v1c = v1s - 2. * dvs;
+        if (v2c > v2s) v2c = v2s + 2. * dvs;
+        nptc = (int64_t)((v2c - v1c) / dvc + 3.01);
+        v2c = v1c + dvc * (double)(nptc - 1);
+        for (int64_t j = 1; j <= nptc; j++) {
+            double c0v = 0.;
+            double vj = v1c + dvc * (double)(j - 1);
+            if ((vj > v1s) && (vj < v2s)) {
+                double dv1 = vj - v1_osc, dv2 = vj - v2_osc, damp1, damp2;
+                if (dv1 < 0.0) damp1 = exp(dv1 / 176.1); else damp1 = 1.0;
+                if (dv2 < 0.0) damp2 = exp(dv2 / 176.1); else damp2 = 1.0;
+                double q1 = dv1 / hw1, q2 = dv2 / hw2;
+                double o2inf = 0.31831 * (((s1 * damp1 / hw1) / (1. + q1 * q1)) + ((s2 * damp2 / hw2) / (1. + q2 * q2))) * 1.054;
+                c0v = o2inf / vj;
+            }
+            c[j - 1] = c0v * adjwo2;
+        }
+        pre_xint(v1s, v2s, v1abs, dvabs, nptabs, &ist, &last);
+        xint(v1c, v2c, dvc, c, 1.0, v1abs, dvabs, absrb, ist, last);
+    }
+
+    /* ---- O2 A band, contnm.f90:773-792, O2INF3 :9282-9330 ---- */
+    if ((v2 > 12961.5) && (v1 < 13221.5) && xo2cn > 0.) {
+        double tau_fac = xo2cn * (wk[6] / XLOSMT) * amagat;
+        accessor_grid(v1abs, v2abs, 12961.5, 1.0, 261, &v1c, &v2c, &dvc, &nptc, &i1);
+        for (int64_t j = 1; j <= nptc; j++) {
+            int64_t i = i1 + (j - 1);
+            double c0v = 0.;
+            if (!(i < 1 || i > 261)) {
+                double vj = v1c + dvc * (double)(j - 1);
+                c0v = MTCKD_O2INF3[i - 1] / vj;
+            }
+            c[j - 1] = tau_fac * c0v;
+        }
+        pre_xint(12961.5, 13221.5, v1abs, dvabs, nptabs, &ist, &last);
+        xint(v1c, v2c, dvc, c, 1.0, v1abs, dvabs, absrb, ist, last);
+    }
+
+    /* ---- O2 visible (Greenblatt et al.), contnm.f90:807-830, O2_vis :9400-9457 ---- */
+    if ((v2 > 15000.0) && (v1 < 29870.) && xo2cn > 0.) {
+        double wo2 = wk[6] * 1.e-20 * ((pave / 1013.) * (273. / tave)) * xo2cn;
+        double chio2 = wk[6] / wtot;
+        double adjwo2 = chio2 * wo2;
+        double q = 55. * 273. / 296.;
+        double factor = 1. / ((XLOSMT * 1.e-20 * (q * q)) * 89.5);
+        accessor_grid(v1abs, v2abs, 15140.0, 10.0, 1474, &v1c, &v2c, &dvc, &nptc, &i1);
+        for (int64_t j = 1; j <= nptc; j++) {
+            int64_t i = i1 + (j - 1);
+            double c0v = 0.;
+            if (!(i < 1 || i > 1474)) {
+                double vj = v1c + dvc * (double)(j - 1);
+                c0v = factor * MTCKD_O2VIS[i - 1] / vj;
+            }
+            c[j - 1] = c0v * adjwo2;
+        }
+        pre_xint(15140.0, 29870.0, v1abs, dvabs, nptabs, &ist, &last);
+        xint(v1c, v2c, dvc, c, 1.0, v1abs, dvabs, absrb, ist, last);
+    }
+
+    /* ---- O2 Herzberg continuum, contnm.f90:834-850, O2HERZ :9808-9852 ---- */
+    if (v2 > 36000.0 && xo2cn > 0.) {
+        double wo2 = wk[6] * 1.e-20 * xo2cn;
+        accessor_grid2(v1abs, v2abs, 36000., 10., 0, 0.01, 0, &v1c, &v2c, &dvc, &nptc, &i1);
+        if (nptc > NPTC_MAX) return fail(23, "O2HERZ: NPTC exceeds C(6000)");
+        for (int64_t j = 1; j <= nptc; j++) {
+            int64_t i = i1 + (j - 1);
+            double c0v = 0.;
+            if (!(i < 1)) {
+                double vj = v1c + dvc * (double)(j - 1);
+                c0v = herzberg(vj, tave, pave) / vj;
+            }
+            c[j - 1] = c0v * wo2;
+        }
+        pre_xint(36000., 99999., v1abs, dvabs, nptabs, &ist, &last);
+        xint(v1c, v2c, dvc, c, 1.0, v1abs, dvabs, absrb, ist, last);
+    }
+
+    /* ---- O2 far UV (Schumann-Runge continuum), contnm.f90:857-875, O2FUV :9952-9994 ---- */
+    if (v2 > 56740.0 && xo2cn > 0.) {
+        double wo2 = wk[6] * 1.e-20 * xo2cn;
+        accessor_grid2(v1abs, v2abs, 56740.0, 20.0, 1512, 1.e-5, 1, &v1c, &v2c, &dvc, &nptc, &i1);
+        for (int64_t j = 1; j <= nptc; j++) {
+            int64_t i = i1 + (j - 1);
+            double c0v = 0.;
+            if (!(i < 1 || i > 1512)) {
+                double vj = v1c + dvc * (double)(j - 1);
+                c0v = MTCKD_O2FUV[i - 1] / vj;
+            }
+            c[j - 1] = c0v * wo2;
+        }
+        pre_xint(56740.0, 86960.0, v1abs, dvabs, nptabs, &ist, &last);
+        xint(v1c, v2c, dvc, c, 1.0, v1abs, dvabs, absrb, ist, last);
+    }
+
+    /* ---- Rayleigh extinction, contnm.f90:1107-1131 (IAERSL = 0 in monoRTM; JRAD = 0: the radiation term MODM applies
+     * later, modm.f90:243, is divided out here) ---- */
+    if (v2 >= 820. && xrayl > 0.) {
+        double conv_cm2mol = xrayl * 1.E-20 / (2.68675e-1 * 1.e5);
+        double xkt = tave / RADCN2ref;
+        for (int64_t i = 1; i <= nptabs; i++) {
+            double vrayleigh = v1abs + (double)(i - 1) * dvabs;
+            double xvrayleigh = vrayleigh / 1.e4;
+            double ray_ext = ((xvrayleigh * xvrayleigh * xvrayleigh) / (9.38076E2 - 10.8426 * (xvrayleigh * xvrayleigh))) *
+                             (wtot * conv_cm2mol);
+            ray_ext = ray_ext * xvrayleigh / orc_radfn(vrayleigh, xkt);
+            absrb[i - 1] = absrb[i - 1] + ray_ext;
+        }
+    }
     return 0;
 }
 

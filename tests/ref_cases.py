@@ -47,6 +47,36 @@ CASES = {
 }
 
 
+def _ir(wn, nlay=3, **kw):
+    """a case above the microwave: a few random lines inside the range + every continuum branch it touches"""
+    return dict(n_filler=16, nlay=nlay, wn=list(wn), irt=1, emis=0.8,
+                line_kw=dict(vmin=float(wn[0]), vmax=float(wn[-1]), with_physical=False), **kw)
+
+
+# the continuum branches of contnm.f90 above 820 cm-1, each range chosen to cross the gates and table ends of the branches
+CASES.update({
+    # H2O foreign > 600 (:436-447), CO2 XFACCO2 (:510-513), O2 fundamental (:657), N2 fundamental (:963), Rayleigh (:1107)
+    "ir_a_620_3050": _ir([620., 700.5, 850., 1000., 1345., 1500.3, 1700., 1849., 1995., 2002., 2100.7, 2385., 2500., 2899.,
+                          2990., 3050.]),
+    # N2 overtone (:1025), O2 1.27 um (:709), first Chappuis points (:536), O2 9100-11000 (:745)
+    "ir_b_4335_9300": _ir([4335., 4400.2, 4600., 4905., 4915., 6000., 7530., 7540.5, 8000., 8495., 8505., 8915., 8925., 9050.,
+                           9105., 9300.4], cntnm=(1., 1., 1., 0.9, 1.1, 1.2, 0.8)),
+    # O2 9100-11000, A band (:773), Chappuis
+    "ir_c_9095_13300": _ir([9095., 9200., 9375., 9439., 10000.5, 10995., 11005., 12000., 12960., 12962., 13100.3, 13221.,
+                            13225., 13300.]),
+    # O2 visible (:807), Chappuis
+    "vis_d_14995_19900": _ir([14995., 15005., 15140., 15145., 16000.5, 17000., 18000., 19900.], nlay=2),
+    # end of Chappuis (24665), start of Hartley-Huggins (27370, :555)
+    "vis_e_24000_28900": _ir([24000., 24560., 24660., 24670., 25000., 27365., 27375., 28000.5, 28900.], nlay=2),
+    # Herzberg (:834), Hartley-Huggins with the save/restore beyond 40800 (:573-599), first UV points (:603)
+    "uv_f_35990_40900": _ir([35990., 36005., 38000., 39999., 40001., 40790., 40805., 40820., 40900.], nlay=2),
+    # UV Hartley-Huggins with the save/restore below 40800 (:619-640)
+    "uv_g_40700_45000": _ir([40700., 40795., 40805., 41000., 43000.5, 45000.], nlay=2),
+    # end of the O3 UV table (54000), O2 far UV (:857), Herzberg
+    "uv_h_53000_57900": _ir([53000., 53990., 54010., 56000., 56735., 56745., 57000.5, 57900.], nlay=2),
+})
+
+
 def build_case(spec):
     spec = dict(spec)
     recipe = spec.pop("wn")
@@ -64,6 +94,8 @@ def build_case(spec):
         wn = 0.2 + spec["dvset"] * np.arange(33)
     elif recipe == "wide":
         wn = np.array([0.1, 0.74, 1.9, 2.05, 3.96, 6.11, 10.8, 18.6, 25.1, 33.0, 47.0, 54.9])
+    elif isinstance(recipe, (list, tuple)):
+        wn = np.array(recipe, dtype=np.float64)
     else:
         raise ValueError(recipe)
     return harness.make_case(wn=wn, **spec)

@@ -112,6 +112,7 @@ def test_tables_regenerate_identically(tmp_path):
     keep = str(tmp_path / "keep")
     shutil.copytree(tabs, keep)
     subprocess.check_call([sys.executable, os.path.join(ROOT, "tools", "gen_tables.py")], stdout=subprocess.DEVNULL)
+    subprocess.check_call([sys.executable, os.path.join(ROOT, "tools", "gen_tables_ir.py")], stdout=subprocess.DEVNULL)
     for f in os.listdir(keep):
         assert open(os.path.join(keep, f)).read() == open(os.path.join(tabs, f)).read(), f
 
