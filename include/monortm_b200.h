@@ -46,7 +46,9 @@ enum {
     MRTM_EIDU = 8,         /* IDU != 1: RTMmono.f90:173 STOP */
     MRTM_ENOMEM = 9,
     MRTM_EIO = 10,         /* host helpers: file missing / malformed */
-    MRTM_ETIPS = 11        /* partition sum <= 0 or T outside 70..3000 K: tips_2003.f90:271-277 */
+    MRTM_ETIPS = 11,       /* partition sum <= 0 or T outside 70..3000 K: tips_2003.f90:271-277 */
+    MRTM_EXSEC = 12        /* cross sections: resampled grid beyond xspd_int(0:10000000) (monortm_sub.F90:1755) or a
+                              convolution that cannot terminate (the reference overruns the array / loops forever) */
 };
 
 typedef struct mrtm_ctx mrtm_ctx;
@@ -76,6 +78,12 @@ typedef struct mrtm_opts {
     /* Asynchronous device-resident mode: CUDA stream (cudaStream_t) to run on; NULL =
      * the context's own stream. */
     void *stream;
+    /* Cross sections (IXSECT=1): XAMNT(ld_xamnt, nlay) of COMMON /PATHX/ (src/monortm.f90:233), molecules in the order the
+     * regions were staged with (mrtm_stage_xsec).  With ixsect == 1 and xamnt non-NULL mrtm_modm evaluates
+     * MONORTM_XSEC_SUB itself, as MODM does (modm.f90:197-198), and returns it in odxsec; with xamnt == NULL the caller's
+     * odxsec is the input (round-1 behaviour). */
+    const double *xamnt;
+    int64_t ld_xamnt;
 } mrtm_opts;
 
 /* ---- context ------------------------------------------------------------------------- */
@@ -117,6 +125,28 @@ int mrtm_modm(mrtm_ctx *ctx, int64_t nwn, const double *wn, double dvset, int64_
               int64_t nmol, const double *wkl, const double *wbrodl,
               double sclcpl, double sclhw, double y0res, const double cntnm[7],
               int64_t ixsect, int64_t ibrd, const double *scor, const mrtm_opts *opts);
+
+/* ---- cross sections --------------------------------------------------------- */
+/* One spectral region of one cross-section molecule, as MONORTM_XSEC_SUB holds it after the READs of loop 3000
+ * (src/monortm_sub.F90:1656-1671): FSCDXS range (XSREAD, :1380-1386), header of the LAST temperature file read, the
+ * per-temperature tables in ascending temperature order (pressures in mb: TORR already converted, :1665-1669). */
+typedef struct mrtm_xs_region {
+    int32_t ixmol;            /* 0-based row of XAMNT (the IXMOL of loop 6000) */
+    int32_t ntemp;            /* NTEMPF(ixsr,ixmol), 1..6 */
+    int64_t npts;             /* NPTSx */
+    double v1fx, v2fx;        /* V1FX, V2FX: decide whether the region is processed (:1647-1652) */
+    double v1x, v2x;          /* file header */
+    double xdoplr;            /* XDOPLR(ixsr,ixmol) */
+    double tx[6], pdx[6];
+    const double *xsdat[6];   /* npts values per temperature */
+} mrtm_xs_region;
+/* Stage the tables once (the reference re-reads the files for every profile).  Regions ordered by molecule, then by
+ * spectral region.  nreg == 0 clears the store. */
+int mrtm_stage_xsec(mrtm_ctx *ctx, int64_t nreg, const mrtm_xs_region *regs);
+/* Replaces CALL MONORTM_XSEC_SUB(wn,nwn,p,t,nlay,odxsec)  (src/monortm_sub.F90:1540, call src/modm.f90:198) with its
+ * COMMON /PATHX/ input XAMNT passed explicitly: xamnt (ld_xamnt, nlay); odxsec (nwn, nlay). */
+int mrtm_xsec(mrtm_ctx *ctx, int64_t nwn, const double *wn, int64_t nlay, const double *p, const double *t,
+              int64_t ld_xamnt, const double *xamnt, double *odxsec);
 
 /* ---- CALCTMR / RTM --------------------------------------------------------------------- */
 /* CALL CALCTMR(NLAYRS,NWN,WN,T,TZ,O,TMR)  (src/RTMmono.f90:239).  tz is (0:nlayrs). */
@@ -187,6 +217,12 @@ int mrtm_host_get_lnfl(const char *hfile, double v1, double v2, int64_t iim, int
                        double *brd_mol_shft);
 /* TIPS_2003 (src/tips_2003.f90:2-298): scor(42,9) = Q(296)/Q(T) for molecules 1..mol_max. */
 int mrtm_host_tips_2003(int64_t mol_max, double temp, double *scor);
+/* XSREAD (src/monortm_sub.F90:1246-1420) for `ixmols` molecule names (10 characters each, left-justified or not) over
+ * [xv1, xv2], followed by the file READs of MONORTM_XSEC_SUB (:1656-1671): parses <dir>/FSCDXS and the tables it names
+ * (paths relative to dir).  *regs is allocated by the library (tables included); release with mrtm_host_xs_free. */
+int mrtm_host_xsread(const char *dir, int64_t ixmols, const char *names, double xv1, double xv2,
+                     int64_t *nreg, mrtm_xs_region **regs);
+void mrtm_host_xs_free(mrtm_xs_region *regs, int64_t nreg);
 
 /* ---- host driver (PROGRAM MONORTM around the hot path, layer input IATM=0; no
  * Fortran compiler needed).  The parsing / formatting entry points need no GPU. ------------------- */

@@ -28,7 +28,15 @@ class MrtmOpts(C.Structure):
         ("sel_count", c_int64_p),
         ("sel_hash", c_uint64_p),
         ("stream", C.c_void_p),
+        ("xamnt", c_double_p),
+        ("ld_xamnt", C.c_int64),
     ]
+
+
+class MrtmXsRegion(C.Structure):
+    _fields_ = [("ixmol", C.c_int32), ("ntemp", C.c_int32), ("npts", C.c_int64), ("v1fx", C.c_double), ("v2fx", C.c_double),
+                ("v1x", C.c_double), ("v2x", C.c_double), ("xdoplr", C.c_double), ("tx", C.c_double * 6), ("pdx", C.c_double * 6),
+                ("xsdat", C.c_void_p * 6)]
 
 
 class MrtmStats(C.Structure):
@@ -68,6 +76,10 @@ SIGNATURES = {
     "mrtm_num_lines": (C.c_int64, [_P]),
     "mrtm_modm": (C.c_int, [_P, _I, _P, _D, _I, _P, _P, _P, _P, _P, _P, _P, _P, _I, _P, _P,
                             _D, _D, _D, _P, _I, _I, _P, _P]),
+    "mrtm_stage_xsec": (C.c_int, [_P, _I, _P]),
+    "mrtm_xsec": (C.c_int, [_P, _I, _P, _I, _P, _P, _I, _P, _P]),
+    "mrtm_host_xsread": (C.c_int, [C.c_char_p, _I, C.c_char_p, _D, _D, c_int64_p, C.POINTER(C.POINTER(MrtmXsRegion))]),
+    "mrtm_host_xs_free": (None, [C.POINTER(MrtmXsRegion), _I]),
     "mrtm_calctmr": (C.c_int, [_P, _I, _I, _P, _P, _P, _P, _P]),
     "mrtm_rtm": (C.c_int, [_P, _I, _I, _I, _P, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I]),
     "mrtm_profiles": (C.c_int, [_P, _I, _I, _P, _D, _I, _P, _P, _P, _P, _I, _P, _P, _P, _D, _D, _D,

@@ -46,6 +46,28 @@ def tips_2003(mol_max, temp):
     return scor
 
 
+def host_xsread(directory, names, xv1, xv2):
+    """XSREAD + the table READs through the C++ host helper; returns regions in the layout of xsfile.read_regions."""
+    lib = _capi.load_library()
+    n = C.c_int64()
+    regs = C.POINTER(_capi.MrtmXsRegion)()
+    buf = b"".join(nm.encode().ljust(10)[:10] for nm in names)
+    rc = lib.mrtm_host_xsread(str(directory).encode(), len(names), buf, float(xv1), float(xv2), C.byref(n), C.byref(regs))
+    if rc:
+        raise MonortmError(rc, lib.mrtm_host_last_error().decode())
+    out = []
+    try:
+        for i in range(n.value):
+            g = regs[i]
+            files = [dict(v1x=g.v1x, v2x=g.v2x, npts=int(g.npts), t=g.tx[k], pres=g.pdx[k],
+                          data=np.ctypeslib.as_array(C.cast(g.xsdat[k], _capi.c_double_p), shape=(int(g.npts),)).copy())
+                     for k in range(g.ntemp)]
+            out.append(dict(ixmol=int(g.ixmol), v1fx=g.v1fx, v2fx=g.v2fx, xdoplr=g.xdoplr, files=files))
+    finally:
+        lib.mrtm_host_xs_free(regs, n.value)
+    return out
+
+
 def scor_for_layers(nmol, t):
     """scor(42,9,nlay[,nprof]) for layer temperatures t (what the Fortran host passes per layer)."""
     t = np.asarray(t, dtype=np.float64)
@@ -96,6 +118,32 @@ class Session:
         self._check(self.lib.mrtm_stage_lines(self.h, _ptr(ls.nblm), ls.iim, *ls.pointers()))
         return int(self.lib.mrtm_num_lines(self.h))
 
+    # ---- cross sections -----------------------------------------------------------
+    def stage_xsec(self, regs):
+        """regs: regions as monortm_b200.xsfile.read_regions / host_xsread return them (list of dicts), ordered by molecule."""
+        arr = (_capi.MrtmXsRegion * max(len(regs), 1))()
+        keep = []
+        for i, r in enumerate(regs):
+            a, last = arr[i], r["files"][-1]
+            a.ixmol, a.ntemp, a.npts = r["ixmol"], len(r["files"]), last["npts"]
+            a.v1fx, a.v2fx, a.v1x, a.v2x, a.xdoplr = r["v1fx"], r["v2fx"], last["v1x"], last["v2x"], r["xdoplr"]
+            for j, f in enumerate(r["files"]):
+                a.tx[j], a.pdx[j] = f["t"], f["pres"]
+                d = np.ascontiguousarray(f["data"], dtype=np.float64)
+                keep.append(d)
+                a.xsdat[j] = d.ctypes.data
+        self._check(self.lib.mrtm_stage_xsec(self.h, len(regs), C.addressof(arr)))
+
+    def xsec(self, wn, p, t, xamnt):
+        """MONORTM_XSEC_SUB (src/monortm_sub.F90:1540): xamnt (ld, nlay) column amounts of the staged molecules -> odxsec (nwn, nlay)."""
+        wn = _f(wn)
+        nwn, nlay = wn.shape[0], np.asarray(p).shape[0]
+        p, t = _f(p, (nlay,)), _f(t, (nlay,))
+        xamnt = np.asfortranarray(xamnt, dtype=np.float64)
+        od = np.zeros((nwn, nlay), order="F")
+        self._check(self.lib.mrtm_xsec(self.h, nwn, _ptr(wn), nlay, _ptr(p), _ptr(t), xamnt.shape[0], _ptr(xamnt), _ptr(od)))
+        return od
+
     def stats(self):
         st = MrtmStats()
         self._check(self.lib.mrtm_get_stats(self.h, C.byref(st)))
@@ -110,9 +158,12 @@ class Session:
         return v.value
 
     @staticmethod
-    def _opts(v1=None, v2=None, iw0=0, sel=None, line_mode=0):
+    def _opts(v1=None, v2=None, iw0=0, sel=None, line_mode=0, xamnt=None):
         o = MrtmOpts()
         o.line_mode = int(line_mode)
+        if xamnt is not None:
+            o.xamnt = xamnt.ctypes.data_as(_capi.c_double_p)
+            o.ld_xamnt = int(xamnt.shape[0])
         if v1 is not None:
             o.use_global_range = 1
             o.v1_global, o.v2_global, o.iw0 = float(v1), float(v2), int(iw0)
@@ -124,9 +175,9 @@ class Session:
     # ---- MODM ---------------------------------------------------------------------------------
     def modm(self, wn, dvset, p, t, clw, nmol, wkl, wbrodl, scor, cntnm=CNTNM_ALL_ONE,
              sclcpl=1.0, sclhw=1.0, y0res=0.0, ixsect=0, odxsec=None, ibrd=0,
-             want_by_mol=True, selection=False, global_range=None, line_mode=0):
+             want_by_mol=True, selection=False, global_range=None, line_mode=0, xamnt=None):
         """Returns dict(o, o_by_mol, oc, o_clw, odxsec[, sel_count, sel_hash]); shapes as in
-        src/monortm.f90:352-353 with mxlay -> nlay."""
+        src/monortm.f90:352-353 with mxlay -> nlay.  ixsect=1 with xamnt (ld, nlay): MONORTM_XSEC_SUB runs inside, as in MODM."""
         wn = _f(wn)
         nwn, nlay = wn.shape[0], np.asarray(p).shape[0]
         p, t, clw, wbrodl = _f(p, (nlay,)), _f(t, (nlay,)), _f(clw, (nlay,)), _f(wbrodl, (nlay,))
@@ -141,7 +192,8 @@ class Session:
         if selection:
             sel = (np.zeros((nwn, nlay), np.int64, order="F"), np.zeros((nwn, nlay), np.uint64, order="F"))
         gr = global_range or (None, None, 0)
-        opts = self._opts(gr[0], gr[1], gr[2], sel, line_mode)
+        xa = None if xamnt is None else np.asfortranarray(xamnt, dtype=np.float64)
+        opts = self._opts(gr[0], gr[1], gr[2], sel, line_mode, xa)
         c7 = _f(np.array(cntnm, dtype=np.float64), (7,))
         self._check(self.lib.mrtm_modm(self.h, nwn, _ptr(wn), float(dvset), nlay, _ptr(p), _ptr(t), _ptr(clw),
                                        _ptr(o), _ptr(obm), _ptr(oc), _ptr(o_clw), _ptr(odx), int(nmol),

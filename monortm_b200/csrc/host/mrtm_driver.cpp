@@ -318,11 +318,16 @@ struct Profile {
     int64_t iform = 0, nlay = 0, nmol = 0, irt = 0;
     double secnt0 = 0, h1 = 0, h2 = 0, angle = 0;
     std::vector<double> p, t, clw, wbrodl, altz, pz, tz, wkl;   // wkl (39,nlay) column-major
+    // IXSECT >= 1 (monortm.f90:491-527): cross-section molecule names (10 characters each) and XAMNT (38, nlay)
+    int64_t ixmols = 0;
+    std::string xsnames;
+    std::vector<double> xamnt;
 };
 
 // the MONORTM_PROF.IN block of PROGRAM MONORTM, src/monortm.f90:380-488
 struct ProfReader {
     Unit u;
+    int64_t ixsect = 0;
     // returns false on END= (label 110)
     bool next(Profile& pr)
     {
@@ -377,6 +382,38 @@ struct ProfReader {
                 if (w[0] <= 1.0 && w[0] != 0.0 && wdrair == 0.0) throw Stop(MRTM_EARG, "WMXRAT NOT PROPERLY SPECIFIED IN PATH");
                 for (int64_t m = 1; m <= pr.nmol; m++)
                     if (w[m - 1] < 1.) w[m - 1] = w[m - 1] * wdrair;
+            }
+            if (ixsect >= 1) {                                // monortm.f90:491-527
+                Record a = u.read();                          // 930 FORMAT (I5,5X,I5): IXMOLS, IXSBIN
+                pr.ixmols = a.I(5);
+                if (pr.ixmols < 1 || pr.ixmols > 38) throw Stop(MRTM_EARG, "IXMOLS out of 1..38 (MX_XS, lblparams.f90:29)");
+                pr.xsnames.assign((size_t)pr.ixmols * 10, ' ');
+                for (int64_t i = 0; i < pr.ixmols;) {         // XSREAD :1296-1301: (7A10), then (8A10)
+                    Record nrec = u.read();
+                    const int64_t per = (i == 0) ? 7 : 8;
+                    for (int64_t j = 0; j < per && i < pr.ixmols; j++, i++) {
+                        std::string nm = nrec.A(10);
+                        nm.resize(10, ' ');
+                        std::memcpy(&pr.xsnames[(size_t)i * 10], nm.data(), 10);
+                    }
+                }
+                Record hx = u.read();                         // 900 FORMAT (1X,I1,I3,I5,F10.2,15A4)
+                hx.X(1); hx.I(1);
+                const int64_t nlayxs = hx.I(3), ixmol = hx.I(5);
+                if (ixmol == 0) throw Stop(MRTM_EARG, " PATH - IXMOL 0 ");
+                if (ixmol != pr.ixmols) throw Stop(MRTM_EARG, " PATH - IXMOL .NE. IXMOLS ");
+                if (pr.nlay != nlayxs) throw Stop(MRTM_EARG, " PATH - NLAYRS .NE. NLAYXS ");
+                pr.xamnt.assign((size_t)38 * n, 0.);
+                for (size_t il = 0; il < n; il++) {
+                    u.read();                                 // 910 / 915: PAVX, TAVX, ... (not used)
+                    Record x1 = u.read();                     // 978: XAMNT(1:7,L), WBRODX
+                    double* xa = pr.xamnt.data() + (size_t)38 * il;
+                    for (int k = 0; k < 7; k++) { const double v = x1.F(15, 7); if (k < ixmol) xa[k] = v; }
+                    for (int64_t k = 7; k < ixmol;) {         // XAMNT(8:IXMOL,L), one READ
+                        Record x2 = u.read();
+                        for (int j = 0; j < 8 && k < ixmol; j++, k++) xa[k] = x2.F(15, 7);
+                    }
+                }
             }
         } catch (const IoError& e) {
             throw Stop(MRTM_EIO, std::string(" EXIT; ERROR READING :MONORTM_PROF.IN (") + e.what() + ")");
@@ -548,6 +585,7 @@ StoreState g_store_state;      // the SAVEd variables of STOREOUT for the stand-
 // C ABI
 // ================================================================================================
 extern "C" const char* mrtm_host_last_error(void) { return g_host_err.c_str(); }
+namespace mrtm_hostdrv { int set_host_error(int code, const std::string& msg) { return fail(code, msg); } }   // for mrtm_host.cpp
 
 extern "C" int mrtm_host_read_control(const char* filein, int64_t nwnmx, mrtm_control* out)
 {
@@ -691,8 +729,6 @@ extern "C" int mrtm_host_run_monortm(const char* workdir, int device, int64_t nw
         if (c.iatm != 0)
             throw Stop(MRTM_EARG, "IATM=1 needs LBLATM (src/lblatm.f90), which stays on the Fortran host (SURVEY 2 row 12); "
                                   "this driver handles layer input (IATM=0, MONORTM_PROF.IN)");
-        if (c.ixsect >= 1)
-            throw Stop(MRTM_EARG, "IXSECT=1 needs XSREAD/MONORTM_XSEC_SUB and the cross-section data (SURVEY 8f-3): not built");
         if (c.ispd == 1) throw Stop(MRTM_EARG, " The ISPD=1 option is no longer valid.");
         const int64_t nprof = count_profiles(fileprof, c.ixsect);
         const int64_t nwn = (int64_t)c.wn.size();
@@ -730,6 +766,8 @@ extern "C" int mrtm_host_run_monortm(const char* workdir, int device, int64_t nw
         }
 
         ProfReader rd;
+        rd.ixsect = c.ixsect;
+        std::string xs_staged;                                // names the staged cross sections belong to
         if (!rd.u.open(fileprof)) throw Stop(MRTM_EIO, " EXIT; ERROR OPENING :" + fileprof);
         StoreState st;
         double tmpsfc = c.tmpbnd;
@@ -757,12 +795,40 @@ extern "C" int mrtm_host_run_monortm(const char* workdir, int device, int64_t nw
                 if (rc) throw Stop(rc, "TIPS_2003: temperature outside 70..3000 K or partition sum <= 0 (tips_2003.f90:271-277)");
             }
             std::vector<double> o((size_t)nwn * (size_t)pr.nlay);
+            mrtm_opts xo;
+            std::memset(&xo, 0, sizeof xo);
+            if (c.ixsect >= 1) {                              // XSREAD (monortm.f90:494-497) + the tables, staged when the names change
+                if (pr.xsnames != xs_staged) {
+                    double xv1 = c.wn[0], xv2 = c.wn[0];
+                    for (double w : c.wn) { xv1 = std::min(xv1, w); xv2 = std::max(xv2, w); }
+                    int64_t nreg = 0;
+                    mrtm_xs_region* regs = nullptr;
+                    rc = mrtm_host_xsread(dir.c_str(), pr.ixmols, pr.xsnames.data(), xv1, xv2, &nreg, &regs);
+                    if (rc) throw Stop(rc, g_host_err);
+                    rc = mrtm_stage_xsec(ctx, nreg, regs);
+                    mrtm_host_xs_free(regs, nreg);
+                    if (rc) throw Stop(rc, std::string("mrtm_stage_xsec: ") + (mrtm_last_error(ctx) ? mrtm_last_error(ctx) : ""));
+                    xs_staged = pr.xsnames;
+                }
+                xo.xamnt = pr.xamnt.data();
+                xo.ld_xamnt = 38;
+            }
             // MODM + CALCTMR + RTM (monortm.f90:557-574) on the GPU
             rc = mrtm_profiles(ctx, 1, nwn, c.wn.data(), c.dvset, pr.nlay, pr.p.data(), pr.t.data(), pr.tz.data(), pr.clw.data(),
                                pr.nmol, pr.wkl.data(), pr.wbrodl.data(), scor.data(), 1., 1., 0., c.cntnm, c.ibrd, pr.irt, c.iplot, 1,
                                &tmpsfc, emiss.data(), reflc.data(), rad.data(), tb.data(), tmr.data(), trtot.data(), rup.data(),
-                               rdn.data(), o.data(), obm.data(), nullptr);
+                               rdn.data(), o.data(), obm.data(), c.ixsect >= 1 ? &xo : nullptr);
             if (rc) throw Stop(rc, std::string("mrtm_profiles: ") + (mrtm_last_error(ctx) ? mrtm_last_error(ctx) : mrtm_strerror(rc)));
+            if (c.ixsect >= 1) {                              // ODXTOT (:645, 650): the cross-section part alone, layer sum
+                std::vector<double> odx((size_t)nwn * (size_t)pr.nlay);
+                rc = mrtm_xsec(ctx, nwn, c.wn.data(), pr.nlay, pr.p.data(), pr.t.data(), 38, pr.xamnt.data(), odx.data());
+                if (rc) throw Stop(rc, std::string("mrtm_xsec: ") + (mrtm_last_error(ctx) ? mrtm_last_error(ctx) : mrtm_strerror(rc)));
+                for (int64_t iw = 0; iw < nwn; iw++) {
+                    double sx = 0.;
+                    for (int64_t j = 0; j < pr.nlay; j++) sx = sx + odx[(size_t)iw + (size_t)nwn * (size_t)j];
+                    odxtot[(size_t)iw] = sx;
+                }
+            }
             for (int64_t iw = 0; iw < nwn; iw++) {            // OTOT (:643-646)
                 double s = 0.;
                 for (int64_t j = 0; j < pr.nlay; j++) s = s + o[(size_t)iw + (size_t)nwn * (size_t)j];

@@ -75,6 +75,11 @@ struct mrtm_ctx {
     PlanKey plan_key;
     bool plan_key_valid = false;
     DevBuf b_layer, b_scorc, b_absrb, b_planes, b_lcplanes, b_o, b_obm, b_oc, b_in[16], b_out[16], b_sel[2], b_tmps, b_fbeta;
+    // cross sections (mrtm_stage_xsec): region descriptors, staged tables, per-call scratch
+    std::vector<XsRegionDev> xs_regs;
+    int64_t xs_tab_per_layer = 0;                 // sum over regions of (npts + 3)
+    int xs_nmol = 0;
+    DevBuf b_xsreg, b_xsdat, b_xslay, b_xstab, b_xsneed, b_xsod, b_xsin[4];
     mrtm_stats st;
     size_t planes_budget = (size_t)8 << 30;
 };
@@ -142,6 +147,7 @@ extern "C" const char* mrtm_strerror(int code)
     case MRTM_EIDU: return "ERROR IN IDU. OPTION NOT SUPPORTED YET";
     case MRTM_ENOMEM: return "out of (device) memory";
     case MRTM_EIO: return "file missing or malformed";
+    case MRTM_EXSEC: return "cross sections: not staged, the resampled grid exceeds the reference's xspd_int(0:10000000), or the convolution does not terminate";
     case MRTM_ETIPS: return "TIPS: temperature outside 70-3000 K or partition sum <= 0";
     default: return "unknown error";
     }
@@ -229,7 +235,8 @@ extern "C" int mrtm_free(mrtm_ctx* ctx)
     cudaStreamSynchronize(ctx->stream);
     free_lines(ctx);
     for (void* p : ctx->table_allocs) cudaFree(p);
-    DevBuf* bufs[] = {&ctx->b_pcache, &ctx->b_t3, &ctx->b_pool3, &ctx->b_segof3, &ctx->b_ov, &ctx->b_lvoigt, &ctx->b_vtmax, &ctx->b_layer, &ctx->b_scorc, &ctx->b_absrb, &ctx->b_planes, &ctx->b_lcplanes, &ctx->b_o, &ctx->b_obm, &ctx->b_oc, &ctx->b_sel[0], &ctx->b_sel[1], &ctx->b_tmps, &ctx->b_fbeta, &ctx->b_npieces};
+    DevBuf* bufs[] = {&ctx->b_xsreg, &ctx->b_xsdat, &ctx->b_xslay, &ctx->b_xstab, &ctx->b_xsneed, &ctx->b_xsod, &ctx->b_xsin[0], &ctx->b_xsin[1],
+                      &ctx->b_xsin[2], &ctx->b_xsin[3], &ctx->b_pcache, &ctx->b_t3, &ctx->b_pool3, &ctx->b_segof3, &ctx->b_ov, &ctx->b_lvoigt, &ctx->b_vtmax, &ctx->b_layer, &ctx->b_scorc, &ctx->b_absrb, &ctx->b_planes, &ctx->b_lcplanes, &ctx->b_o, &ctx->b_obm, &ctx->b_oc, &ctx->b_sel[0], &ctx->b_sel[1], &ctx->b_tmps, &ctx->b_fbeta, &ctx->b_npieces};
     for (DevBuf* b : bufs) if (b->p) cudaFree(b->p);
     for (int i = 0; i < kMaxLevels; i++) {
         if (ctx->b_plan[i].p) cudaFree(ctx->b_plan[i].p);
@@ -427,6 +434,8 @@ struct RunDesc {
     double* o;                      // (nwn,nlay,nprof) or null
     double *o_by_mol, *oc, *o_clw;  // modm-style outputs, nprof==1 only
     const double* odxsec;
+    const double* xamnt;            // device (ld_xamnt, nlay, nprof) or null: cross-section amounts, odxsec computed here
+    int64_t ld_xamnt;
     long long* sel_count;
     unsigned long long* sel_hash;
     bool do_lines, do_tmr, do_rtm;
@@ -475,6 +484,9 @@ static void launch_lines(const LinesArgs& la, dim3 grid, bool sel, cudaStream_t 
     if (far_done) cudaStreamWaitEvent(s, far_done, 0);     // the far-field coefficients come from the side stream
     final_kernel<F, NT><<<grid, NT, 0, s>>>(la);
 }
+
+static int run_xsec_device(mrtm_ctx* ctx, int64_t nwn, const double* wn, int64_t nlay, const double* p, const double* t,
+                           int64_t ld_xamnt, const double* xamnt, double* od, cudaStream_t s);
 
 static int run_device(mrtm_ctx* ctx, const RunDesc& r, cudaStream_t s)
 {
@@ -654,6 +666,16 @@ static int run_device(mrtm_ctx* ctx, const RunDesc& r, cudaStream_t s)
             la.obm_ldk = nwn * MRTM_MXMOL;
             la.o_clw = r.o_clw;
             la.odxsec = r.odxsec;
+            if (r.xamnt) {                  // cross sections of the batch's profiles, laid out like O
+                if ((rc = ensure(ctx, ctx->b_xsod, (size_t)nb * nwn * nlay * 8))) return rc;
+                for (int64_t ip = 0; ip < nb; ip++) {
+                    const int64_t gp = b0 + ip;
+                    if ((rc = run_xsec_device(ctx, nwn, r.wn, nlay, r.p + (size_t)gp * nlay, r.t + (size_t)gp * nlay, r.ld_xamnt,
+                                              r.xamnt + (size_t)gp * r.ld_xamnt * nlay, (double*)ctx->b_xsod.p + (size_t)ip * nwn * nlay, s)))
+                        return rc;
+                }
+                la.odxsec = (const double*)ctx->b_xsod.p;
+            }
             la.sel_count = r.sel_count ? r.sel_count + (size_t)b0 * nwn * nlay : nullptr;
             la.sel_hash = r.sel_hash ? r.sel_hash + (size_t)b0 * nwn * nlay : nullptr;
             la.errflag = ctx->errflag_dev;
@@ -919,6 +941,7 @@ static int run_device(mrtm_ctx* ctx, const RunDesc& r, cudaStream_t s)
         st.direct_evals = (double)cnt[1];
         if (flag & 1) return set_err(ctx, MRTM_ETIPS, mrtm_strerror(MRTM_ETIPS));
         if (flag & 2) return set_err(ctx, MRTM_ESDVOIGT, mrtm_strerror(MRTM_ESDVOIGT));
+        if (flag & (16 | 32)) return set_err(ctx, MRTM_EXSEC, mrtm_strerror(MRTM_EXSEC));
     }
     return MRTM_OK;
 }
@@ -932,6 +955,113 @@ static int h2d(mrtm_ctx* ctx, DevBuf& b, const void* src, size_t bytes, cudaStre
     if (rc) return rc;
     if (src && bytes) CU(cudaMemcpyAsync(b.p, src, bytes, cudaMemcpyHostToDevice, s));
     *out = (const double*)b.p;
+    return MRTM_OK;
+}
+
+
+// ---- cross sections ---------------------------------------------------------------------------
+extern "C" int mrtm_stage_xsec(mrtm_ctx* ctx, int64_t nreg, const mrtm_xs_region* regs)
+{
+    if (!ctx || nreg < 0 || (nreg > 0 && !regs)) return MRTM_EARG;
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaStreamSynchronize(ctx->stream));
+    ctx->xs_regs.clear();
+    ctx->xs_tab_per_layer = 0;
+    ctx->xs_nmol = 0;
+    std::vector<double> dat;
+    for (int64_t i = 0; i < nreg; i++) {
+        const mrtm_xs_region& g = regs[i];
+        if (g.ntemp < 1 || g.ntemp > 6 || g.npts < 2 || g.ixmol < 0 || g.ixmol >= 38 || !(g.v2x > g.v1x))
+            return set_err(ctx, MRTM_EARG, "mrtm_stage_xsec: bad region (ntemp 1..6, npts >= 2, ixmol 0..37, v2x > v1x)");
+        if (i > 0 && g.ixmol < regs[i - 1].ixmol) return set_err(ctx, MRTM_EARG, "mrtm_stage_xsec: regions must be ordered by molecule");
+        XsRegionDev d;
+        std::memset(&d, 0, sizeof d);
+        d.ixmol = g.ixmol; d.ntemp = g.ntemp; d.npts = g.npts;
+        d.v1fx = g.v1fx; d.v2fx = g.v2fx; d.v1x = g.v1x; d.v2x = g.v2x; d.xdoplr = g.xdoplr;
+        for (int k = 0; k < g.ntemp; k++) {
+            if (!g.xsdat[k]) return set_err(ctx, MRTM_EARG, "mrtm_stage_xsec: null table");
+            d.tx[k] = g.tx[k]; d.pdx[k] = g.pdx[k];
+            d.dat_off[k] = (int64_t)dat.size();
+            dat.insert(dat.end(), g.xsdat[k], g.xsdat[k] + g.npts);
+        }
+        d.tab_off = 0;                                    // set per call (depends on nlay)
+        ctx->xs_regs.push_back(d);
+        ctx->xs_tab_per_layer += g.npts + 3;
+        ctx->xs_nmol = std::max(ctx->xs_nmol, (int)g.ixmol + 1);
+    }
+    int rc;
+    if ((rc = ensure(ctx, ctx->b_xsdat, std::max<size_t>(dat.size(), 1) * 8))) return rc;
+    if (!dat.empty()) CU(cudaMemcpy(ctx->b_xsdat.p, dat.data(), dat.size() * 8, cudaMemcpyHostToDevice));
+    return MRTM_OK;
+}
+
+// MONORTM_XSEC_SUB for one profile; all pointers on the device; od (nwn, nlay).  Asynchronous on s; the error flag is
+// checked by the caller (bits 4, 5 of errflag_dev)
+static int run_xsec_device(mrtm_ctx* ctx, int64_t nwn, const double* wn, int64_t nlay, const double* p, const double* t,
+                           int64_t ld_xamnt, const double* xamnt, double* od, cudaStream_t s)
+{
+    const int nreg = (int)ctx->xs_regs.size();
+    if (ld_xamnt < ctx->xs_nmol) return set_err(ctx, MRTM_EARG, "xamnt: leading dimension smaller than the number of staged cross-section molecules");
+    if (nreg == 0) { CU(cudaMemsetAsync(od, 0, (size_t)nwn * nlay * 8, s)); return MRTM_OK; }
+    int rc;
+    std::vector<XsRegionDev> regs = ctx->xs_regs;
+    int64_t off = 0, maxpts = 0;
+    for (auto& g : regs) { g.tab_off = off; off += (g.npts + 3) * nlay; maxpts = std::max<int64_t>(maxpts, g.npts + 3); }
+    if ((rc = ensure(ctx, ctx->b_xsreg, regs.size() * sizeof(XsRegionDev)))) return rc;
+    if ((rc = ensure(ctx, ctx->b_xslay, (size_t)nreg * nlay * sizeof(XsLayerDev)))) return rc;
+    if ((rc = ensure(ctx, ctx->b_xstab, (size_t)off * 8))) return rc;
+    if ((rc = ensure(ctx, ctx->b_xsneed, (size_t)nreg * sizeof(int)))) return rc;
+    CU(cudaMemcpyAsync(ctx->b_xsreg.p, regs.data(), regs.size() * sizeof(XsRegionDev), cudaMemcpyHostToDevice, s));
+    CU(cudaStreamSynchronize(s));                         // regs is a stack copy
+    CU(cudaMemsetAsync(ctx->b_xsneed.p, 0, (size_t)nreg * sizeof(int), s));
+    XsArgs a;
+    std::memset(&a, 0, sizeof a);
+    a.nreg = nreg; a.nlay = (int32_t)nlay; a.nwn = (int32_t)nwn; a.ld_xamnt = (int32_t)ld_xamnt;
+    a.reg = (const XsRegionDev*)ctx->b_xsreg.p;
+    a.dat = (const double*)ctx->b_xsdat.p;
+    a.lay = (XsLayerDev*)ctx->b_xslay.p;
+    a.tab = (double*)ctx->b_xstab.p;
+    a.need = (int*)ctx->b_xsneed.p;
+    a.wn = wn; a.p = p; a.t = t; a.xamnt = xamnt; a.odxsec = od;
+    a.errflag = ctx->errflag_dev;
+    xs_layer_kernel<<<(unsigned)((nreg * nlay + 127) / 128), 128, 0, s>>>(a);
+    xs_table_kernel<<<dim3((unsigned)((maxpts + 255) / 256), (unsigned)nlay, (unsigned)nreg), 256, 0, s>>>(a);
+    xs_need_kernel<<<(unsigned)((nwn + 255) / 256), 256, 0, s>>>(a);
+    xs_conv_kernel<<<dim3((unsigned)((nwn + 127) / 128), (unsigned)nlay), 128, 0, s>>>(a);
+    ctx->st.kernel_launches += 4;
+    CU(cudaGetLastError());
+    return MRTM_OK;
+}
+
+static int check_xsec_flags(mrtm_ctx* ctx, cudaStream_t s)
+{
+    int flag = 0;
+    CU(cudaMemcpyAsync(&flag, ctx->errflag_dev, sizeof(int), cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    if (flag & 16) return set_err(ctx, MRTM_EXSEC, "convolve: NPTS exceeds xspd_int(0:10000000) (monortm_sub.F90:1755): layer pressure too close to / below the table pressure for this region width");
+    if (flag & 32) return set_err(ctx, MRTM_EXSEC, "convolve: the outward sum does not terminate (zero or NaN table around a frequency; the reference loops forever, monortm_sub.F90:1800-1821)");
+    return MRTM_OK;
+}
+
+extern "C" int mrtm_xsec(mrtm_ctx* ctx, int64_t nwn, const double* wn, int64_t nlay, const double* p, const double* t,
+                         int64_t ld_xamnt, const double* xamnt, double* odxsec)
+{
+    if (!ctx) return MRTM_EARG;
+    if (!wn || !p || !t || !xamnt || !odxsec || nwn < 1 || nlay < 1 || ld_xamnt < 1) return set_err(ctx, MRTM_EARG, "mrtm_xsec: null input or bad dimension");
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->stream;
+    int rc;
+    const double *dwn, *dp, *dt, *dx;
+    if ((rc = h2d(ctx, ctx->b_xsin[0], wn, nwn * 8, s, &dwn))) return rc;
+    if ((rc = h2d(ctx, ctx->b_xsin[1], p, nlay * 8, s, &dp))) return rc;
+    if ((rc = h2d(ctx, ctx->b_xsin[2], t, nlay * 8, s, &dt))) return rc;
+    if ((rc = h2d(ctx, ctx->b_xsin[3], xamnt, (size_t)ld_xamnt * nlay * 8, s, &dx))) return rc;
+    if ((rc = ensure(ctx, ctx->b_xsod, (size_t)nwn * nlay * 8))) return rc;
+    CU(cudaMemsetAsync(ctx->errflag_dev, 0, sizeof(int), s));
+    if ((rc = run_xsec_device(ctx, nwn, dwn, nlay, dp, dt, ld_xamnt, dx, (double*)ctx->b_xsod.p, s))) return rc;
+    if ((rc = check_xsec_flags(ctx, s))) return rc;
+    CU(cudaMemcpyAsync(odxsec, ctx->b_xsod.p, (size_t)nwn * nlay * 8, cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
     return MRTM_OK;
 }
 
@@ -977,7 +1107,16 @@ extern "C" int mrtm_modm(mrtm_ctx* ctx, int64_t nwn, const double* wn, double dv
     if ((rc = h2d(ctx, ctx->b_in[4], wkl, nlay * MRTM_MXMOL * 8, s, &r.wkl))) return rc;
     if ((rc = h2d(ctx, ctx->b_in[5], wbrodl, nlay * 8, s, &r.wbrodl))) return rc;
     if (scor) { if ((rc = h2d(ctx, ctx->b_in[6], scor, (size_t)nlay * MRTM_NSCOR1 * MRTM_NSCOR2 * 8, s, &r.scor))) return rc; }
-    if (ixsect == 1 && odxsec) { if ((rc = h2d(ctx, ctx->b_in[7], odxsec, fl, s, &r.odxsec))) return rc; }
+    const bool own_xs = (ixsect == 1) && opts && opts->xamnt;     // CALL MONORTM_XSEC_SUB inside MODM (modm.f90:197-198)
+    if (own_xs) {
+        const double* dx;
+        if ((rc = h2d(ctx, ctx->b_xsin[3], opts->xamnt, (size_t)opts->ld_xamnt * nlay * 8, s, &dx))) return rc;
+        if ((rc = ensure(ctx, ctx->b_in[7], fl))) return rc;
+        CU(cudaMemsetAsync(ctx->errflag_dev, 0, sizeof(int), s));
+        if ((rc = run_xsec_device(ctx, nwn, r.wn, nlay, r.p, r.t, opts->ld_xamnt, dx, (double*)ctx->b_in[7].p, s))) return rc;
+        if ((rc = check_xsec_flags(ctx, s))) return rc;
+        r.odxsec = (const double*)ctx->b_in[7].p;
+    } else if (ixsect == 1 && odxsec) { if ((rc = h2d(ctx, ctx->b_in[7], odxsec, fl, s, &r.odxsec))) return rc; }
     if ((rc = ensure(ctx, ctx->b_out[0], fl))) return rc;
     r.o = (double*)ctx->b_out[0].p;
     if (o_by_mol) { if ((rc = ensure(ctx, ctx->b_obm, fml))) return rc; r.o_by_mol = (double*)ctx->b_obm.p; CU(cudaMemsetAsync(r.o_by_mol, 0, fml, s)); }
@@ -990,6 +1129,7 @@ extern "C" int mrtm_modm(mrtm_ctx* ctx, int64_t nwn, const double* wn, double dv
     if (o_by_mol) CU(cudaMemcpyAsync(o_by_mol, r.o_by_mol, fml, cudaMemcpyDeviceToHost, s));
     if (oc) CU(cudaMemcpyAsync(oc, r.oc, fml, cudaMemcpyDeviceToHost, s));
     if (o_clw) CU(cudaMemcpyAsync(o_clw, r.o_clw, fl, cudaMemcpyDeviceToHost, s));
+    if (own_xs && odxsec) CU(cudaMemcpyAsync(odxsec, r.odxsec, fl, cudaMemcpyDeviceToHost, s));
     if (r.sel_count) CU(cudaMemcpyAsync(opts->sel_count, r.sel_count, fl, cudaMemcpyDeviceToHost, s));
     if (r.sel_hash) CU(cudaMemcpyAsync(opts->sel_hash, r.sel_hash, fl, cudaMemcpyDeviceToHost, s));
     CU(cudaStreamSynchronize(s));
@@ -1136,6 +1276,11 @@ extern "C" int mrtm_profiles(mrtm_ctx* ctx, int64_t nprof, int64_t nwn, const do
     if ((rc = h2d(ctx, ctx->b_in[5], wbrodl, L * 8, s, &r.wbrodl))) return rc;
     if (scor) { if ((rc = h2d(ctx, ctx->b_in[6], scor, L * MRTM_NSCOR1 * MRTM_NSCOR2 * 8, s, &r.scor))) return rc; }
     if ((rc = h2d(ctx, ctx->b_in[8], tz, (size_t)nprof * (nlay + 1) * 8, s, &r.tz))) return rc;
+    if (opts && opts->xamnt) {            // IXSECT=1: MONORTM_XSEC_SUB per profile inside (modm.f90:197-198)
+        if (opts->ld_xamnt < 1) return set_err(ctx, MRTM_EARG, "mrtm_opts.ld_xamnt must be >= 1");
+        if ((rc = h2d(ctx, ctx->b_xsin[3], opts->xamnt, (size_t)opts->ld_xamnt * L * 8, s, &r.xamnt))) return rc;
+        r.ld_xamnt = opts->ld_xamnt;
+    }
     {   // emissivity / reflectivity are only read by rt_kernel: their copies ride the second stream beside the kernels
         cudaStream_t sc = (ctx->use_side && ctx->side && ctx->ev_in) ? ctx->side : s;
         if ((rc = h2d(ctx, ctx->b_in[9], emiss, nwn * 8, sc, &r.emiss))) return rc;

@@ -237,3 +237,153 @@ extern "C" int mrtm_host_get_lnfl(const char* hfile, double v1, double v2, int64
     std::fclose(f);
     return MRTM_OK;
 }
+
+// ---------------------------------------------------------------------------------------------
+// Cross sections: XSREAD (src/monortm_sub.F90:1246-1420) + the table READs of MONORTM_XSEC_SUB
+// (:1656-1671).  ALIAS / XSMASS: BLOCK DATA BXSECT (:1445-1474).
+// ---------------------------------------------------------------------------------------------
+#include <cstdlib>
+#include <fstream>
+#include <sstream>
+#include <string>
+
+namespace {
+
+const char* const kXsAlias[15][4] = {
+    {"CLONO2", "CLNO3", nullptr, nullptr}, {"HNO4", nullptr, nullptr, nullptr}, {"CHCL2F", "CFC21", "CFC21", "F21"},
+    {"CCL4", nullptr, nullptr, nullptr}, {"CCL3F", "CFCL3", "CFC11", "F11"}, {"CCL2F2", "CF2CL2", "CFC12", "F12"},
+    {"C2CL2F4", "C2F4CL2", "CFC114", "F114"}, {"C2CL3F3", "C2F3CL3", "CFC113", "F113"}, {"N2O5", nullptr, nullptr, nullptr},
+    {"HNO3", nullptr, nullptr, nullptr}, {"CF4", nullptr, "CFC14", "F14"}, {"CHCLF2", "CHF2CL", "CFC22", "F22"},
+    {"CCLF3", nullptr, "CFC13", "F13"}, {"C2CLF5", nullptr, "CFC115", "F115"}, {"NO2", nullptr, nullptr, nullptr}};
+const double kXsMass[15] = {97.46, 79.01, 102.92, 153.82, 137.37, 120.91, 170.92, 187.38, 108.01, 63.01, 88.00, 86.47, 104.46, 154.47, 45.99};
+
+std::string xs_trim(const std::string& s)
+{
+    size_t a = s.find_first_not_of(' '), b = s.find_last_not_of(" \r\n");
+    return a == std::string::npos ? std::string() : s.substr(a, b - a + 1);
+}
+std::string xs_field(const std::string& rec, size_t off, size_t len) { return off < rec.size() ? rec.substr(off, len) : std::string(); }
+double xs_num(const std::string& f)
+{
+    std::string t;                                            // blanks inside a numeric field are ignored by a formatted READ
+    for (char c : f) if (c != ' ' && c != '\r' && c != '\n') t += (c == 'D' || c == 'd') ? 'E' : c;
+    return t.empty() ? 0. : std::strtod(t.c_str(), nullptr);
+}
+bool xs_matches(const std::string& name, int j)
+{
+    for (int k = 0; k < 4; k++) if (kXsAlias[j][k] && name == kXsAlias[j][k]) return true;
+    return false;
+}
+
+static int xs_fail(int code, const std::string& msg);
+
+}  // namespace
+
+extern "C" const char* mrtm_host_last_error(void);
+namespace mrtm_hostdrv { int set_host_error(int code, const std::string& msg); }
+namespace { int xs_fail(int code, const std::string& msg) { return mrtm_hostdrv::set_host_error(code, msg); } }
+
+extern "C" void mrtm_host_xs_free(mrtm_xs_region* regs, int64_t nreg)
+{
+    if (!regs) return;
+    for (int64_t i = 0; i < nreg; i++)
+        for (int k = 0; k < 6; k++) delete[] const_cast<double*>(regs[i].xsdat[k]);
+    delete[] regs;
+}
+
+extern "C" int mrtm_host_xsread(const char* dir, int64_t ixmols, const char* names, double xv1, double xv2,
+                                int64_t* nreg, mrtm_xs_region** regs_out)
+{
+    if (!dir || !names || !nreg || !regs_out || ixmols < 1 || ixmols > 38) return xs_fail(MRTM_EARG, "mrtm_host_xsread: bad argument");
+    *nreg = 0;
+    *regs_out = nullptr;
+    std::string d(dir);
+    if (!d.empty() && d.back() != '/') d += '/';
+    std::vector<int> ixindx((size_t)ixmols);
+    std::vector<std::string> xsname((size_t)ixmols);
+    for (int64_t i = 0; i < ixmols; i++) {                    // :1296-1330: left-justify, match against ALIAS
+        xsname[(size_t)i] = xs_trim(std::string(names + 10 * i, 10));
+        int found = -1;
+        for (int j = 0; j < 15 && found < 0; j++) if (xs_matches(xsname[(size_t)i], j)) found = j;
+        if (found < 0) return xs_fail(MRTM_EIO, "  THE NAME: " + xsname[(size_t)i] + " IS NOT ONE OF THE CROSS SECTION MOLECULES. CHECK THE SPELLING.");
+        ixindx[(size_t)i] = found;
+    }
+    std::ifstream f(d + "FSCDXS");
+    if (!f) return xs_fail(MRTM_EIO, "FSCDXS does not exist - XSREAD");
+    std::string rec;
+    std::getline(f, rec);                                     // FORMAT 905 (/): two records skipped
+    std::getline(f, rec);
+    std::vector<std::vector<mrtm_xs_region>> per((size_t)ixmols);
+    std::vector<char> flg((size_t)ixmols, 0);
+    auto cleanup = [&]() {
+        for (auto& v : per) for (auto& g : v) for (int k = 0; k < 6; k++) delete[] const_cast<double*>(g.xsdat[k]);
+    };
+    while (std::getline(f, rec)) {
+        if (rec.empty()) rec = " ";
+        if (rec[0] == '*') continue;
+        if (rec[0] == '%') break;
+        rec.resize(120, ' ');                                 // FORMAT 915 (A10,2F10.4,F10.8,I5,5X,I5,A1,4X,6A10)
+        const std::string xname = xs_trim(xs_field(rec, 0, 10));
+        const double v1x = xs_num(xs_field(rec, 10, 10)), v2x = xs_num(xs_field(rec, 20, 10));
+        const int ntemp = (int)xs_num(xs_field(rec, 40, 5));
+        for (int64_t i = 0; i < ixmols; i++) {
+            if (!xs_matches(xname, ixindx[(size_t)i])) continue;
+            flg[(size_t)i] = 1;
+            if (!(v2x > xv1 && v1x < xv2)) continue;
+            if (per[(size_t)i].size() >= 5) { cleanup(); return xs_fail(MRTM_EIO, " XSREAD - NSPECR .GT. 5 (the arrays hold five regions per molecule)"); }
+            if (ntemp < 1 || ntemp > 6) { cleanup(); return xs_fail(MRTM_EIO, "FSCDXS: NTEMP out of 1..6 for " + xname); }
+            mrtm_xs_region g;
+            std::memset(&g, 0, sizeof g);
+            g.ixmol = (int32_t)i;
+            g.ntemp = ntemp;
+            g.v1fx = v1x;
+            g.v2fx = v2x;
+            g.xdoplr = 3.58115E-07 * (0.5 * (v1x + v2x)) * std::sqrt(296.0 / kXsMass[ixindx[(size_t)i]]);   // :1385-1386
+            for (int k = 0; k < ntemp; k++) {                 // MONORTM_XSEC_SUB :1656-1671
+                const std::string fn = xs_trim(xs_field(rec, 60 + 10 * (size_t)k, 10));
+                std::ifstream x(d + fn);
+                std::string hdr;
+                if (!x || !std::getline(x, hdr)) { cleanup(); return xs_fail(MRTM_EIO, "cross-section file missing or empty: " + d + fn); }
+                hdr.resize(100, ' ');                         // FORMAT 910 (A10,2F10.4,I10,3G10.3,3A10)
+                g.v1x = xs_num(xs_field(hdr, 10, 10));
+                g.v2x = xs_num(xs_field(hdr, 20, 10));
+                g.npts = (int64_t)xs_num(xs_field(hdr, 30, 10));
+                g.tx[k] = xs_num(xs_field(hdr, 40, 10));
+                const double pres = xs_num(xs_field(hdr, 50, 10));
+                g.pdx[k] = (xs_field(hdr, 90, 10) == "      TORR") ? pres * (1013. / 760) : pres;
+                if (g.npts < 2 || g.npts > 150000) { cleanup(); return xs_fail(MRTM_EIO, "cross-section file: NPTS out of 2..150000 (xsdat(150000,6)): " + fn); }
+                double* dat = new double[(size_t)g.npts];
+                g.xsdat[k] = dat;
+                // values written with 1PE10.3 touch when negative ("0.000E+00-1.025E-26" in the shipped HNO3 files): walk the
+                // number syntax instead of splitting on blanks
+                int64_t n = 0;
+                std::string line;
+                while (n < g.npts && std::getline(x, line)) {
+                    for (auto& c : line) if (c == 'D' || c == 'd') c = 'E';
+                    const char* q = line.c_str();
+                    while (n < g.npts && *q) {
+                        while (*q == ' ' || *q == ',' || *q == '\t' || *q == '\r') q++;
+                        if (!*q) break;
+                        char* end = nullptr;
+                        const double v = std::strtod(q, &end);
+                        if (end == q) break;
+                        dat[n++] = v;
+                        q = end;
+                    }
+                }
+                if (n < g.npts) { per[(size_t)i].push_back(g); cleanup(); return xs_fail(MRTM_EIO, "cross-section file shorter than its header says: " + fn); }
+            }
+            per[(size_t)i].push_back(g);
+        }
+    }
+    for (int64_t i = 0; i < ixmols; i++)
+        if (!flg[(size_t)i]) { cleanup(); return xs_fail(MRTM_EIO, "******* MOLECULE SELECTED -" + xsname[(size_t)i] + "- IS NOT FOUND ON FILE FSCDXS *******"); }
+    size_t tot = 0;
+    for (auto& v : per) tot += v.size();
+    mrtm_xs_region* out = new mrtm_xs_region[std::max<size_t>(tot, 1)];
+    size_t k = 0;
+    for (auto& v : per) for (auto& g : v) out[k++] = g;
+    *nreg = (int64_t)tot;
+    *regs_out = out;
+    return MRTM_OK;
+}

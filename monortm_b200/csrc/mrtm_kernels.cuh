@@ -51,5 +51,6 @@ struct TipsDev {
 #include "kernels/voigt.cuh"
 #include "kernels/final.cuh"
 #include "kernels/rt.cuh"
+#include "kernels/xsec.cuh"
 
 }  // namespace mrtm

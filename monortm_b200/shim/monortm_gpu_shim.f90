@@ -22,12 +22,14 @@ module monortm_gpu_shim
 
   type, bind(c) :: mrtm_opts
      integer(c_int32_t) :: use_global_range = 0
-     integer(c_int32_t) :: reserved0 = 0
+     integer(c_int32_t) :: line_mode = 0
      real(c_double)     :: v1_global = 0, v2_global = 0
      integer(c_int64_t) :: iw0 = 0
      type(c_ptr)        :: sel_count = c_null_ptr
      type(c_ptr)        :: sel_hash = c_null_ptr
      type(c_ptr)        :: stream = c_null_ptr
+     type(c_ptr)        :: xamnt = c_null_ptr        ! XAMNT of COMMON /PATHX/ (IXSECT=1), c_loc(XAMNT)
+     integer(c_int64_t) :: ld_xamnt = 0              ! MX_XS
   end type mrtm_opts
 
   interface

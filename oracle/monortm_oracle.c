@@ -1590,6 +1590,171 @@ int orc_calctmr(int64_t nlayrs, int64_t nwn, const double *wn, const double *t,
     return 0;
 }
 
+
+/* ======================================================================= */
+/*  monortm_sub.F90: cross sections                                          */
+/* ======================================================================= */
+#define XSPD_INT_MAX 10000000      /* xspd_int(0:10000000), monortm_sub.F90:1755 */
+
+/* convolve, monortm_sub.F90:1751-1834.  xspd is 1-based in the reference (xspd[i-1] = xspd(i)); reads one element past
+ * the table at the upper edge (xspd(ind+2) with ind+2 = nptsx+1, :1779) -- the caller's array is xspd(150000), so that
+ * element exists and holds whatever an earlier region left there; it is multiplied by coef = 0 up to rounding.  Here the
+ * table is passed with its length and elements beyond it read as 0. */
+static int convolve(const double *xspd, int64_t nxspd, double v1x, double v2x, double delvx, double pd, double hwdop,
+                    double tave, double pave, const double *wn, int64_t nwn, double *xspave, double *xspd_int)
+{
+    const double p0 = 1013.;
+#define XSPD(i) (((i) >= 1 && (i) <= nxspd) ? xspd[(i) - 1] : 0.)
+    double hwpave = 0.1 * (pave / p0) * (273.15 / tave);
+    double hwd = 0.1 * (pd / p0) * (273.15 / tave);
+    hwd = hwd > hwdop ? hwd : hwdop;
+    if (hwd > hwpave) hwpave = 1.001 * hwd;
+    double hwb = hwpave - hwd;
+    double ratio = 0.25;
+    double step = ratio * hwb;
+    if (step > delvx) step = delvx;
+    double q = (v2x - v1x) / step;
+    if (!(q < (double)XSPD_INT_MAX + 1.)) return fail(52, "convolve: NPTS exceeds xspd_int(0:10000000) (monortm_sub.F90:1755)");
+    int64_t npts = (int64_t)q;
+    step = (v2x - v1x) / (double)npts;
+    ratio = step / hwb;
+    for (int64_t i = 0; i <= npts; i++) {
+        double vv = v1x + (double)i * step;
+        double delvv = vv - v1x;
+        int64_t ind = (int64_t)(delvv / delvx);
+        double coef = (delvv - (double)ind * delvx) / delvx;
+        xspd_int[i] = (1. - coef) * XSPD(ind + 1) + coef * XSPD(ind + 2);
+    }
+    double hwb2 = hwb * hwb;
+    for (int64_t iwn = 1; iwn <= nwn; iwn++) {
+        double w = wn[iwn - 1];
+        if (w < v1x || w > v2x) { xspave[iwn - 1] = 0.; continue; }
+        if (hwb / hwd > 0.1) {
+            double wn_v1x = w - v1x;
+            int64_t ind = (int64_t)(wn_v1x / step);
+            double dvlo = w - (v1x + (double)ind * step);
+            double dvhi = w - (v1x + (double)(ind + 1) * step);
+            /* xspd_int(ind+1) with ind = npts at w = v2x is one past what loop 500 filled: stale in the reference, 0 here */
+            double xi1 = (ind + 1 <= npts) ? xspd_int[ind + 1] : 0.;
+            double answer = (hwb / (hwb2 + dvlo * dvlo)) * xspd_int[ind] + (hwb / (hwb2 + dvhi * dvhi)) * xi1;
+            int64_t j = 1;
+            for (;;) {
+                double contlo, conthi;
+                double vlo = v1x + (double)(ind - j) * step;
+                if (vlo > v1x) {
+                    dvlo = w - vlo;
+                    contlo = (hwb / (hwb2 + dvlo * dvlo)) * xspd_int[ind - j];
+                } else contlo = 0.;
+                double vhi = v1x + (double)(ind + j + 1) * step;
+                if (vhi < v2x) {
+                    dvhi = w - vhi;
+                    conthi = (hwb / (hwb2 + dvhi * dvhi)) * xspd_int[ind + j + 1];
+                } else conthi = 0.;
+                double xincr = contlo + conthi;
+                if ((xincr / answer) < ratio * 1e-6) break;
+                answer = answer + xincr;
+                j = j + 1;
+                /* zero or NaN table around the frequency: 0/0 is never < ratio*1e-6 and the reference loops forever */
+                if (j > npts + 2) return fail(53, "convolve: the outward sum does not terminate (monortm_sub.F90:1800-1821)");
+            }
+            xspave[iwn - 1] = answer * step / 3.14159;
+        } else {
+            double wn_v1x = w - v1x;
+            int64_t ind = (int64_t)(wn_v1x / delvx);
+            double coef = (wn_v1x - (double)ind * delvx) / delvx;
+            xspave[iwn - 1] = (1. - coef) * XSPD(ind) + coef * XSPD(ind + 1);      /* xspd(0) at w = v1x: 0 here */
+        }
+    }
+#undef XSPD
+    return 0;
+}
+
+int orc_convolve(const double *xspd, int64_t nxspd, double v1x, double v2x, double delvx, double pd, double hwdop,
+                 double tave, double pave, const double *wn, int64_t nwn, double *xspave)
+{
+    double *xi = (double *)calloc((size_t)XSPD_INT_MAX + 2, sizeof(double));
+    if (!xi) return fail(50, "out of memory");
+    int rc = convolve(xspd, nxspd, v1x, v2x, delvx, pd, hwdop, tave, pave, wn, nwn, xspave, xi);
+    free(xi);
+    return rc;
+}
+
+/* MONORTM_XSEC_SUB, monortm_sub.F90:1540-1749 */
+int orc_xsec_sub(int64_t nwn, const double *wn, int64_t nlay, const double *p, const double *t,
+                 int64_t nreg, const orc_xs_region *regs, int64_t ld_xamnt, const double *xamnt, double *odxsec)
+{
+    const double dvbuf = 1.0;
+    size_t nn = (size_t)nwn * (size_t)nlay;
+    double *xstot = (double *)calloc(nn ? nn : 1, sizeof(double));
+    double *xsmoltot = (double *)calloc(nn ? nn : 1, sizeof(double));
+    double *xspave = (double *)calloc((size_t)nwn + 1, sizeof(double));
+    double *xi = (double *)calloc((size_t)XSPD_INT_MAX + 2, sizeof(double));
+    int64_t maxpts = 1;
+    for (int64_t r = 0; r < nreg; r++) if (regs[r].npts > maxpts) maxpts = regs[r].npts;
+    double *xspd = (double *)calloc((size_t)maxpts + 2, sizeof(double));
+    if (!xstot || !xsmoltot || !xspave || !xi || !xspd) return fail(50, "out of memory");
+    int rc = 0;
+    int64_t r = 0;
+    while (r < nreg && !rc) {
+        int32_t ixmol = regs[r].ixmol;
+        memset(xsmoltot, 0, nn * sizeof(double));                                  /* :1644 */
+        for (; r < nreg && regs[r].ixmol == ixmol && !rc; r++) {                   /* loop 5000 */
+            const orc_xs_region *g = &regs[r];
+            int need = 0;                                                          /* :1647-1653 */
+            for (int64_t ipt = 1; ipt <= nwn; ipt++)
+                if (wn[ipt - 1] >= g->v1fx - dvbuf && wn[ipt - 1] <= g->v2fx + dvbuf) { need = 1; break; }
+            if (!need) continue;
+            for (int64_t il = 1; il <= nlay && !rc; il++) {                        /* loop 4000 */
+                double pave = p[il - 1], tave = t[il - 1];
+                double coef1 = 1., coef2 = 0.;
+                int ind1, ind2 = 1, it = 1;
+                if (g->ntemp == 1 || tave <= g->tx[it - 1]) {
+                    ind1 = 1;
+                } else {
+                    for (;;) {
+                        it = it + 1;
+                        if (it > g->ntemp) { ind1 = g->ntemp; ind2 = g->ntemp; break; }
+                        else if (tave <= g->tx[it - 1]) {
+                            ind1 = it - 1;
+                            ind2 = it;
+                            coef1 = (tave - g->tx[it - 1]) / (g->tx[it - 2] - g->tx[it - 1]);
+                            coef2 = 1. - coef1;
+                            break;
+                        }
+                    }
+                }
+                double pd = coef1 * g->pdx[ind1 - 1] + coef2 * g->pdx[ind2 - 1];
+                double xkt1 = g->tx[ind1 - 1] / RADCN2ref, xkt2 = g->tx[ind2 - 1] / RADCN2ref;
+                double delvx = (g->v2x - g->v1x) / (double)(g->npts - 1);
+                for (int64_t i = 1; i <= g->npts; i++) {                           /* loop 3300 */
+                    double vv = g->v1x + (double)(i - 1) * delvx;
+                    xspd[i - 1] = coef1 * g->xsdat[ind1 - 1][i - 1] / orc_radfn(vv, xkt1) +
+                                  coef2 * g->xsdat[ind2 - 1][i - 1] / orc_radfn(vv, xkt2);
+                }
+                double hwdop = g->xdoplr * sqrt(tave / 296.);
+                rc = convolve(xspd, g->npts, g->v1x, g->v2x, delvx, pd, hwdop, tave, pave, wn, nwn, xspave, xi);
+                if (rc) break;
+                for (int64_t iw = 0; iw < nwn; iw++)
+                    xsmoltot[(size_t)iw + (size_t)(il - 1) * nwn] = xsmoltot[(size_t)iw + (size_t)(il - 1) * nwn] + xspave[iw];
+            }
+        }
+        for (int64_t il = 1; il <= nlay; il++)                                     /* loop 5500 */
+            for (int64_t iw = 0; iw < nwn; iw++) {
+                size_t k = (size_t)iw + (size_t)(il - 1) * nwn;
+                xstot[k] = xstot[k] + xamnt[(size_t)ixmol + (size_t)(il - 1) * ld_xamnt] * xsmoltot[k];
+            }
+    }
+    for (int64_t il = 1; il <= nlay; il++) {                                       /* loop 6500 */
+        double xkt = t[il - 1] / RADCN2ref;
+        for (int64_t iw = 0; iw < nwn; iw++) {
+            size_t k = (size_t)iw + (size_t)(il - 1) * nwn;
+            odxsec[k] = xstot[k] * orc_radfn(wn[iw], xkt);
+        }
+    }
+    free(xstot); free(xsmoltot); free(xspave); free(xi); free(xspd);
+    return rc;
+}
+
 /* ---- building blocks exported for the reference-text pins (tests/test_ref_goldens.py) ---------------------- */
 double orc_lsf_lortz(double xf, double rp, double rp2, double aip, double bip, double hwhm, double wn, double xnu, int64_t mol)
 {

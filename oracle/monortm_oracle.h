@@ -102,6 +102,31 @@ void orc_branch_counts(int64_t out[8]);
 uint64_t orc_line_key(int64_t mol, int64_t rec);  /* splitmix64 of (mol<<32 | rec), 1-based */
 const char *orc_last_error(void);
 
+/* ---- cross sections ------------------------------------------------------------------------------
+ * One spectral region of one cross-section molecule as MONORTM_XSEC_SUB holds it after its READs
+ * (src/monortm_sub.F90:1656-1671): the FSCDXS range that decides whether the region is processed (:1647-1652), the
+ * header values of the LAST temperature file read (V1x, V2x, NPTSx stay those of the last file, :1662) and the
+ * per-temperature tables in ascending temperature order. */
+typedef struct {
+    int32_t ixmol;              /* 0-based index of the molecule in XAMNT's first dimension (loop 6000) */
+    int32_t ntemp;              /* NTEMPF(ixsr,ixmol) <= 6 */
+    int64_t npts;               /* NPTSx */
+    double v1fx, v2fx;          /* V1FX, V2FX from FSCDXS */
+    double v1x, v2x;            /* file header */
+    double xdoplr;              /* XDOPLR(ixsr,ixmol), XSREAD :1385-1386 */
+    double tx[6], pdx[6];       /* temperature, pressure in mb (TORR converted, :1665-1669) */
+    const double *xsdat[6];     /* npts values each */
+} orc_xs_region;
+
+/* MONORTM_XSEC_SUB (src/monortm_sub.F90:1540-1749) with convolve (:1751-1834).  regs must be ordered by molecule, then
+ * by spectral region (the loop order 6000 / 5000).  xamnt is (ld_xamnt, nlay) column-major; odxsec (nwn,nlay).
+ * Returns 52 where the reference would run off xspd_int(0:10000000) (:1755, 1773-1774). */
+int orc_xsec_sub(int64_t nwn, const double *wn, int64_t nlay, const double *p, const double *t,
+                 int64_t nreg, const orc_xs_region *regs, int64_t ld_xamnt, const double *xamnt, double *odxsec);
+/* convolve alone (pins against the executed reference text) */
+int orc_convolve(const double *xspd, int64_t nxspd, double v1x, double v2x, double delvx, double pd, double hwdop,
+                 double tave, double pave, const double *wn, int64_t nwn, double *xspave);
+
 #ifdef __cplusplus
 }
 #endif

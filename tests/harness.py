@@ -179,6 +179,67 @@ def oracle_rtm(iout, irt, wn, t, tz, o, tmpsfc, reflc, emiss, idu=1):
     return dict(rad=rad, tb=tb, rup=rup, rdn=rdn, trtot=trtot, tmpsfc=ts.value)
 
 
+# --------------------------------------------------------------------------------------- cross sections
+class OrcXsRegion(C.Structure):
+    _fields_ = [("ixmol", C.c_int32), ("ntemp", C.c_int32), ("npts", C.c_int64), ("v1fx", C.c_double), ("v2fx", C.c_double),
+                ("v1x", C.c_double), ("v2x", C.c_double), ("xdoplr", C.c_double), ("tx", C.c_double * 6), ("pdx", C.c_double * 6),
+                ("xsdat", C.c_void_p * 6)]
+
+
+def xs_region_array(regs, cls=OrcXsRegion):
+    """regions as monortm_b200.xsfile.read_regions returns them -> C array (+ the numpy arrays that must stay alive)"""
+    arr = (cls * max(len(regs), 1))()
+    keep = []
+    for i, r in enumerate(regs):
+        a, last = arr[i], r["files"][-1]
+        a.ixmol, a.ntemp, a.npts = r["ixmol"], len(r["files"]), last["npts"]
+        a.v1fx, a.v2fx, a.v1x, a.v2x, a.xdoplr = r["v1fx"], r["v2fx"], last["v1x"], last["v2x"], r["xdoplr"]
+        for j, f in enumerate(r["files"]):
+            a.tx[j], a.pdx[j] = f["t"], f["pres"]
+            d = np.ascontiguousarray(f["data"], dtype=np.float64)
+            keep.append(d)
+            a.xsdat[j] = d.ctypes.data
+    return arr, keep
+
+
+def oracle_xsec(regs, wn, p, t, xamnt):
+    lib = oracle_lib()
+    lib.orc_xsec_sub.restype = C.c_int
+    lib.orc_xsec_sub.argtypes = [C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64,
+                                 C.c_void_p, C.c_void_p]
+    wn, p, t = (np.ascontiguousarray(a, dtype=np.float64) for a in (wn, p, t))
+    xa = np.asfortranarray(xamnt, dtype=np.float64)
+    od = np.zeros((len(wn), len(p)), order="F")
+    arr, keep = xs_region_array(regs)
+    rc = lib.orc_xsec_sub(len(wn), _p(wn), len(p), _p(p), _p(t), len(regs), C.addressof(arr), xa.shape[0], _p(xa), _p(od))
+    if rc:
+        raise RuntimeError("orc_xsec_sub rc=%d: %s" % (rc, lib.orc_last_error().decode()))
+    return od
+
+
+def oracle_convolve(xspd, v1x, v2x, delvx, pd, hwdop, tave, pave, wn):
+    lib = oracle_lib()
+    lib.orc_convolve.restype = C.c_int
+    lib.orc_convolve.argtypes = [C.c_void_p, C.c_int64] + [C.c_double] * 7 + [C.c_void_p, C.c_int64, C.c_void_p]
+    xspd, wn = np.ascontiguousarray(xspd, dtype=np.float64), np.ascontiguousarray(wn, dtype=np.float64)
+    out = np.zeros(len(wn))
+    rc = lib.orc_convolve(_p(xspd), len(xspd), v1x, v2x, delvx, pd, hwdop, tave, pave, _p(wn), len(wn), _p(out))
+    if rc:
+        raise RuntimeError("orc_convolve rc=%d: %s" % (rc, lib.orc_last_error().decode()))
+    return out
+
+
+def xsec_case(spec, directory):
+    """the seeded synthetic cross-section case of tests/golden/ref_xsec_synth.npz: (regions, wn, p, t, xamnt)"""
+    from monortm_b200 import xsfile
+    wn, p, t = np.array(spec["wn"]), np.array(spec["p"]), np.array(spec["t"])
+    xamnt = np.zeros((xsfile.MX_XS, len(p)), order="F")
+    xamnt[:len(spec["names"])] = np.array(spec["xamnt"])
+    xsfile.synthetic_set(directory, seed=spec["seed"])
+    regs = xsfile.read_regions(directory, spec["names"], float(wn.min()), float(wn.max()))
+    return regs, wn, p, t, xamnt
+
+
 # --------------------------------------------------------------------------------------- cases
 _tape_cache = {}
 

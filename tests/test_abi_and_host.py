@@ -149,3 +149,29 @@ def test_oracle_on_reference_profile_fixture():
     assert np.all(clear["tb"] > 5) and np.all(clear["tb"] < 150)           # downwelling TBs (synthetic filler lines add to the real ones)
     assert np.all(cloudy["tb"] > clear["tb"] + 1.0)                        # 0.1 mm of liquid adds several K
     assert np.all(cloudy["o_clw"][:, 2:5] > 0) and np.all(cloudy["o_clw"][:, :2] == 0)
+
+
+def test_mrtm_opts_layout_matches_the_header_the_ctypes_mirror_and_the_fortran_shim(tmp_path):
+    """sizeof / offsetof of mrtm_opts as the C compiler lays it out for include/monortm_b200.h against the ctypes mirror
+    (monortm_b200/_capi.py) and the member order of the bind(c) type in the Fortran shim (which cannot be compiled here)."""
+    import re
+    import subprocess
+    src = tmp_path / "lay.c"
+    names = [n for n, _ in _capi.MrtmOpts._fields_]
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "monortm_b200.h"\nint main(void){printf("%zu", sizeof(mrtm_opts));' +
+                   "".join('printf(" %%zu", offsetof(mrtm_opts, %s));' % n for n in names) +
+                   'printf(" %zu", sizeof(mrtm_xs_region));return 0;}\n')
+    exe = tmp_path / "lay"
+    subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), "-o", str(exe), str(src)])
+    vals = [int(x) for x in subprocess.check_output([str(exe)]).split()]
+    assert vals[0] == C.sizeof(_capi.MrtmOpts)
+    assert vals[1:-1] == [getattr(_capi.MrtmOpts, n).offset for n in names]
+    assert vals[-1] == C.sizeof(_capi.MrtmXsRegion)
+    shim = open(os.path.join(ROOT, "monortm_b200", "shim", "monortm_gpu_shim.f90")).read()
+    body = shim[shim.index("type, bind(c) :: mrtm_opts"):shim.index("end type mrtm_opts")]
+    members = []
+    for line in body.split("\n")[1:]:
+        m = re.match(r"\s*(integer\(c_int32_t\)|integer\(c_int64_t\)|real\(c_double\)|type\(c_ptr\))\s*::\s*(.*?)(!.*)?$", line)
+        if m:
+            members += [x.split("=")[0].strip() for x in m.group(2).split(",")]
+    assert members == names

@@ -28,8 +28,9 @@ def _prof_lines(name, angle=None):
     return src
 
 
-def _expected(workdir, ctrl, nprof, scale=None):
-    """Oracle spectra of every profile of workdir/MONORTM_PROF.IN -> the text STOREOUT would write."""
+def _expected(workdir, ctrl, nprof, scale=None, xs=None):
+    """Oracle spectra of every profile of workdir/MONORTM_PROF.IN -> the text STOREOUT would write.
+    xs = (regions, xamnt): cross sections through the oracle's MONORTM_XSEC_SUB (IXSECT=1)."""
     wn = ctrl["wn"]
     ls = linefile.read_tape3(os.path.join(workdir, "TAPE3"), float(wn[0]), float(wn[-1]))
     emiss, reflc = driver.emiss_reflec(ctrl, wn)
@@ -43,14 +44,15 @@ def _expected(workdir, ctrl, nprof, scale=None):
             for m, f in scale.items():
                 wkl[m - 1, :] = wkl[m - 1, :] * f
         scor = api.scor_for_layers(nmol, pr["t"][:, 0])
+        odx_in = harness.oracle_xsec(xs[0], wn, pr["p"][:, 0], pr["t"][:, 0], xs[1]) if xs else None
         m = harness.oracle_modm(ls, wn, ctrl["dvset"], pr["p"][:, 0], pr["t"][:, 0], pr["clw"][:, 0], nmol, wkl,
-                                pr["wbrodl"][:, 0], scor, cntnm=ctrl["cntnm"], ibrd=ctrl["ibrd"], selection=False)
+                                pr["wbrodl"][:, 0], scor, cntnm=ctrl["cntnm"], ibrd=ctrl["ibrd"], selection=False, odxsec_in=odx_in)
         tmr = harness.oracle_calctmr(wn, pr["t"][:, 0], pr["tz"][:, 0], m["o"])
         r = harness.oracle_rtm(ctrl["iplot"], pr["irt"], wn, pr["t"][:, 0], pr["tz"][:, 0], m["o"], tmpsfc, reflc, emiss)
         tmpsfc = r["tmpsfc"]                                   # RTM leaves 2.75 behind for IRT 2,3 (RTMmono.f90:122)
         if ids is None:
             ids = sref.id_mols(wkl, pr["wbrodl"][:, 0], nmol)
-        otot, obm, odx = sref.layer_sums(m["o"], m["o_by_mol"], m["oc"])
+        otot, obm, odx = sref.layer_sums(m["o"], m["o_by_mol"], m["oc"], odx_in)
         wv = 0.0
         for l in range(nlay):
             wv = wv + wkl[0, l]
@@ -129,6 +131,41 @@ def test_library_driver_gridded_scaled_profile_with_layer_files(tmp_path):
     assert od[0] == "NWN :       9" and len(od) == 12
     vals = np.array([float(x.split()[1]) for x in od[2:11]])
     assert np.allclose(vals, layers[0][:, 2], rtol=6e-4)             # e12.4 keeps four digits
+
+
+def test_driver_with_cross_sections(tmp_path):
+    """IXSECT=1 end to end: the cross-section block of MONORTM_PROF.IN (monortm.f90:491-527), XSREAD on
+    FSCDXS, MONORTM_XSEC_SUB inside the step, the XSEC_OD column of MONORTM.OUT."""
+    from monortm_b200 import xsfile
+    wd = str(tmp_path)
+    xsfile.synthetic_set(wd)
+    r13 = "     3.000    11.000" + " " * 10 + "     1.000"
+    with open(os.path.join(wd, "MONORTM.IN"), "w") as f:
+        f.write("\n".join(["$ cross sections", rec12(ixsect=1), r13, "   288.20       0.9       0.0       0.0       0.1", "%"]) + "\n")
+    prof = _prof_lines("MONORTM_PROF.IN_sav", 180.0)
+    nlay = 19
+    rng = np.random.default_rng(5)
+    xamnt = np.zeros((38, nlay), order="F")
+    xamnt[0] = 10.0 ** rng.uniform(14, 16, nlay)
+    xamnt[1] = 10.0 ** rng.uniform(12, 14, nlay)
+    prof += ["%5d%5s%5d" % (2, "", 0), "%-10s%-10s" % ("HNO3", "CFC11"),
+             " 1%3d%5d  1.000000XS AMOUNTS      H1=    0.00 H2=   20.00 ANG= 180.000 LEN= 0" % (nlay, 2)]
+    for l in range(nlay):
+        prof.append("  0.0000000E+00    0.0000    0.0000   0")
+        prof.append("".join("%15.7E" % v for v in list(xamnt[:7, l]) + [0.0]))
+        xamnt[:, l] = [float("%15.7E" % v) for v in xamnt[:, l]]
+    with open(os.path.join(wd, "MONORTM_PROF.IN"), "w") as f:
+        f.write("\n".join(prof) + "\n")
+    _write_tape3(wd)
+    driver.run_monortm(wd)
+    ctrl = driver.read_control(os.path.join(wd, "MONORTM.IN"))
+    assert ctrl["ixsect"] == 1 and len(ctrl["wn"]) == 9
+    regs = xsfile.read_regions(wd, ["HNO3", "CFC11"], 3.0, 11.0)
+    assert [(r["ixmol"], r["v1fx"]) for r in regs] == [(0, 2.0)]                  # the F11 regions lie outside 3-11 cm-1
+    want, _ = _expected(wd, ctrl, 1, xs=(regs, xamnt))
+    got = open(os.path.join(wd, "MONORTM.OUT")).read().split("\n")
+    _same_records(got[:-1], want)
+    assert all(float(g.split()[-1]) > 0 for g in got[4:-1])                       # XSEC_OD column
 
 
 def test_driver_stops_like_the_reference(tmp_path):

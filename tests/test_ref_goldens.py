@@ -158,3 +158,19 @@ def test_the_goldens_cover_the_branches_they_claim():
     case = ref_cases.build_case(json.loads(str(g["spec"])))
     br = harness.run_oracle(case)["branches"]
     assert br["sdep"] > 100 and br["co2"] > 50 and br["co2_lc1"] > 30 and br["generic_lc"] > 50 and br["o2_lc"] > 10 and br["neg_res"] > 50
+
+
+def test_cross_sections_match_the_reference_text(tmp_path):
+    """MONORTM_XSEC_SUB + convolve (monortm_sub.F90:1540-1834): oracle vs the executed reference text on the seeded synthetic
+    cross-section set (two molecules, three regions, 1-4 temperature files, a TORR file; Lorentz convolution and the
+    interpolation shortcut; table edges; frequencies outside every region)."""
+    g = np.load(os.path.join(GOLD, "ref_xsec_synth.npz"))
+    spec = json.loads(str(g["spec"]))
+    regs, wn, p, t, xamnt = harness.xsec_case(spec, str(tmp_path))
+    assert [(r["ixmol"], r["v1fx"], len(r["files"])) for r in regs] == [(0, 2.0, 4), (0, 40.0, 2), (1, 18.0, 1)]   # F11 300-310 skipped
+    od = harness.oracle_xsec(regs, wn, p, t, xamnt)
+    assert np.array_equal(od == 0, g["odxsec"] == 0) and (g["odxsec"] != 0).sum() >= 60
+    assert _rel(od, g["odxsec"]) < 1e-14
+    for (pd, tt, pp), ref in zip(g["conv_args"], g["conv"]):
+        got = harness.oracle_convolve(g["conv_tab"], 5.0, 6.0, 0.0025, pd, 1.1e-5, tt, pp, g["conv_wn"])
+        assert np.array_equal(got == 0, ref == 0) and _rel(got, ref) < 1e-14

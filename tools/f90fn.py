@@ -1410,6 +1410,20 @@ class Emitter:
 
     # ---------------------------------------------------------------- statements
     def block(self, u, stmts, ind, loop_labels=()):
+        # a label of this statement list that a LATER goto names (a backward jump: the hand-written loops "1000 continue ...
+        # goto 1000"): the list runs inside "while True"; a pending jump to one of its labels restarts the list, and the
+        # guards skip everything up to the label
+        back = sorted(st["label"] for st in stmts if st.get("label") is not None and u.has_goto and
+                      st["label"] in getattr(u, "back_targets", ()))
+        if back:
+            if any(st["k"] in ("exit", "cycle") for st in stmts):
+                raise TranslateError("%s: EXIT/CYCLE next to the target of a backward GOTO" % u.name)
+            inner = self._block_plain(u, stmts, ind + "    ")
+            return [ind + "while True:"] + inner + ["%s    if _g in (%s,): continue" % (ind, ", ".join(str(b) for b in back)),
+                                                    ind + "    break"]
+        return self._block_plain(u, stmts, ind)
+
+    def _block_plain(self, u, stmts, ind):
         out = []
         g = u.has_goto
         for st in stmts:
@@ -1591,6 +1605,8 @@ class Emitter:
         tr = self.tr
         u.goto_targets = set()
         self._find_targets(u, u.body, u.goto_targets)
+        u.back_targets = set()
+        self._find_back_targets(u.body, set(), u.back_targets)
         sig = []
         for a in u.args:
             v = u.vars[a]
@@ -1750,6 +1766,21 @@ class Emitter:
                 self._collect_names(br[1], acc)
             for cs in st.get("cases", []):
                 self._collect_names(cs[1], acc)
+
+    def _find_back_targets(self, block, seen, acc):
+        """labels that a goto names after they have been passed in textual order"""
+        for st in block:
+            if st.get("label") is not None:
+                seen.add(st["label"])
+            tgt = st["target"] if st["k"] == "goto" else (st["inner"]["target"] if st["k"] == "if_stmt" and st["inner"]["k"] == "goto" else None)
+            if tgt is not None and tgt in seen:
+                acc.add(tgt)
+            if "body" in st:
+                self._find_back_targets(st["body"], seen, acc)
+            for br in st.get("branches", []):
+                self._find_back_targets(br[1], seen, acc)
+            for cs in st.get("cases", []):
+                self._find_back_targets(cs[1], seen, acc)
 
     def _find_targets(self, u, block, acc):
         for st in block:
