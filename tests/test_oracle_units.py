@@ -162,14 +162,17 @@ def test_continuum_scaling_and_selectors():
     assert np.all(n2[3:-3] > 0) and np.all(co2[3:-3] > 0)
     # N2 CIA scales with density squared: doubling pressure quadruples amagat*rho... tau_fac ~ amagat
     assert np.allclose(_contnm(22, one, pave=400.) * 2, n2, rtol=1e-12)
-    # out-of-range request is refused rather than silently wrong
+    # a request beyond the microwave runs the branches above 820 cm-1 (round 1 refused it): the 100-900 cm-1 H2O continuum is
+    # finite and positive, Rayleigh (selector 99) switches on at V2 >= 820 (contnm.f90:1107), O3 has nothing below 8920
     lib = harness.oracle_lib()
     wk = np.zeros(60)
-    ab = np.zeros(2000)
+    wk[0], wk[6] = 1e22, 2e23
     f = np.ones(7)
-    rc = lib.orc_contnm_one(1, f.ctypes.data_as(C.c_void_p), 800., 270., wk.ctypes.data_as(C.c_void_p), 1e24, 22,
-                            100., 900., 97., 904., 808, ab.ctypes.data_as(C.c_void_p))
-    assert rc != 0
+    for im, expect in ((1, True), (99, True), (3, False)):
+        ab = np.zeros(2000)
+        rc = lib.orc_contnm_one(im, f.ctypes.data_as(C.c_void_p), 800., 270., wk.ctypes.data_as(C.c_void_p), 1e24, 22,
+                                100., 900., 97., 904., 808, ab.ctypes.data_as(C.c_void_p))
+        assert rc == 0 and np.all(np.isfinite(ab)) and (np.all(ab[3:805] > 0) if expect else np.all(ab == 0))
 
 
 def test_modm_selection_counts_and_totals():
