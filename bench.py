@@ -428,7 +428,8 @@ def run_c4(args):
     ptrs = {k: v.data_ptr() for k, v in d.items()}
     for i, k in enumerate(("rad", "tb", "tmr", "trtot", "rup", "rdn")):
         ptrs[k] = outs[i].data_ptr()
-    stream = torch.cuda.current_stream()
+    stream = torch.cuda.Stream(device=dev)       # the library call is asynchronous on the stream it is given: time on that stream
+    torch.cuda.set_stream(stream)
 
     def step_dev():
         sess.profiles_dev(nprof, nwn, NLAY, 22, 0.0, ptrs, float(wn[0]), float(wn[-1]), 0, inp["irt"], stream=stream.cuda_stream)
@@ -608,7 +609,10 @@ def main():
     for i, k in enumerate(("rad", "tb", "tmr", "trtot", "rup", "rdn")):
         ptrs[k] = outs[i].data_ptr()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-    stream = torch.cuda.current_stream()
+    # everything timed runs on ONE explicit stream: the library call is asynchronous on the stream it is given (a NULL /
+    # legacy-default handle would send it to the context's own stream, outside the events below)
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
 
     def step_dev(line_mode=0):
         sess.profiles_dev(1, nwn, NLAY, 22, 0.0, ptrs, inp["v1"], inp["v2"], inp["iw0"], inp["irt"], stream=stream.cuda_stream,

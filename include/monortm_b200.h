@@ -88,6 +88,16 @@ typedef struct mrtm_opts {
 
 /* ---- context ------------------------------------------------------------------------- */
 int mrtm_init(int device, mrtm_ctx **ctx);
+/* One context that drives several GPUs of the node from ONE host process (the reference is a single process,
+ * src/monortm.f90; SURVEY 8b proposed mrtm_init(device_mask, ...)).  Bit d of device_mask selects CUDA device d; 0 = every
+ * visible device.  mrtm_stage_lines / mrtm_stage_xsec replicate the staged data on every GPU; mrtm_profiles splits its work
+ * (SURVEY 8e): nprof >= number of GPUs -> contiguous blocks of profiles (monortm.f90:357), otherwise contiguous blocks of
+ * the frequency list (modm.f90:253; v1, v2 and the grid origin stay those of the whole list), with block sizes that follow
+ * the time each GPU needed for its share of the previous call on the same list.  One host thread per GPU, no collective:
+ * every result lands directly in the caller's arrays.  The other entry points (mrtm_modm, mrtm_calctmr, mrtm_rtm,
+ * mrtm_xsec, mrtm_profiles_dev) run on the first GPU of the context. */
+int mrtm_init_multi(uint64_t device_mask, mrtm_ctx **ctx);
+int mrtm_num_devices(mrtm_ctx *ctx);
 int mrtm_free(mrtm_ctx *ctx);
 const char *mrtm_strerror(int code);
 const char *mrtm_last_error(mrtm_ctx *ctx);   /* detail of the last failure on ctx (may be NULL ctx) */
@@ -179,7 +189,10 @@ int mrtm_profiles(mrtm_ctx *ctx, int64_t nprof, int64_t nwn, const double *wn, d
 
 /* Same computation with every array already resident in device memory (layouts as above),
  * asynchronous on opts->stream; nothing is copied to the host.  Used when the caller keeps
- * inputs/outputs in HBM (ensembles, multi-GPU shards gathered with NCCL). */
+ * inputs/outputs in HBM (ensembles, multi-GPU shards gathered with NCCL).  When the profiles fit one
+ * batch of derived planes (MRTM_PLANES_GB) the call returns without waiting for the device: kernel times, counters and
+ * device-detected errors (TIPS range, SDVOIGT, cross sections) are collected by the next mrtm_sync / mrtm_get_stats (which
+ * return the deferred error code) or at the start of the next call. */
 int mrtm_profiles_dev(mrtm_ctx *ctx, int64_t nprof, int64_t nwn, const double *wn_dev, double dvset,
                       int64_t nlay, const double *p, const double *t, const double *tz,
                       const double *clw, int64_t nmol, const double *wkl, const double *wbrodl,
@@ -188,6 +201,9 @@ int mrtm_profiles_dev(mrtm_ctx *ctx, int64_t nprof, int64_t nwn, const double *w
                       double *tmpsfc, const double *emiss_dev, const double *reflc_dev,
                       double *rad_dev, double *tb_dev, double *tmr_dev, double *trtot_dev,
                       double *rup_dev, double *rdn_dev, double *o_dev, const mrtm_opts *opts);
+
+/* Wait for the last asynchronous call on ctx; returns its deferred error code (0 = none). */
+int mrtm_sync(mrtm_ctx *ctx);
 
 /* ---- instrumentation ------------------------------------------------------------------- */
 typedef struct mrtm_stats {

@@ -68,6 +68,9 @@ class MrtmControl(C.Structure):
 _D, _I, _P = C.c_double, C.c_int64, C.c_void_p
 SIGNATURES = {
     "mrtm_init": (C.c_int, [C.c_int, C.POINTER(_P)]),
+    "mrtm_init_multi": (C.c_int, [C.c_uint64, C.POINTER(_P)]),
+    "mrtm_num_devices": (C.c_int, [_P]),
+    "mrtm_sync": (C.c_int, [_P]),
     "mrtm_free": (C.c_int, [_P]),
     "mrtm_strerror": (C.c_char_p, [C.c_int]),
     "mrtm_last_error": (C.c_char_p, [_P]),

@@ -84,10 +84,15 @@ def scor_for_layers(nmol, t):
 class Session:
     """One mrtm_ctx (one GPU).  Not re-entrant, like the reference's process-global state."""
 
-    def __init__(self, device=0):
+    def __init__(self, device=0, device_mask=None):
+        """device: one GPU.  device_mask (int, bit d = CUDA device d, 0 = all): one context over several GPUs of the node
+        (mrtm_init_multi): profiles() splits by profile or by frequency inside the library."""
         self.lib = _capi.load_library()
         h = C.c_void_p()
-        rc = self.lib.mrtm_init(int(device), C.byref(h))
+        if device_mask is not None:
+            rc = self.lib.mrtm_init_multi(int(device_mask), C.byref(h))
+        else:
+            rc = self.lib.mrtm_init(int(device), C.byref(h))
         if rc:
             msg = self.lib.mrtm_last_error(h if h else None)
             if h:
@@ -143,6 +148,13 @@ class Session:
         od = np.zeros((nwn, nlay), order="F")
         self._check(self.lib.mrtm_xsec(self.h, nwn, _ptr(wn), nlay, _ptr(p), _ptr(t), xamnt.shape[0], _ptr(xamnt), _ptr(od)))
         return od
+
+    def num_devices(self):
+        return int(self.lib.mrtm_num_devices(self.h))
+
+    def sync(self):
+        """wait for the last asynchronous profiles_dev call; raises its deferred error"""
+        self._check(self.lib.mrtm_sync(self.h))
 
     def stats(self):
         st = MrtmStats()

@@ -8,7 +8,9 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <chrono>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "mrtm_kernels.cuh"
@@ -32,6 +34,12 @@ struct DevBuf {   // grow-only device scratch
 };
 
 struct mrtm_ctx {
+    // mrtm_init_multi: a context without device resources of its own that drives one single-device context per GPU
+    std::vector<mrtm_ctx*> peers;
+    std::vector<int64_t> mg_bounds;               // frequency partition of the last frequency-split call (ndev + 1 entries)
+    std::vector<double> mg_ms;                    // host-measured time of each device's share of that call
+    int64_t mg_nwn = 0;
+    int mg_mode = 0;                              // last split: 0 none, 1 by profile, 2 by frequency
     int device = 0;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[8];
@@ -81,6 +89,9 @@ struct mrtm_ctx {
     int xs_nmol = 0;
     DevBuf b_xsreg, b_xsdat, b_xslay, b_xstab, b_xsneed, b_xsod, b_xsin[4];
     mrtm_stats st;
+    // asynchronous device-resident calls (mrtm_profiles_dev): timing events and device flags are read back lazily
+    bool pending = false, pending_lines = false, pending_rt = false;
+    int deferred_rc = MRTM_OK;
     size_t planes_budget = (size_t)8 << 30;
 };
 
@@ -231,6 +242,11 @@ static void free_lines(mrtm_ctx* ctx)
 extern "C" int mrtm_free(mrtm_ctx* ctx)
 {
     if (!ctx) return MRTM_OK;
+    if (!ctx->peers.empty()) {
+        for (mrtm_ctx* c : ctx->peers) mrtm_free(c);
+        delete ctx;
+        return MRTM_OK;
+    }
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     free_lines(ctx);
@@ -257,7 +273,33 @@ extern "C" int mrtm_free(mrtm_ctx* ctx)
     return MRTM_OK;
 }
 
-extern "C" int64_t mrtm_num_lines(mrtm_ctx* ctx) { return (ctx && ctx->have_lines) ? ctx->hl.n : 0; }
+extern "C" int64_t mrtm_num_lines(mrtm_ctx* ctx)
+{
+    if (ctx && !ctx->peers.empty()) ctx = ctx->peers[0];
+    return (ctx && ctx->have_lines) ? ctx->hl.n : 0;
+}
+
+static int stage_lines_single(mrtm_ctx* ctx, const int64_t nblm[MRTM_MXMOL], int64_t iim,
+                              const int64_t* iso, const double* xnu0, const double* deltnu,
+                              const double* e, const double* alps, const double* alpf,
+                              const double* x, const double* xg, const double* s0,
+                              const double* rmol, const double* sdep,
+                              const int32_t* brd_mol_flg, const double* brd_mol_tmp,
+                              const double* brd_mol_hw, const double* brd_mol_shft);
+
+// run fn(i, peer i) on one host thread per device; returns the first error and copies its text to the parent
+template <class Fn>
+static int for_each_peer(mrtm_ctx* ctx, Fn fn)
+{
+    const size_t n = ctx->peers.size();
+    std::vector<int> rcs(n, MRTM_OK);
+    std::vector<std::thread> th;
+    for (size_t i = 0; i < n; i++) th.emplace_back([&, i]() { rcs[i] = fn((int)i, ctx->peers[i]); });
+    for (auto& t : th) t.join();
+    for (size_t i = 0; i < n; i++)
+        if (rcs[i]) return set_err(ctx, rcs[i], "device " + std::to_string(ctx->peers[i]->device) + ": " + ctx->peers[i]->err);
+    return MRTM_OK;
+}
 
 extern "C" int mrtm_stage_lines(mrtm_ctx* ctx, const int64_t nblm[MRTM_MXMOL], int64_t iim,
                                 const int64_t* iso, const double* xnu0, const double* deltnu,
@@ -266,6 +308,23 @@ extern "C" int mrtm_stage_lines(mrtm_ctx* ctx, const int64_t nblm[MRTM_MXMOL], i
                                 const double* rmol, const double* sdep,
                                 const int32_t* brd_mol_flg, const double* brd_mol_tmp,
                                 const double* brd_mol_hw, const double* brd_mol_shft)
+{
+    if (ctx && !ctx->peers.empty())                  // replicated on every device
+        return for_each_peer(ctx, [&](int, mrtm_ctx* c) {
+            return stage_lines_single(c, nblm, iim, iso, xnu0, deltnu, e, alps, alpf, x, xg, s0, rmol, sdep, brd_mol_flg, brd_mol_tmp,
+                                      brd_mol_hw, brd_mol_shft);
+        });
+    return stage_lines_single(ctx, nblm, iim, iso, xnu0, deltnu, e, alps, alpf, x, xg, s0, rmol, sdep, brd_mol_flg, brd_mol_tmp,
+                              brd_mol_hw, brd_mol_shft);
+}
+
+static int stage_lines_single(mrtm_ctx* ctx, const int64_t nblm[MRTM_MXMOL], int64_t iim,
+                              const int64_t* iso, const double* xnu0, const double* deltnu,
+                              const double* e, const double* alps, const double* alpf,
+                              const double* x, const double* xg, const double* s0,
+                              const double* rmol, const double* sdep,
+                              const int32_t* brd_mol_flg, const double* brd_mol_tmp,
+                              const double* brd_mol_hw, const double* brd_mol_shft)
 {
     if (!ctx) return MRTM_EARG;
     if (!nblm || !iso || !xnu0 || !deltnu || !e || !alps || !alpf || !x || !xg || !s0 || !rmol || !sdep)
@@ -439,6 +498,7 @@ struct RunDesc {
     long long* sel_count;
     unsigned long long* sel_hash;
     bool do_lines, do_tmr, do_rtm;
+    bool async_ok;                  // the caller does not need timings / device flags before returning (mrtm_profiles_dev)
     double v1, v2;
     int64_t iw0;
     int line_mode;                  // mrtm_opts.line_mode
@@ -488,10 +548,39 @@ static void launch_lines(const LinesArgs& la, dim3 grid, bool sel, cudaStream_t 
 static int run_xsec_device(mrtm_ctx* ctx, int64_t nwn, const double* wn, int64_t nlay, const double* p, const double* t,
                            int64_t ld_xamnt, const double* xamnt, double* od, cudaStream_t s);
 
+// what an asynchronous call left undone: kernel times from the recorded events, device counters and error flags
+static int finalize_pending(mrtm_ctx* ctx)
+{
+    if (!ctx->pending) return ctx->deferred_rc;
+    ctx->pending = false;
+    mrtm_stats& st = ctx->st;
+    CU(cudaEventSynchronize(ctx->pending_rt ? ctx->ev[5] : ctx->ev[3]));
+    float ms = 0.f;
+    if (ctx->pending_lines) {
+        cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]); st.last_derive_kernel_ms += ms;
+        cudaEventElapsedTime(&ms, ctx->ev[2], ctx->ev[3]); st.last_lines_kernel_ms += ms;
+    }
+    if (ctx->pending_rt) { cudaEventElapsedTime(&ms, ctx->ev[4], ctx->ev[5]); st.last_rt_kernel_ms += ms; }
+    if (ctx->pending_lines) {
+        int flag = 0;
+        unsigned long long cnt[2] = {0ull, 0ull};
+        CU(cudaMemcpy(&flag, ctx->errflag_dev, sizeof(int), cudaMemcpyDeviceToHost));
+        CU(cudaMemcpy(cnt, ctx->counters_dev, sizeof cnt, cudaMemcpyDeviceToHost));
+        st.far_expansions = (double)cnt[0];
+        st.direct_evals = (double)cnt[1];
+        if (flag & 1) ctx->deferred_rc = set_err(ctx, MRTM_ETIPS, mrtm_strerror(MRTM_ETIPS));
+        else if (flag & 2) ctx->deferred_rc = set_err(ctx, MRTM_ESDVOIGT, mrtm_strerror(MRTM_ESDVOIGT));
+        else if (flag & (16 | 32)) ctx->deferred_rc = set_err(ctx, MRTM_EXSEC, mrtm_strerror(MRTM_EXSEC));
+    }
+    return ctx->deferred_rc;
+}
+
 static int run_device(mrtm_ctx* ctx, const RunDesc& r, cudaStream_t s)
 {
     if (r.nprof < 1 || r.nwn < 1 || r.nlay < 1) return set_err(ctx, MRTM_EARG, "nprof, nwn, nlay must be >= 1");
     if (r.nwn > 0x7fffffff / 64 || r.nlay > 65535) return set_err(ctx, MRTM_EARG, "nwn/nlay too large for one call");
+    finalize_pending(ctx);          // the previous asynchronous call's events and flags (its error, if any, was for mrtm_sync)
+    ctx->deferred_rc = MRTM_OK;
     mrtm_stats& st = ctx->st;
     st.last_lines_kernel_ms = st.last_rt_kernel_ms = st.last_derive_kernel_ms = 0.;
     const int64_t nwn = r.nwn, nlay = r.nlay;
@@ -920,8 +1009,16 @@ static int run_device(mrtm_ctx* ctx, const RunDesc& r, cudaStream_t s)
                 if (r.h_spec[i] && dev_spec[i])
                     CU(cudaMemcpyAsync(r.h_spec[i] + (size_t)b0 * nwn, dev_spec[i] + (size_t)b0 * nwn, (size_t)nb * nwn * 8, cudaMemcpyDeviceToHost, s));
         }
-        // per-batch kernel times (needs the batch to finish; cheap next to the kernels themselves)
-        if (r.nprof > B || true) {
+        // per-batch kernel times (needs the batch to finish; cheap next to the kernels themselves).  A single-batch
+        // asynchronous call returns here without touching the host again: mrtm_sync / mrtm_get_stats / the next call finish it
+        const bool defer = r.async_ok && r.nprof <= B;
+        if (defer) {
+            ctx->pending = true;
+            ctx->pending_lines = r.do_lines;
+            ctx->pending_rt = r.do_tmr || r.do_rtm;
+            return MRTM_OK;
+        }
+        {
             CU(cudaEventSynchronize(r.do_tmr || r.do_rtm ? ctx->ev[5] : ctx->ev[3]));
             float ms = 0.f;
             if (r.do_lines) {
@@ -963,6 +1060,7 @@ static int h2d(mrtm_ctx* ctx, DevBuf& b, const void* src, size_t bytes, cudaStre
 extern "C" int mrtm_stage_xsec(mrtm_ctx* ctx, int64_t nreg, const mrtm_xs_region* regs)
 {
     if (!ctx || nreg < 0 || (nreg > 0 && !regs)) return MRTM_EARG;
+    if (!ctx->peers.empty()) return for_each_peer(ctx, [&](int, mrtm_ctx* c) { return mrtm_stage_xsec(c, nreg, regs); });
     CU(cudaSetDevice(ctx->device));
     CU(cudaStreamSynchronize(ctx->stream));
     ctx->xs_regs.clear();
@@ -1046,6 +1144,7 @@ static int check_xsec_flags(mrtm_ctx* ctx, cudaStream_t s)
 extern "C" int mrtm_xsec(mrtm_ctx* ctx, int64_t nwn, const double* wn, int64_t nlay, const double* p, const double* t,
                          int64_t ld_xamnt, const double* xamnt, double* odxsec)
 {
+    if (ctx && !ctx->peers.empty()) ctx = ctx->peers[0];      // single-device entry point: the first GPU of a multi-GPU context
     if (!ctx) return MRTM_EARG;
     if (!wn || !p || !t || !xamnt || !odxsec || nwn < 1 || nlay < 1 || ld_xamnt < 1) return set_err(ctx, MRTM_EARG, "mrtm_xsec: null input or bad dimension");
     CU(cudaSetDevice(ctx->device));
@@ -1085,6 +1184,7 @@ extern "C" int mrtm_modm(mrtm_ctx* ctx, int64_t nwn, const double* wn, double dv
                          double sclcpl, double sclhw, double y0res, const double cntnm[7],
                          int64_t ixsect, int64_t ibrd, const double* scor, const mrtm_opts* opts)
 {
+    if (ctx && !ctx->peers.empty()) ctx = ctx->peers[0];      // single-device entry point: the first GPU of a multi-GPU context
     if (!ctx) return MRTM_EARG;
     if (!wn || !p || !t || !clw || !wkl || !wbrodl || !cntnm || nwn < 1 || nlay < 1)
         return set_err(ctx, MRTM_EARG, "mrtm_modm: null input or bad dimension");
@@ -1190,6 +1290,7 @@ static int run_rt_host(mrtm_ctx* ctx, bool do_tmr, bool do_rtm, int64_t iout, in
 extern "C" int mrtm_calctmr(mrtm_ctx* ctx, int64_t nlayrs, int64_t nwn, const double* wn,
                             const double* t, const double* tz, const double* o, double* tmr)
 {
+    if (ctx && !ctx->peers.empty()) ctx = ctx->peers[0];      // single-device entry point: the first GPU of a multi-GPU context
     return run_rt_host(ctx, true, false, 0, 3, nwn, wn, nlayrs, t, tz, o, nullptr, nullptr, nullptr, nullptr,
                        nullptr, nullptr, nullptr, nullptr, tmr, 1);
 }
@@ -1199,6 +1300,7 @@ extern "C" int mrtm_rtm(mrtm_ctx* ctx, int64_t iout, int64_t irt, int64_t nwn, c
                         double* tmpsfc, double* rup, double* trtot, double* rdn,
                         const double* reflc, const double* emiss, double* rad, double* tb, int64_t idu)
 {
+    if (ctx && !ctx->peers.empty()) ctx = ctx->peers[0];      // single-device entry point: the first GPU of a multi-GPU context
     return run_rt_host(ctx, false, true, iout, irt, nwn, wn, nlay, t, tz, o, tmpsfc, rup, trtot, rdn, reflc,
                        emiss, rad, tb, nullptr, idu);
 }
@@ -1212,6 +1314,7 @@ extern "C" int mrtm_profiles_dev(mrtm_ctx* ctx, int64_t nprof, int64_t nwn, cons
                                  double* rad_dev, double* tb_dev, double* tmr_dev, double* trtot_dev,
                                  double* rup_dev, double* rdn_dev, double* o_dev, const mrtm_opts* opts)
 {
+    if (ctx && !ctx->peers.empty()) ctx = ctx->peers[0];      // single-device entry point: the first GPU of a multi-GPU context
     if (!ctx) return MRTM_EARG;
     if (!wn_dev || !p || !t || !tz || !clw || !wkl || !wbrodl || !cntnm || !tmpsfc || !emiss_dev || !reflc_dev)
         return set_err(ctx, MRTM_EARG, "mrtm_profiles_dev: null input");
@@ -1240,10 +1343,22 @@ extern "C" int mrtm_profiles_dev(mrtm_ctx* ctx, int64_t nprof, int64_t nwn, cons
     r.do_lines = true; r.do_tmr = true; r.do_rtm = true;
     r.line_mode = opts->line_mode;
     r.v1 = opts->v1_global; r.v2 = opts->v2_global; r.iw0 = opts->iw0;
+    r.async_ok = true;
     return run_device(ctx, r, s);
 }
 
-extern "C" int mrtm_profiles(mrtm_ctx* ctx, int64_t nprof, int64_t nwn, const double* wn, double dvset,
+extern "C" int mrtm_sync(mrtm_ctx* ctx)
+{
+    if (ctx && !ctx->peers.empty()) ctx = ctx->peers[0];      // single-device entry point: the first GPU of a multi-GPU context
+    if (!ctx) return MRTM_EARG;
+    CU(cudaSetDevice(ctx->device));
+    const int rc = finalize_pending(ctx);
+    ctx->deferred_rc = MRTM_OK;                     // reported once
+    CU(cudaStreamSynchronize(ctx->stream));
+    return rc;
+}
+
+static int profiles_single(mrtm_ctx* ctx, int64_t nprof, int64_t nwn, const double* wn, double dvset,
                              int64_t nlay, const double* p, const double* t, const double* tz,
                              const double* clw, int64_t nmol, const double* wkl, const double* wbrodl,
                              const double* scor, double sclcpl, double sclhw, double y0res,
@@ -1352,16 +1467,223 @@ extern "C" int mrtm_profiles(mrtm_ctx* ctx, int64_t nprof, int64_t nwn, const do
     return MRTM_OK;
 }
 
+// ---------------------------------------------------------------------------------------------
+// several GPUs behind one context: one host thread per device, no data-path collective
+// ---------------------------------------------------------------------------------------------
+extern "C" int mrtm_init_multi(uint64_t device_mask, mrtm_ctx** out)
+{
+    if (!out) return MRTM_EARG;
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev <= 0)
+        return set_err(nullptr, MRTM_ENODEV, std::string("cudaGetDeviceCount: ") + cudaGetErrorString(e));
+    if (device_mask == 0) device_mask = (ndev >= 64) ? ~0ull : ((1ull << ndev) - 1ull);
+    mrtm_ctx* ctx = new mrtm_ctx();
+    ctx->device = -1;
+    std::memset(&ctx->st, 0, sizeof ctx->st);
+    // MRTM_MULTI_CONTEXTS_PER_DEVICE=n: n contexts on every selected device (exercises the partitioning on a single-GPU box)
+    int dup = 1;
+    if (const char* sdup = std::getenv("MRTM_MULTI_CONTEXTS_PER_DEVICE")) dup = std::min(std::max(std::atoi(sdup), 1), 8);
+    for (int dd = 0; dd < 64 * dup; dd++) {
+        const int d = dd / dup;
+        if (!((device_mask >> d) & 1ull)) continue;
+        mrtm_ctx* c = nullptr;
+        int rc = (d < ndev) ? mrtm_init(d, &c) : set_err(nullptr, MRTM_EARG, "device_mask names a device that does not exist");
+        if (rc) {
+            if (c) mrtm_free(c);
+            for (mrtm_ctx* q : ctx->peers) mrtm_free(q);
+            delete ctx;
+            return rc;
+        }
+        ctx->peers.push_back(c);
+    }
+    *out = ctx;
+    return MRTM_OK;
+}
+
+extern "C" int mrtm_num_devices(mrtm_ctx* ctx) { return !ctx ? 0 : (ctx->peers.empty() ? 1 : (int)ctx->peers.size()); }
+
+// frequency partition for the next call: equal counts the first time a grid is seen, afterwards each device's share is
+// rescaled by the time it needed for its last share (the cost per frequency depends on the spectral position: more
+// expansions where negative-frequency resonances and window edges fall inside the coarse tiles), blocks in multiples of
+// 512 frequencies (the tile of the dense-grid kernels)
+static void mg_partition(mrtm_ctx* ctx, int64_t nwn, int ndev)
+{
+    const int64_t q = 512;
+    std::vector<double> share((size_t)ndev, 1.0 / ndev);
+    const bool have = ctx->mg_nwn == nwn && (int)ctx->mg_bounds.size() == ndev + 1 && (int)ctx->mg_ms.size() == ndev;
+    if (have) {
+        double tmin = 1e300, tmax = 0., sum = 0.;
+        for (int i = 0; i < ndev; i++) { tmin = std::min(tmin, ctx->mg_ms[(size_t)i]); tmax = std::max(tmax, ctx->mg_ms[(size_t)i]); }
+        if (tmin > 0. && tmax / tmin < 1.02) return;                   // balanced: keep the partition (and the cached plans)
+        for (int i = 0; i < ndev; i++) {
+            const double cnt = (double)(ctx->mg_bounds[(size_t)i + 1] - ctx->mg_bounds[(size_t)i]);
+            share[(size_t)i] = (ctx->mg_ms[(size_t)i] > 0. && cnt > 0.) ? cnt / ctx->mg_ms[(size_t)i] : 1.0;   // frequencies per ms
+            sum += share[(size_t)i];
+        }
+        for (auto& v : share) v /= sum;
+    }
+    if (have) {                                     // damped: half way to the shares the last timings suggest
+        for (int i = 0; i < ndev; i++) {
+            const double old_share = (double)(ctx->mg_bounds[(size_t)i + 1] - ctx->mg_bounds[(size_t)i]) / (double)nwn;
+            share[(size_t)i] = 0.5 * (share[(size_t)i] + old_share);
+        }
+    }
+    const int64_t min_blk = (nwn >= (int64_t)ndev * 4 * q) ? 2 * q : 0;       // every device keeps a share
+    ctx->mg_bounds.assign((size_t)ndev + 1, 0);
+    double acc = 0.;
+    for (int i = 1; i < ndev; i++) {
+        acc += share[(size_t)i - 1];
+        int64_t b = (int64_t)std::llround(acc * (double)nwn / (double)q) * q;
+        b = std::max(b, ctx->mg_bounds[(size_t)i - 1] + min_blk);
+        b = std::min(b, nwn - (int64_t)(ndev - i) * min_blk);
+        ctx->mg_bounds[(size_t)i] = std::min(std::max<int64_t>(b, 0), nwn);
+    }
+    ctx->mg_bounds[(size_t)ndev] = nwn;
+    ctx->mg_nwn = nwn;
+}
+
+static int profiles_multi(mrtm_ctx* ctx, int64_t nprof, int64_t nwn, const double* wn, double dvset,
+                          int64_t nlay, const double* p, const double* t, const double* tz,
+                          const double* clw, int64_t nmol, const double* wkl, const double* wbrodl,
+                          const double* scor, double sclcpl, double sclhw, double y0res,
+                          const double cntnm[7], int64_t ibrd, int64_t irt, int64_t iout, int64_t idu,
+                          double* tmpsfc, const double* emiss, const double* reflc,
+                          double* rad, double* tb, double* tmr, double* trtot, double* rup, double* rdn,
+                          double* o, double* otot_by_mol, const mrtm_opts* opts)
+{
+    if (!wn || !p || !t || !tz || !clw || !wkl || !wbrodl || !cntnm || !tmpsfc || !emiss || !reflc || nprof < 1 || nwn < 1 || nlay < 1)
+        return set_err(ctx, MRTM_EARG, "mrtm_profiles: null input or bad dimension");
+    const int ndev = (int)ctx->peers.size();
+    mrtm_opts base;
+    std::memset(&base, 0, sizeof base);
+    if (opts) base = *opts;
+    base.stream = nullptr;
+    const size_t NL = (size_t)nlay, NW = (size_t)nwn;
+    auto offd = [](double* q, size_t n) { return q ? q + n : nullptr; };
+    auto offc = [](const double* q, size_t n) { return q ? q + n : nullptr; };
+    if (nprof >= ndev) {
+        // ---- profiles are independent (monortm.f90:357): contiguous blocks of profiles, nothing to reassemble
+        ctx->mg_mode = 1;
+        return for_each_peer(ctx, [&](int i, mrtm_ctx* c) {
+            const int64_t b = nprof / ndev, rem = nprof % ndev;
+            const int64_t s0 = (int64_t)i * b + std::min<int64_t>(i, rem), cnt = b + (i < rem ? 1 : 0);
+            if (cnt == 0) return (int)MRTM_OK;
+            const size_t S = (size_t)s0;
+            mrtm_opts oi = base;
+            if (oi.sel_count) oi.sel_count += S * NW * NL;
+            if (oi.sel_hash) oi.sel_hash += S * NW * NL;
+            if (oi.xamnt) oi.xamnt += S * (size_t)oi.ld_xamnt * NL;
+            return profiles_single(c, cnt, nwn, wn, dvset, nlay, p + S * NL, t + S * NL, tz + S * (NL + 1), clw + S * NL, nmol,
+                                   wkl + S * NL * MRTM_MXMOL, wbrodl + S * NL, offc(scor, S * NL * MRTM_NSCOR1 * MRTM_NSCOR2), sclcpl, sclhw,
+                                   y0res, cntnm, ibrd, irt, iout, idu, tmpsfc + S, emiss, reflc, offd(rad, S * NW), offd(tb, S * NW),
+                                   offd(tmr, S * NW), offd(trtot, S * NW), offd(rup, S * NW), offd(rdn, S * NW), offd(o, S * NW * NL),
+                                   offd(otot_by_mol, S * NW * MRTM_MXMOL), &oi);
+        });
+    }
+    // ---- fewer profiles than devices: every frequency is independent (modm.f90:253, RTMmono.f90:177,286): contiguous
+    // blocks of the frequency list per device; v1, v2 and the grid origin stay those of the whole list
+    ctx->mg_mode = 2;
+    const int use = (int)std::max<int64_t>(1, std::min<int64_t>(ndev, nwn / 2048));       // tiny lists: fewer devices
+    mg_partition(ctx, nwn, use);
+    const double v1g = base.use_global_range ? base.v1_global : wn[0], v2g = base.use_global_range ? base.v2_global : wn[nwn - 1];
+    const int64_t iw0g = base.use_global_range ? base.iw0 : 0;
+    std::vector<double> ms((size_t)use, 0.);
+    for (int64_t ip = 0; ip < nprof; ip++) {
+        const size_t P = (size_t)ip;
+        std::vector<double> ts((size_t)use, tmpsfc[ip]);
+        int rc = for_each_peer(ctx, [&](int i, mrtm_ctx* c) {
+            if (i >= use) return (int)MRTM_OK;
+            const int64_t f0 = ctx->mg_bounds[(size_t)i], cnt = ctx->mg_bounds[(size_t)i + 1] - f0;
+            if (cnt <= 0) return (int)MRTM_OK;
+            const auto t_beg = std::chrono::steady_clock::now();
+            const size_t F0 = (size_t)f0, C = (size_t)cnt;
+            mrtm_opts oi = base;
+            oi.use_global_range = 1;
+            oi.v1_global = v1g; oi.v2_global = v2g; oi.iw0 = iw0g + f0;
+            // (frequency, layer) arrays are strided by the full list: computed into a block of their own, scattered below
+            std::vector<double> o_blk(o ? C * NL : 0);
+            std::vector<int64_t> sc_blk(base.sel_count ? C * NL : 0);
+            std::vector<uint64_t> sh_blk(base.sel_hash ? C * NL : 0);
+            oi.sel_count = base.sel_count ? sc_blk.data() : nullptr;
+            oi.sel_hash = base.sel_hash ? sh_blk.data() : nullptr;
+            if (oi.xamnt) oi.xamnt += P * (size_t)oi.ld_xamnt * NL;
+            int r1 = profiles_single(c, 1, cnt, wn + F0, dvset, nlay, p + P * NL, t + P * NL, tz + P * (NL + 1), clw + P * NL, nmol,
+                                     wkl + P * NL * MRTM_MXMOL, wbrodl + P * NL, offc(scor, P * NL * MRTM_NSCOR1 * MRTM_NSCOR2), sclcpl, sclhw,
+                                     y0res, cntnm, ibrd, irt, iout, idu, &ts[(size_t)i], emiss + F0, reflc + F0, offd(rad, P * NW + F0),
+                                     offd(tb, P * NW + F0), offd(tmr, P * NW + F0), offd(trtot, P * NW + F0), offd(rup, P * NW + F0),
+                                     offd(rdn, P * NW + F0), o ? o_blk.data() : nullptr,
+                                     offd(otot_by_mol, P * NW * MRTM_MXMOL + F0 * MRTM_MXMOL), &oi);
+            if (r1) return r1;
+            for (size_t k = 0; k < NL; k++) {
+                if (o) std::memcpy(o + P * NW * NL + k * NW + F0, o_blk.data() + k * C, C * 8);
+                if (base.sel_count) std::memcpy(base.sel_count + P * NW * NL + k * NW + F0, sc_blk.data() + k * C, C * 8);
+                if (base.sel_hash) std::memcpy(base.sel_hash + P * NW * NL + k * NW + F0, sh_blk.data() + k * C, C * 8);
+            }
+            ms[(size_t)i] += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_beg).count();
+            return (int)MRTM_OK;
+        });
+        if (rc) return rc;
+        for (int i = 0; i < use; i++)                                  // RTM leaves 2.75 behind for IRT 2, 3 (RTMmono.f90:122)
+            if (ctx->mg_bounds[(size_t)i + 1] > ctx->mg_bounds[(size_t)i]) { tmpsfc[ip] = ts[(size_t)i]; break; }
+    }
+    ctx->mg_ms = ms;
+    return MRTM_OK;
+}
+
+extern "C" int mrtm_profiles(mrtm_ctx* ctx, int64_t nprof, int64_t nwn, const double* wn, double dvset,
+                             int64_t nlay, const double* p, const double* t, const double* tz,
+                             const double* clw, int64_t nmol, const double* wkl, const double* wbrodl,
+                             const double* scor, double sclcpl, double sclhw, double y0res,
+                             const double cntnm[7], int64_t ibrd, int64_t irt, int64_t iout, int64_t idu,
+                             double* tmpsfc, const double* emiss, const double* reflc,
+                             double* rad, double* tb, double* tmr, double* trtot, double* rup, double* rdn,
+                             double* o, double* otot_by_mol, const mrtm_opts* opts)
+{
+    if (!ctx) return MRTM_EARG;
+    if (idu != 1) return set_err(ctx, MRTM_EIDU, mrtm_strerror(MRTM_EIDU));
+    if (!ctx->peers.empty())
+        return profiles_multi(ctx, nprof, nwn, wn, dvset, nlay, p, t, tz, clw, nmol, wkl, wbrodl, scor, sclcpl, sclhw, y0res, cntnm, ibrd,
+                              irt, iout, idu, tmpsfc, emiss, reflc, rad, tb, tmr, trtot, rup, rdn, o, otot_by_mol, opts);
+    return profiles_single(ctx, nprof, nwn, wn, dvset, nlay, p, t, tz, clw, nmol, wkl, wbrodl, scor, sclcpl, sclhw, y0res, cntnm, ibrd,
+                           irt, iout, idu, tmpsfc, emiss, reflc, rad, tb, tmr, trtot, rup, rdn, o, otot_by_mol, opts);
+}
+
 extern "C" int mrtm_get_stats(mrtm_ctx* ctx, mrtm_stats* st)
 {
     if (!ctx || !st) return MRTM_EARG;
+    if (!ctx->peers.empty()) {          // counts add up, times are the slowest device's
+        std::memset(st, 0, sizeof *st);
+        int rc = MRTM_OK;
+        for (mrtm_ctx* c : ctx->peers) {
+            mrtm_stats q;
+            const int r1 = mrtm_get_stats(c, &q);
+            if (r1 && !rc) rc = r1;
+            st->kernel_launches += q.kernel_launches;
+            st->lines_staged = q.lines_staged;
+            st->nominal_evals += q.nominal_evals;
+            st->far_expansions += q.far_expansions;
+            st->direct_evals += q.direct_evals;
+            st->inwindow_evals = (q.inwindow_evals < 0 || st->inwindow_evals < 0) ? -1. : st->inwindow_evals + q.inwindow_evals;
+            st->last_lines_kernel_ms = std::max(st->last_lines_kernel_ms, q.last_lines_kernel_ms);
+            st->last_rt_kernel_ms = std::max(st->last_rt_kernel_ms, q.last_rt_kernel_ms);
+            st->last_derive_kernel_ms = std::max(st->last_derive_kernel_ms, q.last_derive_kernel_ms);
+            st->last_prep_ms = std::max(st->last_prep_ms, q.last_prep_ms);
+        }
+        return rc;
+    }
+    cudaSetDevice(ctx->device);
+    const int rc = finalize_pending(ctx);
+    ctx->deferred_rc = MRTM_OK;                     // reported once
     *st = ctx->st;
-    return MRTM_OK;
+    return rc;
 }
 
 extern "C" int mrtm_reset_stats(mrtm_ctx* ctx)
 {
     if (!ctx) return MRTM_EARG;
+    if (!ctx->peers.empty()) { for (mrtm_ctx* c : ctx->peers) mrtm_reset_stats(c); return MRTM_OK; }
     int64_t keep = ctx->st.lines_staged;
     std::memset(&ctx->st, 0, sizeof ctx->st);
     ctx->st.lines_staged = keep;
@@ -1370,6 +1692,7 @@ extern "C" int mrtm_reset_stats(mrtm_ctx* ctx)
 
 extern "C" int mrtm_fp64_peak(mrtm_ctx* ctx, double* tflops)
 {
+    if (ctx && !ctx->peers.empty()) ctx = ctx->peers[0];      // single-device entry point: the first GPU of a multi-GPU context
     if (!ctx || !tflops) return MRTM_EARG;
     CU(cudaSetDevice(ctx->device));
     cudaDeviceProp prop;
