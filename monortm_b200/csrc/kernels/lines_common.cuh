@@ -37,6 +37,8 @@ struct LinesArgs {
     const double* coef[kMaxLevels];     // lv >= 1: [tile][L][slot][kFarK] from far_kernel
     int32_t nslot, pad0;
     const NearPiece* near_pieces;       // [ntiles][kMaxNearPieces] (plan_kernel, level 0); null: near2_kernel not in use
+    // Voigt-zone candidates per tile (vplan_kernel) or null: line indices, their segments, count (-1: walk the whole zone)
+    const int* vcand; const unsigned char* vcand_seg; const int* vcand_count;
     const unsigned long long* layer_voigt;   // [L] bits of the smallest |Xnu| of the layer's Voigt-capable lines (derive_kernel), all ones = none
     const int32_t* slot_mol;            // [nslot]
     // continuum

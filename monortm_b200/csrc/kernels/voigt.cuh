@@ -72,7 +72,11 @@ __global__ void __launch_bounds__(NT, MRTM_VOIGT_MINB) voigt_kernel(LinesArgs a)
         s_zoff[a.nseg] = tot;
     }
     __syncthreads();
-    const int total = s_zoff[a.nseg];
+    // coarse tiles: only the zone lines that have a frequency of the tile within reach (vplan_kernel)
+    const int ncand = a.vcand_count ? a.vcand_count[blockIdx.x] : -1;
+    const int* cand = a.vcand ? a.vcand + (size_t)blockIdx.x * kVCandMax : nullptr;
+    const unsigned char* cand_seg = a.vcand_seg ? a.vcand_seg + (size_t)blockIdx.x * kVCandMax : nullptr;
+    const int total = (ncand >= 0) ? ncand : s_zoff[a.nseg];
     if (total == 0) return;
     int err = 0;
     unsigned short* lst = s_list[wid];
@@ -82,12 +86,18 @@ __global__ void __launch_bounds__(NT, MRTM_VOIGT_MINB) voigt_kernel(LinesArgs a)
         if (e0 > 0) __syncthreads();
         for (int i = tid; i < n; i += NT) {
             const int e = e0 + i;
-            int sg = 0;
-            while (s_zoff[sg + 1] <= e) sg++;
-            const int q = s_zlo[sg] + (e - s_zoff[sg]);
+            int sg = 0, q;
+            if (ncand >= 0) {
+                sg = cand_seg[e];
+                q = cand[e];
+            } else {
+                while (s_zoff[sg + 1] <= e) sg++;
+                q = s_zlo[sg] + (e - s_zoff[sg]);
+            }
             const int cls = a.seg[sg].cls, mol = a.seg[sg].mol;
             const int kind = (cls == CLS_PED) ? 0 : ((cls == CLS_O2) ? 1 : ((cls == CLS_O2_LC35) ? 2 : 3));
-            const double vt = __ldg(pVT + q);
+            // a candidate of a molecule without amount in this layer is skipped like its whole segment (:318-321)
+            const double vt = (ncand >= 0 && ly.wk[mol - 1] == 0.) ? -1. : __ldg(pVT + q);
             s_vt[i] = vt;
             s_x[i] = __ldg(pXNU + q);
             s_q[i] = q;

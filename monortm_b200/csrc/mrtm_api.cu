@@ -71,6 +71,8 @@ struct mrtm_ctx {
     DevBuf b_ov;
     int use_side = 1;                             // MRTM_SIDE_STREAM=0: everything on one stream
     int use_near2 = 1;                            // per-warp re-planning near-field kernel (MRTM_NEAR2=0 disables)
+    int use_neart = 1;                            // transposed direct kernel for coarse frequency lists (MRTM_NEART=0: near_kernel)
+    DevBuf b_vcand, b_vcseg, b_vccount;
     int use_near3 = 1;                            // plan-driven near-field kernel of the production path (MRTM_NEAR3=0: near2_kernel)
     int force_f = 0;                              // MRTM_LINES_F: frequencies per thread of the line kernels (1, 2, 4; 0 = chosen per call)
     int near3_lb = 0;                             // layers per CTA of near3_kernel (MRTM_NEAR3_LB; 0 = chosen per call)
@@ -201,6 +203,7 @@ extern "C" int mrtm_init(int device, mrtm_ctx** out)
     if (const char* s = std::getenv("MRTM_NEAR2")) ctx->use_near2 = std::atoi(s) != 0;
     if (const char* s = std::getenv("MRTM_PLAN_CACHE")) ctx->use_plan_cache = std::atoi(s) != 0;
     if (const char* s = std::getenv("MRTM_NEAR3")) ctx->use_near3 = std::atoi(s) != 0;
+    if (const char* s = std::getenv("MRTM_NEART")) ctx->use_neart = std::atoi(s);      // 0 off, 1 by tile width, 2 every F = 1 call
     if (const char* s = std::getenv("MRTM_LINES_F")) ctx->force_f = std::atoi(s);
     if (const char* s = std::getenv("MRTM_NEAR3_LB")) ctx->near3_lb = std::max(std::atoi(s), 0);
     if (const char* s = std::getenv("MRTM_FFW_RATIO")) ctx->ffw_ratio = std::max(std::atof(s), 4.0);
@@ -251,7 +254,7 @@ extern "C" int mrtm_free(mrtm_ctx* ctx)
     cudaStreamSynchronize(ctx->stream);
     free_lines(ctx);
     for (void* p : ctx->table_allocs) cudaFree(p);
-    DevBuf* bufs[] = {&ctx->b_xsreg, &ctx->b_xsdat, &ctx->b_xslay, &ctx->b_xstab, &ctx->b_xsneed, &ctx->b_xsod, &ctx->b_xsin[0], &ctx->b_xsin[1],
+    DevBuf* bufs[] = {&ctx->b_vcand, &ctx->b_vcseg, &ctx->b_vccount, &ctx->b_xsreg, &ctx->b_xsdat, &ctx->b_xslay, &ctx->b_xstab, &ctx->b_xsneed, &ctx->b_xsod, &ctx->b_xsin[0], &ctx->b_xsin[1],
                       &ctx->b_xsin[2], &ctx->b_xsin[3], &ctx->b_pcache, &ctx->b_t3, &ctx->b_pool3, &ctx->b_segof3, &ctx->b_ov, &ctx->b_lvoigt, &ctx->b_vtmax, &ctx->b_layer, &ctx->b_scorc, &ctx->b_absrb, &ctx->b_planes, &ctx->b_lcplanes, &ctx->b_o, &ctx->b_obm, &ctx->b_oc, &ctx->b_sel[0], &ctx->b_sel[1], &ctx->b_tmps, &ctx->b_fbeta, &ctx->b_npieces};
     for (DevBuf* b : bufs) if (b->p) cudaFree(b->p);
     for (int i = 0; i < kMaxLevels; i++) {
@@ -509,11 +512,19 @@ struct RunDesc {
 
 template <int F, int NT>
 static void launch_lines(const LinesArgs& la, dim3 grid, bool sel, cudaStream_t s, cudaEvent_t far_done, cudaStream_t sv,
-                         const Near3Args* n3)
+                         const Near3Args* n3, bool neart)
 {
     // near field (direct), Voigt branch, then polynomial + continuum + totals
     const size_t dyn = sizeof(double) * kStages * 4 * kTile + (size_t)std::max(la.nseg, 1) * sizeof(SegWork);
-    if (la.near_pieces && n3 && F == 4) {      // production path: plan-driven lists, a group of layers per CTA
+    if (neart && F == 1) {                     // coarse frequency lists: lanes own lines, warps own frequencies
+        if (sel) {
+            cudaFuncSetAttribute(nearT_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+            nearT_kernel<true><<<grid, 32 * kNTW, dyn, s>>>(la);
+        } else {
+            cudaFuncSetAttribute(nearT_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+            nearT_kernel<false><<<grid, 32 * kNTW, dyn, s>>>(la);
+        }
+    } else if (la.near_pieces && n3 && F == 4) {      // production path: plan-driven lists, a group of layers per CTA
         cudaFuncSetAttribute(near3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kN3Smem);
         near3_kernel<<<dim3(grid.x, (grid.y + n3->lb - 1) / n3->lb, grid.z), 256, kN3Smem, s>>>(la, *n3);
     } else if (la.near_pieces) {       // tiles whose direct lines fit the staging area: per-warp re-planning kernel
@@ -527,7 +538,8 @@ static void launch_lines(const LinesArgs& la, dim3 grid, bool sel, cudaStream_t 
             near2_kernel<F, false, NT><<<grid, NT, dyn2, s>>>(la);
         }
     }
-    if (sel) {
+    if (neart && F == 1) {
+    } else if (sel) {
         cudaFuncSetAttribute(near_kernel<F, true, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
         near_kernel<F, true, NT><<<grid, NT, dyn, s>>>(la);
     } else {
@@ -802,6 +814,11 @@ static int run_device(mrtm_ctx* ctx, const RunDesc& r, cudaStream_t s)
             la.S = ctx->ff_S;
             la.nslot = nslot;
             const bool use3 = ctx->use_near3 && ctx->use_near2 && la.ff_ratio > 0. && !sel && combined && F == 4;
+            // a handful of channels (sounder sets): lanes own lines, warps own frequencies -- thread-per-frequency leaves most
+            // lanes idle there (measured on B200: 27 % faster on 19 channels; about even on 1000 log-spaced channels, 24 %
+            // slower on a 5.5e-3 cm-1 grid, where near_kernel stays)
+            const bool neart = ctx->use_neart && F == 1 && NTsel == 128 && (ctx->use_neart > 1 || nwn < 64);
+            const bool vplan = F == 1 && NTsel == 128;      // Voigt-zone candidates: every coarse-tile call
             // ---- plan cache: buffers first (a reallocation invalidates the cached plans), then the device-side check
             const size_t npc_words = 1 + std::max<size_t>(1, h.segments.size());
             if ((rc = ensure(ctx, ctx->b_pcache, (npc_words + 4) * 8))) return rc;
@@ -816,6 +833,11 @@ static int run_device(mrtm_ctx* ctx, const RunDesc& r, cudaStream_t s)
                 if ((rc = ensure(ctx, ctx->b_pool3, (size_t)ntiles[0] * kN3Pool * sizeof(unsigned short)))) return rc;
                 if ((rc = ensure(ctx, ctx->b_segof3, (size_t)ntiles[0] * kNearCap))) return rc;
             }
+            if (vplan) {
+                if ((rc = ensure(ctx, ctx->b_vcand, (size_t)ntiles[0] * kVCandMax * sizeof(int)))) return rc;
+                if ((rc = ensure(ctx, ctx->b_vcseg, (size_t)ntiles[0] * kVCandMax))) return rc;
+                if ((rc = ensure(ctx, ctx->b_vccount, (size_t)ntiles[0] * sizeof(int)))) return rc;
+            }
             unsigned long long* pc_have = (unsigned long long*)ctx->b_pcache.p;          // [npc_words] cached margins
             unsigned long long* pc_hash = pc_have + npc_words;                            // [2]
             int* pc_replan = (int*)(pc_hash + 2);
@@ -823,9 +845,10 @@ static int run_device(mrtm_ctx* ctx, const RunDesc& r, cudaStream_t s)
                 mrtm_ctx::PlanKey key;
                 std::memset(&key, 0, sizeof key);
                 key.nwn = nwn; key.stage_gen = ctx->stage_gen; key.F = F; key.nlev = nlev; key.S = ctx->ff_S; key.nseg = nseg_i;
-                key.near2 = ctx->use_near2; key.near3 = use3 ? 1 : 0; key.ff_ratio = la.ff_ratio; key.ffw_ratio = ctx->ffw_ratio;
+                key.near2 = ctx->use_near2; key.near3 = (use3 ? 1 : 0) | (neart ? 2 : 0); key.ff_ratio = la.ff_ratio; key.ffw_ratio = ctx->ffw_ratio;
                 int nb_ = 0;
                 for (int lv = 0; lv < nlev; lv++) { key.bufs[nb_++] = ctx->b_pieces[lv].p; key.bufs[nb_++] = ctx->b_plan[lv].p; key.bufs[nb_++] = ctx->b_hdr[lv].p; }
+                key.bufs[nb_++] = ctx->b_vcand.p; key.bufs[nb_++] = ctx->b_vccount.p;
                 key.bufs[nb_++] = ctx->b_npieces.p; key.bufs[nb_++] = ctx->b_t3.p; key.bufs[nb_++] = ctx->b_pool3.p; key.bufs[nb_++] = ctx->b_pcache.p;
                 const bool same = ctx->use_plan_cache && ctx->plan_key_valid && std::memcmp(&key, &ctx->plan_key, sizeof key) == 0;
                 if (!same) CU(cudaMemsetAsync(ctx->b_pcache.p, 0, (npc_words + 4) * 8, sp));
@@ -864,7 +887,7 @@ static int run_device(mrtm_ctx* ctx, const RunDesc& r, cudaStream_t s)
                 pl.pplan = (lv + 1 < nlev) ? (const SegWork*)ctx->b_plan[lv + 1].p : nullptr;
                 pl.S = ctx->ff_S;
                 pl.pieces = (FarPiece*)ctx->b_pieces[lv].p;
-                if (lv == 0 && la.ff_ratio > 0. && ctx->use_near2) {
+                if (lv == 0 && la.ff_ratio > 0. && ctx->use_near2 && !neart) {
                     if ((rc = ensure(ctx, ctx->b_npieces, (size_t)ntiles[0] * kMaxNearPieces * sizeof(NearPiece)))) return rc;
                     pl.near_pieces = (NearPiece*)ctx->b_npieces.p;
                     la.near_pieces = pl.near_pieces;
@@ -876,6 +899,18 @@ static int run_device(mrtm_ctx* ctx, const RunDesc& r, cudaStream_t s)
                 la.coef[lv] = (la.ff_ratio > 0.) ? (const double*)ctx->b_coef[lv].p : nullptr;
             }
             la.slot_mol = ctx->ld.slot_mol;
+            if (vplan) {                        // Voigt-zone candidates of the coarse tiles (layer independent, cached with the plans)
+                VPlanArgs vp;
+                std::memset(&vp, 0, sizeof vp);
+                vp.nwn = (int32_t)nwn; vp.nseg = nseg_i; vp.tile_freqs = (int32_t)tfreq[0];
+                vp.wn = r.wn; vp.seg = ctx->seg_dev; vp.xnu0 = ctx->ld.xnu0;
+                vp.plan = (const SegWork*)ctx->b_plan[0].p;
+                vp.sm_max_bits = pc_have; vp.vtmax_seg = pc_have + 1; vp.replan = pc_replan;
+                vp.cand = (int*)ctx->b_vcand.p; vp.cand_seg = (unsigned char*)ctx->b_vcseg.p; vp.count = (int*)ctx->b_vccount.p;
+                vplan_kernel<<<(unsigned)ntiles[0], 128, 0, sp>>>(vp);
+                st.kernel_launches++;
+                la.vcand = vp.cand; la.vcand_seg = vp.cand_seg; la.vcand_count = vp.count;
+            }
             // production path (one sum over all molecules, no selection instrumentation, 512-frequency tiles): plan-driven lists
             Near3Args n3;
             std::memset(&n3, 0, sizeof n3);
@@ -959,9 +994,9 @@ static int run_device(mrtm_ctx* ctx, const RunDesc& r, cudaStream_t s)
                 la.o_v = (double*)ctx->b_ov.p;
                 sv = sp;
             }
-            if (F == 4) launch_lines<4, 128>(la, grid, sel, s, far_done, sv, use3 ? &n3 : nullptr);
-            else if (F == 2) launch_lines<2, 128>(la, grid, sel, s, far_done, sv, nullptr);
-            else launch_lines<1, 128>(la, grid, sel, s, far_done, sv, nullptr);
+            if (F == 4) launch_lines<4, 128>(la, grid, sel, s, far_done, sv, use3 ? &n3 : nullptr, false);
+            else if (F == 2) launch_lines<2, 128>(la, grid, sel, s, far_done, sv, nullptr, false);
+            else launch_lines<1, 128>(la, grid, sel, s, far_done, sv, nullptr, neart);
             CU(cudaEventRecord(ctx->ev[3], s));
             st.kernel_launches++;
             CU(cudaGetLastError());

@@ -48,6 +48,7 @@ struct TipsDev {
 #include "kernels/far.cuh"
 #include "kernels/near.cuh"
 #include "kernels/near3.cuh"
+#include "kernels/sparse.cuh"
 #include "kernels/voigt.cuh"
 #include "kernels/final.cuh"
 #include "kernels/rt.cuh"
