@@ -46,6 +46,7 @@ def parse():
     ap.add_argument("--cpu-sample-nwn", type=int, default=32)
     ap.add_argument("--direct-steps", type=int, default=3, help="extra steps timed with line_mode=1 (direct evaluation)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-balance", action="store_true", help="N > 1: equal frequency counts per GPU instead of equal measured cost")
     ap.add_argument("--config", default="c3", choices=["c3", "c4"],
                     help="c3 (default, the headline): dense sweep sharded by frequency; c4: retrieval ensemble "
                          "(1000 channels x 100 layers x --nprof-per-gpu profiles) sharded by profile")
@@ -69,7 +70,7 @@ def oracle_only_store(n_filler, v1, v2):
         os.unlink(path)
 
 
-def build_inputs(nwn, rank, world, n_filler=N_FILLER, oracle_only=False):
+def build_inputs(nwn, rank, world, n_filler=N_FILLER, oracle_only=False, iw0=None):
     """Synthetic C3 shard: a contiguous block of `nwn` frequencies of the GLOBAL 1e6-point grid, centred
     in this rank's 1/world-th of the grid; one 100-layer profile.  v1, v2 are the global range.
     oracle_only: line file and TIPS through the oracle's own readers (the reference arm loads no product library)."""
@@ -77,7 +78,8 @@ def build_inputs(nwn, rank, world, n_filler=N_FILLER, oracle_only=False):
     from monortm_b200 import synth
     v1, v2 = DV * 1, DV * NWN_GLOBAL_FULL
     part = NWN_GLOBAL_FULL // world
-    iw0 = rank * part + max(0, (part - nwn) // 2)
+    if iw0 is None:
+        iw0 = rank * part + max(0, (part - nwn) // 2)
     wn = DV * np.arange(iw0 + 1, iw0 + nwn + 1, dtype=np.float64)
     prof = synth.synthetic_profiles(1, NLAY, seed0=1000, clw_layers=False, nmol=22)
     if oracle_only:
@@ -562,6 +564,50 @@ def run_c4(args):
         raise SystemExit("bench.py: parity_check failed (see the JSON line): the throughput above is not valid")
 
 
+def balance_shards(args, world, rank, dev, sess, inp0, torch, dist):
+    """Per-rank frequency counts of equal measured cost (see the call site).  Collective: every rank returns the same list."""
+    counts = [args.nwn_per_gpu] * world
+    total = args.nwn_per_gpu * world
+    part = NWN_GLOBAL_FULL // world
+    pr = inp0["prof"]
+
+    def dv(a):
+        return torch.from_numpy(np.ascontiguousarray(np.asarray(a).reshape(-1, order="F"))).to(dev)
+    d = {k: dv(pr[k]) for k in ("p", "t", "tz", "clw", "wkl", "wbrodl")}
+    d["scor"] = dv(inp0["scor"])
+    d["tmpsfc"] = torch.tensor([inp0["tmpsfc"]], dtype=torch.float64, device=dev)
+    stream = torch.cuda.Stream(device=dev)
+    for rnd in range(3):
+        n = counts[rank]
+        iw0 = sum(counts[:rank]) if total == NWN_GLOBAL_FULL else rank * part + max(0, (part - n) // 2)
+        wn = DV * np.arange(iw0 + 1, iw0 + n + 1, dtype=np.float64)
+        d["wn"], d["emiss"], d["reflc"] = dv(wn), dv(np.full(n, 0.9)), dv(np.full(n, 0.1))
+        outs = torch.zeros(6, n, dtype=torch.float64, device=dev)
+        ptrs = {k: v.data_ptr() for k, v in d.items()}
+        for i, k in enumerate(("rad", "tb", "tmr", "trtot", "rup", "rdn")):
+            ptrs[k] = outs[i].data_ptr()
+        with torch.cuda.stream(stream):
+            for _ in range(2):
+                sess.profiles_dev(1, n, NLAY, 22, 0.0, ptrs, inp0["v1"], inp0["v2"], iw0, inp0["irt"], stream=stream.cuda_stream)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            for _ in range(3):
+                sess.profiles_dev(1, n, NLAY, 22, 0.0, ptrs, inp0["v1"], inp0["v2"], iw0, inp0["irt"], stream=stream.cuda_stream)
+            e1.record(stream)
+        stream.synchronize()
+        sess.sync()
+        t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        ts = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(ts, t)
+        ts = [float(x.item()) for x in ts]
+        rate = [c / max(x, 1e-9) for c, x in zip(counts, ts)]              # frequencies per ms on each rank's part of the grid
+        share = [r / sum(rate) for r in rate]
+        new = [max(512, int(round(0.5 * (c + s_ * total) / 512.0)) * 512) for c, s_ in zip(counts, share)]      # damped
+        new[-1] += total - sum(new)                                        # keep the sum
+        counts = new
+    return counts
+
+
 def main():
     args = parse()
     if args.config == "c4":
@@ -595,6 +641,21 @@ def main():
     sess = api.Session(local)
     nlines = sess.stage_lines(inp["ls"])
     pr = inp["prof"]
+    shard_counts = [nwn] * world
+    if world > 1 and not args.no_balance:
+        # ---- shards of equal COST, not equal count (frequencies are independent; the cost per frequency depends
+        # on the spectral position -- more far-field expansions where window edges and negative-frequency resonances fall
+        # inside the coarse tiles).  Untimed: every rank times three steps of its block, the times are all-gathered and the
+        # block sizes (multiples of 512, their sum stays world x nwn-per-gpu) are rescaled; three rounds.
+        shard_counts = balance_shards(args, world, rank, dev, sess, inp, torch, dist)
+        part = NWN_GLOBAL_FULL // world
+        if sum(shard_counts) == NWN_GLOBAL_FULL:                      # the blocks tile the whole grid
+            iw0 = sum(shard_counts[:rank])
+        else:                                                         # each block centred in its 1/world-th of the grid
+            iw0 = rank * part + max(0, (part - shard_counts[rank]) // 2)
+        nwn = shard_counts[rank]
+        inp = build_inputs(nwn, rank, world, args.n_filler, iw0=iw0)
+    nmax = max(shard_counts)
 
     # ---- device-resident buffers (torch is only the allocator / stream / NCCL plumbing)
     def dv(a):
@@ -603,8 +664,8 @@ def main():
     d["wn"], d["scor"] = dv(inp["wn"]), dv(inp["scor"])
     d["emiss"], d["reflc"] = dv(inp["emiss"]), dv(inp["reflc"])
     d["tmpsfc"] = torch.tensor([inp["tmpsfc"]], dtype=torch.float64, device=dev)
-    outs = torch.zeros(6, nwn, dtype=torch.float64, device=dev)            # rad,tb,tmr,trtot,rup,rdn
-    gathered = torch.zeros(world, 6, nwn, dtype=torch.float64, device=dev) if world > 1 else None
+    outs = torch.zeros(6, nmax, dtype=torch.float64, device=dev)           # rad,tb,tmr,trtot,rup,rdn (rows padded to the largest shard)
+    gathered = torch.zeros(world, 6, nmax, dtype=torch.float64, device=dev) if world > 1 else None
     ptrs = {k: v.data_ptr() for k, v in d.items()}
     for i, k in enumerate(("rad", "tb", "tmr", "trtot", "rup", "rdn")):
         ptrs[k] = outs[i].data_ptr()
@@ -652,7 +713,7 @@ def main():
     if world > 1:
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
     ms_per_step = float(tmax.item()) / args.steps
-    nominal_per_step = float(nlines) * NLAY * nwn * world
+    nominal_per_step = float(nlines) * NLAY * float(sum(shard_counts))
     value = nominal_per_step / (ms_per_step * 1e-3)
 
     # ---- the same steps with every in-window triple evaluated directly (line_mode=1): the classic
@@ -691,8 +752,8 @@ def main():
     d2h_bytes = 6 * nwn * 8
 
     # the six spectra land in pinned host memory owned by the caller (reused every step)
-    hout_t = torch.zeros(6, nwn, dtype=torch.float64).pin_memory()
-    hout = {k: hout_t[i].numpy().reshape(nwn, 1, order="F") for i, k in enumerate(("rad", "tb", "tmr", "trtot", "rup", "rdn"))}
+    hout_t = torch.zeros(6, nmax, dtype=torch.float64).pin_memory()
+    hout = {k: hout_t[i, :nwn].numpy().reshape(nwn, 1, order="F") for i, k in enumerate(("rad", "tb", "tmr", "trtot", "rup", "rdn"))}
 
     def step_e2e():
         return sess.profiles(hp["wn"].numpy(), 0.0, hprof, hscor, inp["irt"], inp["tmpsfc"], hp["emiss"].numpy(),
@@ -744,7 +805,9 @@ def main():
             "metric": "line x layer x frequency evaluations/s", "value": value, "unit": "evals/s",
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": workload_config(args),
+            "config": dict(workload_config(args), shard_frequencies=[int(c) for c in shard_counts],
+                           shard_balance="blocks of equal measured cost (three untimed feedback rounds), sum = n_gpus x nwn_per_gpu"
+                           if (world > 1 and not args.no_balance) else "equal counts"),
             "spectra_per_s": world / (ms_per_step * 1e-3),
             "inwindow_evals_per_s": value * inwin_frac, "inwindow_fraction": inwin_frac, "logical_lines": nlines,
             "e2e": {"value": e2e_value, "unit": "evals/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,

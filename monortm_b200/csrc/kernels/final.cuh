@@ -7,7 +7,9 @@
 #ifndef MRTM_FINAL_MINB
 #define MRTM_FINAL_MINB 8
 #endif
-template <int F, int NT>
+// kMwOnly: the call lies below 820 cm-1 with no O3 / O2 / Rayleigh component (the usual microwave case): their planes are
+// not touched
+template <int F, int NT, bool kMwOnly>
 __global__ void __launch_bounds__(NT, MRTM_FINAL_MINB) final_kernel(LinesArgs a)
 {
     const int tid = threadIdx.x;
@@ -106,6 +108,7 @@ __global__ void __launch_bounds__(NT, MRTM_FINAL_MINB) final_kernel(LinesArgs a)
         const double rf = radfn(wn[f], ly.xkt);
 #pragma unroll
         for (int c = 0; c < 5; c++) {
+            if (kMwOnly && (c == CP_O3 || c == CP_O2)) continue;       // microwave call: O3 and O2 have no component (compile time)
             if (!((a.cont_mask >> c) & 1)) continue;                   // no component of this species fires: its oc stays 0
             double v = 0.;
             if (in_rng) v = 0. + xint_point(ab + (size_t)c * a.nptabs_pad, a.v1abs, 1.0, vi) * 1.0;
@@ -114,7 +117,7 @@ __global__ void __launch_bounds__(NT, MRTM_FINAL_MINB) final_kernel(LinesArgs a)
             if (a.oc) a.oc[(size_t)iw + (size_t)(cont_mol[c] - 1) * a.obm_ldm + (size_t)L * a.obm_ldk] = v;
         }
         double oray = 0.;                                              // modm.f90:231-244 (zero below 820 cm-1)
-        if ((a.cont_mask >> CP_RAYL) & 1) {
+        if (!kMwOnly && ((a.cont_mask >> CP_RAYL) & 1)) {
             if (in_rng) oray = 0. + xint_point(ab + (size_t)CP_RAYL * a.nptabs_pad, a.v1abs, 1.0, vi) * 1.0;
             oray = oray * wn[f] / 1.0e4;
         }

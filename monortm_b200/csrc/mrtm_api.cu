@@ -71,9 +71,11 @@ struct mrtm_ctx {
     DevBuf b_ov;
     int use_side = 1;                             // MRTM_SIDE_STREAM=0: everything on one stream
     int use_near2 = 1;                            // per-warp re-planning near-field kernel (MRTM_NEAR2=0 disables)
+    int coarse_f = 2;                             // MRTM_COARSE_F: frequencies per thread on 128-frequency tiles (CTA of 128/F threads)
     int use_neart = 1;                            // transposed direct kernel for coarse frequency lists (MRTM_NEART=0: near_kernel)
     DevBuf b_vcand, b_vcseg, b_vccount;
-    int use_near3 = 1;                            // plan-driven near-field kernel of the production path (MRTM_NEAR3=0: near2_kernel)
+    int use_near3 = 0;                            // MRTM_NEAR3=1: plan-driven near-field kernel (813 us alone against near2_kernel's 890 us,
+                                                  // 26 % fewer instructions; inside the two-stream step near2_kernel is 1 % faster: default)
     int force_f = 0;                              // MRTM_LINES_F: frequencies per thread of the line kernels (1, 2, 4; 0 = chosen per call)
     int near3_lb = 0;                             // layers per CTA of near3_kernel (MRTM_NEAR3_LB; 0 = chosen per call)
     DevBuf b_t3, b_pool3, b_segof3;
@@ -203,6 +205,7 @@ extern "C" int mrtm_init(int device, mrtm_ctx** out)
     if (const char* s = std::getenv("MRTM_NEAR2")) ctx->use_near2 = std::atoi(s) != 0;
     if (const char* s = std::getenv("MRTM_PLAN_CACHE")) ctx->use_plan_cache = std::atoi(s) != 0;
     if (const char* s = std::getenv("MRTM_NEAR3")) ctx->use_near3 = std::atoi(s) != 0;
+    if (const char* s = std::getenv("MRTM_COARSE_F")) { const int v = std::atoi(s); ctx->coarse_f = (v == 2 || v == 4) ? v : 1; }
     if (const char* s = std::getenv("MRTM_NEART")) ctx->use_neart = std::atoi(s);      // 0 off, 1 by tile width, 2 every F = 1 call
     if (const char* s = std::getenv("MRTM_LINES_F")) ctx->force_f = std::atoi(s);
     if (const char* s = std::getenv("MRTM_NEAR3_LB")) ctx->near3_lb = std::max(std::atoi(s), 0);
@@ -554,7 +557,8 @@ static void launch_lines(const LinesArgs& la, dim3 grid, bool sel, cudaStream_t 
         voigt_kernel<F, NT><<<grid, NT, 0, s>>>(la);
     }
     if (far_done) cudaStreamWaitEvent(s, far_done, 0);     // the far-field coefficients come from the side stream
-    final_kernel<F, NT><<<grid, NT, 0, s>>>(la);
+    if ((la.cont_mask & ((1 << CP_O3) | (1 << CP_O2) | (1 << CP_RAYL))) == 0) final_kernel<F, NT, true><<<grid, NT, 0, s>>>(la);
+    else final_kernel<F, NT, false><<<grid, NT, 0, s>>>(la);
 }
 
 static int run_xsec_device(mrtm_ctx* ctx, int64_t nwn, const double* wn, int64_t nlay, const double* p, const double* t,
@@ -793,6 +797,7 @@ static int run_device(mrtm_ctx* ctx, const RunDesc& r, cudaStream_t s)
                 while (Fh > 1 && 128. * Fh * (r.wn_span / (double)(nwn - 1)) > ctx->tile_width) Fh >>= 1;
             const int F = (force_f == 1 || force_f == 2 || force_f == 4) ? force_f : Fh;
             const int T0 = NTsel * F;
+            const int Fc = (F == 1 && nwn >= 64) ? ctx->coarse_f : 1;       // 128-frequency tiles: Fc frequencies per thread, 128/Fc threads
             dim3 grid((unsigned)((nwn + T0 - 1) / T0), (unsigned)nlay, (unsigned)nb);
             CU(cudaEventRecord(ctx->ev[2], s));
             // ---- plans (layer independent) and the upper levels of the far-field hierarchy
@@ -996,6 +1001,8 @@ static int run_device(mrtm_ctx* ctx, const RunDesc& r, cudaStream_t s)
             }
             if (F == 4) launch_lines<4, 128>(la, grid, sel, s, far_done, sv, use3 ? &n3 : nullptr, false);
             else if (F == 2) launch_lines<2, 128>(la, grid, sel, s, far_done, sv, nullptr, false);
+            else if (Fc == 2) launch_lines<2, 64>(la, grid, sel, s, far_done, sv, nullptr, false);
+            else if (Fc == 4) launch_lines<4, 32>(la, grid, sel, s, far_done, sv, nullptr, false);
             else launch_lines<1, 128>(la, grid, sel, s, far_done, sv, nullptr, neart);
             CU(cudaEventRecord(ctx->ev[3], s));
             st.kernel_launches++;

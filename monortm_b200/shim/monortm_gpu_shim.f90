@@ -38,6 +38,29 @@ module monortm_gpu_shim
        integer(c_int), value :: device
        type(c_ptr) :: ctx
      end function
+     integer(c_int) function c_mrtm_init_multi(device_mask, ctx) bind(c, name="mrtm_init_multi")
+       import :: c_int, c_ptr, c_int64_t
+       integer(c_int64_t), value :: device_mask          ! uint64_t bit mask, 0 = every visible GPU
+       type(c_ptr) :: ctx
+     end function
+     integer(c_int) function c_mrtm_host_xsread(dir, ixmols, names, xv1, xv2, nreg, regs) bind(c, name="mrtm_host_xsread")
+       import :: c_int, c_ptr, c_int64_t, c_double, c_char
+       character(kind=c_char) :: dir(*), names(*)
+       integer(c_int64_t), value :: ixmols
+       real(c_double), value :: xv1, xv2
+       integer(c_int64_t) :: nreg
+       type(c_ptr) :: regs
+     end function
+     integer(c_int) function c_mrtm_stage_xsec(ctx, nreg, regs) bind(c, name="mrtm_stage_xsec")
+       import :: c_int, c_ptr, c_int64_t
+       type(c_ptr), value :: ctx, regs
+       integer(c_int64_t), value :: nreg
+     end function
+     subroutine c_mrtm_host_xs_free(regs, nreg) bind(c, name="mrtm_host_xs_free")
+       import :: c_ptr, c_int64_t
+       type(c_ptr), value :: regs
+       integer(c_int64_t), value :: nreg
+     end subroutine
      integer(c_int) function c_mrtm_free(ctx) bind(c, name="mrtm_free")
        import :: c_int, c_ptr
        type(c_ptr), value :: ctx
@@ -98,6 +121,34 @@ contains
     if (.not. c_associated(ctx)) call check(c_mrtm_init(int(device, c_int), ctx), 'mrtm_init')
   end subroutine
 
+  !  every GPU of the node behind one context (bit d of mask = CUDA device d, 0 = all): the library splits each call
+  subroutine mrtm_gpu_init_multi(mask)
+    integer, intent(in) :: mask
+    if (.not. c_associated(ctx)) call check(c_mrtm_init_multi(int(mask, c_int64_t), ctx), 'mrtm_init_multi')
+  end subroutine
+
+  !  IXSECT=1: call after XSREAD (src/monortm.f90:497).  The tables MONORTM_XSEC_SUB would re-read for every profile
+  !  (src/monortm_sub.F90:1656-1671) are read once from the same FSCDXS / xs files in the working directory and staged.
+  subroutine mrtm_gpu_stage_xsec(xv1, xv2)
+    use lblparams, only: mx_xs, mxlay
+    real*8, intent(in) :: xv1, xv2
+    character*10 :: XSFILE, XSNAME, ALIAS
+    common /XSECTF/ XSFILE(6,5,mx_xs), XSNAME(mx_xs), ALIAS(4,mx_xs)
+    common /PATHX/ IXMAX, IXMOLS, IXINDX(mx_xs), XAMNT(mx_xs,mxlay)
+    character(kind=c_char) :: names(10 * mx_xs)
+    integer(c_int64_t) :: nreg
+    type(c_ptr) :: regs
+    integer :: i, j
+    do i = 1, IXMOLS
+       do j = 1, 10
+          names(10 * (i - 1) + j) = XSNAME(i)(j:j)
+       end do
+    end do
+    call check(c_mrtm_host_xsread('.' // c_null_char, int(IXMOLS, c_int64_t), names, xv1, xv2, nreg, regs), 'mrtm_host_xsread')
+    call check(c_mrtm_stage_xsec(ctx, nreg, regs), 'mrtm_stage_xsec')
+    call c_mrtm_host_xs_free(regs, nreg)
+  end subroutine
+
   !  call once, right after GET_LNFL has filled the lnfl_mod module arrays (modm.f90:187-190)
   subroutine mrtm_gpu_stage_lines()
     use lnfl_mod, only: NBLM, ISO, XNU0, DELTNU, E, ALPS, ALPF, X, XG, S0, RMOL, SDEP, &
@@ -117,6 +168,13 @@ contains
     real :: o(nwn, *), o_by_mol(nwn, 39, *), oc(nwn, 39, *), o_clw(nwn, *), odxsec(nwn, *)
     real, allocatable :: scor(:, :, :)
     integer :: k
+    type(mrtm_opts), target :: opts
+    real, target :: XAMNT
+    common /PATHX/ IXMAX, IXMOLS, IXINDX(38), XAMNT(38, 603)      ! mx_xs, mxlay (src/lblparams.f90:29)
+    if (ixsect == 1) then               ! MODM calls MONORTM_XSEC_SUB itself (modm.f90:197-198): XAMNT crosses through opts
+       opts%xamnt = c_loc(XAMNT)
+       opts%ld_xamnt = 38
+    end if
     allocate(scor(42, 9, nlay))
     scor = 0.
     do k = 1, nlay
@@ -124,7 +182,7 @@ contains
     end do
     call check(c_mrtm_modm(ctx, int(nwn, c_int64_t), wn, dvset, int(nlay, c_int64_t), p, t, clw, o, o_by_mol, oc, &
          o_clw, odxsec, int(nmol, c_int64_t), wkl, wbrodl, sclcpl, sclhw, y0res, cntnm7, &
-         int(ixsect, c_int64_t), int(ibrd, c_int64_t), scor, c_null_ptr), 'mrtm_modm')
+         int(ixsect, c_int64_t), int(ibrd, c_int64_t), scor, c_loc(opts)), 'mrtm_modm')
     deallocate(scor)
   end subroutine
 
