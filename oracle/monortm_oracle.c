@@ -10,7 +10,10 @@
  *
  * Build: gcc -O0 -ffp-contract=off -fcx-fortran-rules (oracle/Makefile).
  *
- * PARITY UNPINNED by reference-owned goldens (none exist).  What anchors this file instead:
+ * PARITY PIN (see monortm_oracle.h): the reference cannot be compiled here (Fortran), so its own source TEXT is executed
+ * through the mechanical translator tools/f90fn.py and this file is held to those outputs (tests/golden/ref_*.npz,
+ * tests/test_ref_goldens.py): scalar routines to a few ulp, MODM + CALCTMR + RTM cases from 0.1 to 57900 cm-1 to 1e-13
+ * (measured 0 .. 5e-16), MONORTM_XSEC_SUB + convolve bit-identical.  Further independent pins:
  * tests/test_oracle_units.py -- from-scratch numpy evaluations of the textbook expressions (isolated Lorentz line,
  * O2 line with first-order mixing, Voigt branch against scipy, layer-exact radiative transfer, the self continuum at
  * its table nodes), analytic identities and scipy.special.wofz for W4.
