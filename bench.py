@@ -713,6 +713,12 @@ def main():
     if world > 1:
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
     ms_per_step = float(tmax.item()) / args.steps
+    # every rank's own kernel time per step (line path + derive + RT, without the gather): shows what is left of the imbalance
+    own = torch.tensor([float(np.mean(lines_ms)) + float(np.mean(derive_ms)) + float(np.mean(rt_ms))], dtype=torch.float64, device=dev)
+    owns = [torch.zeros_like(own) for _ in range(world)]
+    if world > 1:
+        dist.all_gather(owns, own)
+    rank_kernel_ms = [float(x.item()) for x in owns] if world > 1 else [float(own.item())]
     nominal_per_step = float(nlines) * NLAY * float(sum(shard_counts))
     value = nominal_per_step / (ms_per_step * 1e-3)
 
@@ -808,7 +814,7 @@ def main():
             "config": dict(workload_config(args), shard_frequencies=[int(c) for c in shard_counts],
                            shard_balance="blocks of equal measured cost (three untimed feedback rounds), sum = n_gpus x nwn_per_gpu"
                            if (world > 1 and not args.no_balance) else "equal counts"),
-            "spectra_per_s": world / (ms_per_step * 1e-3),
+            "spectra_per_s": world / (ms_per_step * 1e-3), "rank_kernel_ms": rank_kernel_ms,
             "inwindow_evals_per_s": value * inwin_frac, "inwindow_fraction": inwin_frac, "logical_lines": nlines,
             "e2e": {"value": e2e_value, "unit": "evals/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
                     "ms_per_step": float(te.item())},

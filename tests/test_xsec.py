@@ -46,6 +46,22 @@ def test_cpp_xsread_on_the_reference_fscdxs():
     assert [f["t"] for f in regs[0]["files"]] == [203., 213., 233., 253., 273., 296.] and regs[0]["files"][0]["npts"] == 21801
 
 
+@pytest.mark.skipif(not os.path.exists("/root/reference/cross-sections/FSCDXS"), reason="reference tree not present")
+def test_oracle_on_the_shipped_hno3_microwave_table():
+    """The one microwave band of the shipped data (HNO3 0-109 cm-1).  Its table starts at 0 cm-1 where the radiation term
+    MONORTM_XSEC_SUB divides out vanishes (0/0): near the surface the resampling step equals the table step and the NaN point
+    is never touched; in thinner layers it is, the running sum turns NaN and the reference's GOTO loop never ends
+    (monortm_sub.F90:1800-1821) -- the oracle (and the product, MRTM_EXSEC) report that instead of hanging."""
+    regs = xsfile.read_regions("/root/reference/cross-sections", ["HNO3"], 0.5, 100.0)
+    wn = np.array([0.7417, 30.0])                      # 22.235 GHz and the band maximum
+    xamnt = np.zeros((xsfile.MX_XS, 1))
+    xamnt[0] = [1e16]
+    od = harness.oracle_xsec(regs, wn, np.array([1000.]), np.array([288.]), xamnt)
+    assert np.all(np.isfinite(od)) and np.all(od > 0) and od[1, 0] > od[0, 0]
+    with pytest.raises(RuntimeError, match="rc=53"):  # a frequency near 0 cm-1 in a thin layer: the sum walks into the NaN point
+        harness.oracle_xsec(regs, wn[:1], np.array([300.]), np.array([270.]), xamnt)
+
+
 @pytest.mark.gpu
 def test_gpu_cross_sections_against_the_reference_text_and_the_oracle(tmp_path):
     g = np.load(os.path.join(GOLD, "ref_xsec_synth.npz"))
