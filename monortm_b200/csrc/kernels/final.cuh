@@ -5,7 +5,7 @@
 // the continuum interpolation + RADFN (:218-230), cloud liquid water (:264) and the total (:265-269).
 // =============================================================================================
 #ifndef MRTM_FINAL_MINB
-#define MRTM_FINAL_MINB 8
+#define MRTM_FINAL_MINB 10
 #endif
 // kMwOnly: the call lies below 820 cm-1 with no O3 / O2 / Rayleigh component (the usual microwave case): their planes are
 // not touched

@@ -238,7 +238,7 @@ struct NearPiece {
 };
 constexpr int kMaxNearPieces = 192;
 #ifndef MRTM_NEAR2_CAP
-#define MRTM_NEAR2_CAP 640
+#define MRTM_NEAR2_CAP 512
 #endif
 #ifndef MRTM_NEAR2_MINB
 #define MRTM_NEAR2_MINB 5

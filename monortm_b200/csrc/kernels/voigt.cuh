@@ -36,7 +36,10 @@ __global__ void __launch_bounds__(NT, MRTM_VOIGT_MINB) voigt_kernel(LinesArgs a)
     // line, once per CTA (amortised over the NT*F frequencies), everything of LSF_SDVOIGT/SDVOIGT that does not depend
     // on the frequency: 1/alphaD, y = sqrt(ln2)*alphaL/alphaD, STILD*sqrt(ln2/pi)/alphaD, the Voigt pedestal at
     // 25 cm-1 (modm.f90:590) and the mixing factors (:595-596).
-    constexpr int kVCap = 192;
+#ifndef MRTM_VOIGT_CAP
+#define MRTM_VOIGT_CAP 64
+#endif
+    constexpr int kVCap = MRTM_VOIGT_CAP;
     __shared__ double s_vt[kVCap], s_x[kVCap], s_inv[kVCap], s_y[kVCap], s_c[kVCap], s_pd[kVCap], s_g[kVCap], s_b[kVCap];
     __shared__ int s_q[kVCap];
     __shared__ unsigned char s_kind[kVCap], s_mol[kVCap];
