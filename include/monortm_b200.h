@@ -63,7 +63,7 @@ typedef struct mrtm_opts {
      * use_global_range == 0 -> v1 = wn[0], v2 = wn[nwn-1], iw0 = 0. */
     int32_t use_global_range;
     /* Line-shape evaluation mode.  0 (default): lines whose poles are far from a frequency tile are
-     * summed through a 14-term Taylor expansion about the tile centre (truncation <= ~2e-13 of the
+     * summed through a 14-term Taylor expansion about the tile centre (truncation <= ~1.3e-11 of the
      * line's own contribution), everything else -- near lines, window edges, the Voigt zone -- is
      * evaluated per (line, frequency) like the reference does.  1: every in-window triple is
      * evaluated directly (no expansion); same results to rounding, used for verification. */

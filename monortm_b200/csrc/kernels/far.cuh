@@ -314,7 +314,7 @@ __global__ void __launch_bounds__(128, MRTM_FAR_MINB) far_kernel(FarArgs a)
 // per lane than far_kernel has per thread, which amortises the set-up, reduction and translation.
 // =============================================================================================
 #ifndef MRTM_FARW_MINB
-#define MRTM_FARW_MINB 5
+#define MRTM_FARW_MINB 7
 #endif
 constexpr int kFarWarps = 4;
 __global__ void __launch_bounds__(32 * kFarWarps, MRTM_FARW_MINB) far_warp_kernel(FarArgs a)

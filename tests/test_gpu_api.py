@@ -63,7 +63,7 @@ def test_frequency_shards_reproduce_the_unsharded_run():
         # the frequency tiling (hence the grouping of the per-line sums) differs between the runs, so
         # agreement is to rounding, not bitwise
         for k in ("rad", "tb", "tmr", "trtot", "o"):
-            assert harness.rel_diff(np.concatenate([p[k] for p in parts], axis=0), full[k]) < 1e-12, (k, dvset)
+            assert harness.rel_diff(np.concatenate([p[k] for p in parts], axis=0), full[k]) < 1e-10, (k, dvset)
 
 
 def test_profile_batches_and_memory_budget_split(monkeypatch):

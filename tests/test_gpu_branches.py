@@ -193,12 +193,12 @@ def test_production_near_field_kernel_on_dense_grids(i0, nlay, lb, monkeypatch):
     fast = harness.run_gpu(case, by_mol=False, selection=False)
     assert fast["stats"]["far_expansions"] > 0
     assert harness.rel_diff(fast["o"][idx], ref["o"]) < OD_RTOL
-    assert harness.rel_diff(fast["o"], direct["o"]) < 1e-11
+    assert harness.rel_diff(fast["o"], direct["o"]) < 1e-10
     assert np.max(np.abs(fast["tb"][idx] - ref["tb"])) < TB_ATOL
     assert np.max(np.abs(fast["tb"] - direct["tb"])) < 1e-7
     # the instrumented path (near2_kernel) gives the same numbers and the oracle's selection
     inst = harness.run_gpu(case, by_mol=False, selection=True)
-    assert harness.rel_diff(inst["o"], fast["o"]) < 1e-11
+    assert harness.rel_diff(inst["o"], fast["o"]) < 1e-10
     assert np.array_equal(inst["sel_hash"][idx], ref["sel_hash"])
     monkeypatch.setattr(harness, "_session", None)
 

@@ -50,7 +50,7 @@ def test_in_library_multi_gpu_matches_single_gpu():
         for rep in range(3):                         # the second and third call run on the rebalanced partition
             b = multi.profiles(wn, 0.0, one, scor, irt, 285.0, em, rf, **kw)
             assert np.array_equal(a["sel_count"], b["sel_count"]) and np.array_equal(a["sel_hash"], b["sel_hash"])
-            assert harness.rel_diff(b["o"], a["o"]) < 1e-11 and harness.rel_diff(b["otot_by_mol"], a["otot_by_mol"], floor=1e-300) < 1e-11
+            assert harness.rel_diff(b["o"], a["o"]) < 1e-10 and harness.rel_diff(b["otot_by_mol"], a["otot_by_mol"], floor=1e-300) < 1e-10
             assert np.max(np.abs(a["tb"] - b["tb"])) < 1e-8 and np.max(np.abs(a["tmr"] - b["tmr"])) < 1e-8
             for k in ("rad", "trtot", "rup", "rdn"):
                 assert harness.rel_diff(b[k], a[k], floor=1e-300) < 1e-10, k
@@ -60,7 +60,7 @@ def test_in_library_multi_gpu_matches_single_gpu():
     em, rf = np.full(len(wn), 0.8), np.full(len(wn), 0.2)
     a = single.profiles(wn, 0.002, one, scor, 1, 285.0, em, rf, want_o=True)
     b = multi.profiles(wn, 0.002, one, scor, 1, 285.0, em, rf, want_o=True)
-    assert harness.rel_diff(b["o"], a["o"]) < 1e-11
+    assert harness.rel_diff(b["o"], a["o"]) < 1e-10
     st = multi.stats()
     assert st["kernel_launches"] > 0 and st["lines_staged"] == single.stats()["lines_staged"]
     multi.close()

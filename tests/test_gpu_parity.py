@@ -24,7 +24,7 @@ def check_case(case, od_rtol=OD_RTOL):
     gpu = harness.run_gpu(case)
     _check_against(ref, gpu, od_rtol)
     assert np.array_equal(gpu["sel_hash"], direct["sel_hash"])
-    assert harness.rel_diff(gpu["o"], direct["o"]) < 1e-11
+    assert harness.rel_diff(gpu["o"], direct["o"]) < 1e-10
     assert np.max(np.abs(gpu["tb"] - direct["tb"])) < 1e-7
     assert direct["stats"]["far_expansions"] == 0
     # the production variants: no selection instrumentation, with and without per-molecule outputs
@@ -32,7 +32,7 @@ def check_case(case, od_rtol=OD_RTOL):
     for by_mol in (True, False):
         fast = harness.run_gpu(case, by_mol=by_mol, selection=False)
         assert harness.rel_diff(fast["o"], ref["o"]) < od_rtol
-        assert harness.rel_diff(fast["o"], gpu["o"]) < 1e-11
+        assert harness.rel_diff(fast["o"], gpu["o"]) < 1e-10
         assert np.max(np.abs(fast["tb"] - ref["tb"])) < TB_ATOL
         if by_mol:
             scale = np.abs(ref["o"])[:, None, :]
@@ -116,7 +116,7 @@ def test_large_frequency_tiles():
 
 def test_dense_grid_far_field_expansion():
     """C3-like dense grid (5.5e-5 cm-1 spacing): most in-window lines take the far-field Taylor path; the
-    result must still match the oracle to 1e-9 and the direct mode to 1e-11, selection bit-exact."""
+    result must still match the oracle to 1e-9 and the direct mode to 1e-10 (the 14-term series at ratio 6 truncates at 1.3e-11), selection bit-exact."""
     for i0 in (1, 13400, 400000):          # next to zero frequency, across the 22 GHz line, mid-band
         wn = 5.5e-5 * np.arange(i0, i0 + 1536)
         case = harness.make_case(n_filler=1536, nlay=6, wn=wn, irt=1, line_kw=dict(n_co2=4, n_generic_lc=4))
@@ -145,7 +145,7 @@ def test_kernel_variants_on_the_dense_grid(env, monkeypatch):
     for by_mol in (True, False):
         gpu = harness.run_gpu(case, by_mol=by_mol, selection=by_mol)
         assert harness.rel_diff(gpu["o"], ref["o"]) < OD_RTOL
-        assert harness.rel_diff(gpu["o"], direct["o"]) < 1e-11
+        assert harness.rel_diff(gpu["o"], direct["o"]) < 1e-10
         assert np.max(np.abs(gpu["tb"] - ref["tb"])) < TB_ATOL
         assert gpu["stats"]["far_expansions"] > 0
         if by_mol:
