@@ -18,6 +18,28 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 
+def xs_case(sess):
+    """cross-section optical depths (mrtm_xsec, host buffers): the seeded synthetic set, 4000 frequencies x 100 layers"""
+    import tempfile
+    import harness  # noqa: F401
+    from monortm_b200 import api, synth, xsfile
+    with tempfile.TemporaryDirectory() as d:
+        xsfile.synthetic_set(d)
+        wn = np.linspace(2.0, 44.0, 4000)
+        sess.stage_xsec(api.host_xsread(d, ["HNO3", "F11"], float(wn[0]), float(wn[-1])))
+        prof = synth.synthetic_profiles(1, 100, seed0=1000, clw_layers=False, nmol=22)
+        keep = prof["p"][:, 0] > 260.0                     # above the table pressures: the reference's usable domain
+        p, t = prof["p"][keep, 0], prof["t"][keep, 0]
+        xamnt = np.zeros((38, len(p)), order="F")
+        xamnt[0], xamnt[1] = 1e15, 1e13
+        sess.xsec(wn, p, t, xamnt)
+        t0 = time.time()
+        od = sess.xsec(wn, p, t, xamnt)
+        dt = time.time() - t0
+        print(json.dumps({"config": "xs", "what": "mrtm_xsec: 3 regions (2 molecules) x %d frequencies x %d layers, host buffers" % (len(wn), len(p)),
+                          "s_per_call": dt, "frequency_layer_pairs_per_s": len(wn) * len(p) / dt, "max_od": float(od.max())}))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--nprof", type=int, default=256)
@@ -41,6 +63,9 @@ def main():
                    what="C5 cloudy: 10000 frequencies x 300 layers (3 cloud layers), IRT=1 then IRT=3"),
     }
     for name in args.configs.split(","):
+        if name == "xs":
+            xs_case(sess)
+            continue
         c = cases[name]
         wn = np.asarray(c["wn"], dtype=np.float64)
         prof = synth.synthetic_profiles(c["nprof"], c["nlay"], seed0=1000, clw_layers=c["clw"], nmol=22)
