@@ -669,6 +669,17 @@ def main():
     ptrs = {k: v.data_ptr() for k, v in d.items()}
     for i, k in enumerate(("rad", "tb", "tmr", "trtot", "rup", "rdn")):
         ptrs[k] = outs[i].data_ptr()
+    # N > 1: the spectra of step i are all-gathered on a second stream while step i+1 computes (two output / gather buffers);
+    # a step waits for the gather that last used its buffer, and the last gathers are added to the timed total
+    outs_b = torch.zeros_like(outs) if world > 1 else None
+    gathered_b = torch.zeros_like(gathered) if world > 1 else None
+    ptrs_b = dict(ptrs)
+    if world > 1:
+        for i, k in enumerate(("rad", "tb", "tmr", "trtot", "rup", "rdn")):
+            ptrs_b[k] = outs_b[i].data_ptr()
+    gstream = torch.cuda.Stream(device=dev) if world > 1 else None
+    gdone = [None, None]
+    step_no = [0]
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     # everything timed runs on ONE explicit stream: the library call is asynchronous on the stream it is given (a NULL /
     # legacy-default handle would send it to the context's own stream, outside the events below)
@@ -676,10 +687,26 @@ def main():
     torch.cuda.set_stream(stream)
 
     def step_dev(line_mode=0):
-        sess.profiles_dev(1, nwn, NLAY, 22, 0.0, ptrs, inp["v1"], inp["v2"], inp["iw0"], inp["irt"], stream=stream.cuda_stream,
-                          line_mode=line_mode)
+        b = step_no[0] & 1
+        step_no[0] += 1
+        if world > 1 and gdone[b] is not None:
+            stream.wait_event(gdone[b])                       # the gather that read this output buffer two steps ago
+        sess.profiles_dev(1, nwn, NLAY, 22, 0.0, ptrs_b if (world > 1 and b) else ptrs, inp["v1"], inp["v2"], inp["iw0"], inp["irt"],
+                          stream=stream.cuda_stream, line_mode=line_mode)
         if world > 1:
-            dist.all_gather_into_tensor(gathered, outs)
+            e = torch.cuda.Event()
+            e.record(stream)
+            gstream.wait_event(e)
+            with torch.cuda.stream(gstream):
+                dist.all_gather_into_tensor(gathered_b if b else gathered, outs_b if b else outs)
+                gdone[b] = torch.cuda.Event()
+                gdone[b].record(gstream)
+
+    def drain_gathers():
+        """the compute stream waits for the gathers still in flight (timed by the caller)"""
+        for g in gdone:
+            if g is not None:
+                stream.wait_event(g)
 
     def barrier():
         if world > 1:
@@ -689,6 +716,7 @@ def main():
     # ---- warm-up, then K timed steps (per-step CUDA events, L2 flushed between steps)
     for _ in range(max(args.warmup, 3)):
         step_dev()
+    drain_gathers()
     barrier()
     sess.reset_stats()
     sampler = ClockSampler(local)
@@ -705,9 +733,13 @@ def main():
         st = sess.stats()
         lines_ms.append(st["last_lines_kernel_ms"]); rt_ms.append(st["last_rt_kernel_ms"]); derive_ms.append(st["last_derive_kernel_ms"])
         far_exp.append(st["far_expansions"]); direct_ev.append(st["direct_evals"])
+    tail = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+    tail[0].record(stream)
+    drain_gathers()
+    tail[1].record(stream)
     barrier()
     t_wall = time.time() - t_wall0
-    dev_ms = sum(a.elapsed_time(b) for a, b in ev)
+    dev_ms = sum(a.elapsed_time(b) for a, b in ev) + tail[0].elapsed_time(tail[1])
     launches = sess.stats()["kernel_launches"]
     tmax = torch.tensor([dev_ms], dtype=torch.float64, device=dev)
     if world > 1:
@@ -812,6 +844,8 @@ def main():
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": dict(workload_config(args), shard_frequencies=[int(c) for c in shard_counts],
+                           gather="none (one GPU)" if world == 1 else "NCCL all-gather of the six spectra of step i on a second stream while step i+1 "
+                                  "computes (two buffers); the gathers still in flight after the last step are inside the timed total",
                            shard_balance="blocks of equal measured cost (three untimed feedback rounds), sum = n_gpus x nwn_per_gpu"
                            if (world > 1 and not args.no_balance) else "equal counts"),
             "spectra_per_s": world / (ms_per_step * 1e-3), "rank_kernel_ms": rank_kernel_ms,
