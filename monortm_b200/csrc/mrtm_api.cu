@@ -98,7 +98,7 @@ struct mrtm_ctx {
     // asynchronous device-resident calls (mrtm_profiles_dev): timing events and device flags are read back lazily
     bool pending = false, pending_lines = false, pending_rt = false;
     int deferred_rc = MRTM_OK;
-    size_t planes_budget = (size_t)8 << 30;
+    size_t planes_budget = (size_t)24 << 30;   // of the 180 GB (ensemble: 24 GB batches are 5 % faster than 8 GB)
 };
 
 static thread_local std::string g_err_noctx;
