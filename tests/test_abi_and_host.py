@@ -175,3 +175,33 @@ def test_mrtm_opts_layout_matches_the_header_the_ctypes_mirror_and_the_fortran_s
         if m:
             members += [x.split("=")[0].strip() for x in m.group(2).split(",")]
     assert members == names
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/src"), reason="reference tree not present")
+def test_generated_tables_agree_with_a_second_extraction_route():
+    """The oracle and the product share csrc/tables/*.inc (tools/gen_tables.py parses the DATA statements with regular
+    expressions).  A second, independent route -- the mechanical translator executes the BLOCK DATA units and the numbers are
+    read out of the COMMON storage the accessor routines index -- must give the same values, so an extraction error cannot
+    hide as a common-mode error of oracle and product."""
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import ref_exec
+    ns = ref_exec.load()
+
+    def inc(fname, name):
+        src = open(os.path.join(ROOT, "monortm_b200", "csrc", "tables", fname)).read()
+        m = re.search(r"static const double %s\[(\d+)\] = \{(.*?)\};" % name, src, re.S)
+        v = np.array([float(x) for x in m.group(2).replace("\n", " ").split(",") if x.strip()])
+        assert len(v) == int(m.group(1))
+        return v
+
+    for blk, members in (("sh2o", [("MTCKD_SH2O_296", 2003)]), ("s260", [("MTCKD_SH2O_260", 2003)]), ("fh2o", [("MTCKD_FH2O", 2003)]),
+                         ("fco2", [("MTCKD_FCO2", 5003)]), ("n2rt296", [("MTCKD_N2RT_296", 73), ("MTCKD_N2RT_296_SF", 73)]),
+                         ("n2rt220", [("MTCKD_N2RT_220", 73), ("MTCKD_N2RT_220_SF", 73)])):
+        s = ns["C_" + blk].s
+        off = 4
+        for name, n in members:
+            assert np.array_equal(inc("mtckd_tables.inc", name), np.array([float(x) for x in s[off:off + n]])), name
+            off += n
+    smass = np.array([float(x) for x in ns["C_isvect"].s[39:39 + 39 * 9]]).reshape((39, 9), order="F")
+    assert np.array_equal(inc("smass_table.inc", "ISO_SMASS").reshape(39, 9), smass)
