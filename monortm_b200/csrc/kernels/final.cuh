@@ -36,6 +36,7 @@ __global__ void __launch_bounds__(NT, MRTM_FINAL_MINB) final_kernel(LinesArgs a)
         wn[f] = a.wn[valid[f] ? iw : (a.nwn - 1)];
         sv[f] = (wn[f] - cen) * hinv;
     }
+    const double hinv_2t = 0.5 * ly.inv_t;
     const double* cf = have_far ? a.coef[0] + ((size_t)blockIdx.x * Ltot + L) * a.nslot * kFarK : nullptr;
     double osum[F];
     if (!a.o_by_mol) {
@@ -54,7 +55,7 @@ __global__ void __launch_bounds__(NT, MRTM_FINAL_MINB) final_kernel(LinesArgs a)
                 for (int i = kFarK - 2; i >= 0; i--) p = fma(p, sv[f], s_coef[i]);
                 v += p;
             }
-            const double rft = wn[f] * tanh((ly.radct * wn[f]) / (2 * ly.t));   // modm.f90:257
+            const double rft = wn[f] * tanh((ly.radct * wn[f]) * hinv_2t);   // modm.f90:257 (the division by 2T as a product)
             osum[f] = rft * v;
         }
     } else {
@@ -74,7 +75,7 @@ __global__ void __launch_bounds__(NT, MRTM_FINAL_MINB) final_kernel(LinesArgs a)
                 double p = c[kFarK - 1];
 #pragma unroll
                 for (int i = kFarK - 2; i >= 0; i--) p = fma(p, sv[f], c[i]);
-                const double rft = wn[f] * tanh((ly.radct * wn[f]) / (2 * ly.t));
+                const double rft = wn[f] * tanh((ly.radct * wn[f]) * hinv_2t);
                 const double ol = (w == 0.) ? 0. : rft * (a.o_by_mol[idx] + w * p);     // modm.f90:436-438
                 a.o_by_mol[idx] = ol;
                 osum[f] = osum[f] + ol;                                              // :265-267 (molecule order)
@@ -105,7 +106,7 @@ __global__ void __launch_bounds__(NT, MRTM_FINAL_MINB) final_kernel(LinesArgs a)
             long long ihi = (long long)((a.v2abs - 1.0 - vi) / 1.0 + 0.999);
             in_rng = (ilo <= 1) && (ihi >= 1);
         }
-        const double rf = radfn(wn[f], ly.xkt);
+        const double rf = radfn_r(wn[f], ly.xkt);
 #pragma unroll
         for (int c = 0; c < 5; c++) {
             if (kMwOnly && (c == CP_O3 || c == CP_O2)) continue;       // microwave call: O3 and O2 have no component (compile time)

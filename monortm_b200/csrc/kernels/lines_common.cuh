@@ -116,6 +116,21 @@ __device__ __forceinline__ double radfn(double vi, double xkt)
     return vi;
 }
 
+// the same with the quotient (1-e)/(1+e) through a Newton reciprocal (~1 ulp); the branch variable x stays the exact quotient
+__device__ __forceinline__ double radfn_r(double vi, double xkt)
+{
+    if (xkt > 0.0) {
+        double x = vi / xkt;
+        if (x <= 0.01) return 0.5 * x * vi;
+        if (x <= 10.0) {
+            double e = exp(-x);
+            return (vi * (1. - e)) * rcp3(1. + e);
+        }
+        return vi;
+    }
+    return vi;
+}
+
 // ODCLW_TKC / Forward_TKC, CloudOptProp.f90:29-157 (binary64 here; the parity build evaluates
 // the d0-literal expressions in binary128 and rounds, a ~1e-16 relative difference)
 __device__ __noinline__ double odclw_tkc(double wn, double temp, double clw)

@@ -111,6 +111,7 @@ __global__ void layer_prep_kernel(LayerPrepArgs a)
     o.rt = xdiv(tt, kT0);
     o.lnrt = log(o.rt);
     o.dinvt = 1. / kT0 - 1. / tt;
+    o.inv_t = 1. / tt;
     o.rhorat = xdiv(xn, xn0);
     for (int k = 0; k < 7; k++) o.rho_molec[k] = xdiv(xmul(o.rhorat, wk[k]), wtot);
     for (int m = 0; m < MRTM_MXMOL; m++) {
@@ -460,7 +461,7 @@ __device__ __forceinline__ unsigned long long derive_one(const DeriveArgs& a, in
     const LayerDev& ly = a.lay[L];
     const int mol = a.ln.mol[q], xf = a.ln.xf[q], cls = a.ln.cls[q];
     const double rhorat = ly.rhorat, rho_self = ly.rho_self[mol - 1];
-    const double radct = ly.radct, t = ly.t;
+    const double radct = ly.radct;
 
     double aip = 0., bip = 0.;
     const int lci = a.ln.lcidx[q];
@@ -501,12 +502,15 @@ __device__ __forceinline__ unsigned long long derive_one(const DeriveArgs& a, in
         xnu = xadd(xnu, s);
     }
 
-    // INTENS
+    // INTENS.  The divisions of the reference (:860-865, :453, :419) are regrouped into multiplications by per-layer and
+    // per-line reciprocals and a Newton reciprocal (~1 ulp each; the bar on optical depths is 1e-9).
     const double xipsf = a.scorc[(size_t)L * a.ln.nsi + a.ln.sidx[q]];
     const double es = a.ln.e[q];
     // exp(-c2 E/T)/exp(-c2 E/T0) as one exponential (modm.f90 INTENS)
     double s = a.ln.s0adj[q] * exp(radct * es * ly.dinvt) * xipsf;
-    double stild = s * ((1 + exp(-(radct * xnu / t))) / (xnu * (1 - exp(-(radct * xnu / kT0)))));
+    const double rx = radct * xnu;
+    const double stim_n = 1 + exp(-(rx * ly.inv_t)), stim_d = xnu * (1 - exp(-(rx * (1. / kT0))));
+    double stild = (stim_d > 1e-280 && stim_d < 1e280) ? s * (stim_n * rcp3(stim_d)) : s * (stim_n / stim_d);
 
     // HALFWHM_C
     const double af = a.ln.alpf[q], as = a.ln.alps[q];
@@ -523,15 +527,19 @@ __device__ __forceinline__ unsigned long long derive_one(const DeriveArgs& a, in
         hwhm_c = (rhorat - sflgrho) * alfa0i + alfsum;
         if (brd[mol - 1] == 0.) hwhm_c = hwhm_c + rho_self * (hwhmsi - alfa0i);
     }
-    // HALFWHM_D
-    const double hwhm_d = (xnu / kCLIGHT) * sqrt(2. * log(2.) * ((kBOLTZ * t) / (a.ln.mass[q] / kAVOGAD)));
+    // HALFWHM_D = (Xnu/c)*sqrt(2 ln2 kT/(M/N_A)): the constants and the mass are folded per line at staging (dopf)
+    const double hwhm_d = xnu * (a.ln.dopf[q] * ly.sqrt_t);
     if (xf == -3) hwhm_c = hwhm_c * (1 - (aip * ly.rp) - (bip * ly.rp2));
-    const double zeta = hwhm_c / (hwhm_c + hwhm_d);
+    // zeta = HWHM_C/(HWHM_C+HWHM_D) decides Voigt or Lorentz at 0.99 (:419): the exact quotient only where the fast one is
+    // too close to the threshold to decide
+    const double zsum = hwhm_c + hwhm_d;
+    double zeta = (zsum > 1e-280 && zsum < 1e280) ? hwhm_c * rcp3(zsum) : hwhm_c / zsum;
+    if (fabs(zeta - 0.99) < 1e-12) zeta = hwhm_c / zsum;
 
     const double h2 = hwhm_c * hwhm_c;
-    const double cn = stild * hwhm_c / kPI;
+    const double cn = (stild * hwhm_c) * (1. / kPI);
     double p3 = 0.;
-    if (cls == CLS_PED) p3 = cn / (kDELTNUC * kDELTNUC + h2);
+    if (cls == CLS_PED) p3 = cn * rcp3(kDELTNUC * kDELTNUC + h2);
     if (cls == CLS_O2_LC1) p3 = cn * (1. + bip * ly.rp2);
     const size_t np = a.ln.n_pad;
     pl[(size_t)D_XNU * np + q] = xnu;

@@ -72,6 +72,7 @@ struct LayerDev {
     double shift_margin;   // >= max |Xnu-Xnu0| over staged lines for this layer
     double sqrt_t;
     double lnrt;        // log(rt): rt^x = exp(x*lnrt) in derive_kernel
+    double inv_t;       // 1/T
     double dinvt;       // 1/T0 - 1/T: Boltzmann ratio exp(-c2 E/T)/exp(-c2 E/T0) = exp(c2*E*dinvt)
     double rho_molec[7];
     double wk[MRTM_MXMOL];     // column amounts (W_species), zero beyond nmol

@@ -17,7 +17,7 @@ namespace mrtm {
 struct LinesDev {
     int32_t n, n_pad;
     const int32_t *mol, *iso, *xf, *cls, *sidx, *lcidx, *brdidx, *segidx;
-    const double *xnu0, *s0adj, *e, *alpf, *alps, *x, *deltnu, *sdep, *mass;
+    const double *xnu0, *s0adj, *e, *alpf, *alps, *x, *deltnu, *sdep, *mass, *dopf;
     const unsigned long long* key;
     const unsigned long long* keypre;   // [n_pad+1]
     const double* lc;          // [nlc][16]
@@ -50,6 +50,7 @@ struct TipsDev {
 #include "kernels/near3.cuh"
 #include "kernels/sparse.cuh"
 #include "kernels/voigt.cuh"
+#include "kernels/voigt_t.cuh"
 #include "kernels/final.cuh"
 #include "kernels/rt.cuh"
 #include "kernels/xsec.cuh"

@@ -182,6 +182,9 @@ int stage_lines_host(const int64_t nblm[MRTM_MXMOL], int64_t iim, const int64_t*
         out.max_abs_deltnu = std::max(out.max_abs_deltnu, std::fabs(r.deltnu));
     }
     // padding lines sit far outside any window and carry no strength
+    out.dopf.assign(out.n_pad, 0.0);
+    for (int64_t q = 0; q < n; q++)
+        out.dopf[q] = std::sqrt(2. * std::log(2.) * (kBOLTZ / (out.mass[q] / kAVOGAD))) / kCLIGHT;
     for (int64_t q = n; q < out.n_pad; q++) {
         out.xnu0[q] = 1.0e30;
         out.mol[q] = 0;

@@ -10,6 +10,7 @@ struct HostLines {
     // static per-line planes, staged order = (molecule asc, class asc, xnu0 asc [stable])
     std::vector<int32_t> mol, iso, xf, cls, sidx, lcidx, brdidx, rec, segidx;
     std::vector<double> xnu0, s0adj, e, alpf, alps, x, deltnu, sdep, mass;
+    std::vector<double> dopf;      // sqrt(2 ln2 k N_A / M)/c per line: HWHM_D = Xnu*dopf*sqrt(T) (modm.f90:453 with the constants folded)
     std::vector<uint64_t> key;
     // compact line-coupling table: 16 doubles per coupled line: A[4],B[4] foreign, A2[4],B2[4] self
     std::vector<double> lc;        // size nlc*16

@@ -221,3 +221,47 @@ def test_production_near_field_kernel_unsorted_and_voigt_zone():
         harness._session = None
     assert harness.rel_diff(fast["o"], ref["o"]) < OD_RTOL
     assert np.max(np.abs(fast["tb"] - ref["tb"])) < TB_ATOL
+
+
+def _run_with_env(case, env, **kw):
+    """One run of `case` on a fresh library context created under `env` (the library reads its MRTM_* switches in mrtm_init)."""
+    import os
+    from monortm_b200 import api
+    old = {k: os.environ.get(k) for k in env}
+    os.environ.update(env)
+    saved = harness._session
+    try:
+        harness._session = api.Session(0)
+        return harness.run_gpu(case, **kw)
+    finally:
+        harness._session = saved
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+
+
+@pytest.mark.parametrize("F", ["4", "2"])
+def test_transposed_voigt_kernel_on_every_voigt_branch(F):
+    """voigtT_kernel (dense tiles: lines over warps, lanes over each line's run of frequencies) on the Voigt-zone branch
+    case -- speed dependence, CO2, coupled lines of other molecules, coupled O2, the negative-frequency resonance -- plus a
+    dense stretch across the 22 GHz line, with the dense-tile kernels forced (MRTM_LINES_F): against the oracle (1e-9, both
+    with per-molecule outputs and with one sum over all molecules) and against voigt_kernel on the same tiles (MRTM_VOIGT_T=0)."""
+    sd, co2, glc, o2lc = _special_centres(384, KW)
+    wn = zone_frequencies(sd + co2 + glc + o2lc)
+    wn = np.unique(np.concatenate([wn[(wn > 0.4) & (wn < 55.0)], 0.741691 + np.linspace(-3e-4, 3e-4, 700)]))
+    case = harness.make_case(n_filler=384, nlay=24, wn=wn, irt=1, line_kw=KW)
+    ref = harness.run_oracle(case)
+    assert ref["branches"]["sdep"] > 500 and ref["branches"]["co2_lc1"] > 100 and ref["branches"]["generic_lc"] > 200
+    scale = np.abs(ref["o"])[:, None, :]
+    new = _run_with_env(case, {"MRTM_LINES_F": F, "MRTM_VOIGT_T": "1"})
+    _check_against(ref, new, OD_RTOL)
+    old = _run_with_env(case, {"MRTM_LINES_F": F, "MRTM_VOIGT_T": "0"})
+    _check_against(ref, old, OD_RTOL)
+    assert harness.rel_diff(new["o"], old["o"]) < 1e-12
+    assert np.max(np.abs(new["o_by_mol"] - old["o_by_mol"]) / scale) < 1e-12
+    fast = _run_with_env(case, {"MRTM_LINES_F": F, "MRTM_VOIGT_T": "1"}, by_mol=False, selection=False)
+    assert harness.rel_diff(fast["o"], ref["o"]) < OD_RTOL
+    assert harness.rel_diff(fast["o"], new["o"]) < 1e-10
+    assert np.max(np.abs(fast["tb"] - ref["tb"])) < TB_ATOL
