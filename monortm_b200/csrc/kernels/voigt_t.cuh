@@ -27,7 +27,7 @@ __global__ void __launch_bounds__(NT, MRTM_VOIGTT_MINB) voigtT_kernel(LinesArgs 
 {
     constexpr int NW = NT / 32, TF = NT * F;
     constexpr int kVCap = MRTM_VOIGTT_CAP;
-    static_assert(kVCap <= NT, "one staging thread per line of a chunk");
+    static_assert(2 * kVCap <= NT, "two staging threads per line of a chunk");
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int k = blockIdx.y, prof = blockIdx.z;
     const int64_t L = (int64_t)prof * a.nlay + k;
@@ -42,11 +42,10 @@ __global__ void __launch_bounds__(NT, MRTM_VOIGTT_MINB) voigtT_kernel(LinesArgs 
     const double* __restrict__ lcp = a.lcplanes + (size_t)L * LCP_NPLANES * a.nlc_pad;
     const SegWork* plan = a.plan[0] + (size_t)blockIdx.x * a.nseg;
     __shared__ double s_vt[kVCap], s_x[kVCap], s_inv[kVCap], s_y[kVCap], s_c[kVCap], s_pd[kVCap], s_g[kVCap], s_b[kVCap];
-    __shared__ double s_fa[kVCap], s_fb[kVCap], s_fa2[kVCap], s_fcy[kVCap], s_fcpd[kVCap];
     __shared__ double s_h2[kVCap], s_cn[kVCap], s_p3[kVCap], s_p4[kVCap];
     __shared__ int s_q[kVCap];
     __shared__ short s_lo[kVCap], s_hi[kVCap];
-    __shared__ unsigned char s_kind[kVCap], s_mol[kVCap];
+    __shared__ unsigned char s_kind[kVCap], s_mol[kVCap], s_single[kVCap];
     __shared__ int s_zlo[kMaxSegments], s_zoff[kMaxSegments + 1];
     __shared__ double s_wn[TF];
     __shared__ double s_acc[NW][TF];
@@ -99,69 +98,77 @@ __global__ void __launch_bounds__(NT, MRTM_VOIGTT_MINB) voigtT_kernel(LinesArgs 
     for (int e0 = 0; e0 < total; e0 += kVCap) {
         const int n = min(kVCap, total - e0);
         if (e0 > 0) __syncthreads();
-        if (tid < n) {
-            const int i = tid, e = e0 + i;
-            int sg = 0;
-            while (s_zoff[sg + 1] <= e) sg++;
-            const int q = s_zlo[sg] + (e - s_zoff[sg]);
-            const int cls = a.seg[sg].cls, mol = a.seg[sg].mol;
-            const int kind = (cls == CLS_PED) ? 0 : ((cls == CLS_O2) ? 1 : ((cls == CLS_O2_LC35) ? 2 : 3));
-            const double vt = __ldg(pVT + q);
-            const double xq = __ldg(pXNU + q);
-            s_vt[i] = vt;
-            s_x[i] = xq;
-            s_q[i] = q;
-            s_kind[i] = (unsigned char)kind;
-            s_mol[i] = (unsigned char)mol;
-            int lo = 0, hi = 0;
-            if (vt >= 0.) {
-                // the run of tile frequencies that can pass |WN-Xnu| <= vt (the test itself is repeated per pair)
-                hi = nf;
-                if (sorted) {
-                    int b = 0, e2 = nf;
-                    while (b < e2) { const int mid = (b + e2) >> 1; if ((s_wn[mid] - xq) < -vt) b = mid + 1; else e2 = mid; }
-                    lo = b;
-                    e2 = nf;
-                    while (b < e2) { const int mid = (b + e2) >> 1; if ((s_wn[mid] - xq) > vt) e2 = mid; else b = mid + 1; }
-                    hi = b;
-                }
-                const ColdLine cl = cold_line(pl, a.n_pad, q, a.lcidx_s, lcp, a.nlc_pad);
-                const double hw = cl.hw, ad = cl.ad;
-                const double zeta = hw / (hw + ad);
-                const double wl = by_mol ? 1. : ly.wk[mol - 1];
-                const double h2 = __ldg(pH2 + q), cn = __ldg(pCN + q);
-                s_h2[i] = h2;
-                s_cn[i] = wl * cn;
-                s_p3[i] = wl * __ldg(pP3 + q);
-                s_p4[i] = (kind == 3) ? wl * lc1_slope(cn, h2, cl.aip, rp) : 0.;
-                if (fabs(__ldg(a.sdep_s + q)) > 1.0e-4 || !(zeta < 1.0)) {
-                    s_inv[i] = -1.;        // speed dependence / degenerate Doppler width: the general routine per pair
-                    s_c[i] = wl;
-                } else {
-                    const double inv = 1. / ad;
-                    const double y = sl2 * (hw * inv);
-                    s_inv[i] = inv;
-                    s_y[i] = y;
-                    s_c[i] = wl * (cl.stild * (0.46971863934982516 * inv));   // sqrt(log(2)/PI), 13-digit PI
-                    s_pd[i] = (kind == 0) ? w4_re_fast(sl2 * (kDELTNUC * inv), y) : 0.;
-                    s_g[i] = (kind == 3) ? (cl.aip * (1 / hw) * rp) : 0.;
-                    s_b[i] = (kind == 3) ? (cl.bip * rp2) : 0.;
-                    // fast form: plain line, the window test cannot fail inside the zone, and no frequency of the run has
-                    // the second resonance (WN+Xnu-25 <= 0, modm.f90:746; the rounded sum is monotone in WN)
-                    const double wfirst = (sorted && lo < nf) ? s_wn[lo] : wmin_tile;
-                    if (kind == 0 && vt <= kDELTNUC && ((wfirst + xq) - kDELTNUC) > 0.) {
-                        const double y2 = y * y, aa = .5 + y2;
-                        s_fa[i] = aa;
-                        s_fb[i] = 2. * y2 - 1.;
-                        s_fa2[i] = aa * aa;
-                        s_fcy[i] = s_c[i] * (.5641896 * y);
-                        s_fcpd[i] = s_c[i] * s_pd[i];
-                        s_kind[i] = (unsigned char)(kind | 0x80);
+        // two threads per line: one forms the frequency-independent terms, the other brackets the line's run of frequencies
+        {
+            const int i = tid & (kVCap - 1);
+            const bool searcher = tid >= kVCap;
+            if (i < n && tid < 2 * kVCap) {
+                const int e = e0 + i;
+                int sg = 0;
+                while (s_zoff[sg + 1] <= e) sg++;
+                const int q = s_zlo[sg] + (e - s_zoff[sg]);
+                const double vt = __ldg(pVT + q);
+                const double xq = __ldg(pXNU + q);
+                if (searcher) {
+                    int lo = 0, hi = 0;
+                    if (vt >= 0.) {
+                        // the run of tile frequencies that can pass |WN-Xnu| <= vt (the test itself is repeated per pair)
+                        hi = nf;
+                        if (sorted) {
+                            int b = 0, e2 = nf;
+                            while (b < e2) { const int mid = (b + e2) >> 1; if ((s_wn[mid] - xq) < -vt) b = mid + 1; else e2 = mid; }
+                            lo = b;
+                            e2 = nf;
+                            while (b < e2) { const int mid = (b + e2) >> 1; if ((s_wn[mid] - xq) > vt) e2 = mid; else b = mid + 1; }
+                            hi = b;
+                        }
                     }
+                    // no frequency of the run has the second resonance (WN+Xnu-25 <= 0, modm.f90:746; the rounded sum is
+                    // monotone in WN)
+                    const double wfirst = (sorted && lo < nf) ? s_wn[lo] : wmin_tile;
+                    s_single[i] = (((wfirst + xq) - kDELTNUC) > 0.) ? 1 : 0;
+                    s_lo[i] = (short)lo;
+                    s_hi[i] = (short)hi;
+                } else {
+                    const int cls = a.seg[sg].cls, mol = a.seg[sg].mol;
+                    const int kind = (cls == CLS_PED) ? 0 : ((cls == CLS_O2) ? 1 : ((cls == CLS_O2_LC35) ? 2 : 3));
+                    s_vt[i] = vt;
+                    s_x[i] = xq;
+                    s_q[i] = q;
+                    s_mol[i] = (unsigned char)mol;
+                    int kflag = kind;
+                    if (vt >= 0.) {
+                        const ColdLine cl = cold_line(pl, a.n_pad, q, a.lcidx_s, lcp, a.nlc_pad);
+                        const double hw = cl.hw, ad = cl.ad;
+                        // vt >= 0 says zeta <= 0.99 (derive_kernel): the degenerate case zeta >= 1 of SDVOIGT (modm.f90:1075)
+                        // can only be a vanishing Doppler width
+                        const bool degenerate = !(ad > 0.) || !(hw < 1e300);
+                        const double wl = by_mol ? 1. : ly.wk[mol - 1];
+                        const double h2 = __ldg(pH2 + q), cn = __ldg(pCN + q);
+                        s_h2[i] = h2;
+                        s_cn[i] = wl * cn;
+                        s_p3[i] = wl * __ldg(pP3 + q);
+                        s_p4[i] = (kind == 3) ? wl * lc1_slope(cn, h2, cl.aip, rp) : 0.;
+                        if (fabs(__ldg(a.sdep_s + q)) > 1.0e-4 || degenerate) {
+                            s_inv[i] = -1.;        // speed dependence / degenerate Doppler width: the general routine per pair
+                            s_c[i] = wl;
+                        } else {
+                            const double inv = 1. / ad;
+                            const double y = sl2 * (hw * inv);
+                            s_inv[i] = inv;
+                            s_y[i] = y;
+                            s_c[i] = wl * (cl.stild * (0.46971863934982516 * inv));   // sqrt(log(2)/PI), 13-digit PI
+                            s_pd[i] = (kind == 0) ? w4_re_fast(sl2 * (kDELTNUC * inv), y) : 0.;
+                            s_g[i] = (kind == 3) ? (cl.aip * (1 / hw) * rp) : 0.;
+                            s_b[i] = (kind == 3) ? (cl.bip * rp2) : 0.;
+                            // fast form: plain line and the window test cannot fail inside the zone (the second resonance
+                            // is the searcher's s_single)
+                            if (kind == 0 && vt <= kDELTNUC) kflag |= 0x80;
+                        }
+                    }
+                    s_kind[i] = (unsigned char)kflag;
                 }
             }
-            s_lo[i] = (short)lo;
-            s_hi[i] = (short)hi;
         }
         __syncthreads();
         // groups of staged lines that share one sum: everything (the molecule's amount is folded into the line terms) or,
@@ -179,23 +186,23 @@ __global__ void __launch_bounds__(NT, MRTM_VOIGTT_MINB) voigtT_kernel(LinesArgs 
                 const double xnu = s_x[i], vt = s_vt[i], inv = s_inv[i];
                 const double h2 = s_h2[i], cn = s_cn[i], p3 = s_p3[i], c = s_c[i];
                 const int kraw = s_kind[i];
-                if (kraw & 0x80) {
-                    const double y = s_y[i], fa = s_fa[i], fb = s_fb[i], fa2 = s_fa2[i], fcy = s_fcy[i], fcpd = s_fcpd[i];
-#pragma unroll 2
-                    for (int j = lo + lane; j < hi; j += 32) {
-                        const double dm = s_wn[j] - xnu;
-                        if (fabs(dm) <= vt) {
-                            const double x = sl2 * (dm * inv);
-                            const double lor = fma(cn, rcp3(fma(dm, dm, h2)), -p3);
-                            double v;
-                            if (!(fabs(x) + y < 15.)) {
-                                const double q = x * x;
-                                v = fma(fcy * (fa + q), rcp3(fma(q, q + fb, fa2)), -fcpd) - lor;
-                            } else {
-                                v = (c * w4_re_near(x, y) - fcpd) - lor;
-                            }
-                            acc[j] += v;
-                        }
+                if ((kraw & 0x80) && s_single[i]) {
+                    // Region I: Re w = y*(a+q)/(q*(q+b)+a*a), q = x*x, a = .5+y*y, b = 2*y*y-1 -- the reference's
+                    // t*.5641896/(.5+t*t) (modm.f90:1105) multiplied out.  Every lane forms it; the lanes next to the centre
+                    // replace it by their own region's value.
+                    const double y = s_y[i], y2 = y * y, fa = .5 + y2, fb = 2. * y2 - 1., fa2 = fa * fa;
+                    const double fcy = c * (.5641896 * y), fcpd = c * s_pd[i];
+                    for (int jb = lo; jb < hi; jb += 32) {
+                        const int j = jb + lane;
+                        const bool inr = j < hi;
+                        const double dm = s_wn[inr ? j : lo] - xnu;
+                        const bool take = inr && (fabs(dm) <= vt);
+                        const double x = sl2 * (dm * inv);
+                        const double lor = fma(cn, rcp3(fma(dm, dm, h2)), -p3);
+                        const double q = x * x;
+                        double v = fcy * (fa + q) * rcp3(fma(q, q + fb, fa2));
+                        if (take && (fabs(x) + y < 15.)) v = c * w4_re_near(x, y);     // regions II-IV next to the centre
+                        if (take) acc[j] += (v - fcpd) - lor;
                     }
                     continue;
                 }
@@ -291,3 +298,4 @@ __global__ void __launch_bounds__(NT, MRTM_VOIGTT_MINB) voigtT_kernel(LinesArgs 
     }
     if (err) atomicOr(a.errflag, 2);
 }
+

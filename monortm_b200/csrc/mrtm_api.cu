@@ -69,7 +69,7 @@ struct mrtm_ctx {
     cudaEvent_t ev_in = nullptr;                  // emiss / reflc arrived (host-buffer path)
     double tile_width = 0.1;                      // cm-1, MRTM_TILE_WIDTH (see the tile-size choice in run_device)
     const void* span_ptr = nullptr; int64_t span_nwn = 0; double span_val = -1.;   // cached span of a device-resident wn
-    int use_voigt_t = 1;                          // MRTM_VOIGT_T=0: voigt_kernel also on dense tiles (comparison arm)
+    int use_voigt_t = 1;                          // dense tiles: 1 voigtT_kernel, 0 voigt_kernel (MRTM_VOIGT_T, comparison arm)
     int voigt_side = 0;                           // MRTM_VOIGT_SIDE=1: Voigt branch on the side stream into a scratch plane (measured: no gain, off by default)
     DevBuf b_ov;
     int use_side = 1;                             // MRTM_SIDE_STREAM=0: everything on one stream
@@ -203,7 +203,7 @@ extern "C" int mrtm_init(int device, mrtm_ctx** out)
     if (const char* s = std::getenv("MRTM_SIDE_STREAM")) ctx->use_side = std::atoi(s) != 0;
     if (const char* s = std::getenv("MRTM_TILE_WIDTH")) ctx->tile_width = std::atof(s);
     if (const char* s = std::getenv("MRTM_VOIGT_SIDE")) ctx->voigt_side = std::atoi(s) != 0;
-    if (const char* s = std::getenv("MRTM_VOIGT_T")) ctx->use_voigt_t = std::atoi(s) != 0;
+    if (const char* s = std::getenv("MRTM_VOIGT_T")) ctx->use_voigt_t = std::atoi(s);
     if (const char* s = std::getenv("MRTM_PLANES_GB")) ctx->planes_budget = (size_t)(std::atof(s) * (double)(1ull << 30));
     if (const char* s = std::getenv("MRTM_FF_LEVELS")) ctx->ff_levels = std::min(std::max(std::atoi(s), 1), kMaxLevels);
     if (const char* s = std::getenv("MRTM_NEAR2")) ctx->use_near2 = std::atoi(s) != 0;
@@ -519,7 +519,7 @@ struct RunDesc {
 
 template <int F, int NT>
 static void launch_lines(const LinesArgs& la, dim3 grid, bool sel, cudaStream_t s, cudaEvent_t far_done, cudaStream_t sv,
-                         const Near3Args* n3, bool neart, bool voigt_t)
+                         const Near3Args* n3, bool neart, int voigt_t)
 {
     // near field (direct), Voigt branch, then polynomial + continuum + totals
     const size_t dyn = sizeof(double) * kStages * 4 * kTile + (size_t)std::max(la.nseg, 1) * sizeof(SegWork);
@@ -556,7 +556,7 @@ static void launch_lines(const LinesArgs& la, dim3 grid, bool sel, cudaStream_t 
     // with a scratch plane for its sums the Voigt branch runs on the side stream (after the far field, beside the near field)
     // dense tiles (no candidate lists from vplan_kernel): lines over warps, lanes over each line's run of frequencies
     constexpr bool kHasT = (NT == 128 && F >= 2);
-    const bool vt_dense = kHasT && voigt_t && !la.vcand_count;
+    const bool vt_dense = kHasT && voigt_t != 0 && !la.vcand_count;
     cudaStream_t svk = (la.o_v && sv) ? sv : s;
     if constexpr (kHasT) {
         if (vt_dense) voigtT_kernel<F, NT><<<grid, NT, 0, svk>>>(la);
@@ -1008,11 +1008,11 @@ static int run_device(mrtm_ctx* ctx, const RunDesc& r, cudaStream_t s)
                 la.o_v = (double*)ctx->b_ov.p;
                 sv = sp;
             }
-            if (F == 4) launch_lines<4, 128>(la, grid, sel, s, far_done, sv, use3 ? &n3 : nullptr, false, ctx->use_voigt_t != 0);
-            else if (F == 2) launch_lines<2, 128>(la, grid, sel, s, far_done, sv, nullptr, false, ctx->use_voigt_t != 0);
-            else if (Fc == 2) launch_lines<2, 64>(la, grid, sel, s, far_done, sv, nullptr, false, false);
-            else if (Fc == 4) launch_lines<4, 32>(la, grid, sel, s, far_done, sv, nullptr, false, false);
-            else launch_lines<1, 128>(la, grid, sel, s, far_done, sv, nullptr, neart, false);
+            if (F == 4) launch_lines<4, 128>(la, grid, sel, s, far_done, sv, use3 ? &n3 : nullptr, false, ctx->use_voigt_t);
+            else if (F == 2) launch_lines<2, 128>(la, grid, sel, s, far_done, sv, nullptr, false, ctx->use_voigt_t);
+            else if (Fc == 2) launch_lines<2, 64>(la, grid, sel, s, far_done, sv, nullptr, false, 0);
+            else if (Fc == 4) launch_lines<4, 32>(la, grid, sel, s, far_done, sv, nullptr, false, 0);
+            else launch_lines<1, 128>(la, grid, sel, s, far_done, sv, nullptr, neart, 0);
             CU(cudaEventRecord(ctx->ev[3], s));
             st.kernel_launches++;
             CU(cudaGetLastError());

@@ -178,21 +178,40 @@ __device__ __forceinline__ double cdiv_re(cplx a, cplx b)
 {
     return (a.re * b.re + a.im * b.im) * rcp3(b.re * b.re + b.im * b.im);
 }
-__device__ __noinline__ double w4_re_near(double x, double y)
+// the three near regions one by one ...
+__device__ __forceinline__ double w4_re_region2(double x, double y)
 {
     const cplx t = cmk(y, -x);
-    const double s = fabs(x) + y;
-    if (!(s < 5.5)) {                    // region II
-        const cplx u = t * t;
-        return cdiv_re(t * (1.410474 + u * .5641896), .75 + u * (3. + u));
-    }
-    if (!(y < 0.195 * fabs(x) - 0.176))  // region III
-        return cdiv_re(16.4955 + t * (20.20933 + t * (11.96482 + t * (3.778987 + t * .5642236))),
-                       16.4955 + t * (38.82363 + t * (39.27121 + t * (21.69274 + t * (6.699398 + t)))));
-    const cplx u = t * t;                // region IV
+    const cplx u = t * t;
+    return cdiv_re(t * (1.410474 + u * .5641896), .75 + u * (3. + u));
+}
+__device__ __forceinline__ double w4_re_region3(double x, double y)
+{
+    const cplx t = cmk(y, -x);
+    return cdiv_re(16.4955 + t * (20.20933 + t * (11.96482 + t * (3.778987 + t * .5642236))),
+                   16.4955 + t * (38.82363 + t * (39.27121 + t * (21.69274 + t * (6.699398 + t)))));
+}
+__device__ __forceinline__ double w4_re_region4(double x, double y)
+{
+    const cplx t = cmk(y, -x);
+    const cplx u = t * t;
     const cplx num = t * (36183.31 - u * (3321.9905 - u * (1540.787 - u * (219.0313 - u * (35.76683 - u * (1.320522 - u * .56419))))));
     const cplx den = 32066.6 - u * (24322.84 - u * (9022.228 - u * (2186.181 - u * (364.2191 - u * (61.57037 - u * (1.841439 - u))))));
     return cexpd(u).re - cdiv_re(num, den);
+}
+// 0: region II (5.5 <= s < 15), 1: region III, 2: region IV -- the boundaries of modm.f90:1111, 1117 for s = |x|+y < 15
+__device__ __forceinline__ int w4_near_region(double x, double y)
+{
+    if (!(fabs(x) + y < 5.5)) return 0;
+    return !(y < 0.195 * fabs(x) - 0.176) ? 1 : 2;
+}
+// ... and behind one entry point
+__device__ __noinline__ double w4_re_near(double x, double y)
+{
+    const int r = w4_near_region(x, y);
+    if (r == 0) return w4_re_region2(x, y);
+    if (r == 1) return w4_re_region3(x, y);
+    return w4_re_region4(x, y);
 }
 __device__ __forceinline__ double w4_re_fast(double x, double y)
 {

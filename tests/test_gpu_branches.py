@@ -243,7 +243,7 @@ def _run_with_env(case, env, **kw):
 
 
 @pytest.mark.parametrize("F", ["4", "2"])
-def test_transposed_voigt_kernel_on_every_voigt_branch(F):
+def test_transposed_voigt_kernel_on_every_voigt_branch(F, variant="1"):
     """voigtT_kernel (dense tiles: lines over warps, lanes over each line's run of frequencies) on the Voigt-zone branch
     case -- speed dependence, CO2, coupled lines of other molecules, coupled O2, the negative-frequency resonance -- plus a
     dense stretch across the 22 GHz line, with the dense-tile kernels forced (MRTM_LINES_F): against the oracle (1e-9, both
@@ -255,13 +255,13 @@ def test_transposed_voigt_kernel_on_every_voigt_branch(F):
     ref = harness.run_oracle(case)
     assert ref["branches"]["sdep"] > 500 and ref["branches"]["co2_lc1"] > 100 and ref["branches"]["generic_lc"] > 200
     scale = np.abs(ref["o"])[:, None, :]
-    new = _run_with_env(case, {"MRTM_LINES_F": F, "MRTM_VOIGT_T": "1"})
+    new = _run_with_env(case, {"MRTM_LINES_F": F, "MRTM_VOIGT_T": variant})
     _check_against(ref, new, OD_RTOL)
     old = _run_with_env(case, {"MRTM_LINES_F": F, "MRTM_VOIGT_T": "0"})
     _check_against(ref, old, OD_RTOL)
     assert harness.rel_diff(new["o"], old["o"]) < 1e-12
     assert np.max(np.abs(new["o_by_mol"] - old["o_by_mol"]) / scale) < 1e-12
-    fast = _run_with_env(case, {"MRTM_LINES_F": F, "MRTM_VOIGT_T": "1"}, by_mol=False, selection=False)
+    fast = _run_with_env(case, {"MRTM_LINES_F": F, "MRTM_VOIGT_T": variant}, by_mol=False, selection=False)
     assert harness.rel_diff(fast["o"], ref["o"]) < OD_RTOL
     assert harness.rel_diff(fast["o"], new["o"]) < 1e-10
     assert np.max(np.abs(fast["tb"] - ref["tb"])) < TB_ATOL

@@ -17,8 +17,8 @@ cd ../..
 for name in "${names[@]}"; do
   case $name in *_F2) export MRTM_LINES_F=2;; *) unset MRTM_LINES_F;; esac
   MRTM_LIB=/tmp/lib_$name.so timeout 200 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --direct-steps 0 2> $out/sw_$name.err | tail -1 > $out/sw_$name.json
-  MRTM_LIB=/tmp/lib_$name.so timeout 200 ncu --metrics gpu__time_duration.sum --clock-control none -s 60 -c 60 --csv --log-file $out/sw_${name}_launches.csv \
+  MRTM_LIB=/tmp/lib_$name.so timeout 200 ncu --metrics gpu__time_duration.sum --clock-control none -s 60 -c 70 --csv --log-file $out/sw_${name}_launches.csv \
       python bench.py --steps 2 --warmup 3 --no-cpu-baseline --direct-steps 0 > /dev/null 2>&1
   echo "== $name: $(python -c "import json;d=json.load(open('$out/sw_$name.json'));print('ms/step',round(d['ms_per_step'],4),'lines',round(d['roofline']['kernel_ms'],4))" 2>&1)"
-  python tools/launch_summary.py $out/sw_${name}_launches.csv | grep -E "near2_kernel<., 0|near_kernel<., 0|far_kernel|voigt_kernel<|final_kernel<|derive|rt_kernel|plan_kernel" | awk -F'|' '{printf "   %s avg %s\n",$2,$5}'
+  python tools/launch_summary.py $out/sw_${name}_launches.csv | grep -E "near2_kernel<., 0|near_kernel<., 0|far_kernel|voigtT?_kernel<|final_kernel<|derive|rt_kernel|plan_kernel" | awk -F'|' '{printf "   %s avg %s\n",$2,$5}'
 done
