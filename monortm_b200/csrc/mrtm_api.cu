@@ -74,6 +74,7 @@ struct mrtm_ctx {
     DevBuf b_ov;
     int use_side = 1;                             // MRTM_SIDE_STREAM=0: everything on one stream
     int use_near2 = 1;                            // per-warp re-planning near-field kernel (MRTM_NEAR2=0 disables)
+    int coarse_tile = 32;                         // MRTM_COARSE_TILE: channels per tile on channel lists (128, 64, 32)
     int coarse_f = 2;                             // MRTM_COARSE_F: frequencies per thread on 128-frequency tiles (CTA of 128/F threads)
     int use_neart = 1;                            // transposed direct kernel for coarse frequency lists (MRTM_NEART=0: near_kernel)
     DevBuf b_vcand, b_vcseg, b_vccount;
@@ -209,6 +210,7 @@ extern "C" int mrtm_init(int device, mrtm_ctx** out)
     if (const char* s = std::getenv("MRTM_NEAR2")) ctx->use_near2 = std::atoi(s) != 0;
     if (const char* s = std::getenv("MRTM_PLAN_CACHE")) ctx->use_plan_cache = std::atoi(s) != 0;
     if (const char* s = std::getenv("MRTM_NEAR3")) ctx->use_near3 = std::atoi(s) != 0;
+    if (const char* s = std::getenv("MRTM_COARSE_TILE")) ctx->coarse_tile = std::atoi(s);
     if (const char* s = std::getenv("MRTM_COARSE_F")) { const int v = std::atoi(s); ctx->coarse_f = (v == 2 || v == 4) ? v : 1; }
     if (const char* s = std::getenv("MRTM_NEART")) ctx->use_neart = std::atoi(s);      // 0 off, 1 by tile width, 2 every F = 1 call
     if (const char* s = std::getenv("MRTM_LINES_F")) ctx->force_f = std::atoi(s);
@@ -805,8 +807,13 @@ static int run_device(mrtm_ctx* ctx, const RunDesc& r, cudaStream_t s)
             if (r.wn_span >= 0. && nwn > 1)
                 while (Fh > 1 && 128. * Fh * (r.wn_span / (double)(nwn - 1)) > ctx->tile_width) Fh >>= 1;
             const int F = (force_f == 1 || force_f == 2 || force_f == 4) ? force_f : Fh;
-            const int T0 = NTsel * F;
-            const int Fc = (F == 1 && nwn >= 64) ? ctx->coarse_f : 1;       // 128-frequency tiles: Fc frequencies per thread, 128/Fc threads
+            // Channel lists (F == 1): a 128-channel tile is spectrally wide (cm-1), so hardly a line is far from it; with
+            // tiles of coarse_tile channels (MRTM_COARSE_TILE: 32 by default, one warp per (tile, layer)) the level-0
+            // expansions take most of the window.  Measured (profiles/r02_sweeps.md): 1000 log-spaced channels x 64 profiles
+            // 98.5 ms (128) / 97.7 (64) / 83.9 (32); 10000 frequencies x 300 layers 27.9 / 25.2 / 25.9 ms.
+            const int Tc = (F == 1 && nwn >= 64 && (ctx->coarse_tile == 64 || ctx->coarse_tile == 32)) ? ctx->coarse_tile : 0;
+            const int T0 = Tc ? Tc : NTsel * F;
+            const int Fc = (F == 1 && nwn >= 64 && !Tc) ? ctx->coarse_f : 1;       // 128-frequency tiles: Fc frequencies per thread, 128/Fc threads
             dim3 grid((unsigned)((nwn + T0 - 1) / T0), (unsigned)nlay, (unsigned)nb);
             CU(cudaEventRecord(ctx->ev[2], s));
             // ---- plans (layer independent) and the upper levels of the far-field hierarchy
@@ -831,7 +838,7 @@ static int run_device(mrtm_ctx* ctx, const RunDesc& r, cudaStream_t s)
             // a handful of channels (sounder sets): lanes own lines, warps own frequencies -- thread-per-frequency leaves most
             // lanes idle there (measured on B200: 27 % faster on 19 channels; about even on 1000 log-spaced channels, 24 %
             // slower on a 5.5e-3 cm-1 grid, where near_kernel stays)
-            const bool neart = ctx->use_neart && F == 1 && NTsel == 128 && (ctx->use_neart > 1 || nwn < 64);
+            const bool neart = ctx->use_neart && F == 1 && NTsel == 128 && !Tc && (ctx->use_neart > 1 || nwn < 64);
             const bool vplan = F == 1 && NTsel == 128;      // Voigt-zone candidates: every coarse-tile call
             // ---- plan cache: buffers first (a reallocation invalidates the cached plans), then the device-side check
             const size_t npc_words = 1 + std::max<size_t>(1, h.segments.size());
@@ -1008,7 +1015,9 @@ static int run_device(mrtm_ctx* ctx, const RunDesc& r, cudaStream_t s)
                 la.o_v = (double*)ctx->b_ov.p;
                 sv = sp;
             }
-            if (F == 4) launch_lines<4, 128>(la, grid, sel, s, far_done, sv, use3 ? &n3 : nullptr, false, ctx->use_voigt_t);
+            if (Tc == 64) launch_lines<2, 32>(la, grid, sel, s, far_done, sv, nullptr, false, 0);
+            else if (Tc == 32) launch_lines<1, 32>(la, grid, sel, s, far_done, sv, nullptr, false, 0);
+            else if (F == 4) launch_lines<4, 128>(la, grid, sel, s, far_done, sv, use3 ? &n3 : nullptr, false, ctx->use_voigt_t);
             else if (F == 2) launch_lines<2, 128>(la, grid, sel, s, far_done, sv, nullptr, false, ctx->use_voigt_t);
             else if (Fc == 2) launch_lines<2, 64>(la, grid, sel, s, far_done, sv, nullptr, false, 0);
             else if (Fc == 4) launch_lines<4, 32>(la, grid, sel, s, far_done, sv, nullptr, false, 0);
