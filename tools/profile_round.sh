@@ -8,7 +8,7 @@ mkdir -p $out
 timeout 600 python bench.py --steps 20 --warmup 3 2> $out/${tag}_bench.err | tail -1 > $out/${tag}_bench.json
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $out/${tag}_launches.csv \
     python bench.py --steps 2 --warmup 3 --no-cpu-baseline --direct-steps 0 > $out/${tag}_launches.log 2>&1
-for k in near2_kernel far_warp_kernel far_kernel derive_kernel voigt_kernel rt_kernel final_kernel plan_kernel; do
+for k in near2_kernel far_warp_kernel far_kernel derive_kernel voigtT_kernel rt_kernel final_kernel plan_kernel; do
   skip=3
   [ $k = far_warp_kernel ] && skip=7  # the level-0 launch of the 4th step (two far_warp levels per step)
   [ $k = plan_kernel ] && skip=11
@@ -18,10 +18,10 @@ done
 ls -la $out | tail -20
 # reports are ~9 MB each and gpurun brings back at most 64 MiB: summarise on the box, keep only the summaries
 python tools/ncu_summary.py $out/${tag}_*.ncu-rep > $out/${tag}_ncu_summary.md 2>&1
-for k in near2_kernel far_warp_kernel voigt_kernel final_kernel derive_kernel rt_kernel; do
+for k in near2_kernel far_warp_kernel voigtT_kernel final_kernel derive_kernel rt_kernel; do
   m=$k      # mangled-name substring of the instantiation that was captured (templates have several)
   [ $k = near2_kernel ] && m=near2_kernelILi4ELb0E
-  [ $k = voigt_kernel ] && m=voigt_kernelILi4E
+  [ $k = voigtT_kernel ] && m=voigtT_kernelILi4E
   [ $k = final_kernel ] && m=final_kernelILi4E
   python tools/ncu_lines.py $out/${tag}_$k.ncu-rep monortm_b200/lib/libmonortm_b200.so $m 40 > $out/${tag}_lines_$k.txt 2>&1
 done
