@@ -296,7 +296,7 @@ def ncu_traffic(args):
     try:
         if args.nwn_per_gpu != 125000 or args.n_filler != N_FILLER:
             return None
-        with open(os.path.join(ROOT, "profiles", "r02_v30_traffic.json")) as f:
+        with open(os.path.join(ROOT, "profiles", "r02_v34_traffic.json")) as f:
             return float(json.load(f)["lines_group_bytes_per_step"])
     except Exception:
         return None
@@ -857,7 +857,7 @@ def main():
             "clocks": sampler.summary(),
             "roofline": {"bound": "fp64", "achieved": achieved, "peak": fp64_peak,
                          "unit": "TFLOP/s", "frac": achieved / fp64_peak if fp64_peak else None, "traffic": ncu_traffic(args),
-                         "traffic_source": "profiles/r02_v30_traffic.json: dram bytes read+written by the line-path kernels of one step "
+                         "traffic_source": "profiles/r02_v34_traffic.json: dram bytes read+written by the line-path kernels of one step "
                                            "(ncu --set full, default workload only; null otherwise)",
                          "kernel": "plan+far+near2+voigt+final (the line path of one step)",
                          "peak_source": "measured live: mrtm_fp64_peak DFMA probe (MEASURED_PEAKS.json has no FP64 figure)",

@@ -442,10 +442,23 @@ struct DeriveArgs {
 };
 
 #ifndef MRTM_DERIVE_MINB
-#define MRTM_DERIVE_MINB 6
+#define MRTM_DERIVE_MINB 4
 #endif
+// the static parameters of one line: read once per thread, used for kDeriveLayers layers
+struct LineStatic {
+    int32_t mol, xf, cls, lci, bi, sidx;
+    double xnu0, deltnu, es, s0adj, af, as, x, dopf;
+};
+__device__ __forceinline__ LineStatic load_line_static(const LinesDev& ln, int q)
+{
+    LineStatic t;
+    t.mol = ln.mol[q]; t.xf = ln.xf[q]; t.cls = ln.cls[q]; t.lci = ln.lcidx[q]; t.bi = ln.brdidx[q]; t.sidx = ln.sidx[q];
+    t.xnu0 = ln.xnu0[q]; t.deltnu = ln.deltnu[q]; t.es = ln.e[q]; t.s0adj = ln.s0adj[q];
+    t.af = ln.alpf[q]; t.as = ln.alps[q]; t.x = ln.x[q]; t.dopf = ln.dopf[q];
+    return t;
+}
 // one (line, layer): returns the bits of |Xnu| when the line can take the Voigt branch in this layer, else all ones
-__device__ __forceinline__ unsigned long long derive_one(const DeriveArgs& a, int q, int64_t L)
+__device__ __forceinline__ unsigned long long derive_one(const DeriveArgs& a, int q, int64_t L, const LineStatic& ls)
 {
     const unsigned long long kNone = ~0ull;
     if (q >= a.ln.n_pad) return kNone;
@@ -459,12 +472,12 @@ __device__ __forceinline__ unsigned long long derive_one(const DeriveArgs& a, in
         return kNone;
     }
     const LayerDev& ly = a.lay[L];
-    const int mol = a.ln.mol[q], xf = a.ln.xf[q], cls = a.ln.cls[q];
+    const int mol = ls.mol, xf = ls.xf, cls = ls.cls;
     const double rhorat = ly.rhorat, rho_self = ly.rho_self[mol - 1];
     const double radct = ly.radct;
 
     double aip = 0., bip = 0.;
-    const int lci = a.ln.lcidx[q];
+    const int lci = ls.lci;
     if (lci >= 0) {
         const double* c = a.ln.lc + (size_t)lci * 16;
         double A[4] = {c[0], c[1], c[2], c[3]}, B[4] = {c[4], c[5], c[6], c[7]};
@@ -490,9 +503,9 @@ __device__ __forceinline__ unsigned long long derive_one(const DeriveArgs& a, in
     }
 
     // shifted line centre: exactly Xnu0 + deltnu*(Xn/XN0) [+ sum(rho*flg*(shft-deltnu))], no FMA
-    const double xnu0 = a.ln.xnu0[q], deltnu = a.ln.deltnu[q];
+    const double xnu0 = ls.xnu0, deltnu = ls.deltnu;
     double xnu = xadd(xnu0, xmul(deltnu, rhorat));
-    const int bi = a.ln.brdidx[q];
+    const int bi = ls.bi;
     const bool use_brd = (mol <= MRTM_MXBRDMOL) && (a.ibrd != 0);
     const double* brd = (bi >= 0) ? a.ln.brd + (size_t)bi * 28 : nullptr;
     if (use_brd) {
@@ -504,17 +517,17 @@ __device__ __forceinline__ unsigned long long derive_one(const DeriveArgs& a, in
 
     // INTENS.  The divisions of the reference (:860-865, :453, :419) are regrouped into multiplications by per-layer and
     // per-line reciprocals and a Newton reciprocal (~1 ulp each; the bar on optical depths is 1e-9).
-    const double xipsf = a.scorc[(size_t)L * a.ln.nsi + a.ln.sidx[q]];
-    const double es = a.ln.e[q];
+    const double xipsf = a.scorc[(size_t)L * a.ln.nsi + ls.sidx];
+    const double es = ls.es;
     // exp(-c2 E/T)/exp(-c2 E/T0) as one exponential (modm.f90 INTENS)
-    double s = a.ln.s0adj[q] * exp(radct * es * ly.dinvt) * xipsf;
+    double s = ls.s0adj * exp(radct * es * ly.dinvt) * xipsf;
     const double rx = radct * xnu;
     const double stim_n = 1 + exp(-(rx * ly.inv_t)), stim_d = xnu * (1 - exp(-(rx * (1. / kT0))));
     double stild = (stim_d > 1e-280 && stim_d < 1e280) ? s * (stim_n * rcp3(stim_d)) : s * (stim_n / stim_d);
 
     // HALFWHM_C
-    const double af = a.ln.alpf[q], as = a.ln.alps[q];
-    const double rtx = exp(a.ln.x[q] * ly.lnrt);         // (T/T0)^x with the layer's log(T/T0)
+    const double af = ls.af, as = ls.as;
+    const double rtx = exp(ls.x * ly.lnrt);         // (T/T0)^x with the layer's log(T/T0)
     const double alfa0i = af * rtx, hwhmsi = as * rtx;
     double hwhm_c = alfa0i * (rhorat - rho_self) + hwhmsi * rho_self;
     if (use_brd && brd) {
@@ -528,7 +541,7 @@ __device__ __forceinline__ unsigned long long derive_one(const DeriveArgs& a, in
         if (brd[mol - 1] == 0.) hwhm_c = hwhm_c + rho_self * (hwhmsi - alfa0i);
     }
     // HALFWHM_D = (Xnu/c)*sqrt(2 ln2 kT/(M/N_A)): the constants and the mass are folded per line at staging (dopf)
-    const double hwhm_d = xnu * (a.ln.dopf[q] * ly.sqrt_t);
+    const double hwhm_d = xnu * (ls.dopf * ly.sqrt_t);
     if (xf == -3) hwhm_c = hwhm_c * (1 - (aip * ly.rp) - (bip * ly.rp2));
     // zeta = HWHM_C/(HWHM_C+HWHM_D) decides Voigt or Lorentz at 0.99 (:419): the exact quotient only where the fast one is
     // too close to the threshold to decide
@@ -556,22 +569,33 @@ __device__ __forceinline__ unsigned long long derive_one(const DeriveArgs& a, in
     return (vt >= 0.) ? (unsigned long long)__double_as_longlong(fabs(xnu)) : kNone;
 }
 
+#ifndef MRTM_DERIVE_LAYERS
+#define MRTM_DERIVE_LAYERS 8        // measured (profiles/r02_sweeps.md): 1 layer/thread 171 us, 4 at 64 registers 138, 8: 133
+#endif
+constexpr int kDeriveLayers = MRTM_DERIVE_LAYERS;      // layers per thread: the line's static parameters are read once for all of them
 __global__ void __launch_bounds__(256, MRTM_DERIVE_MINB) derive_kernel(DeriveArgs a)
 {
-    const int64_t L = blockIdx.y;
-    unsigned long long xb = derive_one(a, blockIdx.x * blockDim.x + threadIdx.x, L);
-    // smallest |Xnu| of the layer's Voigt-capable lines: warp minimum, block minimum, one global atomic per block at most
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    LineStatic ls;
+    if (q < a.ln.n) ls = load_line_static(a.ln, q);
     __shared__ unsigned long long s_min[8];
+    for (int i = 0; i < kDeriveLayers; i++) {
+        const int64_t L = (int64_t)blockIdx.y * kDeriveLayers + i;
+        if (L >= a.nlayers) break;
+        unsigned long long xb = derive_one(a, q, L, ls);
+        // smallest |Xnu| of the layer's Voigt-capable lines: warp minimum, block minimum, one global atomic per block at most
 #pragma unroll
-    for (int off = 16; off > 0; off >>= 1) {
-        const unsigned long long o = __shfl_xor_sync(0xffffffffu, xb, off);
-        xb = o < xb ? o : xb;
-    }
-    if ((threadIdx.x & 31) == 0) s_min[threadIdx.x >> 5] = xb;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        unsigned long long m = s_min[0];
-        for (int w = 1; w < 8; w++) m = s_min[w] < m ? s_min[w] : m;
-        if (m < *(volatile unsigned long long*)(a.layer_voigt + L)) atomicMin(a.layer_voigt + L, m);
+        for (int off = 16; off > 0; off >>= 1) {
+            const unsigned long long o = __shfl_xor_sync(0xffffffffu, xb, off);
+            xb = o < xb ? o : xb;
+        }
+        if (i > 0) __syncthreads();                        // s_min of the previous layer has been read
+        if ((threadIdx.x & 31) == 0) s_min[threadIdx.x >> 5] = xb;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            unsigned long long m = s_min[0];
+            for (int w = 1; w < 8; w++) m = s_min[w] < m ? s_min[w] : m;
+            if (m < *(volatile unsigned long long*)(a.layer_voigt + L)) atomicMin(a.layer_voigt + L, m);
+        }
     }
 }

@@ -736,7 +736,7 @@ static int run_device(mrtm_ctx* ctx, const RunDesc& r, cudaStream_t s)
             CU(cudaMemsetAsync(ctx->b_lvoigt.p, 0xff, (size_t)Lb * sizeof(unsigned long long), s));
             da.layer_voigt = (unsigned long long*)ctx->b_lvoigt.p;
             CU(cudaEventRecord(ctx->ev[0], s));
-            derive_kernel<<<dim3((unsigned)((n_pad + 255) / 256), (unsigned)Lb), 256, 0, s>>>(da);
+            derive_kernel<<<dim3((unsigned)((n_pad + 255) / 256), (unsigned)((Lb + kDeriveLayers - 1) / kDeriveLayers)), 256, 0, s>>>(da);
             CU(cudaEventRecord(ctx->ev[1], s));
             if (side_on) CU(cudaEventRecord(ctx->evf[1], s));
             st.kernel_launches++;

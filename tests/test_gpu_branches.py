@@ -265,3 +265,33 @@ def test_transposed_voigt_kernel_on_every_voigt_branch(F, variant="1"):
     assert harness.rel_diff(fast["o"], ref["o"]) < OD_RTOL
     assert harness.rel_diff(fast["o"], new["o"]) < 1e-10
     assert np.max(np.abs(fast["tb"] - ref["tb"])) < TB_ATOL
+
+
+@pytest.mark.parametrize("tile", ["128", "64", "32"])
+def test_channel_tile_sizes_agree(tile):
+    """Channel lists run with one frequency per thread and tiles of MRTM_COARSE_TILE channels (32 by default: one warp per
+    (tile, layer), the level-0 far field takes most of the window).  A 200-channel log-spaced list (ragged last tile) with
+    cloud, against the oracle under each tile size."""
+    wn = np.exp(np.linspace(np.log(0.1), np.log(30.0), 200))
+    case = harness.make_case(n_filler=1024, nlay=20, wn=wn, irt=1, clw=True, tmpsfc=285.0, emis=0.85)
+    ref = harness.run_oracle(case)
+    gpu = _run_with_env(case, {"MRTM_COARSE_TILE": tile})
+    _check_against(ref, gpu, OD_RTOL)
+    fast = _run_with_env(case, {"MRTM_COARSE_TILE": tile}, by_mol=False, selection=False)
+    assert harness.rel_diff(fast["o"], ref["o"]) < OD_RTOL
+    assert np.max(np.abs(fast["tb"] - ref["tb"])) < TB_ATOL
+    if tile != "128":
+        assert fast["stats"]["far_expansions"] > 0
+
+
+def test_transposed_voigt_kernel_on_an_unsorted_dense_list():
+    """voigtT_kernel brackets each line's run of frequencies by binary search on an ascending tile; a tile that is not
+    ascending keeps the whole tile as the run and relies on the per-pair test of the reference."""
+    rng = np.random.default_rng(5)
+    wn = np.concatenate([0.741691 + np.linspace(-3e-4, 3e-4, 1500), 2.0 + np.linspace(-0.02, 0.02, 548)])
+    rng.shuffle(wn)
+    case = harness.make_case(n_filler=256, nlay=40, wn=wn, irt=3)
+    ref = harness.run_oracle(case)
+    assert ref["n_voigt"] > 0
+    gpu = _run_with_env(case, {"MRTM_LINES_F": "4", "MRTM_VOIGT_T": "1"})
+    _check_against(ref, gpu, OD_RTOL)
