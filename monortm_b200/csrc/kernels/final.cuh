@@ -37,7 +37,6 @@ __global__ void __launch_bounds__(NT, MRTM_FINAL_MINB) final_kernel(LinesArgs a)
         sv[f] = (wn[f] - cen) * hinv;
     }
     const double hinv_2t = 0.5 * ly.inv_t;
-    const double inv_xkt = ly.xkt > 0. ? 1. / ly.xkt : 0.;
     const double* cf = have_far ? a.coef[0] + ((size_t)blockIdx.x * Ltot + L) * a.nslot * kFarK : nullptr;
     double osum[F];
     if (!a.o_by_mol) {
@@ -107,7 +106,7 @@ __global__ void __launch_bounds__(NT, MRTM_FINAL_MINB) final_kernel(LinesArgs a)
             long long ihi = (long long)((a.v2abs - 1.0 - vi) / 1.0 + 0.999);
             in_rng = (ilo <= 1) && (ihi >= 1);
         }
-        const double rf = radfn_r(wn[f], ly.xkt, inv_xkt);
+        const double rf = radfn_r(wn[f], ly.xkt);
 #pragma unroll
         for (int c = 0; c < 5; c++) {
             if (kMwOnly && (c == CP_O3 || c == CP_O2)) continue;       // microwave call: O3 and O2 have no component (compile time)

@@ -116,13 +116,12 @@ __device__ __forceinline__ double radfn(double vi, double xkt)
     return vi;
 }
 
-// the same with the quotient (1-e)/(1+e) through a Newton reciprocal and x = vi/xkt as vi*(1/xkt) (~1 ulp each); the exact
-// quotient decides the branch where the product is too close to a threshold to tell (the two forms differ by 8e-6 at x = 0.01)
-__device__ __forceinline__ double radfn_r(double vi, double xkt, double inv_xkt)
+// the same with the quotient (1-e)/(1+e) through a Newton reciprocal (~1 ulp); the branch variable x stays the exact quotient
+// (x as vi*(1/xkt) with an exact fallback next to the thresholds was measured: final_kernel 197 -> 207 us, not kept)
+__device__ __forceinline__ double radfn_r(double vi, double xkt)
 {
     if (xkt > 0.0) {
-        double x = vi * inv_xkt;
-        if (fabs(x - 0.01) < 1e-13 || fabs(x - 10.0) < 1e-10) x = vi / xkt;
+        double x = vi / xkt;
         if (x <= 0.01) return 0.5 * x * vi;
         if (x <= 10.0) {
             double e = exp(-x);
