@@ -16,6 +16,7 @@ template <int F, bool SEL, int NT>
 __global__ void __launch_bounds__(NT, (MRTM_LINES_MINB * 128) / NT) near_kernel(LinesArgs a)
 {
     constexpr int NW = NT / 32;
+    constexpr int kSt = near_stages<NT>();        // stages of the tile ring
     const int tid = threadIdx.x;
     if (a.near_pieces) {                          // near2_kernel took the tiles whose direct lines fit its staging area
         const TileHdr th0 = a.hdr[0][blockIdx.x];
@@ -33,13 +34,13 @@ __global__ void __launch_bounds__(NT, (MRTM_LINES_MINB * 128) / NT) near_kernel(
     const double* __restrict__ lcp = a.lcplanes + (size_t)L * LCP_NPLANES * a.nlc_pad;
     const double* __restrict__ pVT = pl + (size_t)D_VT * a.n_pad;
 
-    __shared__ __align__(8) uint64_t s_bar[kStages];
+    __shared__ __align__(8) uint64_t s_bar[kSt];
     __shared__ __align__(8) uint64_t s_all_bar;
     __shared__ double s_ped[2][NW];
     __shared__ unsigned char s_act[kMaxSegments];
     extern __shared__ __align__(128) unsigned char s_dyn[];
-    double (*s_tile)[4][kTile] = reinterpret_cast<double (*)[4][kTile]>(s_dyn);      // [kStages][4][kTile]
-    SegWork* s_work = reinterpret_cast<SegWork*>(s_dyn + sizeof(double) * kStages * 4 * kTile);
+    double (*s_tile)[4][kTile] = reinterpret_cast<double (*)[4][kTile]>(s_dyn);      // [kSt][4][kTile]
+    SegWork* s_work = reinterpret_cast<SegWork*>(s_dyn + sizeof(double) * kSt * 4 * kTile);
 
     const int nseg = a.nseg;
     {
@@ -50,7 +51,7 @@ __global__ void __launch_bounds__(NT, (MRTM_LINES_MINB * 128) / NT) near_kernel(
         for (int s = tid; s < nseg; s += NT) s_act[s] = (ly.wk[a.seg[s].mol - 1] != 0.) ? 1 : 0;   // W_SPECIES == 0: skipped (:318-321)
     }
     if (tid == 0) {
-        for (int i = 0; i < kStages; i++) mbar_init(&s_bar[i], 1);
+        for (int i = 0; i < kSt; i++) mbar_init(&s_bar[i], 1);
         mbar_init(&s_all_bar, 32);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -69,7 +70,7 @@ __global__ void __launch_bounds__(NT, (MRTM_LINES_MINB * 128) / NT) near_kernel(
     __syncthreads();
     // Staging: when all direct runs of the CTA fit the tile memory (the usual case with the far field on) they
     // are staged at once -- one mbarrier wait, no per-tile hand-shake; otherwise tiles stream through the ring.
-    constexpr int kCap = kStages * kTile;
+    constexpr int kCap = kSt * kTile;
     const bool stage_all = a.hdr[0][blockIdx.x].total_lines <= kCap;
     double* s_all = reinterpret_cast<double*>(s_dyn);       // [4][kCap] in stage-all mode
 
@@ -129,7 +130,7 @@ __global__ void __launch_bounds__(NT, (MRTM_LINES_MINB * 128) / NT) near_kernel(
         }
         mbar_wait(&s_all_bar, 0u);
     } else if (tid == 0) {
-        for (int i = 0; i < kStages - 1 && more; i++) {
+        for (int i = 0; i < kSt - 1 && more; i++) {
             more = advance(pjs, pjr, pjt);
             if (more) issue(pjs, pjr, pjt, i);
         }
@@ -147,7 +148,7 @@ __global__ void __launch_bounds__(NT, (MRTM_LINES_MINB * 128) / NT) near_kernel(
         return t;
     };
 
-    int gtile = 0;              // global tile counter: stage = gtile % kStages, mbarrier parity = (gtile / kStages) & 1
+    int gtile = 0;              // global tile counter: stage = gtile % kSt, mbarrier parity = (gtile / kSt) & 1
 
     double osum[F], sf[F];
     long long cnt[F];
@@ -234,12 +235,12 @@ __global__ void __launch_bounds__(NT, (MRTM_LINES_MINB * 128) / NT) near_kernel(
                         tb = t0;
                         thi = rhi;
                     } else {
-                        const int st = gtile % kStages;
+                        const int st = gtile % kSt;
                         if (tid == 0 && more) {        // refill the stage the previous tile released
                             more = advance(pjs, pjr, pjt);
-                            if (more) issue(pjs, pjr, pjt, (gtile + kStages - 1) % kStages);
+                            if (more) issue(pjs, pjr, pjt, (gtile + kSt - 1) % kSt);
                         }
-                        mbar_wait(&s_bar[st], (uint32_t)(gtile / kStages) & 1u);
+                        mbar_wait(&s_bar[st], (uint32_t)(gtile / kSt) & 1u);
                         tX = s_tile[st][0]; tH = s_tile[st][1]; tC = s_tile[st][2]; tP = s_tile[st][3];
                         tb = t0 + t * kTile;
                         thi = (tb + kTile) < rhi ? (tb + kTile) : rhi;

@@ -524,14 +524,15 @@ static void launch_lines(const LinesArgs& la, dim3 grid, bool sel, cudaStream_t 
                          const Near3Args* n3, bool neart, int voigt_t)
 {
     // near field (direct), Voigt branch, then polynomial + continuum + totals
-    const size_t dyn = sizeof(double) * kStages * 4 * kTile + (size_t)std::max(la.nseg, 1) * sizeof(SegWork);
+    const size_t dyn = sizeof(double) * near_stages<NT>() * 4 * kTile + (size_t)std::max(la.nseg, 1) * sizeof(SegWork);
+    const size_t dynT = sizeof(double) * kStages * 4 * kTile + (size_t)std::max(la.nseg, 1) * sizeof(SegWork);     // nearT_kernel's ring
     if (neart && F == 1) {                     // coarse frequency lists: lanes own lines, warps own frequencies
         if (sel) {
-            cudaFuncSetAttribute(nearT_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
-            nearT_kernel<true><<<grid, 32 * kNTW, dyn, s>>>(la);
+            cudaFuncSetAttribute(nearT_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dynT);
+            nearT_kernel<true><<<grid, 32 * kNTW, dynT, s>>>(la);
         } else {
-            cudaFuncSetAttribute(nearT_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
-            nearT_kernel<false><<<grid, 32 * kNTW, dyn, s>>>(la);
+            cudaFuncSetAttribute(nearT_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dynT);
+            nearT_kernel<false><<<grid, 32 * kNTW, dynT, s>>>(la);
         }
     } else if (la.near_pieces && n3 && F == 4) {      // production path: plan-driven lists, a group of layers per CTA
         cudaFuncSetAttribute(near3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kN3Smem);
