@@ -193,12 +193,6 @@ __device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src_gmem
 #ifndef MRTM_LINES_MINB
 #define MRTM_LINES_MINB 4
 #endif
-#ifndef MRTM_UNROLL_F1
-#define MRTM_UNROLL_F1 4         // near_kernel, one frequency per thread: lines unrolled in the streamed loops
-#endif
-#ifndef MRTM_UNROLL_QUAD_F1
-#define MRTM_UNROLL_QUAD_F1 2    // ... and groups of four lines in the shared-reciprocal loop
-#endif
 #ifndef MRTM_UNROLL_BOTH
 #define MRTM_UNROLL_BOTH 2
 #endif

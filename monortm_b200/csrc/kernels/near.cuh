@@ -17,8 +17,6 @@ __global__ void __launch_bounds__(NT, (MRTM_LINES_MINB * 128) / NT) near_kernel(
 {
     constexpr int NW = NT / 32;
     constexpr int kSt = near_stages<NT>();        // stages of the tile ring
-    // lines in flight per thread in the streamed loops: with one frequency per thread a line is ONE dependent FP64 chain
-    constexpr int kUB = (F == 1) ? MRTM_UNROLL_F1 : MRTM_UNROLL_BOTH, kUQ = (F == 1) ? MRTM_UNROLL_QUAD_F1 : 1;
     const int tid = threadIdx.x;
     if (a.near_pieces) {                          // near2_kernel took the tiles whose direct lines fit its staging area
         const TileHdr th0 = a.hdr[0][blockIdx.x];
@@ -262,7 +260,6 @@ __global__ void __launch_bounds__(NT, (MRTM_LINES_MINB * 128) / NT) near_kernel(
                             // ---- band loops: the reference's exact per-(line,frequency) tests
                             const bool edge = (mode & M_EDGE) != 0, negtest = (mode & M_NEG) != 0, vz = (mode & M_VOIGT) != 0;
                             if (negall || negtest) {
-#pragma unroll kUB
                                 for (int q = lo; q < hi; q++) {
                                     const int j = q - tb;
                                     const double xnu = tX[j], h2 = tH[j], cn = tC[j], ped = tP[j];
@@ -280,7 +277,6 @@ __global__ void __launch_bounds__(NT, (MRTM_LINES_MINB * 128) / NT) near_kernel(
                                     }
                                 }
                             } else {
-#pragma unroll kUB
                                 for (int q = lo; q < hi; q++) {
                                     const int j = q - tb;
                                     const double xnu = tX[j], h2 = tH[j], cn = tC[j], ped = tP[j];
@@ -310,7 +306,7 @@ __global__ void __launch_bounds__(NT, (MRTM_LINES_MINB * 128) / NT) near_kernel(
                         }
                         if (negall) {
                             // ---- interior, both resonances: cn*(1/a+1/b) = cn*(a+b)/(a*b), one reciprocal
-#pragma unroll kUB
+MRTM_UNROLL(MRTM_UNROLL_BOTH)
                             for (int q = lo; q < hi; q++) {
                                 const int j = q - tb;
                                 const double xnu = tX[j], h2 = tH[j], cn = tC[j];
@@ -327,7 +323,6 @@ __global__ void __launch_bounds__(NT, (MRTM_LINES_MINB * 128) / NT) near_kernel(
                             // sum c_i/a_i = N/(a1 a2 a3 a4), N = (c1 a2 + c2 a1)(a3 a4) + (c3 a4 + c4 a3)(a1 a2);
                             // 21 FP64 ops + 1 MUFU per 4 evaluations
                             int q = lo;
-#pragma unroll kUQ
                             for (; q + 4 <= hi; q += 4) {
                                 const int j = q - tb;
                                 const double x1 = tX[j], x2 = tX[j + 1], x3 = tX[j + 2], x4 = tX[j + 3];
