@@ -190,6 +190,9 @@ __device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src_gmem
                  ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
+#ifndef MRTM_LINES_MINB_32
+#define MRTM_LINES_MINB_32 16       // near_kernel on one-warp CTAs: resident CTAs per SM the register budget is sized for
+#endif
 #ifndef MRTM_LINES_MINB
 #define MRTM_LINES_MINB 4
 #endif

@@ -13,7 +13,7 @@
 //    requested, W_mol*SF_mol to O_BY_MOL; final_kernel completes them
 // =============================================================================================
 template <int F, bool SEL, int NT>
-__global__ void __launch_bounds__(NT, (MRTM_LINES_MINB * 128) / NT) near_kernel(LinesArgs a)
+__global__ void __launch_bounds__(NT, NT <= 32 ? MRTM_LINES_MINB_32 : (MRTM_LINES_MINB * 128) / NT) near_kernel(LinesArgs a)
 {
     constexpr int NW = NT / 32;
     constexpr int kSt = near_stages<NT>();        // stages of the tile ring
