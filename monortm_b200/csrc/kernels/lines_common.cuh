@@ -191,7 +191,7 @@ __device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src_gmem
 }
 
 #ifndef MRTM_LINES_MINB_32
-#define MRTM_LINES_MINB_32 16       // near_kernel on one-warp CTAs: resident CTAs per SM the register budget is sized for
+#define MRTM_LINES_MINB_32 20       // near_kernel on one-warp CTAs: resident CTAs per SM the register budget is sized for
 #endif
 #ifndef MRTM_LINES_MINB
 #define MRTM_LINES_MINB 4
@@ -202,7 +202,7 @@ __device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src_gmem
 #define MRTM_PRAGMA(x) _Pragma(#x)
 #define MRTM_UNROLL(n) MRTM_PRAGMA(unroll n)
 #ifndef MRTM_NEAR_STAGES_32
-#define MRTM_NEAR_STAGES_32 3
+#define MRTM_NEAR_STAGES_32 2
 #endif
 #ifndef MRTM_NEAR_STAGES_64
 #define MRTM_NEAR_STAGES_64 4
@@ -210,7 +210,7 @@ __device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src_gmem
 constexpr int kTile = 128;      // lines per smem tile
 constexpr int kStages = 8;      // tile ring
 // near_kernel's ring per CTA size: a one-warp CTA (32-channel tiles of channel lists) consumes a 128-line stage in some 5000 cycles,
-// three stages cover the copy latency and leave room for 13 CTAs per SM instead of 6 (36 KB of ring at eight stages)
+// two stages cover the copy latency and leave room for 20 CTAs per SM instead of 6 (36 KB of ring at eight stages; measured 3: 64.9 ms, 2 with a 96-register budget: 62.9 ms per 64 profiles of the ensemble)
 template <int NT> __host__ __device__ constexpr int near_stages() { return NT <= 32 ? MRTM_NEAR_STAGES_32 : (NT <= 64 ? MRTM_NEAR_STAGES_64 : kStages); }
 constexpr int kPrefetch = 5;    // TMA jobs in flight ahead of the consumer; a warp may run kStages-kPrefetch tiles ahead of the slowest
 #ifndef MRTM_FARK
