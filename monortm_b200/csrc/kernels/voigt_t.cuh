@@ -4,10 +4,11 @@
 // Same job and same arithmetic per (line, frequency) pair as voigt_kernel (modm.f90:427-431 -> LSF_SDVOIGT :567-704): for
 // the pairs with |WN-Xnu| <= 100*HWHM_D it adds W*STILD*(SLS_Voigt - SLS_Lorentz) to O [and O_BY_MOL].  The mapping is
 // transposed: on a dense grid the zone of a line covers a contiguous run of some 10 ... 300 frequencies of the tile, so
-//   * the CTA (frequency tile, layer, profile) stages its zone lines and their frequency-independent terms once,
-//     each staging thread also brackets its line's run [lo, hi) of tile frequencies by two binary searches in shared
-//     memory (exact: the rounded difference WN-Xnu is monotone in WN, so the reference's test is a monotone predicate on
-//     an ascending tile; a tile that is not ascending keeps the whole tile as the run and relies on the per-pair test),
+//   * the CTA (frequency tile, layer, profile) stages its zone lines once, two threads per line: one forms the
+//     frequency-independent terms, the other brackets the line's run [lo, hi) of tile frequencies by two binary searches
+//     in shared memory (exact: the rounded difference WN-Xnu is monotone in WN, so the reference's test is a monotone
+//     predicate on an ascending tile; a tile that is not ascending keeps the whole tile as the run and relies on the
+//     per-pair test),
 //   * each warp takes every NW-th line, holds the line's terms in registers and strides its lanes over the run; the
 //     per-pair test of the reference stays in the loop, so the selected pairs are unchanged,
 //   * sums go to a per-warp accumulator tile in shared memory (no atomics: the order of the additions is fixed), the
